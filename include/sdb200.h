@@ -1,0 +1,190 @@
+/*
+ * sdb200.h — C-ABI of libsdb200.so: the B200 (sm_100a) kernels behind the latent-diffusion
+ * sampling hot path of ProgramerSalar/stable-diffusion-from-scratch.
+ *
+ * The reference has no FFI: the boundary is its Python nn.Module API (UNetModel.forward,
+ * DDIMSampler.sample, AutoencoderKL.decode).  The host-side mirror of that API lives in
+ * stable-diffusion-from-scratch_b200/*.py and binds these entry points with ctypes.  Each entry
+ * point below names the reference op (file:line under the reference tree) whose arithmetic it
+ * replaces.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers + sizes only; every pointer is a DEVICE pointer unless marked host
+ *   - activations are channels-last: images [N, H, W, C] ("NHWC"), tokens [rows, C]
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued, never synchronised
+ *   - returns 0 on success, negative sdb code otherwise (sdb_last_error_string() explains);
+ *     no entry point allocates device memory: workspaces are passed in by the caller
+ *   - dtype codes: SDB_F32 = 0, SDB_BF16 = 1
+ */
+#ifndef SDB200_H
+#define SDB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDB_OK            0
+#define SDB_ERR_INVALID  -1   /* bad argument / unsupported shape */
+#define SDB_ERR_CUDA     -2   /* CUDA runtime/driver error at enqueue time */
+#define SDB_ERR_NOTMA    -3   /* cuTensorMapEncode* entry point unavailable */
+
+#define SDB_F32   0
+#define SDB_BF16  1
+
+/* ---- library ------------------------------------------------------------------------------ */
+int         sdb_version(void);                 /* 10000*major + 100*minor + patch */
+const char* sdb_last_error_string(void);       /* thread-local, valid until the next failing call */
+int         sdb_device_sm_count(void);         /* SMs of the current device (148 on B200) */
+/* number of kernel launches enqueued by this library in this process (bench `gpu_launches`) */
+unsigned long long sdb_launch_count(void);
+
+/* ---- layout ------------------------------------------------------------------------------- */
+/* NCHW fp32 <-> NHWC fp32/bf16.  Replaces nothing arithmetic: the reference computes in NCHW
+ * (openai_model/model.py:572-595); the kernels compute in NHWC, this is the boundary transpose. */
+int sdb_nchw_to_nhwc(const float* src, void* dst, int dst_dtype, int N, int C, int HW, void* stream);
+int sdb_nhwc_to_nchw(const float* src, float* dst, int N, int C, int HW, void* stream);
+
+/* ---- GroupNorm(32) [+ SiLU] over NHWC, optional two-source channel concat -------------------
+ * Replaces GroupNorm32.forward + nn.SiLU (openai_model/utils.py:15-22, model.py:178-181,202-205,
+ * 528-531), Normalize eps=1e-6 (openai_model/attention.py:10-11,317; ldm/modules/
+ * diffusionmodules/model.py:40-41) and `nonlinearity` x*sigmoid(x) (model.py:35-37), and the
+ * torch.cat([h, hs.pop()], 1) feeding it (openai_model/model.py:586).
+ *   x0 [N,HW,C0] fp32, x1 [N,HW,C1] fp32 or NULL (C1 = 0); C = C0 + C1, C % (4*groups)... see .cu
+ *   out [N,HW,C] (out_dtype), ws: float/double scratch of sdb_groupnorm_ws_bytes() bytes.
+ *   act: 0 = none, 1 = SiLU.  exact != 0 uses expf (fp32 parity mode) instead of __expf. */
+long long sdb_groupnorm_ws_bytes(int N, int HW, int C, int groups);
+int sdb_groupnorm_nhwc(const float* x0, int C0, const float* x1, int C1, int N, int HW, int groups,
+                       float eps, const float* gamma, const float* beta, int act, int exact,
+                       void* out, int out_dtype, void* ws, void* stream);
+
+/* ---- LayerNorm over the last dim ---------------------------------------------------------------
+ * Replaces nn.LayerNorm(dim) x3 per BasicTransformerBlock (openai_model/attention.py:216-218,
+ * 251-253), eps 1e-5.  x [rows, C] fp32 -> out [rows, C] (out_dtype). C % 4 == 0, C <= 4096. */
+int sdb_layernorm(const float* x, int rows, int C, float eps, const float* gamma, const float* beta,
+                  void* out, int out_dtype, void* stream);
+
+/* ---- elementwise ---------------------------------------------------------------------------
+ * sdb_cast_concat: out[n, oh, ow, :] = concat(x0, x1)[n, oh/up, ow/up, :] as out_dtype.
+ * Replaces torch.cat (openai_model/model.py:586), F.interpolate(scale_factor=2, "nearest")
+ * (openai_model/model.py:127; ldm/modules/diffusionmodules/model.py:56) and the dtype cast
+ * feeding a conv. up is 1 or 2. H, W are the INPUT spatial dims. */
+int sdb_cast_concat(const float* x0, int C0, const float* x1, int C1, int N, int H, int W, int up,
+                    void* out, int out_dtype, void* stream);
+/* out = act(x) (+ optional cast); act 0 none, 1 SiLU (emb_layers' nn.SiLU, model.py:195-196),
+ * 2 GELU-erf (DDPM/models/unet.py:29). n elements. */
+int sdb_activation(const float* x, void* out, int out_dtype, long long n, int act, void* stream);
+/* GEGLU: out[r, j] = h[r, j] * gelu_erf(h[r, inner + j]) (openai_model/attention.py:140-141).
+ * h [rows, 2*inner] fp32 -> out [rows, inner] (out_dtype). */
+int sdb_geglu(const float* h, int rows, int inner, void* out, int out_dtype, void* stream);
+/* row softmax with pre-scale: out[r,:] = softmax(scale * s[r,:]) ; s fp32 [rows, L], row stride lds.
+ * Replaces softmax in AttnBlock (ldm/modules/diffusionmodules/model.py:191-192) and the fp32-mode
+ * attention (flash_attn_func semantics, openai_model/attention.py:106-112). */
+int sdb_softmax_rows(const float* s, long long rows, int L, long long lds, float scale, void* out,
+                     int out_dtype, long long ldo, void* stream);
+/* y = a*x + b*y style helpers */
+int sdb_add(const float* a, const float* b, float* out, long long n, void* stream);
+
+/* ---- timestep embedding ------------------------------------------------------------------------
+ * Replaces timestep_embedding (openai_model/utils.py:225-245): emb[b] = [cos(t_b*f), sin(t_b*f)].
+ * freqs: device fp32 [half] (built on the host exactly as the reference does). t: device fp32 [B]. */
+int sdb_timestep_embedding(const float* t, const float* freqs, int B, int half, float* emb, void* stream);
+/* pe_matrix[t] lookup for the DDPM UNet (DDPM/models/layers.py:32-34): table fp32 [T, dim]. */
+int sdb_gather_rows(const float* table, const long long* idx, int B, int dim, float* out, void* stream);
+
+/* ---- skinny GEMM (M <= 32 rows): y[M,N] = act_in(x)[M,K] @ W[N,K]^T + b ------------------------
+ * Replaces time_embed / emb_layers Linear on [B,1280] (openai_model/model.py:353-357,195-201,241).
+ * W fp32 [N,K] row-major. act_in: 0 none, 1 SiLU applied to x on load. act_out: 0 none, 1 SiLU. */
+int sdb_skinny_linear(const float* x, int M, int K, const float* W, const float* bias, int N,
+                      int act_in, int act_out, float* y, void* stream);
+
+/* ---- DDIM update ---------------------------------------------------------------------------
+ * Replaces p_sample_ddim's arithmetic (ldm/diffusion/ddim.py:175-205 == DDIM/ddim.py):
+ *   e = e_uncond + cfg_scale*(e_cond - e_uncond)      (if e_uncond != NULL)
+ *   pred_x0 = (x - sqrt_one_minus_at*e) / sqrt(a_t)
+ *   x_prev  = sqrt(a_prev)*pred_x0 + sqrt(1 - a_prev - sigma^2)*e + sigma*temperature*noise
+ * all fp32, every operation individually rounded (no FMA contraction) like the eager reference.
+ * noise may be NULL when sigma == 0. n = number of elements. */
+int sdb_ddim_step(const float* x, const float* e_cond, const float* e_uncond, float cfg_scale,
+                  const float* noise, float a_t, float a_prev, float sigma_t, float sqrt_one_minus_at,
+                  float temperature, float* x_prev, float* pred_x0, long long n, void* stream);
+
+/* ---- fp32 SIMT contraction (the fp32 parity mode; also the C_in=4 / tiny layers) --------------
+ * One kernel family: out[m, n] = alpha * sum_k A(m,k) * B(n,k) + bias[n] + rowvec[img(m), n]
+ *                                + residual[m, n]
+ * conv mode (kh*kw > 0 and H > 0): A(m,k) gathers x NHWC fp32 [NB,IH,IW,Cin] with stride/pad
+ *   (+ nearest-2x fold: `up`), B = weights packed [kh*kw][Cout][Cin] ("RSKC").
+ *   Replaces nn.Conv2d 3x3/1x1 (openai_model/model.py:88-90,117,181,207,218,365,531;
+ *   openai_model/attention.py:319-334; ldm/modules/diffusionmodules/model.py:49,94,104,...).
+ * gemm mode: A [M,K] lda, B [N,K] ldb (b_kn = 0) or [K,N] ldb (b_kn = 1); two-level batch.
+ *   Replaces nn.Linear (openai_model/attention.py:40-47,133,159-167) and torch.bmm
+ *   (ldm/modules/diffusionmodules/model.py:188,197). */
+typedef struct sdb_simt_args {
+    const float* A; const float* B; float* out;
+    const float* bias;       /* [N] or NULL */
+    const float* rowvec;     /* [NB, ldv] per-image vector (time-emb add) or NULL; conv mode only */
+    const float* residual;   /* [M, ldr] or NULL */
+    long long lda, ldb, ldc, ldr, ldv;
+    int M, N, K;
+    float alpha;
+    int b_kn;
+    /* batch: z = b1*nb2 + b2 */
+    int nb1, nb2;
+    long long sa1, sa2, sb1, sb2, sc1, sc2;
+    /* conv geometry; kh = 0 means plain gemm */
+    int kh, kw, stride, pad, up;
+    int NB, IH, IW, Cin, OH, OW;
+    int out_dtype;           /* SDB_F32 or SDB_BF16 */
+} sdb_simt_args;
+int sdb_simt_contract(const sdb_simt_args* args /* host */, void* stream);
+
+/* ---- tcgen05 contraction (bf16 operands, fp32 TMEM accumulation) -----------------------------
+ * TMA -> 128B-swizzled smem ring -> tcgen05.mma (cta_group::1, M=128, N=BN, K=16) -> TMEM ->
+ * tcgen05.ld epilogue.  Same algebra as sdb_simt_contract with bf16 A/B:
+ *   gemm mode: A bf16 [M,K] (lda), B bf16 [N,K] (ldb)
+ *   conv mode: A bf16 NHWC [NB,IH,IW,Cin] (pixel stride ldx), B bf16 packed [taps][CoutPad][Cin]
+ * epilogue: + bias[n] + rowvec[img, n] + residual[m, n]; optional GEGLU pairing
+ * (openai_model/attention.py:140-141) when geglu != 0 (B rows packed a|gate per BN tile);
+ * optional column-group remap (n -> (n / cg)*cgs + n % cg) used to write q/k/v heads padded.
+ * split_k > 1 accumulates with red.global.add.f32 into a pre-zeroed fp32 `out`. */
+typedef struct sdb_tc_args {
+    const void* A; const void* B; void* out;
+    const float* bias; const float* rowvec; const float* residual;
+    long long lda, ldb, ldc, ldr, ldv;   /* elements */
+    int M, N, K;
+    int out_dtype;
+    int geglu;
+    int col_group, col_group_stride;     /* 0 = no remap */
+    int split_k;
+    int block_n;                          /* 0 = auto; else 16/32/64/128/160/256 */
+    /* conv geometry; taps = 0 means gemm */
+    int taps;                             /* 1, 4 (2x2) or 9 (3x3) */
+    int kw;                               /* kernel width (taps = kh*kw) */
+    int stride, pad_h, pad_w;
+    int NB, IH, IW, Cin, OH, OW;          /* OH/OW: conv output dims (before out_* remap) */
+    int cout_pad;                         /* rows of B per tap */
+    /* output pixel remap (sub-pixel upsample phases): oh' = oh*out_sh + out_oh etc. */
+    int out_sh, out_sw, out_oh, out_ow, OHF, OWF;
+} sdb_tc_args;
+int sdb_tc_contract(const sdb_tc_args* args /* host */, void* stream);
+
+/* ---- fused attention forward (bf16, tcgen05) ---------------------------------------------------
+ * Replaces flash_attn_func(q,k,v, softmax_scale, causal=False) (openai_model/attention.py:106-112).
+ * q [B,Sq,H,dpad], k/v [B,Sk,H,dpad] bf16 with explicit element strides; heads zero-padded from d
+ * to dpad (multiple of 64, <= 192). out [B,Sq,H*d] bf16 (row stride ldo). */
+typedef struct sdb_attn_args {
+    const void* q; const void* k; const void* v; void* out;
+    long long q_bs, q_ss, q_hs;   /* batch / seq / head strides (elements) */
+    long long k_bs, k_ss, k_hs;
+    long long v_bs, v_ss, v_hs;
+    long long o_bs, o_ss, o_hs;
+    int B, H, Sq, Sk, d, dpad;
+    float scale;
+} sdb_attn_args;
+int sdb_attention_fwd(const sdb_attn_args* args /* host */, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDB200_H */

@@ -1,0 +1,237 @@
+"""TEST INFRASTRUCTURE — generates tests/golden/*.pt by executing the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+    python oracle/make_golden.py            # everything (spawns a subprocess for the DDPM UNet)
+    python oracle/make_golden.py --part ddpm
+
+Each fixture holds: the seeds, the (key, shape) list of the reference module's state dict (weights
+are regenerated procedurally by oracle/weights.py), the seeded inputs' seeds, and the reference's
+outputs.  While generating, the restatement in oracle/restate.py is checked against the reference
+output (assert), so a committed fixture certifies "restate.py == reference" on that case.
+"""
+import argparse
+import os
+import subprocess
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_harness as RH  # noqa: E402
+from oracle import restate as R  # noqa: E402
+from oracle import weights as W  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+TINY_UNET_CFG = dict(image_size=16, in_channels=4, out_channels=4, model_channels=64, attention_resolutions=[1, 2],
+                     num_res_blocks=1, channel_mult=(1, 2), num_heads=2, use_spatial_transformer=True,
+                     transformer_depth=1, context_dim=64, use_checkpoint=False, legacy=False)
+TINY_VAE_DDCONFIG = dict(double_z=True, z_channels=4, resolution=32, in_channels=3, out_ch=3, ch=64, ch_mult=(1, 2),
+                         num_res_blocks=1, attn_resolutions=[], dropout=0.0)
+
+
+def save(name, obj):
+    os.makedirs(GOLD, exist_ok=True)
+    path = os.path.join(GOLD, name)
+    torch.save(obj, path)
+    print("wrote %s (%.1f KB)" % (path, os.path.getsize(path) / 1024))
+
+
+def gen_unet(name, cfg, B, HW, S_ctx, seed, t_values, with_f64):
+    net = RH.build_unet(cfg)
+    ks = W.key_shapes_of(net)
+    sd = W.make_state_dict(ks, seed)
+    net.load_state_dict(sd, strict=True)
+    x = W.seeded_randn((B, cfg["in_channels"], HW, HW), seed + 1)
+    ctx = W.seeded_randn((B, S_ctx, cfg["context_dim"]), seed + 2)
+    t = torch.tensor(t_values, dtype=torch.long)
+    eps_ref = RH.run_unet(net, x, t, ctx)
+    taps = {}
+    with torch.no_grad():
+        eps_or = R.unet_forward(sd, cfg, x, t, ctx, taps=taps)
+    err = R.rel_l2(eps_or, eps_ref)
+    print("%s: restatement vs reference rel-L2 = %.3e (eps std %.3f)" % (name, err, float(eps_ref.std())))
+    assert err < 2e-5, err
+    out = dict(cfg=cfg, seed=seed, key_shapes=ks, x_shape=tuple(x.shape), ctx_shape=tuple(ctx.shape),
+               t=t, eps_ref=eps_ref.clone(), restate_err=err)
+    # a few intermediate activations from the restatement (for layer-level debugging of the CUDA path)
+    for k in ("input_blocks.1", "middle_block"):
+        if taps[k].numel() <= 1 << 16:
+            out["tap." + k] = taps[k].clone()
+    if with_f64:
+        sd64 = {k: v.double() for k, v in sd.items()}
+        with torch.no_grad():
+            eps64 = R.unet_forward(sd64, cfg, x.double(), t, ctx.double())
+        out["eps_f64"] = eps64.clone()
+        print("   fp32 reference vs f64 restatement rel-L2 = %.3e" % R.rel_l2(eps_ref, eps64))
+    save(name + ".pt", out)
+
+
+def gen_vae(name, ddconfig, B, zres, seed, with_f64):
+    dec = RH.build_decoder(ddconfig)
+    ks_dec = W.key_shapes_of(dec)
+    ks = [("decoder." + k, s) for k, s in ks_dec] + [("post_quant_conv.weight", (ddconfig["z_channels"], 4, 1, 1)),
+                                                      ("post_quant_conv.bias", (ddconfig["z_channels"],))]
+    sd = W.make_state_dict(ks, seed)
+    dec.load_state_dict({k[len("decoder."):]: v for k, v in sd.items() if k.startswith("decoder.")}, strict=True)
+    z = W.seeded_randn((B, 4, zres, zres), seed + 1)
+    with torch.no_grad(), RH.quiet():
+        pq = torch.nn.functional.conv2d(z, sd["post_quant_conv.weight"], sd["post_quant_conv.bias"])   # autoencoder.py:310,338
+        img_ref = dec(pq)
+        img_or = R.autoencoder_decode(sd, ddconfig, z)
+    err = R.rel_l2(img_or, img_ref)
+    print("%s: restatement vs reference rel-L2 = %.3e (img std %.3f)" % (name, err, float(img_ref.std())))
+    assert err < 2e-5, err
+    out = dict(ddconfig=ddconfig, seed=seed, key_shapes=ks, z_shape=tuple(z.shape), img_ref=img_ref.clone(), restate_err=err)
+    if with_f64:
+        with torch.no_grad():
+            img64 = R.autoencoder_decode({k: v.double() for k, v in sd.items()}, ddconfig, z.double())
+        out["img_f64"] = img64.clone()
+        print("   fp32 reference vs f64 restatement rel-L2 = %.3e" % R.rel_l2(img_ref, img64))
+    save(name + ".pt", out)
+
+
+def toy_model_fn(x, t, c):
+    """A cheap analytic eps-model so that sampler goldens do not depend on any network."""
+    s = torch.sin(t.float() * 0.01).view(-1, 1, 1, 1)
+    bias = 0.0 if c is None else c.mean(dim=(1, 2)).view(-1, 1, 1, 1)
+    return 0.3 * x * s + 0.1 * torch.cos(x) + bias
+
+
+def gen_ddim():
+    ddim = RH.ddim_module()
+    out = {}
+    for sched_name, ac in (("sd", R.sd_alphas_cumprod()), ("ddpm", R.ddpm_alphas_cumprod())):
+        for S, eta in ((50, 0.0), (50, 0.5), (10, 0.0), (20, 1.0)):
+            shim = R.ModelShim(toy_model_fn, ac)
+            ref = RH.make_cpu_sampler(shim)
+            with RH.quiet():
+                ref.make_schedule(ddim_num_steps=S, ddim_eta=eta, verbose=False)
+            orc = R.DDIMOracle(shim)
+            orc.make_schedule(S, ddim_eta=eta)
+            tag = "%s.S%d.eta%g" % (sched_name, S, eta)
+            out[tag + ".timesteps"] = torch.as_tensor(np.ascontiguousarray(ref.ddim_timesteps))
+            coefs = []
+            for index in range(S):
+                b = 1
+                # exactly the reference's four lines (ddim.py:191-194)
+                a_t = torch.full((b, 1, 1, 1), ref.ddim_alphas[index])
+                a_prev = torch.full((b, 1, 1, 1), ref.ddim_alphas_prev[index])
+                sigma_t = torch.full((b, 1, 1, 1), ref.ddim_sigmas[index])
+                s1m = torch.full((b, 1, 1, 1), ref.ddim_sqrt_one_minus_alphas[index])
+                assert a_t.dtype == a_prev.dtype == sigma_t.dtype == s1m.dtype == torch.float32
+                o = orc.coefficients(index)
+                for u, v in zip((a_t, a_prev, sigma_t, s1m), o):
+                    assert u.dtype == v.dtype and torch.equal(u, v)
+                coefs.append(torch.stack([a_t.flatten(), a_prev.flatten(), sigma_t.flatten(), s1m.flatten()], 1))
+            out[tag + ".coefs"] = torch.cat(coefs, 0)   # [S, 4] fp32: a_t, a_prev, sigma_t, sqrt(1-a_t)
+            assert np.array_equal(ref.ddim_timesteps, orc.ddim_timesteps)
+    # single steps (eta > 0 exercises the noise term; CFG exercises the combine)
+    ac = R.sd_alphas_cumprod()
+    shim = R.ModelShim(toy_model_fn, ac)
+    for S, eta, cfg_scale in ((50, 0.0, 1.0), (50, 0.5, 1.0), (50, 0.0, 7.5), (20, 1.0, 3.0)):
+        ref = RH.make_cpu_sampler(shim)
+        with RH.quiet():
+            ref.make_schedule(ddim_num_steps=S, ddim_eta=eta, verbose=False)
+        orc = R.DDIMOracle(shim)
+        orc.make_schedule(S, ddim_eta=eta)
+        x = W.seeded_randn((2, 4, 8, 8), 77)
+        c = W.seeded_randn((2, 5, 6), 78)
+        uc = W.seeded_randn((2, 5, 6), 79) if cfg_scale != 1.0 else None
+        for index in (S - 1, S // 2, 0):
+            step = int(ref.ddim_timesteps[index])
+            ts = torch.full((2,), step, dtype=torch.long)
+            torch.manual_seed(4321 + index)
+            with RH.quiet():
+                xp_ref, p0_ref = ref.p_sample_ddim(x, c, ts, index=index, unconditional_guidance_scale=cfg_scale,
+                                                   unconditional_conditioning=uc)
+            torch.manual_seed(4321 + index)
+            noise = torch.randn(x.shape)       # the draw noise_like() makes (diffusion_modules.py:264-267)
+            xp, p0, e_t = orc.p_sample_ddim(x, c, ts, index, unconditional_guidance_scale=cfg_scale,
+                                            unconditional_conditioning=uc, noise=noise)
+            assert torch.equal(xp, xp_ref) and torch.equal(p0, p0_ref), "DDIM step restatement is not bit-exact"
+            tag = "step.S%d.eta%g.cfg%g.i%d" % (S, eta, cfg_scale, index)
+            out[tag] = dict(x=x, c=c, uc=uc, index=index, step=step, noise=noise, e_t=e_t, x_prev=xp_ref, pred_x0=p0_ref)
+    # full trajectories with the toy model
+    for S, cfg_scale in ((10, 1.0), (50, 1.0), (10, 5.0)):
+        ref = RH.make_cpu_sampler(shim)
+        x_T = W.seeded_randn((3, 4, 8, 8), 91)
+        c = W.seeded_randn((3, 5, 6), 92)
+        uc = W.seeded_randn((3, 5, 6), 93) if cfg_scale != 1.0 else None
+        import contextlib
+        import io
+        with RH.quiet(), contextlib.redirect_stderr(io.StringIO()):
+            z_ref, inter = ref.sample(S=S, batch_size=3, shape=(4, 8, 8), conditioning=c, verbose=False, x_T=x_T, eta=0.,
+                                      unconditional_guidance_scale=cfg_scale, unconditional_conditioning=uc)
+        orc = R.DDIMOracle(shim)
+        z, inter_o = orc.sample(S, 3, (4, 8, 8), conditioning=c, eta=0., x_T=x_T,
+                                unconditional_guidance_scale=cfg_scale, unconditional_conditioning=uc)
+        assert torch.equal(z, z_ref), "DDIM trajectory restatement is not bit-exact"
+        assert len(inter["x_inter"]) == len(inter_o["x_inter"])
+        out["traj.S%d.cfg%g" % (S, cfg_scale)] = dict(x_T=x_T, c=c, uc=uc, z=z_ref, n_inter=len(inter["x_inter"]),
+                                                      last_pred_x0=inter["pred_x0"][-1])
+    save("ddim.pt", out)
+
+
+def gen_ddpm():
+    net = RH.build_ddpm_unet()
+    ks = W.key_shapes_of(net)
+    sd = W.make_state_dict(ks, 11)
+    net.load_state_dict(sd, strict=True)
+    x = W.seeded_randn((2, 3, 32, 32), 12)
+    t = torch.tensor([500, 3], dtype=torch.long)
+    with torch.no_grad():
+        y_ref = net(x, t)
+        y_or = R.ddpm_unet_forward(sd, x, t)
+    err = R.rel_l2(y_or, y_ref)
+    print("ddpm_unet: restatement vs reference rel-L2 = %.3e (out std %.3f)" % (err, float(y_ref.std())))
+    assert err < 2e-5, err
+    out = dict(seed=11, key_shapes=ks, x_shape=tuple(x.shape), t=t, y_ref=y_ref.clone(), restate_err=err)
+    # config C1: DDIM-50, B=4, eta=0, reference sampler + reference UNet, end to end
+    import contextlib
+    import io
+    sys.path.insert(0, os.path.join(RH.REF, "DDPM"))
+    shim = R.ModelShim(lambda xx, tt, cc: net(xx, tt), R.ddpm_alphas_cumprod())
+    ref = RH.make_cpu_sampler(shim)
+    x_T = W.seeded_randn((4, 3, 32, 32), 13)
+    with torch.no_grad(), RH.quiet(), contextlib.redirect_stderr(io.StringIO()):
+        z_ref, _ = ref.sample(S=50, batch_size=4, shape=(3, 32, 32), conditioning=None, verbose=False, x_T=x_T, eta=0.)
+    rec = []
+    orc = R.DDIMOracle(R.ModelShim(lambda xx, tt, cc: R.ddpm_unet_forward(sd, xx, tt), R.ddpm_alphas_cumprod()))
+    with torch.no_grad():
+        z_or, _ = orc.sample(50, 4, (3, 32, 32), eta=0., x_T=x_T, record=rec)
+    err = R.rel_l2(z_or, z_ref)
+    print("C1 DDIM-50 B=4: restatement vs reference rel-L2 = %.3e" % err)
+    assert err < 1e-4, err
+    out["c1_x_T_seed"] = 13
+    out["c1_z_ref"] = z_ref.clone()
+    # teacher-forced per-step eps for three steps of the reference trajectory
+    out["c1_steps"] = [dict(x_t=rec[i][0].clone(), t=rec[i][1], e_t=rec[i][2].clone()) for i in (0, 25, 49)]
+    save("ddpm_unet.pt", out)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--part", default="all")
+    a = ap.parse_args()
+    assert RH.available(), "reference tree not found at %s" % RH.REF
+    torch.set_num_threads(os.cpu_count() or 1)
+    if a.part in ("all", "ddim"):
+        gen_ddim()
+    if a.part in ("all", "unet"):
+        gen_unet("unet_tiny", TINY_UNET_CFG, B=2, HW=16, S_ctx=7, seed=21, t_values=[981, 1], with_f64=True)
+        gen_unet("unet_sd", R.SD_UNET_CFG, B=1, HW=64, S_ctx=77, seed=31, t_values=[500], with_f64=True)
+    if a.part in ("all", "vae"):
+        gen_vae("vae_tiny", TINY_VAE_DDCONFIG, B=2, zres=8, seed=41, with_f64=True)
+        gen_vae("vae_sd_z16", R.SD_VAE_DDCONFIG, B=1, zres=16, seed=51, with_f64=True)
+    if a.part == "ddpm":
+        gen_ddpm()
+    if a.part == "all":   # the DDPM tree's top-level `models` package clashes with ldm's aliases
+        subprocess.check_call([sys.executable, os.path.abspath(__file__), "--part", "ddpm"])
+
+
+if __name__ == "__main__":
+    main()

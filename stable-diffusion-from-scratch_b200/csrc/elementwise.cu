@@ -1,0 +1,347 @@
+// sdb200 — layout, elementwise and small-matrix kernels (all HBM/launch-bound).
+#include "common.cuh"
+
+namespace sdb {
+
+// ---- NCHW <-> NHWC (32x32 smem tile transpose, padded against bank conflicts) -------------------
+template <bool OUT_BF16>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, void* __restrict__ dst, int C, int HW) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z;
+    const int hw0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const float* s = src + (long long)n * C * HW;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int c = c0 + i, hw = hw0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && hw < HW) ? s[(long long)c * HW + hw] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int hw = hw0 + i, c = c0 + threadIdx.x;
+        if (hw < HW && c < C) {
+            long long o = ((long long)n * HW + hw) * C + c;
+            float v = tile[threadIdx.x][i];
+            if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(dst)[o] = __float2bfloat16_rn(v);
+            else reinterpret_cast<float*>(dst)[o] = v;
+        }
+    }
+}
+
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int HW) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z;
+    const int hw0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const float* s = src + (long long)n * C * HW;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int hw = hw0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && hw < HW) ? s[(long long)hw * C + c] : 0.f;
+    }
+    __syncthreads();
+    float* d = dst + (long long)n * C * HW;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int c = c0 + i, hw = hw0 + threadIdx.x;
+        if (c < C && hw < HW) d[(long long)c * HW + hw] = tile[threadIdx.x][i];
+    }
+}
+
+// ---- cast (+ channel concat, + nearest 2x upsample) ---------------------------------------------
+// One thread per float4 of the OUTPUT. out [N, H*up, W*up, C0+C1].
+template <bool OUT_BF16>
+__global__ void cast_concat_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1,
+                                   int H, int W, int up, long long total_vec, void* __restrict__ out) {
+    const int C = C0 + C1, V = C >> 2;
+    const int OW = W * up;
+    const long long OHW = (long long)H * up * OW;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
+         i += (long long)gridDim.x * blockDim.x) {
+        int v = (int)(i % V);
+        long long pix = i / V;
+        long long n = pix / OHW;
+        int rem = (int)(pix % OHW);
+        int oh = rem / OW, ow = rem % OW;
+        long long ipix = (n * H + oh / up) * W + ow / up;
+        int c = v * 4;
+        float4 a = (c < C0) ? __ldg(reinterpret_cast<const float4*>(x0 + ipix * C0 + c))
+                            : __ldg(reinterpret_cast<const float4*>(x1 + ipix * C1 + (c - C0)));
+        long long o = pix * C + c;
+        if (OUT_BF16) st_stream_u2(reinterpret_cast<__nv_bfloat16*>(out) + o, pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+        else st_stream_f4(reinterpret_cast<float*>(out) + o, a);
+    }
+}
+
+template <bool OUT_BF16>
+__global__ void activation_kernel(const float* __restrict__ x, void* __restrict__ out, long long n, int act) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float v = x[i];
+        if (act == 1) v = silu_exact(v);
+        else if (act == 2) v = gelu_erf(v);
+        if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
+        else reinterpret_cast<float*>(out)[i] = v;
+    }
+}
+
+template <bool OUT_BF16>
+__global__ void geglu_kernel(const float* __restrict__ h, int rows, int inner, void* __restrict__ out) {
+    const long long total = (long long)rows * inner;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long r = i / inner;
+        int j = (int)(i % inner);
+        float a = h[r * 2 * inner + j], g = h[r * 2 * inner + inner + j];
+        float v = a * gelu_erf(g);
+        if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
+        else reinterpret_cast<float*>(out)[i] = v;
+    }
+}
+
+__global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = a[i] + b[i];
+}
+
+// ---- row softmax: one CTA per row, fp32 statistics ----------------------------------------------
+template <bool OUT_BF16>
+__global__ void softmax_rows_kernel(const float* __restrict__ s, int L, long long lds, float scale,
+                                    void* __restrict__ out, long long ldo) {
+    __shared__ float red[32];
+    const long long row = blockIdx.x;
+    const float* p = s + row * lds;
+    float m = -INFINITY;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) m = fmaxf(m, p[i] * scale);
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : -INFINITY;
+        t = warp_max(t);
+        if (threadIdx.x == 0) red[0] = t;
+    }
+    __syncthreads();
+    m = red[0];
+    __syncthreads();
+    float sum = 0.f;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) sum += expf(p[i] * scale - m);
+    sum = warp_sum(sum);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+        t = warp_sum(t);
+        if (threadIdx.x == 0) red[0] = t;
+    }
+    __syncthreads();
+    const float inv = 1.0f / red[0];
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+        float v = expf(p[i] * scale - m) * inv;
+        if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(out)[row * ldo + i] = __float2bfloat16_rn(v);
+        else reinterpret_cast<float*>(out)[row * ldo + i] = v;
+    }
+}
+
+// ---- timestep embedding (reference openai_model/utils.py:225-245): [cos | sin] ------------------
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, const float* __restrict__ freqs,
+                                          int B, int half, float* __restrict__ emb) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * half) return;
+    int b = i / half, j = i % half;
+    float a = t[b] * freqs[j];
+    emb[(long long)b * 2 * half + j] = cosf(a);
+    emb[(long long)b * 2 * half + half + j] = sinf(a);
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ table, const long long* __restrict__ idx,
+                                   int B, int dim, float* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * dim) return;
+    int b = i / dim, j = i % dim;
+    out[i] = table[idx[b] * dim + j];
+}
+
+// ---- skinny linear: M <= 32 rows; one warp per output column, weights streamed once -------------
+template <int MT>
+__global__ void skinny_linear_kernel(const float* __restrict__ x, int M, int K, const float* __restrict__ W,
+                                     const float* __restrict__ bias, int N, int act_in, int act_out,
+                                     float* __restrict__ y) {
+    extern __shared__ float xs[];   // [M][K] activated input
+    for (int i = threadIdx.x; i < M * K; i += blockDim.x) {
+        float v = x[i];
+        if (act_in == 1) v = silu_exact(v);
+        xs[i] = v;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warps = blockDim.x >> 5;
+    for (int n = blockIdx.x * warps + (threadIdx.x >> 5); n < N; n += gridDim.x * warps) {
+        float acc[MT];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) acc[m] = 0.f;
+        const float* w = W + (long long)n * K;
+        for (int k = lane * 4; k < K; k += 128) {
+            float4 wv = ld_stream_f4(w + k);
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                if (m < M) {
+                    const float* xr = xs + m * K + k;
+                    acc[m] += wv.x * xr[0] + wv.y * xr[1] + wv.z * xr[2] + wv.w * xr[3];
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+            if (m < M) {
+                float v = warp_sum(acc[m]);
+                if (lane == 0) {
+                    if (bias) v += bias[n];
+                    if (act_out == 1) v = silu_exact(v);
+                    y[(long long)m * N + n] = v;
+                }
+            }
+        }
+    }
+}
+
+// ---- DDIM update (reference ldm/diffusion/ddim.py:175-205) --------------------------------------
+// Every operation is a separately rounded fp32 op (__f*_rn blocks FMA contraction) so that, given
+// the same eps, x_prev / pred_x0 are bit-identical to the eager reference arithmetic.
+__global__ void ddim_step_kernel(const float* __restrict__ x, const float* __restrict__ e_c,
+                                 const float* __restrict__ e_u, float cfg, const float* __restrict__ noise,
+                                 float sqrt_at, float sqrt_aprev, float dir_coef, float sigma_t,
+                                 float sqrt_one_minus_at, float temperature,
+                                 float* __restrict__ x_prev, float* __restrict__ pred_x0, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float e = e_c[i];
+        if (e_u) {
+            float u = e_u[i];
+            e = __fadd_rn(u, __fmul_rn(cfg, __fsub_rn(e, u)));
+        }
+        float xv = x[i];
+        float p0 = __fdiv_rn(__fsub_rn(xv, __fmul_rn(sqrt_one_minus_at, e)), sqrt_at);
+        float dir = __fmul_rn(dir_coef, e);
+        float nz = 0.f;
+        if (noise) nz = __fmul_rn(__fmul_rn(sigma_t, noise[i]), temperature);
+        float xp = __fadd_rn(__fadd_rn(__fmul_rn(sqrt_aprev, p0), dir), nz);
+        x_prev[i] = xp;
+        pred_x0[i] = p0;
+    }
+}
+
+static inline int grid_for(long long n, int threads) {
+    long long b = (n + threads - 1) / threads;
+    long long cap = 148LL * 16;
+    return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+}  // namespace sdb
+
+using namespace sdb;
+
+extern "C" {
+
+int sdb_nchw_to_nhwc(const float* src, void* dst, int dst_dtype, int N, int C, int HW, void* stream) {
+    SDB_REQUIRE(src && dst && N > 0 && C > 0 && HW > 0, "nchw_to_nhwc: bad args");
+    dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), N), block(32, 8);
+    if (dst_dtype == SDB_BF16) nchw_to_nhwc_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(src, dst, C, HW);
+    else nchw_to_nhwc_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(src, dst, C, HW);
+    return check_launch("nchw_to_nhwc_kernel");
+}
+
+int sdb_nhwc_to_nchw(const float* src, float* dst, int N, int C, int HW, void* stream) {
+    SDB_REQUIRE(src && dst && N > 0 && C > 0 && HW > 0, "nhwc_to_nchw: bad args");
+    dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), N), block(32, 8);
+    nhwc_to_nchw_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, dst, C, HW);
+    return check_launch("nhwc_to_nchw_kernel");
+}
+
+int sdb_cast_concat(const float* x0, int C0, const float* x1, int C1, int N, int H, int W, int up,
+                    void* out, int out_dtype, void* stream) {
+    SDB_REQUIRE(x0 && out && N > 0 && H > 0 && W > 0, "cast_concat: bad args");
+    SDB_REQUIRE(C0 > 0 && C0 % 4 == 0 && C1 % 4 == 0 && (C1 == 0) == (x1 == nullptr), "cast_concat: bad channels %d %d", C0, C1);
+    SDB_REQUIRE(up == 1 || up == 2, "cast_concat: up must be 1 or 2");
+    long long total = (long long)N * H * up * W * up * ((C0 + C1) / 4);
+    int threads = 256, blocks = grid_for(total, threads);
+    if (out_dtype == SDB_BF16) cast_concat_kernel<true><<<blocks, threads, 0, (cudaStream_t)stream>>>(x0, C0, x1, C1, H, W, up, total, out);
+    else cast_concat_kernel<false><<<blocks, threads, 0, (cudaStream_t)stream>>>(x0, C0, x1, C1, H, W, up, total, out);
+    return check_launch("cast_concat_kernel");
+}
+
+int sdb_activation(const float* x, void* out, int out_dtype, long long n, int act, void* stream) {
+    SDB_REQUIRE(x && out && n > 0, "activation: bad args");
+    int threads = 256, blocks = grid_for(n, threads);
+    if (out_dtype == SDB_BF16) activation_kernel<true><<<blocks, threads, 0, (cudaStream_t)stream>>>(x, out, n, act);
+    else activation_kernel<false><<<blocks, threads, 0, (cudaStream_t)stream>>>(x, out, n, act);
+    return check_launch("activation_kernel");
+}
+
+int sdb_geglu(const float* h, int rows, int inner, void* out, int out_dtype, void* stream) {
+    SDB_REQUIRE(h && out && rows > 0 && inner > 0, "geglu: bad args");
+    int threads = 256, blocks = grid_for((long long)rows * inner, threads);
+    if (out_dtype == SDB_BF16) geglu_kernel<true><<<blocks, threads, 0, (cudaStream_t)stream>>>(h, rows, inner, out);
+    else geglu_kernel<false><<<blocks, threads, 0, (cudaStream_t)stream>>>(h, rows, inner, out);
+    return check_launch("geglu_kernel");
+}
+
+int sdb_softmax_rows(const float* s, long long rows, int L, long long lds, float scale, void* out,
+                     int out_dtype, long long ldo, void* stream) {
+    SDB_REQUIRE(s && out && rows > 0 && L > 0, "softmax_rows: bad args");
+    SDB_REQUIRE(rows < (1LL << 31), "softmax_rows: too many rows");
+    int threads = L >= 1024 ? 256 : (L >= 256 ? 128 : 32);
+    if (out_dtype == SDB_BF16) softmax_rows_kernel<true><<<(unsigned)rows, threads, 0, (cudaStream_t)stream>>>(s, L, lds, scale, out, ldo);
+    else softmax_rows_kernel<false><<<(unsigned)rows, threads, 0, (cudaStream_t)stream>>>(s, L, lds, scale, out, ldo);
+    return check_launch("softmax_rows_kernel");
+}
+
+int sdb_add(const float* a, const float* b, float* out, long long n, void* stream) {
+    SDB_REQUIRE(a && b && out && n > 0, "add: bad args");
+    add_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, out, n);
+    return check_launch("add_kernel");
+}
+
+int sdb_timestep_embedding(const float* t, const float* freqs, int B, int half, float* emb, void* stream) {
+    SDB_REQUIRE(t && freqs && emb && B > 0 && half > 0, "timestep_embedding: bad args");
+    int n = B * half;
+    timestep_embedding_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(t, freqs, B, half, emb);
+    return check_launch("timestep_embedding_kernel");
+}
+
+int sdb_gather_rows(const float* table, const long long* idx, int B, int dim, float* out, void* stream) {
+    SDB_REQUIRE(table && idx && out && B > 0 && dim > 0, "gather_rows: bad args");
+    gather_rows_kernel<<<ceil_div(B * dim, 256), 256, 0, (cudaStream_t)stream>>>(table, idx, B, dim, out);
+    return check_launch("gather_rows_kernel");
+}
+
+int sdb_skinny_linear(const float* x, int M, int K, const float* W, const float* bias, int N,
+                      int act_in, int act_out, float* y, void* stream) {
+    SDB_REQUIRE(x && W && y && M > 0 && M <= 32 && K > 0 && K % 4 == 0 && N > 0, "skinny_linear: bad args M=%d K=%d N=%d", M, K, N);
+    size_t smem = (size_t)M * K * sizeof(float);
+    SDB_REQUIRE(smem <= 200 * 1024, "skinny_linear: M*K too large");
+    int threads = 256;
+    int blocks = ceil_div(N, threads / 32);
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    cudaStream_t st = (cudaStream_t)stream;
+#define SK(MT)                                                                                              \
+    do {                                                                                                    \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(skinny_linear_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        skinny_linear_kernel<MT><<<blocks, threads, smem, st>>>(x, M, K, W, bias, N, act_in, act_out, y);   \
+    } while (0)
+    if (M <= 4) SK(4); else if (M <= 8) SK(8); else if (M <= 16) SK(16); else SK(32);
+#undef SK
+    return check_launch("skinny_linear_kernel");
+}
+
+int sdb_ddim_step(const float* x, const float* e_cond, const float* e_uncond, float cfg_scale,
+                  const float* noise, float a_t, float a_prev, float sigma_t, float sqrt_one_minus_at,
+                  float temperature, float* x_prev, float* pred_x0, long long n, void* stream) {
+    SDB_REQUIRE(x && e_cond && x_prev && pred_x0 && n > 0, "ddim_step: bad args");
+    SDB_REQUIRE(noise || sigma_t == 0.0f, "ddim_step: sigma_t != 0 needs a noise tensor");
+    // coefficient arithmetic in fp32, op by op, as the reference does on [B,1,1,1] fp32 tensors
+    // (ldm/diffusion/ddim.py:191-201): a_t.sqrt(), a_prev.sqrt(), (1 - a_prev - sigma^2).sqrt()
+    float sqrt_at = sqrtf(a_t);
+    float sqrt_aprev = sqrtf(a_prev);
+    float s2 = sigma_t * sigma_t;
+    float t1 = 1.0f - a_prev;
+    float dir_coef = sqrtf(t1 - s2);
+    ddim_step_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        x, e_cond, e_uncond, cfg_scale, noise, sqrt_at, sqrt_aprev, dir_coef, sigma_t, sqrt_one_minus_at,
+        temperature, x_prev, pred_x0, n);
+    return check_launch("ddim_step_kernel");
+}
+
+}  // extern "C"

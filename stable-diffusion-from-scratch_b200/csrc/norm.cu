@@ -1,0 +1,265 @@
+// sdb200 — bandwidth-bound normalisation kernels (NHWC / row-major, fp32 residual stream in,
+// bf16 tensor-core operand or fp32 out).
+//
+//   GroupNorm(32)+SiLU : reference openai_model/utils.py:15-22 + model.py:178-181,202-205,528-531;
+//                        Normalize(eps 1e-6) openai_model/attention.py:10-11, ldm/.../model.py:40-41
+//   LayerNorm          : reference openai_model/attention.py:216-218
+//
+// Roofline: HBM. Algorithmic bytes/element = 4 (fp32 read) + 2 (bf16 write) [bf16 mode] or 4+4
+// [fp32 mode]; the statistics pass re-reads the tensor (L2-resident for the UNet's <=126 MB maps).
+#include "common.cuh"
+
+namespace sdb {
+
+// ---- GroupNorm geometry shared by ws sizing and launches ----------------------------------------
+struct GnGeom {
+    int V;        // float4 vectors per row (C/4)
+    int R;        // rows processed concurrently by one CTA
+    int threads;  // V*R
+    int chunks;   // CTAs along HW per sample
+    int rows_per_chunk;
+};
+
+static GnGeom gn_geom(int N, int HW, int C) {
+    GnGeom g;
+    g.V = C / 4;
+    g.R = 512 / g.V;
+    if (g.R < 1) g.R = 1;
+    if (g.R > 32) g.R = 32;
+    if (g.R > HW) g.R = HW;
+    g.threads = g.V * g.R;
+    int by_rows = ceil_div(HW, g.R);                 // at least one row-slot per CTA
+    int want = ceil_div(592, N);                     // >= 4 waves' worth of CTAs over the batch
+    int cap = ceil_div(HW, g.R * 32);                // <= 32 rows per thread
+    int chunks = want > cap ? want : cap;
+    if (chunks > by_rows) chunks = by_rows;
+    if (chunks < 1) chunks = 1;
+    g.chunks = chunks;
+    g.rows_per_chunk = ceil_div(HW, chunks);
+    return g;
+}
+
+// Pass 1: per-(sample, chunk, group) partial sum / sum of squares.
+// Thread t owns vector column v = t % V for rows rr, rr+R, ...: per-channel fp32 partials in
+// registers, reduced over R in smem, then per-group in fp64.
+__global__ void gn_stats_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1,
+                                int HW, int groups, int V, int R, int rows_per_chunk,
+                                double* __restrict__ partial) {
+    extern __shared__ float red[];   // [2][R][C]
+    const int C = C0 + C1;
+    const int n = blockIdx.y, chunk = blockIdx.x;
+    const int v = threadIdx.x % V, rr = threadIdx.x / V;
+    const int c = v * 4;
+    const float* src;
+    long long ld;
+    int cc;
+    if (c < C0) { src = x0; ld = C0; cc = c; } else { src = x1; ld = C1; cc = c - C0; }
+    const int row0 = chunk * rows_per_chunk;
+    int row1 = row0 + rows_per_chunk;
+    if (row1 > HW) row1 = HW;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+    const float* p = src + ((long long)n * HW) * ld + cc;
+#pragma unroll 4
+    for (int row = row0 + rr; row < row1; row += R) {
+        float4 a = __ldg(reinterpret_cast<const float4*>(p + (long long)row * ld));
+        s0 += a.x; s1 += a.y; s2 += a.z; s3 += a.w;
+        q0 += a.x * a.x; q1 += a.y * a.y; q2 += a.z * a.z; q3 += a.w * a.w;
+    }
+    float* rs = red + (long long)rr * C + c;
+    float* rq = red + (long long)R * C + (long long)rr * C + c;
+    rs[0] = s0; rs[1] = s1; rs[2] = s2; rs[3] = s3;
+    rq[0] = q0; rq[1] = q1; rq[2] = q2; rq[3] = q3;
+    __syncthreads();
+    const int cpg = C / groups;
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        double S = 0.0, Q = 0.0;
+        for (int r = 0; r < R; ++r) {
+            const float* a = red + (long long)r * C + g * cpg;
+            const float* b = red + (long long)R * C + (long long)r * C + g * cpg;
+            for (int j = 0; j < cpg; ++j) { S += (double)a[j]; Q += (double)b[j]; }
+        }
+        double* o = partial + (((long long)n * gridDim.x + chunk) * groups + g) * 2;
+        o[0] = S; o[1] = Q;
+    }
+}
+
+// Pass 2: combine chunk partials -> (mean, rstd) per (sample, group).
+__global__ void gn_finalize_kernel(const double* __restrict__ partial, int chunks, int groups, double count,
+                                   float eps, float2* __restrict__ stats) {
+    const int n = blockIdx.x;
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        double S = 0.0, Q = 0.0;
+        for (int ch = 0; ch < chunks; ++ch) {
+            const double* p = partial + (((long long)n * chunks + ch) * groups + g) * 2;
+            S += p[0]; Q += p[1];
+        }
+        double mean = S / count;
+        double var = Q / count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        double rstd = 1.0 / sqrt(var + (double)eps);
+        stats[n * groups + g] = make_float2((float)mean, (float)rstd);
+    }
+}
+
+// Pass 3: normalise + affine (+ SiLU), emit bf16 (tensor-core operand) or fp32.
+template <bool OUT_BF16, bool EXACT>
+__global__ void gn_apply_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1,
+                                int HW, int groups, int V, int R, int rows_per_chunk,
+                                const float2* __restrict__ stats, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, int act, void* __restrict__ out) {
+    const int C = C0 + C1;
+    const int n = blockIdx.y, chunk = blockIdx.x;
+    const int v = threadIdx.x % V, rr = threadIdx.x / V;
+    const int c = v * 4;
+    const float* src;
+    long long ld;
+    int cc;
+    if (c < C0) { src = x0; ld = C0; cc = c; } else { src = x1; ld = C1; cc = c - C0; }
+    const int cpg = C / groups;
+    float sc[4], sh[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float2 st = stats[n * groups + (c + j) / cpg];
+        float g = gamma[c + j], b = beta[c + j];
+        sc[j] = st.y * g;
+        sh[j] = b - st.x * st.y * g;
+    }
+    const int row0 = chunk * rows_per_chunk;
+    int row1 = row0 + rows_per_chunk;
+    if (row1 > HW) row1 = HW;
+    const float* p = src + ((long long)n * HW) * ld + cc;
+#pragma unroll 4
+    for (int row = row0 + rr; row < row1; row += R) {
+        float4 a = ld_stream_f4(p + (long long)row * ld);
+        float y0 = fmaf(a.x, sc[0], sh[0]), y1 = fmaf(a.y, sc[1], sh[1]);
+        float y2 = fmaf(a.z, sc[2], sh[2]), y3 = fmaf(a.w, sc[3], sh[3]);
+        if (act == 1) {
+            if (EXACT) { y0 = silu_exact(y0); y1 = silu_exact(y1); y2 = silu_exact(y2); y3 = silu_exact(y3); }
+            else       { y0 = silu_f(y0);     y1 = silu_f(y1);     y2 = silu_f(y2);     y3 = silu_f(y3); }
+        }
+        long long o = ((long long)n * HW + row) * C + c;
+        if (OUT_BF16) {
+            st_stream_u2(reinterpret_cast<__nv_bfloat16*>(out) + o, pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+        } else {
+            st_stream_f4(reinterpret_cast<float*>(out) + o, make_float4(y0, y1, y2, y3));
+        }
+    }
+}
+
+// ---- LayerNorm: one warp per row, row held in registers (two-pass mean/variance) ----------------
+template <bool OUT_BF16>
+__global__ void layernorm_kernel(const float* __restrict__ x, int rows, int C, float eps,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 void* __restrict__ out) {
+    constexpr int MAXV = 8;   // C <= 4*32*8 = 4096... capped at 1024 floats/lane-set
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const int V = C >> 2;
+    const float* p = x + (long long)warp * C;
+    float4 r[MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        int v = lane + 32 * i;
+        if (v < V) {
+            r[i] = ld_stream_f4(p + 4 * v);
+            s += (r[i].x + r[i].y) + (r[i].z + r[i].w);
+        }
+    }
+    s = warp_sum(s);
+    const float mean = s / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        int v = lane + 32 * i;
+        if (v < V) {
+            float a = r[i].x - mean, b = r[i].y - mean, c = r[i].z - mean, d = r[i].w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+    }
+    q = warp_sum(q);
+    const float rstd = rsqrtf(q / (float)C + eps);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        int v = lane + 32 * i;
+        if (v < V) {
+            float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + v);
+            float4 b = __ldg(reinterpret_cast<const float4*>(beta) + v);
+            float y0 = (r[i].x - mean) * rstd * g.x + b.x;
+            float y1 = (r[i].y - mean) * rstd * g.y + b.y;
+            float y2 = (r[i].z - mean) * rstd * g.z + b.z;
+            float y3 = (r[i].w - mean) * rstd * g.w + b.w;
+            long long o = (long long)warp * C + 4 * v;
+            if (OUT_BF16) {
+                st_stream_u2(reinterpret_cast<__nv_bfloat16*>(out) + o, pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+            } else {
+                st_stream_f4(reinterpret_cast<float*>(out) + o, make_float4(y0, y1, y2, y3));
+            }
+        }
+    }
+}
+
+}  // namespace sdb
+
+using namespace sdb;
+
+extern "C" {
+
+long long sdb_groupnorm_ws_bytes(int N, int HW, int C, int groups) {
+    if (N <= 0 || HW <= 0 || C <= 0 || groups <= 0 || C % 4) return -1;
+    GnGeom g = gn_geom(N, HW, C);
+    return (long long)N * g.chunks * groups * 2 * sizeof(double) + (long long)N * groups * sizeof(float2) + 256;
+}
+
+int sdb_groupnorm_nhwc(const float* x0, int C0, const float* x1, int C1, int N, int HW, int groups,
+                       float eps, const float* gamma, const float* beta, int act, int exact,
+                       void* out, int out_dtype, void* ws, void* stream) {
+    const int C = C0 + C1;
+    SDB_REQUIRE(x0 && out && ws && gamma && beta, "groupnorm: null pointer");
+    SDB_REQUIRE(N > 0 && HW > 0 && C > 0, "groupnorm: empty tensor N=%d HW=%d C=%d", N, HW, C);
+    SDB_REQUIRE(C0 % 4 == 0 && C1 % 4 == 0, "groupnorm: C0=%d C1=%d must be multiples of 4", C0, C1);
+    SDB_REQUIRE((C1 == 0) == (x1 == nullptr), "groupnorm: x1/C1 mismatch");
+    SDB_REQUIRE(groups > 0 && C % groups == 0, "groupnorm: C=%d not divisible by groups=%d", C, groups);
+    SDB_REQUIRE(C / 4 <= 1024, "groupnorm: C=%d too wide", C);
+    SDB_REQUIRE(out_dtype == SDB_F32 || out_dtype == SDB_BF16, "groupnorm: bad out_dtype");
+    cudaStream_t st = (cudaStream_t)stream;
+    GnGeom g = gn_geom(N, HW, C);
+    double* partial = reinterpret_cast<double*>(ws);
+    float2* stats = reinterpret_cast<float2*>(reinterpret_cast<char*>(ws) +
+                                              (long long)N * g.chunks * groups * 2 * sizeof(double));
+    dim3 grid(g.chunks, N);
+    size_t smem = (size_t)2 * g.R * C * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
+    gn_stats_kernel<<<grid, g.threads, smem, st>>>(x0, C0, x1, C1, HW, groups, g.V, g.R, g.rows_per_chunk, partial);
+    int rc = check_launch("gn_stats_kernel");
+    if (rc) return rc;
+    gn_finalize_kernel<<<N, 32, 0, st>>>(partial, g.chunks, groups, (double)HW * (C / groups), eps, stats);
+    rc = check_launch("gn_finalize_kernel");
+    if (rc) return rc;
+#define LAUNCH_APPLY(BF, EX)                                                                             \
+    gn_apply_kernel<BF, EX><<<grid, g.threads, 0, st>>>(x0, C0, x1, C1, HW, groups, g.V, g.R,          \
+                                                         g.rows_per_chunk, stats, gamma, beta, act, out)
+    if (out_dtype == SDB_BF16) { if (exact) LAUNCH_APPLY(true, true); else LAUNCH_APPLY(true, false); }
+    else                       { if (exact) LAUNCH_APPLY(false, true); else LAUNCH_APPLY(false, false); }
+#undef LAUNCH_APPLY
+    return check_launch("gn_apply_kernel");
+}
+
+int sdb_layernorm(const float* x, int rows, int C, float eps, const float* gamma, const float* beta,
+                  void* out, int out_dtype, void* stream) {
+    SDB_REQUIRE(x && out && gamma && beta, "layernorm: null pointer");
+    SDB_REQUIRE(rows > 0 && C > 0 && C % 4 == 0 && C <= 1024 * 4 / 4 * 4 && C <= 4096, "layernorm: bad shape rows=%d C=%d", rows, C);
+    SDB_REQUIRE(C / 4 <= 32 * 8, "layernorm: C=%d too wide", C);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int threads = 256;
+    const int blocks = ceil_div(rows, threads / 32);
+    if (out_dtype == SDB_BF16) layernorm_kernel<true><<<blocks, threads, 0, st>>>(x, rows, C, eps, gamma, beta, out);
+    else if (out_dtype == SDB_F32) layernorm_kernel<false><<<blocks, threads, 0, st>>>(x, rows, C, eps, gamma, beta, out);
+    else SDB_REQUIRE(false, "layernorm: bad out_dtype");
+    return check_launch("layernorm_kernel");
+}
+
+}  // extern "C"

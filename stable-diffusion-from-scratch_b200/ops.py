@@ -1,0 +1,354 @@
+"""Tensor-level wrappers over the C-ABI (include/sdb200.h).
+
+Every function enqueues hand-written sm_100a kernels from libsdb200.so on the current CUDA stream.
+torch is used for allocation (`torch.empty`) and pointers only.  Activations are channels-last:
+images [N, H, W, C], tokens [rows, C].
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, AttnArgs, SimtArgs, TcArgs, check, dtype_code, ptr, require_cuda, stream_ptr
+
+
+def _L():
+    return _lib.load()
+
+
+# ---- layout ---------------------------------------------------------------------------------------
+def nchw_to_nhwc(x, out_dtype=torch.float32):
+    """[N,C,H,W] fp32 -> [N,H,W,C]."""
+    require_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    N, Cc, H, W = x.shape
+    out = torch.empty((N, H, W, Cc), dtype=out_dtype, device=x.device)
+    check(_L().sdb_nchw_to_nhwc(ptr(x), ptr(out), dtype_code(out_dtype), N, Cc, H * W, stream_ptr()), "nchw_to_nhwc")
+    return out
+
+
+def nhwc_to_nchw(x):
+    require_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    N, H, W, Cc = x.shape
+    out = torch.empty((N, Cc, H, W), dtype=torch.float32, device=x.device)
+    check(_L().sdb_nhwc_to_nchw(ptr(x), ptr(out), N, Cc, H * W, stream_ptr()), "nhwc_to_nchw")
+    return out
+
+
+# ---- normalisation ----------------------------------------------------------------------------------
+def groupnorm(x0, gamma, beta, eps, act=0, out_dtype=torch.float32, x1=None, groups=32, exact=False):
+    """GroupNorm(groups) over the channel-concat of x0 (and x1) [N,H,W,C*], optional SiLU."""
+    require_cuda(x0, x1, gamma, beta)
+    assert x0.dtype == torch.float32 and x0.is_contiguous()
+    N, H, W, C0 = x0.shape
+    C1 = 0
+    if x1 is not None:
+        assert x1.dtype == torch.float32 and x1.is_contiguous() and x1.shape[:3] == x0.shape[:3]
+        C1 = x1.shape[3]
+    Ct = C0 + C1
+    lib = _L()
+    ws_bytes = lib.sdb_groupnorm_ws_bytes(N, H * W, Ct, groups)
+    if ws_bytes < 0:
+        raise _lib.SdbError("groupnorm: unsupported shape N=%d HW=%d C=%d" % (N, H * W, Ct))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x0.device)
+    out = torch.empty((N, H, W, Ct), dtype=out_dtype, device=x0.device)
+    check(lib.sdb_groupnorm_nhwc(ptr(x0), C0, ptr(x1), C1, N, H * W, groups, float(eps), ptr(gamma), ptr(beta),
+                                 int(act), int(bool(exact)), ptr(out), dtype_code(out_dtype), ptr(ws), stream_ptr()),
+          "groupnorm")
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5, out_dtype=torch.float32):
+    """LayerNorm over the last dim of x [..., C] fp32."""
+    require_cuda(x, gamma, beta)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    check(_L().sdb_layernorm(ptr(x), rows, Cc, float(eps), ptr(gamma), ptr(beta), ptr(out), dtype_code(out_dtype), stream_ptr()),
+          "layernorm")
+    return out
+
+
+# ---- elementwise ------------------------------------------------------------------------------------
+def cast_concat(x0, x1=None, up=1, out_dtype=torch.bfloat16):
+    require_cuda(x0, x1)
+    assert x0.dtype == torch.float32 and x0.is_contiguous()
+    N, H, W, C0 = x0.shape
+    C1 = 0 if x1 is None else x1.shape[3]
+    out = torch.empty((N, H * up, W * up, C0 + C1), dtype=out_dtype, device=x0.device)
+    check(_L().sdb_cast_concat(ptr(x0), C0, ptr(x1), C1, N, H, W, up, ptr(out), dtype_code(out_dtype), stream_ptr()),
+          "cast_concat")
+    return out
+
+
+def activation(x, act, out_dtype=torch.float32):
+    require_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    check(_L().sdb_activation(ptr(x), ptr(out), dtype_code(out_dtype), x.numel(), act, stream_ptr()), "activation")
+    return out
+
+
+def geglu(h, out_dtype=torch.float32):
+    require_cuda(h)
+    assert h.dtype == torch.float32 and h.is_contiguous()
+    inner = h.shape[-1] // 2
+    rows = h.numel() // h.shape[-1]
+    out = torch.empty(h.shape[:-1] + (inner,), dtype=out_dtype, device=h.device)
+    check(_L().sdb_geglu(ptr(h), rows, inner, ptr(out), dtype_code(out_dtype), stream_ptr()), "geglu")
+    return out
+
+
+def softmax_rows(s, scale, out_dtype=torch.float32):
+    """softmax(scale * s) over the last dim; s fp32 contiguous."""
+    require_cuda(s)
+    assert s.dtype == torch.float32 and s.is_contiguous()
+    Lk = s.shape[-1]
+    rows = s.numel() // Lk
+    out = torch.empty(s.shape, dtype=out_dtype, device=s.device)
+    check(_L().sdb_softmax_rows(ptr(s), rows, Lk, Lk, float(scale), ptr(out), dtype_code(out_dtype), Lk, stream_ptr()), "softmax_rows")
+    return out
+
+
+def add(a, b):
+    require_cuda(a, b)
+    assert a.dtype == b.dtype == torch.float32 and a.shape == b.shape and a.is_contiguous() and b.is_contiguous()
+    out = torch.empty_like(a)
+    check(_L().sdb_add(ptr(a), ptr(b), ptr(out), a.numel(), stream_ptr()), "add")
+    return out
+
+
+def timestep_embedding(t, freqs):
+    """t fp32 [B], freqs fp32 [half] -> [B, 2*half] = [cos | sin]."""
+    require_cuda(t, freqs)
+    assert t.dtype == torch.float32 and freqs.dtype == torch.float32
+    B, half = t.shape[0], freqs.shape[0]
+    emb = torch.empty((B, 2 * half), dtype=torch.float32, device=t.device)
+    check(_L().sdb_timestep_embedding(ptr(t), ptr(freqs), B, half, ptr(emb), stream_ptr()), "timestep_embedding")
+    return emb
+
+
+def gather_rows(table, idx):
+    require_cuda(table, idx)
+    assert table.dtype == torch.float32 and idx.dtype == torch.int64 and table.is_contiguous()
+    B, dim = idx.shape[0], table.shape[1]
+    out = torch.empty((B, dim), dtype=torch.float32, device=table.device)
+    check(_L().sdb_gather_rows(ptr(table), ptr(idx), B, dim, ptr(out), stream_ptr()), "gather_rows")
+    return out
+
+
+def skinny_linear(x, W, bias=None, act_in=0, act_out=0):
+    """y = act_out(act_in(x) @ W^T + bias); x fp32 [M<=32, K], W fp32 [N, K]."""
+    require_cuda(x, W, bias)
+    assert x.dtype == torch.float32 and W.dtype == torch.float32 and x.is_contiguous() and W.is_contiguous()
+    M, K = x.shape
+    N = W.shape[0]
+    y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    for i in range(0, M, 32):   # the kernel holds at most 32 rows in shared memory
+        m = min(32, M - i)
+        check(_L().sdb_skinny_linear(ptr(x) + 4 * i * K, m, K, ptr(W), ptr(bias), N, act_in, act_out,
+                                     ptr(y) + 4 * i * N, stream_ptr()), "skinny_linear")
+    return y
+
+
+def ddim_step(x, e_cond, a_t, a_prev, sigma_t, sqrt_one_minus_at, e_uncond=None, cfg_scale=1.0, noise=None, temperature=1.0):
+    require_cuda(x, e_cond, e_uncond, noise)
+    assert x.dtype == torch.float32 and e_cond.dtype == torch.float32 and x.is_contiguous() and e_cond.is_contiguous()
+    x_prev = torch.empty_like(x)
+    pred_x0 = torch.empty_like(x)
+    check(_L().sdb_ddim_step(ptr(x), ptr(e_cond), ptr(e_uncond), float(cfg_scale), ptr(noise), float(a_t), float(a_prev),
+                             float(sigma_t), float(sqrt_one_minus_at), float(temperature), ptr(x_prev), ptr(pred_x0),
+                             x.numel(), stream_ptr()), "ddim_step")
+    return x_prev, pred_x0
+
+
+# ---- weight packing (host side, once per load) ----------------------------------------------------------
+def pack_conv_weight(w, dtype):
+    """OIHW [Cout,Cin,kh,kw] -> tap-major [kh*kw, Cout, Cin] contiguous ("RSKC")."""
+    Cout, Cin, kh, kw = w.shape
+    return w.detach().permute(2, 3, 0, 1).reshape(kh * kw, Cout, Cin).to(dtype).contiguous()
+
+
+def pack_geglu_weight(w, b, block_n):
+    """Interleave value/gate rows per block_n tile: tile t = [value rows t*h..(t+1)*h | gate rows ...], h = block_n/2."""
+    two_inner, K = w.shape
+    inner = two_inner // 2
+    h = block_n // 2
+    assert inner % h == 0
+    wv, wg = w[:inner].reshape(inner // h, h, K), w[inner:].reshape(inner // h, h, K)
+    wp = torch.cat([wv, wg], dim=1).reshape(two_inner, K).contiguous()
+    bv, bg = b[:inner].reshape(inner // h, h), b[inner:].reshape(inner // h, h)
+    bp = torch.cat([bv, bg], dim=1).reshape(two_inner).contiguous()
+    return wp, bp
+
+
+# ---- fp32 SIMT contraction ----------------------------------------------------------------------------
+def conv_simt(x, w_rskc, bias, kh, kw, stride=1, pad=0, up=1, rowvec=None, residual=None, out_dtype=torch.float32):
+    """x [N,IH,IW,Cin] fp32 (logical input is the nearest-`up`x upsampling of x), w [kh*kw,Cout,Cin] fp32."""
+    require_cuda(x, w_rskc, bias, rowvec, residual)
+    assert x.dtype == torch.float32 and w_rskc.dtype == torch.float32 and x.is_contiguous() and w_rskc.is_contiguous()
+    N, IH, IW, Cin = x.shape
+    taps, Cout, Cin2 = w_rskc.shape
+    assert Cin2 == Cin and taps == kh * kw
+    OH = (IH * up + 2 * pad - kh) // stride + 1
+    OW = (IW * up + 2 * pad - kw) // stride + 1
+    out = torch.empty((N, OH, OW, Cout), dtype=out_dtype, device=x.device)
+    a = SimtArgs()
+    a.A, a.B, a.out = ptr(x), ptr(w_rskc), ptr(out)
+    a.bias, a.rowvec, a.residual = ptr(bias), ptr(rowvec), ptr(residual)
+    a.lda, a.ldb, a.ldc = Cin, Cin, Cout
+    a.ldr = Cout
+    a.ldv = rowvec.stride(0) if rowvec is not None else 0
+    a.M, a.N, a.K = N * OH * OW, Cout, taps * Cin
+    a.alpha = 1.0
+    a.b_kn = 0
+    a.nb1 = a.nb2 = 1
+    a.kh, a.kw, a.stride, a.pad, a.up = kh, kw, stride, pad, up
+    a.NB, a.IH, a.IW, a.Cin, a.OH, a.OW = N, IH, IW, Cin, OH, OW
+    a.out_dtype = dtype_code(out_dtype)
+    if residual is not None:
+        assert residual.dtype == torch.float32 and residual.shape == out.shape and residual.is_contiguous()
+    check(_L().sdb_simt_contract(C.byref(a), stream_ptr()), "simt conv")
+    return out
+
+
+def gemm_simt(A, B, bias=None, residual=None, alpha=1.0, b_kn=False, out=None, out_dtype=torch.float32,
+              M=None, N=None, K=None, lda=None, ldb=None, ldc=None, batch=(1, 1),
+              sa=(0, 0), sb=(0, 0), sc=(0, 0)):
+    """out[M,N] = alpha * A[M,K] @ (B[N,K]^T or B[K,N]) + bias + residual, two-level batched, explicit strides."""
+    require_cuda(A, B, bias, residual, out)
+    assert A.dtype == torch.float32 and B.dtype == torch.float32
+    if M is None:
+        M, K = A.shape[-2], A.shape[-1]
+        N = B.shape[-1] if b_kn else B.shape[-2]
+    lda = lda if lda is not None else A.stride(-2)
+    ldb = ldb if ldb is not None else B.stride(-2)
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=A.device)
+    ldc = ldc if ldc is not None else out.stride(-2)
+    a = SimtArgs()
+    a.A, a.B, a.out = ptr(A), ptr(B), ptr(out)
+    a.bias, a.rowvec, a.residual = ptr(bias), 0, ptr(residual)
+    a.lda, a.ldb, a.ldc = lda, ldb, ldc
+    a.ldr = residual.stride(-2) if residual is not None else 0
+    a.ldv = 0
+    a.M, a.N, a.K = M, N, K
+    a.alpha = float(alpha)
+    a.b_kn = int(bool(b_kn))
+    a.nb1, a.nb2 = batch
+    a.sa1, a.sa2 = sa
+    a.sb1, a.sb2 = sb
+    a.sc1, a.sc2 = sc
+    a.kh = 0
+    a.out_dtype = dtype_code(out.dtype)
+    check(_L().sdb_simt_contract(C.byref(a), stream_ptr()), "simt gemm")
+    return out
+
+
+# ---- tcgen05 contraction -----------------------------------------------------------------------------
+def conv_tc(x, w_rskc, bias, kh, kw, stride=1, pad=0, rowvec=None, residual=None, out_dtype=torch.float32,
+            split_k=1, block_n=0, out=None, phase=None):
+    """x [N,IH,IW,Cin] bf16, w [kh*kw,Cout,Cin] bf16 -> [N,OH,OW,Cout].
+
+    phase=(sh, sw, oh, ow, OHF, OWF, pad_h, pad_w) writes this conv's OHxOW result into the strided
+    sub-lattice of a larger [N,OHF,OWF,Cout] `out` (sub-pixel decomposition of upsample+conv).
+    """
+    require_cuda(x, w_rskc, bias, rowvec, residual, out)
+    assert x.dtype == torch.bfloat16 and w_rskc.dtype == torch.bfloat16 and x.is_contiguous() and w_rskc.is_contiguous()
+    N, IH, IW, Cin = x.shape
+    taps, Cout, Cin2 = w_rskc.shape
+    assert Cin2 == Cin and taps == kh * kw
+    a = TcArgs()
+    if phase is None:
+        OH = (IH + 2 * pad - kh) // stride + 1
+        OW = (IW + 2 * pad - kw) // stride + 1
+        pad_h = pad_w = pad
+        if out is None:
+            out = torch.empty((N, OH, OW, Cout), dtype=out_dtype, device=x.device)
+        a.out_sh = a.out_sw = 1
+        a.out_oh = a.out_ow = 0
+        a.OHF, a.OWF = OH, OW
+    else:
+        sh, sw, o_h, o_w, OHF, OWF, pad_h, pad_w = phase
+        OH, OW = IH, IW
+        assert out is not None and tuple(out.shape) == (N, OHF, OWF, Cout)
+        a.out_sh, a.out_sw, a.out_oh, a.out_ow, a.OHF, a.OWF = sh, sw, o_h, o_w, OHF, OWF
+    a.A, a.B, a.out = ptr(x), ptr(w_rskc), ptr(out)
+    a.bias, a.rowvec, a.residual = ptr(bias), ptr(rowvec), ptr(residual)
+    a.lda, a.ldb, a.ldc = Cin, Cin, Cout
+    a.ldr = Cout
+    a.ldv = rowvec.stride(0) if rowvec is not None else 0
+    a.M, a.N, a.K = N * OH * OW, Cout, taps * Cin
+    a.out_dtype = dtype_code(out.dtype)
+    a.geglu = 0
+    a.col_group = a.col_group_stride = 0
+    a.split_k = split_k
+    a.block_n = block_n
+    a.taps, a.kw, a.stride, a.pad_h, a.pad_w = taps, kw, stride, pad_h, pad_w
+    a.NB, a.IH, a.IW, a.Cin, a.OH, a.OW = N, IH, IW, Cin, OH, OW
+    a.cout_pad = Cout
+    if residual is not None:
+        assert residual.dtype == torch.float32 and residual.is_contiguous()
+    if split_k > 1:
+        out.zero_()
+    check(_L().sdb_tc_contract(C.byref(a), stream_ptr()), "tc conv")
+    return out
+
+
+def gemm_tc(A, W, bias=None, residual=None, out_dtype=torch.float32, geglu=False, col_group=0, col_group_stride=0,
+            split_k=1, block_n=0, out=None, ldc=None, M=None, lda=None):
+    """out[M,N] = A[M,K] @ W[N,K]^T + bias + residual; A, W bf16 (K contiguous)."""
+    require_cuda(A, W, bias, residual, out)
+    assert A.dtype == torch.bfloat16 and W.dtype == torch.bfloat16 and W.is_contiguous()
+    K = A.shape[-1]
+    if M is None:
+        M = A.numel() // K
+    N = W.shape[0]
+    assert W.shape[1] == K
+    n_out = N // 2 if geglu else N
+    if out is None:
+        width = (N // col_group) * col_group_stride if col_group else n_out
+        if col_group:
+            out = torch.zeros((M, width), dtype=out_dtype, device=A.device)   # pad columns must read as 0
+        else:
+            out = torch.empty((M, width), dtype=out_dtype, device=A.device)
+    a = TcArgs()
+    a.A, a.B, a.out = ptr(A), ptr(W), ptr(out)
+    a.bias, a.rowvec, a.residual = ptr(bias), 0, ptr(residual)
+    a.lda = lda if lda is not None else K
+    a.ldb = K
+    a.ldc = ldc if ldc is not None else out.stride(-2)
+    a.ldr = residual.stride(-2) if residual is not None else 0
+    a.ldv = 0
+    a.M, a.N, a.K = M, N, K
+    a.out_dtype = dtype_code(out.dtype)
+    a.geglu = int(bool(geglu))
+    a.col_group, a.col_group_stride = col_group, col_group_stride
+    a.split_k = split_k
+    a.block_n = block_n
+    a.taps = 0
+    if split_k > 1:
+        out.zero_()
+    check(_L().sdb_tc_contract(C.byref(a), stream_ptr()), "tc gemm")
+    return out
+
+
+def attention_tc(q, k, v, B, H, Sq, Sk, d, dpad, scale, q_strides, k_strides, v_strides, out=None):
+    """q/k/v: bf16 tensors (any views) whose (batch, seq, head) element strides are given; heads padded to dpad.
+    Returns out [B, Sq, H*d] bf16."""
+    require_cuda(q, k, v)
+    assert q.dtype == k.dtype == v.dtype == torch.bfloat16
+    if out is None:
+        out = torch.empty((B, Sq, H * d), dtype=torch.bfloat16, device=q.device)
+    a = AttnArgs()
+    a.q, a.k, a.v, a.out = ptr(q), ptr(k), ptr(v), ptr(out)
+    a.q_bs, a.q_ss, a.q_hs = q_strides
+    a.k_bs, a.k_ss, a.k_hs = k_strides
+    a.v_bs, a.v_ss, a.v_hs = v_strides
+    a.o_bs, a.o_ss, a.o_hs = Sq * H * d, H * d, d
+    a.B, a.H, a.Sq, a.Sk, a.d, a.dpad = B, H, Sq, Sk, d, dpad
+    a.scale = float(scale)
+    check(_L().sdb_attention_fwd(C.byref(a), stream_ptr()), "attention_fwd")
+    return out
