@@ -72,6 +72,8 @@ int sdb_layernorm(const float* x, int rows, int C, float eps, const float* gamma
  * feeding a conv. up is 1 or 2. H, W are the INPUT spatial dims. */
 int sdb_cast_concat(const float* x0, int C0, const float* x1, int C1, int N, int H, int W, int up,
                     void* out, int out_dtype, void* stream);
+/* bilinear x2 upsampling with align_corners=True (DDPM/models/layers.py:68-72); x [N,H,W,C] fp32. */
+int sdb_upsample_bilinear2x(const float* x, int N, int H, int W, int C, void* out, int out_dtype, void* stream);
 /* out = act(x) (+ optional cast); act 0 none, 1 SiLU (emb_layers' nn.SiLU, model.py:195-196),
  * 2 GELU-erf (DDPM/models/unet.py:29). n elements. */
 int sdb_activation(const float* x, void* out, int out_dtype, long long n, int act, void* stream);
@@ -83,19 +85,26 @@ int sdb_geglu(const float* h, int rows, int inner, void* out, int out_dtype, voi
  * attention (flash_attn_func semantics, openai_model/attention.py:106-112). */
 int sdb_softmax_rows(const float* s, long long rows, int L, long long lds, float scale, void* out,
                      int out_dtype, long long ldo, void* stream);
-/* y = a*x + b*y style helpers */
+/* out = a + b (fp32), n elements: residual adds that follow a norm (DDPM/models/layers.py:338). */
 int sdb_add(const float* a, const float* b, float* out, long long n, void* stream);
+/* out[n,p,c] = x[n,p,c] + rowvec[n*ldv + c]: `time_emb[:, :, None, None] + h` (DDPM/models/layers.py:331-333). */
+int sdb_add_rowvec(const float* x, const float* rowvec, long long ldv, int N, long long HW, int C, void* out,
+                   int out_dtype, void* stream);
 
 /* ---- timestep embedding ------------------------------------------------------------------------
  * Replaces timestep_embedding (openai_model/utils.py:225-245): emb[b] = [cos(t_b*f), sin(t_b*f)].
- * freqs: device fp32 [half] (built on the host exactly as the reference does). t: device fp32 [B]. */
-int sdb_timestep_embedding(const float* t, const float* freqs, int B, int half, float* emb, void* stream);
+ * freqs: device fp32 [half] (built on the host exactly as the reference does). t: device fp32 [B].
+ * round_fp16 != 0 rounds every value through IEEE half, restating `t_emb.half()`
+ * (openai_model/model.py:566), which is part of the reference's result even in fp32. */
+int sdb_timestep_embedding(const float* t, const float* freqs, int B, int half, int round_fp16, float* emb,
+                           void* stream);
 /* pe_matrix[t] lookup for the DDPM UNet (DDPM/models/layers.py:32-34): table fp32 [T, dim]. */
 int sdb_gather_rows(const float* table, const long long* idx, int B, int dim, float* out, void* stream);
 
 /* ---- skinny GEMM (M <= 32 rows): y[M,N] = act_in(x)[M,K] @ W[N,K]^T + b ------------------------
  * Replaces time_embed / emb_layers Linear on [B,1280] (openai_model/model.py:353-357,195-201,241).
- * W fp32 [N,K] row-major. act_in: 0 none, 1 SiLU applied to x on load. act_out: 0 none, 1 SiLU. */
+ * W fp32 [N,K] row-major. act_in: 0 none, 1 SiLU applied to x on load. act_out: 0 none, 1 SiLU,
+ * 2 GELU-erf (DDPM/models/unet.py:26-31). */
 int sdb_skinny_linear(const float* x, int M, int K, const float* W, const float* bias, int N,
                       int act_in, int act_out, float* y, void* stream);
 

@@ -81,11 +81,13 @@ SIGNATURES = {
     "sdb_groupnorm_nhwc": (_I, [_P, _I, _P, _I, _I, _I, _I, _F, _P, _P, _I, _I, _P, _I, _P, _P]),
     "sdb_layernorm": (_I, [_P, _I, _I, _F, _P, _P, _P, _I, _P]),
     "sdb_cast_concat": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _P, _I, _P]),
+    "sdb_upsample_bilinear2x": (_I, [_P, _I, _I, _I, _I, _P, _I, _P]),
     "sdb_activation": (_I, [_P, _P, _I, _L, _I, _P]),
     "sdb_geglu": (_I, [_P, _I, _I, _P, _I, _P]),
     "sdb_softmax_rows": (_I, [_P, _L, _I, _L, _F, _P, _I, _L, _P]),
     "sdb_add": (_I, [_P, _P, _P, _L, _P]),
-    "sdb_timestep_embedding": (_I, [_P, _P, _I, _I, _P, _P]),
+    "sdb_add_rowvec": (_I, [_P, _P, _L, _I, _L, _I, _P, _I, _P]),
+    "sdb_timestep_embedding": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "sdb_gather_rows": (_I, [_P, _P, _I, _I, _P, _P]),
     "sdb_skinny_linear": (_I, [_P, _I, _I, _P, _P, _I, _I, _I, _P, _P]),
     "sdb_ddim_step": (_I, [_P, _P, _P, _F, _P, _F, _F, _F, _F, _F, _P, _P, _L, _P]),

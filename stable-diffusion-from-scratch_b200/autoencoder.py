@@ -1,0 +1,308 @@
+"""Drop-in VAE `Decoder` / `AutoencoderKL.decode` (reference: ldm/modules/diffusionmodules/model.py:
+468-574 and ldm/models/autoencoder.py:293-340) running on libsdb200.so.
+
+Same constructor kwargs and state-dict keys (`decoder.conv_in`, `decoder.mid.block_1.norm1`,
+`decoder.up.L.block.K.conv1`, `decoder.up.L.upsample.conv`, `decoder.norm_out`, `decoder.conv_out`,
+`post_quant_conv`) as the reference.  torch.nn layers are parameter holders only.
+`VAE.autoencoder.AutoEncoderKL.decode` (VAE/autoencoder.py:126-132) is served by the same class
+through the `AutoEncoderKL` alias; its fp16-only 8-head mid attention (Unet/attention.py:221-264)
+is NOT replicated — the numerical oracle is the canonical `ldm` decoder.
+"""
+import torch
+from torch import nn
+
+from . import engine, ops
+from .engine import PackedConv, PackedLinear
+
+
+def Normalize(in_channels, num_groups=32):   # ldm/modules/diffusionmodules/model.py:40-41
+    return nn.GroupNorm(num_groups=num_groups, num_channels=in_channels, eps=1e-6, affine=True)
+
+
+class Upsample(nn.Module):
+    def __init__(self, in_channels, with_conv):
+        super().__init__()
+        if not with_conv:
+            raise NotImplementedError("sdb200 VAE Upsample: resamp_with_conv=False is outside the hot path")
+        self.with_conv = with_conv
+        self.conv = nn.Conv2d(in_channels, in_channels, kernel_size=3, stride=1, padding=1)
+
+
+class ResnetBlock(nn.Module):
+    def __init__(self, *, in_channels, out_channels=None, conv_shortcut=False, dropout, temb_channels=512):
+        super().__init__()
+        self.in_channels = in_channels
+        out_channels = in_channels if out_channels is None else out_channels
+        self.out_channels = out_channels
+        self.use_conv_shortcut = conv_shortcut
+        self.norm1 = Normalize(in_channels)
+        self.conv1 = nn.Conv2d(in_channels, out_channels, kernel_size=3, stride=1, padding=1)
+        if temb_channels > 0:
+            self.temb_proj = nn.Linear(temb_channels, out_channels)
+        self.norm2 = Normalize(out_channels)
+        self.dropout = nn.Dropout(dropout)
+        self.conv2 = nn.Conv2d(out_channels, out_channels, kernel_size=3, stride=1, padding=1)
+        if self.in_channels != self.out_channels:
+            if self.use_conv_shortcut:
+                self.conv_shortcut = nn.Conv2d(in_channels, out_channels, kernel_size=3, stride=1, padding=1)
+            else:
+                self.nin_shortcut = nn.Conv2d(in_channels, out_channels, kernel_size=1, stride=1, padding=0)
+
+
+class AttnBlock(nn.Module):
+    def __init__(self, in_channels):
+        super().__init__()
+        self.in_channels = in_channels
+        self.norm = Normalize(in_channels)
+        self.q = nn.Conv2d(in_channels, in_channels, kernel_size=1, stride=1, padding=0)
+        self.k = nn.Conv2d(in_channels, in_channels, kernel_size=1, stride=1, padding=0)
+        self.v = nn.Conv2d(in_channels, in_channels, kernel_size=1, stride=1, padding=0)
+        self.proj_out = nn.Conv2d(in_channels, in_channels, kernel_size=1, stride=1, padding=0)
+
+
+def make_attn(in_channels, attn_type="vanilla"):
+    assert attn_type in ["vanilla", "linear", "none"], f'attn_type {attn_type} unknown'
+    if attn_type == "vanilla":
+        return AttnBlock(in_channels)
+    if attn_type == "none":
+        return nn.Identity(in_channels)
+    raise NotImplementedError("sdb200 VAE: linear attention is outside the hot path")
+
+
+class Decoder(nn.Module):
+    """ldm/modules/diffusionmodules/model.py:468-574."""
+
+    def __init__(self, *, ch, out_ch, ch_mult=(1, 2, 4, 8), num_res_blocks, attn_resolutions, dropout=0.0,
+                 resamp_with_conv=True, in_channels, resolution, z_channels, give_pre_end=False, tanh_out=False,
+                 use_linear_attn=False, attn_type="vanilla", compute_mode=None, **ignorekwargs):
+        super().__init__()
+        if use_linear_attn:
+            attn_type = "linear"
+        if tanh_out or give_pre_end:
+            raise NotImplementedError("sdb200 Decoder: tanh_out / give_pre_end are outside the hot path")
+        self.ch = ch
+        self.temb_ch = 0
+        self.num_resolutions = len(ch_mult)
+        self.num_res_blocks = num_res_blocks
+        self.resolution = resolution
+        self.in_channels = in_channels
+        self.give_pre_end = give_pre_end
+        self.tanh_out = tanh_out
+        self.compute_mode = compute_mode or engine.default_mode()
+        block_in = ch * ch_mult[self.num_resolutions - 1]
+        curr_res = resolution // 2 ** (self.num_resolutions - 1)
+        self.z_shape = (1, z_channels, curr_res, curr_res)
+        self.conv_in = nn.Conv2d(z_channels, block_in, kernel_size=3, stride=1, padding=1)
+        self.mid = nn.Module()
+        self.mid.block_1 = ResnetBlock(in_channels=block_in, out_channels=block_in, temb_channels=self.temb_ch, dropout=dropout)
+        self.mid.attn_1 = make_attn(block_in, attn_type=attn_type)
+        self.mid.block_2 = ResnetBlock(in_channels=block_in, out_channels=block_in, temb_channels=self.temb_ch, dropout=dropout)
+        self.up = nn.ModuleList()
+        for i_level in reversed(range(self.num_resolutions)):
+            block = nn.ModuleList()
+            attn = nn.ModuleList()
+            block_out = ch * ch_mult[i_level]
+            for i_block in range(self.num_res_blocks + 1):
+                block.append(ResnetBlock(in_channels=block_in, out_channels=block_out, temb_channels=self.temb_ch, dropout=dropout))
+                block_in = block_out
+                if curr_res in attn_resolutions:
+                    attn.append(make_attn(block_in, attn_type=attn_type))
+            up = nn.Module()
+            up.block = block
+            up.attn = attn
+            if i_level != 0:
+                up.upsample = Upsample(block_in, resamp_with_conv)
+                curr_res = curr_res * 2
+            self.up.insert(0, up)
+        self.norm_out = Normalize(block_in)
+        self.conv_out = nn.Conv2d(block_in, out_ch, kernel_size=3, stride=1, padding=1)
+        self._packed = {}
+
+    def _invalidate(self):
+        self._packed = {}
+
+    def load_state_dict(self, *a, **k):
+        r = super().load_state_dict(*a, **k)
+        self._invalidate()
+        return r
+
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        self._invalidate()
+        return r
+
+    def _pack(self, mode):
+        if mode in self._packed:
+            return self._packed[mode]
+        P = {}
+        for m in self.modules():
+            if isinstance(m, ResnetBlock):
+                P[("c1", id(m))] = PackedConv(m.conv1.weight, m.conv1.bias, mode)
+                P[("c2", id(m))] = PackedConv(m.conv2.weight, m.conv2.bias, mode)
+                if hasattr(m, "nin_shortcut"):
+                    P[("sc", id(m))] = PackedConv(m.nin_shortcut.weight, m.nin_shortcut.bias, mode)
+                elif hasattr(m, "conv_shortcut"):
+                    P[("sc", id(m))] = PackedConv(m.conv_shortcut.weight, m.conv_shortcut.bias, mode)
+            elif isinstance(m, AttnBlock):
+                Cc = m.in_channels
+                for name in ("q", "k", "proj_out"):
+                    conv = getattr(m, name)
+                    P[(name, id(m))] = PackedLinear(conv.weight.reshape(Cc, Cc), conv.bias, mode)
+                # V is produced transposed ([C, tokens]) by swapping GEMM operands, so its bias (per output ROW)
+                # is added after P.V instead: softmax rows sum to 1, so P (V + 1 b^T) = P V + b^T.
+                P[("v", id(m))] = PackedLinear(m.v.weight.reshape(Cc, Cc), None, mode)
+                P[("vb", id(m))] = m.v.bias.detach().float().contiguous()
+            elif isinstance(m, Upsample):
+                P[("up", id(m))] = PackedConv(m.conv.weight, m.conv.bias, mode)
+        P["conv_in"] = PackedConv(self.conv_in.weight, self.conv_in.bias, mode)
+        P["conv_out"] = PackedConv(self.conv_out.weight, self.conv_out.bias, mode)
+        self._packed[mode] = P
+        return P
+
+    @staticmethod
+    def _gn(norm, x, mode, act, out_dtype):
+        return ops.groupnorm(x, norm.weight, norm.bias, norm.eps, act=act, out_dtype=out_dtype,
+                             groups=norm.num_groups, exact=(mode == "fp32"))
+
+    def _resnet(self, rb, P, mode, x):
+        """ResnetBlock.forward with temb=None (model.py:123-143)."""
+        c1, c2 = P[("c1", id(rb))], P[("c2", id(rb))]
+        h = engine.conv(self._gn(rb.norm1, x, mode, 1, c1.in_dtype), c1)
+        h = self._gn(rb.norm2, h, mode, 1, c2.in_dtype)
+        if ("sc", id(rb)) in P:
+            sc = P[("sc", id(rb))]
+            xs = ops.cast_concat(x, None, out_dtype=sc.in_dtype) if sc.in_dtype == torch.bfloat16 else x
+            xs = engine.conv(xs, sc)
+        else:
+            xs = x
+        return engine.conv(h, c2, residual=xs)
+
+    def _attn(self, ab, P, mode, x):
+        """AttnBlock.forward (model.py:180-204): single head, d = C, scores materialised per image
+        (as the reference's torch.bmm does), all three contractions on the GEMM kernels."""
+        B, Hh, Ww, Cc = x.shape
+        S = Hh * Ww
+        odt = engine.op_dtype(mode)
+        hn = self._gn(ab.norm, x, mode, 0, odt).reshape(B * S, Cc)
+        q = engine.linear(hn, P[("q", id(ab))], out_dtype=odt)
+        k = engine.linear(hn, P[("k", id(ab))], out_dtype=odt)
+        scale = float(int(Cc) ** (-0.5))
+        o = torch.empty((B * S, Cc), dtype=odt, device=x.device)
+        wv = P[("v", id(ab))]
+        for b in range(B):
+            qb, kb, hb = q[b * S:(b + 1) * S], k[b * S:(b + 1) * S], hn[b * S:(b + 1) * S]
+            if mode == "bf16":
+                vT = ops.gemm_tc(wv.w, hb, out_dtype=odt)                                   # [C, S] = Wv @ hn^T
+                sc = ops.gemm_tc(qb, kb)                                                    # [S, S] fp32
+                pm = ops.softmax_rows(sc, scale, out_dtype=odt)
+                ops.gemm_tc(pm, vT, bias=P[("vb", id(ab))], out=o[b * S:(b + 1) * S], out_dtype=odt)
+            else:
+                v = ops.gemm_simt(hb, wv.w, P[("vb", id(ab))])                              # [S, C]
+                sc = ops.gemm_simt(qb, kb)
+                pm = ops.softmax_rows(sc, scale)
+                ops.gemm_simt(pm, v, b_kn=True, out=o[b * S:(b + 1) * S])
+        out = engine.linear(o, P[("proj_out", id(ab))], residual=x.reshape(B * S, Cc))
+        return out.reshape(B, Hh, Ww, Cc)
+
+    def _forward_nhwc(self, z, mode):
+        P = self._pack(mode)
+        h = engine.conv(z, P["conv_in"])
+        h = self._resnet(self.mid.block_1, P, mode, h)
+        if isinstance(self.mid.attn_1, AttnBlock):
+            h = self._attn(self.mid.attn_1, P, mode, h)
+        h = self._resnet(self.mid.block_2, P, mode, h)
+        for i_level in reversed(range(self.num_resolutions)):
+            for i_block in range(self.num_res_blocks + 1):
+                h = self._resnet(self.up[i_level].block[i_block], P, mode, h)
+                if len(self.up[i_level].attn) > 0:
+                    h = self._attn(self.up[i_level].attn[i_block], P, mode, h)
+            if i_level != 0:
+                pc = P[("up", id(self.up[i_level].upsample))]
+                if pc.use_tc:
+                    h = engine.conv(ops.cast_concat(h, None, up=2, out_dtype=torch.bfloat16), pc)
+                else:
+                    h = engine.conv(h, pc, up=2)
+        co = P["conv_out"]
+        h = self._gn(self.norm_out, h, mode, 1, co.in_dtype)
+        return engine.conv(h, co)
+
+    @torch.no_grad()
+    def forward(self, z):
+        """z [N, z_channels, h, w] -> [N, out_ch, 8h, 8w] (fp32 in, fp32 out)."""
+        from ._lib import require_cuda
+        require_cuda(z)
+        self.last_z_shape = z.shape
+        h = ops.nchw_to_nhwc(z.float().contiguous())
+        out = ops.nhwc_to_nchw(self._forward_nhwc(h, self.compute_mode))
+        return out if z.dtype == torch.float32 else out.to(z.dtype)
+
+
+class AutoencoderKL(nn.Module):
+    """Decode side of ldm/models/autoencoder.py:292-340.  The encoder / loss / Lightning training hooks
+    are out of scope; their state-dict keys are tolerated with strict=False."""
+
+    def __init__(self, ddconfig, lossconfig=None, embed_dim=4, ckpt_path=None, ignore_keys=[], image_key="image",
+                 colorize_nlabels=None, monitor=None, compute_mode=None, micro_batch=8):
+        super().__init__()
+        self.image_key = image_key
+        self.decoder = Decoder(**ddconfig, compute_mode=compute_mode)
+        assert ddconfig["double_z"]
+        self.post_quant_conv = nn.Conv2d(embed_dim, ddconfig["z_channels"], 1)
+        self.embed_dim = embed_dim
+        self.micro_batch = micro_batch
+        if monitor is not None:
+            self.monitor = monitor
+        if ckpt_path is not None:
+            self.init_from_ckpt(ckpt_path, ignore_keys=ignore_keys)
+
+    @property
+    def compute_mode(self):
+        return self.decoder.compute_mode
+
+    @compute_mode.setter
+    def compute_mode(self, m):
+        self.decoder.compute_mode = m
+
+    def init_from_ckpt(self, path, ignore_keys=list()):
+        sd = torch.load(path, map_location="cpu")["state_dict"]
+        for k in list(sd.keys()):
+            for ik in ignore_keys:
+                if k.startswith(ik):
+                    del sd[k]
+        self.load_state_dict(sd, strict=False)
+
+    def load_state_dict(self, *a, **k):
+        r = super().load_state_dict(*a, **k)
+        self.decoder._invalidate()
+        self._pq = None
+        return r
+
+    _pq = None
+
+    @torch.no_grad()
+    def decode(self, z):
+        """AutoencoderKL.decode (autoencoder.py:337-340): post_quant_conv (1x1, 4->4) then Decoder.
+        Large batches are decoded in micro-batches of `micro_batch` images (activations at 512^2 are
+        ~0.5 GB/image); results are identical because nothing on the path reduces over the batch."""
+        from ._lib import require_cuda
+        require_cuda(z)
+        mode = self.decoder.compute_mode
+        if self._pq is None or self._pq[0] != mode:
+            # C_in = 4: SIMT fp32 kernel in both modes
+            self._pq = (mode, PackedConv(self.post_quant_conv.weight, self.post_quant_conv.bias, "fp32"))
+        pq = self._pq[1]
+        zf = z.float().contiguous()
+        N = zf.shape[0]
+        outs = []
+        for i in range(0, N, self.micro_batch):
+            h = ops.nchw_to_nhwc(zf[i:i + self.micro_batch].contiguous())
+            h = engine.conv(h, pq)
+            outs.append(ops.nhwc_to_nchw(self.decoder._forward_nhwc(h, mode)))
+        out = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+        return out if z.dtype == torch.float32 else out.to(z.dtype)
+
+    def forward(self, z):
+        return self.decode(z)
+
+
+AutoEncoderKL = AutoencoderKL   # VAE/autoencoder.py spells it with a capital E

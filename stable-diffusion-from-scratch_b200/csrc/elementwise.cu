@@ -1,5 +1,6 @@
 // sdb200 — layout, elementwise and small-matrix kernels (all HBM/launch-bound).
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace sdb {
 
@@ -92,6 +93,22 @@ __global__ void geglu_kernel(const float* __restrict__ h, int rows, int inner, v
     }
 }
 
+// out[n, p, c] = x[n, p, c] + rowvec[n, c]  (time-embedding broadcast add, DDPM/models/layers.py:331-333)
+template <bool OUT_BF16>
+__global__ void add_rowvec_kernel(const float* __restrict__ x, const float* __restrict__ rv, long long ldv,
+                                  long long HW, int C, long long total_vec, void* __restrict__ out) {
+    const int V = C >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+        int v = (int)(i % V);
+        long long n = (i / V) / HW;
+        float4 a = __ldg(reinterpret_cast<const float4*>(x) + i);
+        const float* r = rv + n * ldv + v * 4;
+        a.x += r[0]; a.y += r[1]; a.z += r[2]; a.w += r[3];
+        if (OUT_BF16) st_stream_u2(reinterpret_cast<__nv_bfloat16*>(out) + i * 4, pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+        else st_stream_f4(reinterpret_cast<float*>(out) + i * 4, a);
+    }
+}
+
 __global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long long n) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         out[i] = a[i] + b[i];
@@ -138,13 +155,15 @@ __global__ void softmax_rows_kernel(const float* __restrict__ s, int L, long lon
 
 // ---- timestep embedding (reference openai_model/utils.py:225-245): [cos | sin] ------------------
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, const float* __restrict__ freqs,
-                                          int B, int half, float* __restrict__ emb) {
+                                          int B, int half, int round_fp16, float* __restrict__ emb) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * half) return;
     int b = i / half, j = i % half;
     float a = t[b] * freqs[j];
-    emb[(long long)b * 2 * half + j] = cosf(a);
-    emb[(long long)b * 2 * half + half + j] = sinf(a);
+    float c = cosf(a), s = sinf(a);
+    if (round_fp16) { c = __half2float(__float2half_rn(c)); s = __half2float(__float2half_rn(s)); }
+    emb[(long long)b * 2 * half + j] = c;
+    emb[(long long)b * 2 * half + half + j] = s;
 }
 
 __global__ void gather_rows_kernel(const float* __restrict__ table, const long long* __restrict__ idx,
@@ -191,6 +210,7 @@ __global__ void skinny_linear_kernel(const float* __restrict__ x, int M, int K, 
                 if (lane == 0) {
                     if (bias) v += bias[n];
                     if (act_out == 1) v = silu_exact(v);
+                    else if (act_out == 2) v = gelu_erf(v);
                     y[(long long)m * N + n] = v;
                 }
             }
@@ -220,6 +240,43 @@ __global__ void ddim_step_kernel(const float* __restrict__ x, const float* __res
         float xp = __fadd_rn(__fadd_rn(__fmul_rn(sqrt_aprev, p0), dir), nz);
         x_prev[i] = xp;
         pred_x0[i] = p0;
+    }
+}
+
+// ---- bilinear x2 upsample, align_corners=True (DDPM/models/layers.py:68-72), NHWC ----------------
+template <bool OUT_BF16>
+__global__ void upsample_bilinear2x_kernel(const float* __restrict__ x, int H, int W, int C, long long total_vec,
+                                           void* __restrict__ out) {
+    const int OH = 2 * H, OW = 2 * W, V = C >> 2;
+    // PyTorch's area_pixel_compute_scale for align_corners=True: (in - 1) / (out - 1), 0 when out == 1
+    const float sh = OH > 1 ? (float)(H - 1) / (float)(OH - 1) : 0.f;
+    const float sw = OW > 1 ? (float)(W - 1) / (float)(OW - 1) : 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
+         i += (long long)gridDim.x * blockDim.x) {
+        int v = (int)(i % V);
+        long long pix = i / V;
+        int ow = (int)(pix % OW);
+        long long t = pix / OW;
+        int oh = (int)(t % OH);
+        long long n = t / OH;
+        float fh = sh * oh, fw = sw * ow;
+        int h0 = (int)fh, w0 = (int)fw;
+        int h1 = h0 + (h0 < H - 1 ? 1 : 0), w1 = w0 + (w0 < W - 1 ? 1 : 0);
+        float lh = fh - h0, lw = fw - w0;
+        const float* b = x + (n * H) * (long long)W * C + v * 4;
+        float4 a00 = __ldg(reinterpret_cast<const float4*>(b + ((long long)h0 * W + w0) * C));
+        float4 a01 = __ldg(reinterpret_cast<const float4*>(b + ((long long)h0 * W + w1) * C));
+        float4 a10 = __ldg(reinterpret_cast<const float4*>(b + ((long long)h1 * W + w0) * C));
+        float4 a11 = __ldg(reinterpret_cast<const float4*>(b + ((long long)h1 * W + w1) * C));
+        float w00 = (1.f - lh) * (1.f - lw), w01 = (1.f - lh) * lw, w10 = lh * (1.f - lw), w11 = lh * lw;
+        float4 r;
+        r.x = w00 * a00.x + w01 * a01.x + w10 * a10.x + w11 * a11.x;
+        r.y = w00 * a00.y + w01 * a01.y + w10 * a10.y + w11 * a11.y;
+        r.z = w00 * a00.z + w01 * a01.z + w10 * a10.z + w11 * a11.z;
+        r.w = w00 * a00.w + w01 * a01.w + w10 * a10.w + w11 * a11.w;
+        long long o = pix * C + v * 4;
+        if (OUT_BF16) st_stream_u2(reinterpret_cast<__nv_bfloat16*>(out) + o, pack_bf16x2(r.x, r.y), pack_bf16x2(r.z, r.w));
+        else st_stream_f4(reinterpret_cast<float*>(out) + o, r);
     }
 }
 
@@ -262,6 +319,15 @@ int sdb_cast_concat(const float* x0, int C0, const float* x1, int C1, int N, int
     return check_launch("cast_concat_kernel");
 }
 
+int sdb_upsample_bilinear2x(const float* x, int N, int H, int W, int C, void* out, int out_dtype, void* stream) {
+    SDB_REQUIRE(x && out && N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "upsample_bilinear2x: bad args");
+    long long total = (long long)N * 2 * H * 2 * W * (C / 4);
+    int threads = 256, blocks = grid_for(total, threads);
+    if (out_dtype == SDB_BF16) upsample_bilinear2x_kernel<true><<<blocks, threads, 0, (cudaStream_t)stream>>>(x, H, W, C, total, out);
+    else upsample_bilinear2x_kernel<false><<<blocks, threads, 0, (cudaStream_t)stream>>>(x, H, W, C, total, out);
+    return check_launch("upsample_bilinear2x_kernel");
+}
+
 int sdb_activation(const float* x, void* out, int out_dtype, long long n, int act, void* stream) {
     SDB_REQUIRE(x && out && n > 0, "activation: bad args");
     int threads = 256, blocks = grid_for(n, threads);
@@ -288,16 +354,27 @@ int sdb_softmax_rows(const float* s, long long rows, int L, long long lds, float
     return check_launch("softmax_rows_kernel");
 }
 
+int sdb_add_rowvec(const float* x, const float* rowvec, long long ldv, int N, long long HW, int C, void* out,
+                   int out_dtype, void* stream) {
+    SDB_REQUIRE(x && rowvec && out && N > 0 && HW > 0 && C > 0 && C % 4 == 0, "add_rowvec: bad args");
+    long long total = (long long)N * HW * (C / 4);
+    int threads = 256, blocks = grid_for(total, threads);
+    if (out_dtype == SDB_BF16) add_rowvec_kernel<true><<<blocks, threads, 0, (cudaStream_t)stream>>>(x, rowvec, ldv, HW, C, total, out);
+    else add_rowvec_kernel<false><<<blocks, threads, 0, (cudaStream_t)stream>>>(x, rowvec, ldv, HW, C, total, out);
+    return check_launch("add_rowvec_kernel");
+}
+
 int sdb_add(const float* a, const float* b, float* out, long long n, void* stream) {
     SDB_REQUIRE(a && b && out && n > 0, "add: bad args");
     add_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, out, n);
     return check_launch("add_kernel");
 }
 
-int sdb_timestep_embedding(const float* t, const float* freqs, int B, int half, float* emb, void* stream) {
+int sdb_timestep_embedding(const float* t, const float* freqs, int B, int half, int round_fp16, float* emb,
+                           void* stream) {
     SDB_REQUIRE(t && freqs && emb && B > 0 && half > 0, "timestep_embedding: bad args");
     int n = B * half;
-    timestep_embedding_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(t, freqs, B, half, emb);
+    timestep_embedding_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(t, freqs, B, half, round_fp16, emb);
     return check_launch("timestep_embedding_kernel");
 }
 

@@ -1,0 +1,533 @@
+"""Drop-in `UNetModel` (reference: openai_model/model.py:259-595) running on libsdb200.so.
+
+Same class names, constructor kwargs, state-dict keys and `forward(x, timesteps, context)` signature
+as the reference, so `instantiate_from_config` with `target: sdb200.openai_model.UNetModel` and
+`load_state_dict` of a reference checkpoint work unchanged.  The torch.nn layer objects below are
+parameter HOLDERS only (they give the reference's key names / shapes); their `forward` is never
+called — all arithmetic goes through hand-written sm_100a kernels (ops.py), channels-last.
+
+Scope: the SpatialTransformer variant used by Stable Diffusion v1
+(`use_spatial_transformer=True`), ResBlocks without scale-shift / resblock_updown, no class
+conditioning.  Unsupported constructor options raise NotImplementedError instead of silently
+computing something else.
+"""
+import math
+
+import torch
+from torch import nn
+
+from . import engine, ops
+from .engine import PackedConv, PackedLinear, head_pad
+
+
+class GroupNorm32(nn.GroupNorm):
+    """Holder for GroupNorm32 (openai_model/utils.py:15-22)."""
+
+
+def normalization(channels):
+    return GroupNorm32(32, channels)
+
+
+def Normalize(in_channels):   # openai_model/attention.py:10-11
+    return nn.GroupNorm(num_groups=32, num_channels=in_channels, eps=1e-6, affine=True)
+
+
+def zero_module(module):
+    for p in module.parameters():
+        p.detach().zero_()
+    return module
+
+
+class TimestepBlock(nn.Module):
+    pass
+
+
+class TimestepEmbedSequential(nn.Sequential, TimestepBlock):
+    """openai_model/model.py:37-67 (dispatch happens in UNetModel._run_block)."""
+
+
+class Downsample(nn.Module):
+    """openai_model/model.py:71-97: conv3x3 stride 2 pad 1."""
+
+    def __init__(self, channels, use_conv, dims=2, out_channels=None, padding=1):
+        super().__init__()
+        if dims != 2 or not use_conv:
+            raise NotImplementedError("sdb200 Downsample supports dims=2, use_conv=True")
+        self.channels = channels
+        self.out_channels = out_channels or channels
+        self.op = nn.Conv2d(self.channels, self.out_channels, 3, stride=2, padding=padding)
+
+
+class Upsample(nn.Module):
+    """openai_model/model.py:100-131: nearest x2 then conv3x3."""
+
+    def __init__(self, channels, use_conv, dims=2, out_channels=None, padding=1):
+        super().__init__()
+        if dims != 2 or not use_conv:
+            raise NotImplementedError("sdb200 Upsample supports dims=2, use_conv=True")
+        self.channels = channels
+        self.out_channels = out_channels or channels
+        self.conv = nn.Conv2d(self.channels, self.out_channels, 3, padding=padding)
+
+
+class ResBlock(TimestepBlock):
+    """openai_model/model.py:139-252."""
+
+    def __init__(self, channels, emb_channels, dropout, out_channels=None, use_conv=False,
+                 use_scale_shift_norm=False, dims=2, use_checkpoint=False, up=False, down=False):
+        super().__init__()
+        if use_scale_shift_norm or up or down or dims != 2 or use_conv:
+            raise NotImplementedError("sdb200 ResBlock: scale-shift / updown / 3x3 skip are outside the hot path")
+        self.channels = channels
+        self.emb_channels = emb_channels
+        self.out_channels = out_channels or channels
+        self.in_layers = nn.Sequential(normalization(channels), nn.SiLU(), nn.Conv2d(channels, self.out_channels, 3, padding=1))
+        self.emb_layers = nn.Sequential(nn.SiLU(), nn.Linear(emb_channels, self.out_channels))
+        self.out_layers = nn.Sequential(normalization(self.out_channels), nn.SiLU(), nn.Dropout(p=dropout),
+                                        zero_module(nn.Conv2d(self.out_channels, self.out_channels, 3, padding=1)))
+        if self.out_channels == channels:
+            self.skip_connection = nn.Identity()
+        else:
+            self.skip_connection = nn.Conv2d(channels, self.out_channels, 1)
+
+
+class CrossAttention(nn.Module):
+    """openai_model/attention.py:24-117."""
+
+    def __init__(self, query_dim, context_dim=None, heads=8, dim_head=64, dropout=0.):
+        super().__init__()
+        inner_dim = dim_head * heads
+        context_dim = query_dim if context_dim is None else context_dim
+        self.scale = dim_head ** -0.5
+        self.heads = heads
+        self.dim_head = dim_head
+        self.to_q = nn.Linear(query_dim, inner_dim, bias=False)
+        self.to_k = nn.Linear(context_dim, inner_dim, bias=False)
+        self.to_v = nn.Linear(context_dim, inner_dim, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(inner_dim, query_dim), nn.Dropout(dropout))
+
+
+class GELU(nn.Module):
+    """The reference's GEGLU, class named `GELU` (openai_model/attention.py:129-141)."""
+
+    def __init__(self, dim_in, dim_out):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out * 2)
+
+
+class FeedForward(nn.Module):
+    """openai_model/attention.py:146-172 (glu=True is what BasicTransformerBlock uses)."""
+
+    def __init__(self, dim, dim_out=None, mult=4, glu=False, dropout=0.):
+        super().__init__()
+        if not glu:
+            raise NotImplementedError("sdb200 FeedForward: only the gated (GEGLU) variant is on the hot path")
+        inner_dim = int(dim * mult)
+        dim_out = dim if dim_out is None else dim_out
+        self.net = nn.Sequential(GELU(dim, inner_dim), nn.Dropout(dropout), nn.Linear(inner_dim, dim_out))
+
+
+class BasicTransformerBlock(nn.Module):
+    """openai_model/attention.py:187-257."""
+
+    def __init__(self, dim, n_heads, d_head, dropout=0., context_dim=None, gated_ff=True, checkpoint=True):
+        super().__init__()
+        self.attn1 = CrossAttention(query_dim=dim, heads=n_heads, dim_head=d_head, dropout=dropout)
+        self.ff = FeedForward(dim=dim, dropout=dropout, glu=gated_ff)
+        self.attn2 = CrossAttention(query_dim=dim, context_dim=context_dim, heads=n_heads, dim_head=d_head, dropout=dropout)
+        self.norm1 = nn.LayerNorm(dim)
+        self.norm2 = nn.LayerNorm(dim)
+        self.norm3 = nn.LayerNorm(dim)
+
+
+class SpatialTransformer(nn.Module):
+    """openai_model/attention.py:303-363."""
+
+    def __init__(self, in_channels, n_heads, d_head, depth=1, dropout=0., context_dim=None):
+        super().__init__()
+        self.in_channels = in_channels
+        self.n_heads, self.d_head = n_heads, d_head
+        inner_dim = n_heads * d_head
+        self.norm = Normalize(in_channels)
+        self.proj_in = nn.Conv2d(in_channels, inner_dim, kernel_size=1, stride=1, padding=0)
+        self.transformer_blocks = nn.ModuleList(
+            [BasicTransformerBlock(inner_dim, n_heads, d_head, dropout=dropout, context_dim=context_dim) for _ in range(depth)])
+        self.proj_out = zero_module(nn.Conv2d(inner_dim, in_channels, kernel_size=1, stride=1, padding=0))
+
+
+class UNetModel(nn.Module):
+    """The full UNet with attention and timestep embedding (openai_model/model.py:259-595).
+
+    Extra keyword (not in the reference): `compute_mode` = "bf16" (tcgen05 tensor cores, default) or
+    "fp32" (SIMT, the <= 1e-5 parity mode); also settable later via `.compute_mode`.
+    """
+
+    def __init__(self, image_size, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions,
+                 dropout=0, channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, num_classes=None,
+                 use_checkpoint=False, use_fp16=False, num_heads=-1, num_head_channels=-1, num_heads_upsample=-1,
+                 use_scale_shift_norm=False, resblock_updown=False, use_new_attention_order=False,
+                 use_spatial_transformer=False, transformer_depth=1, context_dim=None, n_embed=None, legacy=True,
+                 compute_mode=None):
+        super().__init__()
+        if use_spatial_transformer:
+            assert context_dim is not None, 'Fool!! You forgot to include the dimension of your cross-attention conditioning...'
+        if context_dim is not None:
+            assert use_spatial_transformer, 'Fool!! You forgot to use the spatial transformer for your cross-attention conditioning...'
+            if not isinstance(context_dim, int):
+                context_dim = list(context_dim)
+        if num_heads_upsample == -1:
+            num_heads_upsample = num_heads
+        if num_heads == -1:
+            assert num_head_channels != -1, 'Either num_heads or num_head_channels has to be set'
+        if num_head_channels == -1:
+            assert num_heads != -1, 'Either num_heads or num_head_channels has to be set'
+        if not use_spatial_transformer:
+            raise NotImplementedError("sdb200 UNetModel: the AttentionBlock (non-transformer) variant is a 'next' row (SURVEY §8f4)")
+        if num_classes is not None or use_scale_shift_norm or resblock_updown or n_embed is not None or dims != 2 or not conv_resample:
+            raise NotImplementedError("sdb200 UNetModel: class-cond / scale-shift / resblock_updown / codebook heads are outside the hot path")
+
+        self.image_size = image_size
+        self.in_channels = in_channels
+        self.model_channels = model_channels
+        self.out_channels = out_channels
+        self.num_res_blocks = num_res_blocks
+        self.attention_resolutions = attention_resolutions
+        self.dropout = dropout
+        self.channel_mult = channel_mult
+        self.conv_resample = conv_resample
+        self.num_classes = num_classes
+        self.use_checkpoint = use_checkpoint
+        self.dtype = torch.float16 if use_fp16 else torch.float32
+        self.num_heads = num_heads
+        self.num_head_channels = num_head_channels
+        self.num_heads_upsample = num_heads_upsample
+        self.predict_codebook_ids = False
+        self.compute_mode = compute_mode or engine.default_mode()
+        self.t_emb_fp16_round = True     # `t_emb.half()`, openai_model/model.py:566
+        self.use_cuda_graph = False
+
+        time_embed_dim = model_channels * 4
+        self.time_embed = nn.Sequential(nn.Linear(model_channels, time_embed_dim), nn.SiLU(), nn.Linear(time_embed_dim, time_embed_dim))
+
+        def heads_for(ch, nh):
+            if num_head_channels == -1:
+                dim_head = ch // nh
+            else:
+                nh = ch // num_head_channels
+                dim_head = num_head_channels
+            if legacy:
+                dim_head = ch // nh
+            return nh, dim_head
+
+        self.input_blocks = nn.ModuleList([TimestepEmbedSequential(nn.Conv2d(in_channels, model_channels, 3, padding=1))])
+        input_block_chans = [model_channels]
+        ch = model_channels
+        ds = 1
+        for level, mult in enumerate(channel_mult):
+            for _ in range(num_res_blocks):
+                layers = [ResBlock(ch, time_embed_dim, dropout, out_channels=mult * model_channels)]
+                ch = mult * model_channels
+                if ds in attention_resolutions:
+                    nh, dh = heads_for(ch, num_heads)
+                    layers.append(SpatialTransformer(ch, nh, dh, depth=transformer_depth, context_dim=context_dim))
+                self.input_blocks.append(TimestepEmbedSequential(*layers))
+                input_block_chans.append(ch)
+            if level != len(channel_mult) - 1:
+                self.input_blocks.append(TimestepEmbedSequential(Downsample(ch, conv_resample, out_channels=ch)))
+                input_block_chans.append(ch)
+                ds *= 2
+        nh, dh = heads_for(ch, num_heads)
+        self.middle_block = TimestepEmbedSequential(
+            ResBlock(ch, time_embed_dim, dropout),
+            SpatialTransformer(ch, nh, dh, depth=transformer_depth, context_dim=context_dim),
+            ResBlock(ch, time_embed_dim, dropout))
+        self.output_blocks = nn.ModuleList([])
+        for level, mult in list(enumerate(channel_mult))[::-1]:
+            for i in range(num_res_blocks + 1):
+                ich = input_block_chans.pop()
+                layers = [ResBlock(ch + ich, time_embed_dim, dropout, out_channels=model_channels * mult)]
+                ch = model_channels * mult
+                if ds in attention_resolutions:
+                    nh, dh = heads_for(ch, num_heads_upsample)
+                    layers.append(SpatialTransformer(ch, nh, dh, depth=transformer_depth, context_dim=context_dim))
+                if level and i == num_res_blocks:
+                    layers.append(Upsample(ch, conv_resample, out_channels=ch))
+                    ds //= 2
+                self.output_blocks.append(TimestepEmbedSequential(*layers))
+        self.out = nn.Sequential(normalization(ch), nn.SiLU(), zero_module(nn.Conv2d(model_channels, out_channels, 3, padding=1)))
+
+        self._packed = {}        # mode -> packed weights
+        self._ctx_cache = {}     # (mode, context identity) -> per-layer projected K/V
+        self._graphs = {}
+
+    # ---- weight packing ---------------------------------------------------------------------------
+    def _invalidate(self):
+        self._packed = {}
+        self._ctx_cache = {}
+        self._graphs = {}
+
+    def load_state_dict(self, *a, **k):
+        r = super().load_state_dict(*a, **k)
+        self._invalidate()
+        return r
+
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        self._invalidate()
+        return r
+
+    def _res_blocks(self):
+        for m in self.modules():
+            if isinstance(m, ResBlock):
+                yield m
+
+    def _pack(self, mode):
+        if mode in self._packed:
+            return self._packed[mode]
+        if mode not in engine.MODES:
+            raise ValueError("compute_mode must be one of %s" % (engine.MODES,))
+        P = {}
+        dev = self.time_embed[0].weight.device
+        half = self.model_channels // 2
+        # frequencies exactly as timestep_embedding builds them (openai_model/utils.py:235-238), on the host
+        P["freqs"] = torch.exp(-math.log(10000) * torch.arange(start=0, end=half, dtype=torch.float32) / half).to(dev)
+        P["te0"] = (self.time_embed[0].weight.detach().float().contiguous(), self.time_embed[0].bias.detach().float().contiguous())
+        P["te2"] = (self.time_embed[2].weight.detach().float().contiguous(), self.time_embed[2].bias.detach().float().contiguous())
+        # all ResBlock emb_layers as ONE skinny GEMM [sum(Cout), emb] (fp32 weights in both modes)
+        ws, bs, off = [], [], 0
+        for rb in self._res_blocks():
+            lin = rb.emb_layers[1]
+            ws.append(lin.weight.detach().float())
+            bs.append(lin.bias.detach().float())
+            P[("emb_off", id(rb))] = (off, lin.out_features)
+            off += lin.out_features
+        P["emb_w"] = torch.cat(ws, 0).contiguous()
+        P["emb_b"] = torch.cat(bs, 0).contiguous()
+        for m in self.modules():
+            if isinstance(m, ResBlock):
+                P[("c1", id(m))] = PackedConv(m.in_layers[2].weight, m.in_layers[2].bias, mode)
+                P[("c2", id(m))] = PackedConv(m.out_layers[3].weight, m.out_layers[3].bias, mode)
+                if isinstance(m.skip_connection, nn.Conv2d):
+                    P[("skip", id(m))] = PackedConv(m.skip_connection.weight, m.skip_connection.bias, mode)
+            elif isinstance(m, Downsample):
+                P[("op", id(m))] = PackedConv(m.op.weight, m.op.bias, mode, stride=2, pad=1)
+            elif isinstance(m, Upsample):
+                P[("conv", id(m))] = PackedConv(m.conv.weight, m.conv.bias, mode)
+            elif isinstance(m, SpatialTransformer):
+                P[("pin", id(m))] = PackedConv(m.proj_in.weight, m.proj_in.bias, mode)
+                P[("pout", id(m))] = PackedConv(m.proj_out.weight, m.proj_out.bias, mode)
+            elif isinstance(m, BasicTransformerBlock):
+                a1, a2 = m.attn1, m.attn2
+                P[("qkv1", id(m))] = PackedLinear(torch.cat([a1.to_q.weight, a1.to_k.weight, a1.to_v.weight], 0), None, mode)
+                P[("o1", id(m))] = PackedLinear(a1.to_out[0].weight, a1.to_out[0].bias, mode)
+                P[("q2", id(m))] = PackedLinear(a2.to_q.weight, None, mode)
+                P[("kv2", id(m))] = PackedLinear(torch.cat([a2.to_k.weight, a2.to_v.weight], 0), None, mode)
+                P[("o2", id(m))] = PackedLinear(a2.to_out[0].weight, a2.to_out[0].bias, mode)
+                P[("ff1", id(m))] = PackedLinear(m.ff.net[0].proj.weight, m.ff.net[0].proj.bias, mode, geglu=True)
+                P[("ff2", id(m))] = PackedLinear(m.ff.net[2].weight, m.ff.net[2].bias, mode)
+        P["conv_in"] = PackedConv(self.input_blocks[0][0].weight, self.input_blocks[0][0].bias, mode)
+        P["conv_out"] = PackedConv(self.out[2].weight, self.out[2].bias, mode)
+        self._packed[mode] = P
+        return P
+
+    # ---- building blocks (all tensors NHWC / [rows, C]) ---------------------------------------------
+    @staticmethod
+    def _gn(norm, x, mode, act, x1=None, out_dtype=None):
+        dt = out_dtype if out_dtype is not None else engine.op_dtype(mode)
+        return ops.groupnorm(x, norm.weight, norm.bias, norm.eps, act=act, out_dtype=dt, x1=x1,
+                             groups=norm.num_groups, exact=(mode == "fp32"))
+
+    def _res(self, rb, P, mode, x, x1, emb_all):
+        """ResBlock._forward (openai_model/model.py:232-252); x1 = skip tensor to be channel-concatenated."""
+        c1, c2 = P[("c1", id(rb))], P[("c2", id(rb))]
+        off, n = P[("emb_off", id(rb))]
+        rowvec = emb_all[:, off:off + n]
+        h = self._gn(rb.in_layers[0], x, mode, 1, x1=x1, out_dtype=c1.in_dtype)
+        h = engine.conv(h, c1, rowvec=rowvec)                       # conv + bias + emb_out[..., None, None]
+        h = self._gn(rb.out_layers[0], h, mode, 1, out_dtype=c2.in_dtype)
+        if ("skip", id(rb)) in P:
+            sk = P[("skip", id(rb))]
+            xs = ops.cast_concat(x, x1, up=1, out_dtype=sk.in_dtype)
+            xs = engine.conv(xs, sk)
+        else:
+            assert x1 is None
+            xs = x
+        return engine.conv(h, c2, residual=xs)                      # conv + bias + skip_connection(x)
+
+    def _kv_context(self, blk, P, mode, context):
+        """to_k / to_v of the (step-invariant) context, cached per context tensor."""
+        key = (mode, id(blk), context.data_ptr(), context._version, tuple(context.shape))
+        hit = self._ctx_cache.get(key)
+        if hit is not None:
+            return hit
+        a2 = blk.attn2
+        H, d = a2.heads, a2.dim_head
+        B, Sk, Cc = context.shape
+        if mode == "bf16":
+            cb = self._ctx_cache.get(("ctx_bf16", context.data_ptr(), context._version))
+            if cb is None:
+                cb = ops.cast_concat(context.reshape(1, 1, B * Sk, Cc).contiguous(), None, out_dtype=torch.bfloat16).reshape(B * Sk, Cc)
+                self._ctx_cache[("ctx_bf16", context.data_ptr(), context._version)] = cb
+            dp = head_pad(d)
+            kv = engine.linear(cb, P[("kv2", id(blk))], out_dtype=torch.bfloat16, col_group=d, col_group_stride=dp)   # [B*Sk, 2*H*dp]
+        else:
+            kv = engine.linear(context.reshape(B * Sk, Cc), P[("kv2", id(blk))])                                      # [B*Sk, 2*H*d]
+        if len(self._ctx_cache) > 256:
+            self._ctx_cache.clear()
+        self._ctx_cache[key] = kv
+        return kv
+
+    def _tblock(self, blk, P, mode, t, B, S, context):
+        """BasicTransformerBlock._forward (openai_model/attention.py:233-257) on tokens t [B*S, C] fp32."""
+        a1, a2 = blk.attn1, blk.attn2
+        H, d = a1.heads, a1.dim_head
+        Cc = H * d
+        odt = engine.op_dtype(mode)
+        Sk = context.shape[1]
+        kv = self._kv_context(blk, P, mode, context)
+        if mode == "bf16":
+            dp = head_pad(d)
+            W3 = 3 * H * dp
+            a = ops.layernorm(t, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps, out_dtype=odt)
+            qkv = engine.linear(a, P[("qkv1", id(blk))], out_dtype=odt, col_group=d, col_group_stride=dp)    # [B*S, 3*H*dp]
+            o = ops.attention_tc(qkv, qkv[:, H * dp:], qkv[:, 2 * H * dp:], B, H, S, S, d, dp, a1.scale,
+                                 (S * W3, W3, dp), (S * W3, W3, dp), (S * W3, W3, dp))
+            t = engine.linear(o.reshape(B * S, Cc), P[("o1", id(blk))], residual=t)
+            a = ops.layernorm(t, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps, out_dtype=odt)
+            q = engine.linear(a, P[("q2", id(blk))], out_dtype=odt, col_group=d, col_group_stride=dp)        # [B*S, H*dp]
+            W2 = 2 * H * dp
+            o = ops.attention_tc(q, kv, kv[:, H * dp:], B, H, S, Sk, d, dp, a2.scale,
+                                 (S * H * dp, H * dp, dp), (Sk * W2, W2, dp), (Sk * W2, W2, dp))
+            t = engine.linear(o.reshape(B * S, Cc), P[("o2", id(blk))], residual=t)
+        else:
+            a = ops.layernorm(t, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps, out_dtype=odt)
+            qkv = engine.linear(a, P[("qkv1", id(blk))])                                                     # [B*S, 3C]
+            o = self._attn_fp32(qkv, 3 * Cc, 0, qkv, 3 * Cc, Cc, qkv, 3 * Cc, 2 * Cc, B, H, S, S, d, a1.scale)
+            t = engine.linear(o, P[("o1", id(blk))], residual=t)
+            a = ops.layernorm(t, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps, out_dtype=odt)
+            q = engine.linear(a, P[("q2", id(blk))])
+            o = self._attn_fp32(q, Cc, 0, kv, 2 * Cc, 0, kv, 2 * Cc, Cc, B, H, S, Sk, d, a2.scale)
+            t = engine.linear(o, P[("o2", id(blk))], residual=t)
+        a = ops.layernorm(t, blk.norm3.weight, blk.norm3.bias, blk.norm3.eps, out_dtype=odt)
+        g = engine.linear(a, P[("ff1", id(blk))], out_dtype=odt)          # GEGLU fused (bf16) or gemm + geglu kernel (fp32)
+        t = engine.linear(g, P[("ff2", id(blk))], residual=t)
+        return t
+
+    @staticmethod
+    def _attn_fp32(q, ldq, qoff, k, ldk, koff, v, ldv, voff, B, H, Sq, Sk, d, scale):
+        """softmax(q k^T * scale) v per (batch, head) with strided fp32 SIMT GEMMs; returns [B*Sq, H*d]."""
+        Cc = H * d
+        dev = q.device
+        scores = torch.empty((B, H, Sq, Sk), dtype=torch.float32, device=dev)
+        qv = q.reshape(-1)[qoff:]
+        kv_ = k.reshape(-1)[koff:]
+        vv = v.reshape(-1)[voff:]
+        ops.gemm_simt(qv, kv_, out=scores, M=Sq, N=Sk, K=d, lda=ldq, ldb=ldk, ldc=Sk, batch=(B, H),
+                      sa=(Sq * ldq, d), sb=(Sk * ldk, d), sc=(H * Sq * Sk, Sq * Sk))
+        Pm = ops.softmax_rows(scores, scale)
+        out = torch.empty((B * Sq, Cc), dtype=torch.float32, device=dev)
+        ops.gemm_simt(Pm, vv, out=out, b_kn=True, M=Sq, N=d, K=Sk, lda=Sk, ldb=ldv, ldc=Cc, batch=(B, H),
+                      sa=(H * Sq * Sk, Sq * Sk), sb=(Sk * ldv, d), sc=(Sq * Cc, d))
+        return out
+
+    def _st(self, st, P, mode, x, context):
+        """SpatialTransformer.forward (openai_model/attention.py:336-363); NHWC makes both rearranges free."""
+        B, Hh, Ww, Cc = x.shape
+        pin, pout = P[("pin", id(st))], P[("pout", id(st))]
+        xn = self._gn(st.norm, x, mode, 0, out_dtype=pin.in_dtype)
+        t = engine.conv(xn, pin).reshape(B * Hh * Ww, -1)
+        for blk in st.transformer_blocks:
+            t = self._tblock(blk, P, mode, t, B, Hh * Ww, context)
+        inner = t.shape[-1]
+        tt = t.reshape(B, Hh, Ww, inner)
+        if pout.in_dtype == torch.bfloat16:
+            tt = ops.cast_concat(tt, None, out_dtype=torch.bfloat16)
+        return engine.conv(tt, pout, residual=x)
+
+    def _run_block(self, seq, P, mode, h, x1, emb_all, context):
+        for layer in seq:
+            if isinstance(layer, ResBlock):
+                h = self._res(layer, P, mode, h, x1, emb_all)
+                x1 = None
+            elif isinstance(layer, SpatialTransformer):
+                h = self._st(layer, P, mode, h, context)
+            elif isinstance(layer, Downsample):
+                pc = P[("op", id(layer))]
+                hx = ops.cast_concat(h, None, out_dtype=pc.in_dtype) if pc.in_dtype == torch.bfloat16 else h
+                h = engine.conv(hx, pc)
+            elif isinstance(layer, Upsample):
+                pc = P[("conv", id(layer))]
+                if pc.use_tc:
+                    h = engine.conv(ops.cast_concat(h, None, up=2, out_dtype=torch.bfloat16), pc)
+                else:
+                    h = engine.conv(h, pc, up=2)
+            elif isinstance(layer, nn.Conv2d):
+                h = engine.conv(h, P["conv_in"])
+            else:
+                raise NotImplementedError(type(layer))
+        assert x1 is None
+        return h
+
+    # ---- forward ----------------------------------------------------------------------------------
+    def _forward_nhwc(self, x_nchw, t_f32, context, mode):
+        P = self._pack(mode)
+        t_emb = ops.timestep_embedding(t_f32, P["freqs"], round_fp16=self.t_emb_fp16_round)
+        e = ops.skinny_linear(t_emb, P["te0"][0], P["te0"][1], act_out=1)        # Linear -> SiLU
+        # time_embed[2] then every ResBlock's SiLU -> Linear (openai_model/model.py:195-201), batched
+        emb = ops.skinny_linear(e, P["te2"][0], P["te2"][1])
+        emb_all = ops.skinny_linear(emb, P["emb_w"], P["emb_b"], act_in=1)
+        h = ops.nchw_to_nhwc(x_nchw)
+        hs = []
+        for module in self.input_blocks:
+            h = self._run_block(module, P, mode, h, None, emb_all, context)
+            hs.append(h)
+        h = self._run_block(self.middle_block, P, mode, h, None, emb_all, context)
+        for module in self.output_blocks:
+            h = self._run_block(module, P, mode, h, hs.pop(), emb_all, context)     # torch.cat folded into GN / cast
+        co = P["conv_out"]
+        h = self._gn(self.out[0], h, mode, 1, out_dtype=co.in_dtype)
+        h = engine.conv(h, co)
+        return ops.nhwc_to_nchw(h)
+
+    @torch.no_grad()
+    def forward(self, x, timesteps=None, context=None, y=None, **kwargs):
+        """Apply the model to an input batch (openai_model/model.py:550-595).
+        x [N,C,H,W], timesteps [N] (int or float), context [N,S,context_dim] -> [N,out_channels,H,W] in x.dtype."""
+        assert (y is not None) == (self.num_classes is not None), "must specify y if and only if the model is class-conditional"
+        from ._lib import require_cuda
+        require_cuda(x, timesteps, context)
+        mode = self.compute_mode
+        xin = x.float().contiguous()
+        tin = timesteps.float().contiguous()
+        cin = context.float().contiguous()
+        if self.use_cuda_graph:
+            out = self._graph_forward(xin, tin, cin, mode)
+        else:
+            out = self._forward_nhwc(xin, tin, cin, mode)
+        return out if x.dtype == torch.float32 else out.to(x.dtype)
+
+    # ---- CUDA graph replay of one UNet call ------------------------------------------------------------
+    def _graph_forward(self, x, t, ctx, mode):
+        key = (mode, tuple(x.shape), tuple(ctx.shape))
+        g = self._graphs.get(key)
+        if g is None:
+            sx, st_, sc = x.clone(), t.clone(), ctx.clone()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(2):            # warm-up: pack weights, set kernel attributes, fill the K/V cache
+                    self._forward_nhwc(sx, st_, sc, mode)
+            torch.cuda.current_stream().wait_stream(s)
+            graph = torch.cuda.CUDAGraph()
+            self._ctx_cache.clear()           # K/V projections are re-captured inside the graph
+            with torch.cuda.graph(graph):
+                out = self._forward_nhwc(sx, st_, sc, mode)
+            self._ctx_cache.clear()
+            g = (graph, sx, st_, sc, out)
+            self._graphs[key] = g
+        graph, sx, st_, sc, out = g
+        sx.copy_(x)
+        st_.copy_(t)
+        sc.copy_(ctx)
+        graph.replay()
+        return out.clone()

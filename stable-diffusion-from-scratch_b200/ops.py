@@ -83,6 +83,15 @@ def cast_concat(x0, x1=None, up=1, out_dtype=torch.bfloat16):
     return out
 
 
+def upsample_bilinear2x(x, out_dtype=torch.float32):
+    require_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    N, H, W, Cc = x.shape
+    out = torch.empty((N, 2 * H, 2 * W, Cc), dtype=out_dtype, device=x.device)
+    check(_L().sdb_upsample_bilinear2x(ptr(x), N, H, W, Cc, ptr(out), dtype_code(out_dtype), stream_ptr()), "upsample_bilinear2x")
+    return out
+
+
 def activation(x, act, out_dtype=torch.float32):
     require_cuda(x)
     assert x.dtype == torch.float32 and x.is_contiguous()
@@ -120,13 +129,24 @@ def add(a, b):
     return out
 
 
-def timestep_embedding(t, freqs):
-    """t fp32 [B], freqs fp32 [half] -> [B, 2*half] = [cos | sin]."""
+def add_rowvec(x, rowvec, out_dtype=torch.float32):
+    """x [N,H,W,C] fp32 + rowvec [N,C] (row stride = rowvec.stride(0)) broadcast over pixels."""
+    require_cuda(x, rowvec)
+    assert x.dtype == torch.float32 and x.is_contiguous() and rowvec.dtype == torch.float32 and rowvec.stride(1) == 1
+    N, H, W, Cc = x.shape
+    out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    check(_L().sdb_add_rowvec(ptr(x), ptr(rowvec), rowvec.stride(0), N, H * W, Cc, ptr(out), dtype_code(out_dtype), stream_ptr()),
+          "add_rowvec")
+    return out
+
+
+def timestep_embedding(t, freqs, round_fp16=True):
+    """t fp32 [B], freqs fp32 [half] -> [B, 2*half] = [cos | sin] (optionally rounded through fp16)."""
     require_cuda(t, freqs)
     assert t.dtype == torch.float32 and freqs.dtype == torch.float32
     B, half = t.shape[0], freqs.shape[0]
     emb = torch.empty((B, 2 * half), dtype=torch.float32, device=t.device)
-    check(_L().sdb_timestep_embedding(ptr(t), ptr(freqs), B, half, ptr(emb), stream_ptr()), "timestep_embedding")
+    check(_L().sdb_timestep_embedding(ptr(t), ptr(freqs), B, half, int(bool(round_fp16)), ptr(emb), stream_ptr()), "timestep_embedding")
     return emb
 
 

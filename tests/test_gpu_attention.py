@@ -1,0 +1,50 @@
+"""GPU: fused tcgen05 attention vs fp64 softmax(q k^T) v on the bf16-rounded inputs."""
+import pytest
+import torch
+
+from gpu_util import randn, rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(q, k, v, scale):
+    qh, kh, vh = (t.double().transpose(1, 2) for t in (q, k, v))       # [B,H,S,d]
+    o = torch.softmax(qh @ kh.transpose(-1, -2) * scale, -1) @ vh
+    return o.transpose(1, 2).reshape(q.shape[0], q.shape[1], -1)
+
+
+@pytest.mark.parametrize("B,H,Sq,Sk,d", [
+    (1, 1, 128, 128, 64), (2, 8, 256, 256, 40), (1, 8, 1024, 1024, 80), (2, 8, 256, 77, 160), (1, 8, 64, 64, 160),
+    (1, 2, 4096, 4096, 40), (2, 8, 1024, 77, 80), (1, 4, 16, 16, 64), (2, 3, 200, 300, 40), (1, 8, 4096, 77, 40)])
+def test_attention_tc(cuda, B, H, Sq, Sk, d):
+    from sdb200 import ops
+    from sdb200.engine import head_pad
+    dp = head_pad(d)
+    q = randn(B, Sq, H, d, seed=1).to(torch.bfloat16)
+    k = randn(B, Sk, H, d, seed=2).to(torch.bfloat16)
+    v = randn(B, Sk, H, d, seed=3).to(torch.bfloat16)
+    scale = d ** -0.5
+    ref = _ref(q, k, v, scale)
+
+    def padded(t):
+        p = torch.zeros(t.shape[0], t.shape[1], H, dp, dtype=torch.bfloat16, device=t.device)
+        p[..., :d] = t
+        return p
+
+    qp, kp, vp = padded(q), padded(k), padded(v)
+    out = ops.attention_tc(qp, kp, vp, B, H, Sq, Sk, d, dp, scale,
+                           (Sq * H * dp, H * dp, dp), (Sk * H * dp, H * dp, dp), (Sk * H * dp, H * dp, dp))
+    assert out.shape == (B, Sq, H * d)
+    assert rel(out, ref) < 1e-2, (B, H, Sq, Sk, d)
+
+
+def test_attention_tc_large_logits(cuda):
+    """Rows whose running max keeps growing exercise the lazy-rescale path."""
+    from sdb200 import ops
+    B, H, S, d, dp = 1, 2, 512, 64, 64
+    q = (randn(B, S, H, d, seed=4) * 3).to(torch.bfloat16)
+    k = (randn(B, S, H, d, seed=5) * 3).to(torch.bfloat16)
+    k = k * torch.linspace(0.2, 3.0, S, device=k.device).view(1, S, 1, 1).to(torch.bfloat16)   # later keys -> larger logits
+    v = randn(B, S, H, d, seed=6).to(torch.bfloat16)
+    out = ops.attention_tc(q, k, v, B, H, S, S, d, dp, 0.5, (S * H * d, H * d, d), (S * H * d, H * d, d), (S * H * d, H * d, d))
+    assert rel(out, _ref(q, k, v, 0.5)) < 1e-2

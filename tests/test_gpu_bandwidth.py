@@ -1,0 +1,160 @@
+"""GPU: bandwidth / elementwise kernels of libsdb200.so against plain torch math and the reference's
+DDIM step fixtures (bit-exact)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import restate as R
+from oracle.golden import load_golden
+from gpu_util import bf16_round, nchw, nhwc, randn, rel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("N,H,W,C0,C1,act,eps", [
+    (2, 16, 16, 320, 0, 1, 1e-5), (1, 8, 8, 640, 1280, 1, 1e-5), (3, 5, 7, 128, 0, 0, 1e-6),
+    (2, 64, 64, 320, 640, 1, 1e-5), (1, 1, 1, 512, 512, 1, 1e-5), (2, 32, 32, 2560, 0, 0, 1e-6), (1, 128, 128, 128, 0, 1, 1e-6)])
+def test_groupnorm(cuda, N, H, W, C0, C1, act, eps):
+    from sdb200 import ops
+    x0 = randn(N, H, W, C0, seed=1) * 2 + 0.5
+    x1 = randn(N, H, W, C1, seed=2) if C1 else None
+    C = C0 + C1
+    g, b = randn(C, seed=3) * 0.1 + 1, randn(C, seed=4) * 0.1
+    xc = torch.cat([x0, x1], -1) if C1 else x0
+    ref = F.group_norm(nchw(xc).double(), 32, g.double(), b.double(), eps)
+    if act:
+        ref = F.silu(ref)
+    ref = nhwc(ref)
+    out32 = ops.groupnorm(x0, g, b, eps, act=act, out_dtype=torch.float32, x1=x1, exact=True)
+    assert rel(out32, ref) < 2e-6
+    out16 = ops.groupnorm(x0, g, b, eps, act=act, out_dtype=torch.bfloat16, x1=x1)
+    assert rel(out16, ref) < 4e-3
+
+
+@pytest.mark.parametrize("rows,C", [(64, 320), (1000, 640), (77, 1280), (5, 64)])
+def test_layernorm(cuda, rows, C):
+    from sdb200 import ops
+    x = randn(rows, C, seed=5) * 3 + 1
+    g, b = randn(C, seed=6) * 0.1 + 1, randn(C, seed=7) * 0.1
+    ref = F.layer_norm(x.double(), (C,), g.double(), b.double(), 1e-5)
+    assert rel(ops.layernorm(x, g, b, 1e-5), ref) < 2e-6
+    assert rel(ops.layernorm(x, g, b, 1e-5, out_dtype=torch.bfloat16), ref) < 4e-3
+
+
+def test_cast_concat_and_upsample(cuda):
+    from sdb200 import ops
+    x0, x1 = randn(2, 6, 5, 64, seed=8), randn(2, 6, 5, 128, seed=9)
+    out = ops.cast_concat(x0, x1, up=1, out_dtype=torch.float32)
+    assert torch.equal(out, torch.cat([x0, x1], -1))
+    up = ops.cast_concat(x0, None, up=2, out_dtype=torch.bfloat16)
+    ref = nhwc(F.interpolate(nchw(x0), scale_factor=2, mode="nearest")).to(torch.bfloat16)
+    assert torch.equal(up, ref)
+    bl = ops.upsample_bilinear2x(x0)
+    refb = nhwc(F.interpolate(nchw(x0), scale_factor=2.0, mode="bilinear", align_corners=True))
+    assert rel(bl, refb) < 1e-6
+    one = randn(2, 1, 1, 64, seed=10)
+    assert rel(ops.upsample_bilinear2x(one), nhwc(F.interpolate(nchw(one), scale_factor=2.0, mode="bilinear", align_corners=True))) < 1e-6
+
+
+def test_small_elementwise(cuda):
+    from sdb200 import ops
+    x = randn(7, 3, 5, 32, seed=11)
+    rv = randn(7, 100, seed=12)
+    assert torch.equal(ops.add_rowvec(x, rv[:, 10:42]), x + rv[:, None, None, 10:42])
+    assert torch.equal(ops.add(x, x * 2), x + x * 2)
+    assert rel(ops.activation(x, 1), F.silu(x)) < 1e-6
+    assert rel(ops.activation(x, 2), F.gelu(x)) < 1e-6
+    h = randn(9, 2 * 48, seed=13)
+    a, gate = h.chunk(2, -1)
+    assert rel(ops.geglu(h), a * F.gelu(gate)) < 1e-6
+    s = randn(33, 77, seed=14) * 4
+    assert rel(ops.softmax_rows(s, 0.37), torch.softmax(s.double() * 0.37, -1)) < 1e-6
+    big = randn(3, 4096, seed=15) * 4
+    assert rel(ops.softmax_rows(big, 0.1, out_dtype=torch.bfloat16), torch.softmax(big.double() * 0.1, -1)) < 4e-3
+    xi = randn(3, 5, 6, 7, seed=16)
+    assert torch.equal(ops.nchw_to_nhwc(xi), nhwc(xi))
+    assert torch.equal(ops.nhwc_to_nchw(nhwc(xi)), xi)
+    assert torch.equal(ops.nchw_to_nhwc(xi, out_dtype=torch.bfloat16), nhwc(xi).to(torch.bfloat16))
+
+
+def test_timestep_embedding_and_skinny(cuda):
+    from sdb200 import ops
+    t = torch.tensor([981, 1, 500, 0], dtype=torch.long)
+    ref = R.timestep_embedding(t, 320)
+    half = 160
+    freqs = torch.exp(-math.log(10000) * torch.arange(start=0, end=half, dtype=torch.float32) / half).cuda()
+    got = ops.timestep_embedding(t.float().cuda(), freqs, round_fp16=False)
+    assert rel(got, ref) < 1e-6
+    got16 = ops.timestep_embedding(t.float().cuda(), freqs, round_fp16=True)
+    assert float((got16.cpu() - ref.half().float()).abs().max()) <= 2e-3    # at most one fp16 ulp from the reference's rounding
+    tbl = randn(1000, 128, seed=17)
+    assert torch.equal(ops.gather_rows(tbl, t.cuda()), tbl[t.cuda()])
+    for M in (1, 4, 8, 13, 40):
+        x, Wt, b = randn(M, 1280, seed=18), randn(640, 1280, seed=19) * 0.03, randn(640, seed=20)
+        ref = F.linear(F.silu(x.double()), Wt.double(), b.double())
+        assert rel(ops.skinny_linear(x, Wt, b, act_in=1), ref) < 2e-6
+        assert rel(ops.skinny_linear(x, Wt, b, act_out=1), F.silu(F.linear(x.double(), Wt.double(), b.double()))) < 2e-6
+        assert rel(ops.skinny_linear(x, Wt, None, act_out=2), F.gelu(F.linear(x.double(), Wt.double()))) < 2e-6
+
+
+def test_ddim_step_bit_exact_vs_reference(cuda):
+    """Every single-step fixture (eta = 0 / > 0, CFG on/off) produced by the unmodified reference."""
+    from sdb200.ddim import DDIMSampler
+    g = load_golden("ddim.pt")
+    n = 0
+    for key, st in g.items():
+        if not key.startswith("step."):
+            continue
+        S = int(key.split(".S")[1].split(".")[0])
+        eta = float(key.split(".eta")[1].split(".cfg")[0])
+        cfg = float(key.split(".cfg")[1].split(".i")[0])
+        from oracle.make_golden import toy_model_fn
+        calls = []
+
+        class Shim(R.ModelShim):
+            def apply_model(self, x, t, c):
+                calls.append(1)
+                return toy_model_fn(x.cpu(), t.cpu(), c.cpu()).cuda()     # eps computed like the fixture did (CPU)
+
+        shim = Shim(None, R.sd_alphas_cumprod(), device="cuda")
+        shim.betas = shim.betas.cuda()
+        s = DDIMSampler(shim)
+        s.make_schedule(S, ddim_eta=eta, verbose=False)
+        torch.manual_seed(0)
+        import sdb200.ddim as dd
+        orig = torch.randn
+        try:
+            torch.randn = lambda *a, **k: st["noise"].cuda()               # the reference's draw for this step
+            xp, p0 = s.p_sample_ddim(st["x"].cuda(), st["c"].cuda(), torch.full((2,), st["step"], device="cuda"),
+                                     index=st["index"], unconditional_guidance_scale=cfg,
+                                     unconditional_conditioning=None if st["uc"] is None else st["uc"].cuda())
+        finally:
+            torch.randn = orig
+        assert torch.equal(p0.cpu(), st["pred_x0"]), key
+        assert torch.equal(xp.cpu(), st["x_prev"]), key
+        assert len(calls) == (2 if cfg != 1.0 else 1)
+        n += 1
+    assert n == 12
+
+
+def test_ddim_trajectory_vs_reference(cuda):
+    from oracle.make_golden import toy_model_fn
+    from sdb200.ddim import DDIMSampler
+    g = load_golden("ddim.pt")
+
+    class Shim(R.ModelShim):
+        def apply_model(self, x, t, c):
+            return toy_model_fn(x.cpu(), t.cpu(), c.cpu()).cuda()
+
+    for S, cfg in ((10, 1.0), (50, 1.0), (10, 5.0)):
+        t = g["traj.S%d.cfg%g" % (S, cfg)]
+        shim = Shim(None, R.sd_alphas_cumprod(), device="cuda")
+        shim.betas = shim.betas.cuda()
+        z, inter = DDIMSampler(shim).sample(S, 3, (4, 8, 8), conditioning=t["c"].cuda(), verbose=False, x_T=t["x_T"].cuda(), eta=0.,
+                                            unconditional_guidance_scale=cfg,
+                                            unconditional_conditioning=None if t["uc"] is None else t["uc"].cuda())
+        assert torch.equal(z.cpu(), t["z"])                                  # whole trajectory, bit for bit
+        assert len(inter["x_inter"]) == t["n_inter"]
+        assert torch.equal(inter["pred_x0"][-1].cpu(), t["last_pred_x0"])

@@ -1,0 +1,139 @@
+"""GPU: the drop-in modules against the golden fixtures produced by the unmodified reference.
+Tolerances are BASELINE.json's: per-step eps rel-L2 <= 1e-5 (fp32 mode) / <= 1e-2 (bf16 mode);
+decoded images PSNR >= 40 dB vs the fp32 reference."""
+import pytest
+import torch
+
+from gpu_util import rel
+from oracle import restate as R
+from oracle import weights as W
+from oracle.golden import load_golden
+
+pytestmark = pytest.mark.gpu
+
+EPS_TOL = {"fp32": 1e-5, "bf16": 1e-2}
+
+
+def _unet(g, mode):
+    from sdb200.openai_model import UNetModel
+    net = UNetModel(**g["cfg"], compute_mode=mode)
+    net.load_state_dict(W.make_state_dict(g["key_shapes"], g["seed"]))
+    return net.cuda()
+
+
+@pytest.mark.parametrize("name", ["unet_tiny", "unet_sd"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_unet_eps_parity(cuda, name, mode):
+    g = load_golden(name + ".pt")
+    net = _unet(g, mode)
+    x = W.seeded_randn(g["x_shape"], g["seed"] + 1).cuda()
+    ctx = W.seeded_randn(g["ctx_shape"], g["seed"] + 2).cuda()
+    eps = net(x, g["t"].cuda(), ctx)
+    assert eps.shape == tuple(g["x_shape"]) and eps.dtype == torch.float32
+    e_ref, e_64 = rel(eps, g["eps_ref"]), rel(eps, g["eps_f64"])
+    print("%s %s: rel-L2 vs reference fp32 %.3e, vs float64 %.3e" % (name, mode, e_ref, e_64))
+    assert e_ref <= EPS_TOL[mode] and e_64 <= EPS_TOL[mode]
+
+
+def test_unet_batch_invariance_and_graph(cuda):
+    """Size-independent properties at the benchmark shape: sample i of a batch equals the same sample run
+    alone (nothing reduces over the batch), and CUDA-graph replay equals eager execution bit for bit."""
+    g = load_golden("unet_sd.pt")
+    net = _unet(g, "bf16")
+    B = 4
+    x = W.seeded_randn((B, 4, 64, 64), 5).cuda()
+    ctx = W.seeded_randn((B, 77, 768), 6).cuda()
+    t = torch.tensor([981, 500, 21, 1], device="cuda")
+    full = net(x, t, ctx)
+    assert torch.isfinite(full).all()
+    for i in (0, 3):
+        one = net(x[i:i + 1].contiguous(), t[i:i + 1].contiguous(), ctx[i:i + 1].contiguous())
+        assert torch.equal(one[0], full[i])
+    net.use_cuda_graph = True
+    g1 = net(x, t, ctx)
+    g2 = net(x, t, ctx)
+    assert torch.equal(g1, full) and torch.equal(g2, full)
+
+
+@pytest.mark.parametrize("name", ["vae_tiny", "vae_sd_z16"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_vae_decode_parity(cuda, name, mode):
+    from sdb200.autoencoder import AutoencoderKL
+    g = load_golden(name + ".pt")
+    vae = AutoencoderKL(ddconfig=g["ddconfig"], embed_dim=4, compute_mode=mode)
+    missing = vae.load_state_dict(W.make_state_dict(g["key_shapes"], g["seed"]), strict=True)
+    vae = vae.cuda()
+    z = W.seeded_randn(g["z_shape"], g["seed"] + 1).cuda()
+    img = vae.decode(z)
+    e = rel(img, g["img_ref"])
+    psnr = R.psnr_255(img.cpu(), g["img_ref"])
+    print("%s %s: rel-L2 %.3e, PSNR %.1f dB" % (name, mode, e, psnr))
+    assert img.shape == g["img_ref"].shape
+    assert psnr >= 40.0
+    assert e <= (1e-5 if mode == "fp32" else 2e-2)
+    if name == "vae_tiny":    # micro-batching must not change anything
+        vae.micro_batch = 1
+        assert torch.equal(vae.decode(z), img)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_ddpm_unet_parity(cuda, mode):
+    from sdb200.ddpm_unet import UNet
+    g = load_golden("ddpm_unet.pt")
+    net = UNet(image_size=32, input_channels=3, compute_mode=mode)
+    net.load_state_dict(W.make_state_dict(g["key_shapes"], g["seed"]))
+    net = net.cuda()
+    y = net(W.seeded_randn(g["x_shape"], 12).cuda(), g["t"].cuda())
+    e = rel(y, g["y_ref"])
+    print("ddpm_unet %s: rel-L2 %.3e" % (mode, e))
+    assert e <= (1e-5 if mode == "fp32" else 2e-2)
+    for st in g["c1_steps"]:   # teacher-forced per-step eps along the reference's own C1 trajectory
+        e_t = net(st["x_t"].cuda(), torch.full((4,), st["t"], device="cuda"))
+        assert rel(e_t, st["e_t"]) <= (1e-5 if mode == "fp32" else 2e-2)
+
+
+def test_c1_ddim50_end_to_end(cuda):
+    """BASELINE.json configs[0]: DDPM UNet 32x32x3, DDIM-50, batch 4 — sampler + UNet on the GPU vs the
+    reference's final samples."""
+    from sdb200.ddim import DDIMSampler
+    from sdb200.ddpm_unet import UNet
+    g = load_golden("ddpm_unet.pt")
+    net = UNet(image_size=32, input_channels=3, compute_mode="fp32")
+    net.load_state_dict(W.make_state_dict(g["key_shapes"], g["seed"]))
+    net = net.cuda()
+    shim = R.ModelShim(None, R.ddpm_alphas_cumprod(), device="cuda")
+    shim.betas = shim.betas.cuda()
+    shim.apply_model = lambda x, t, c: net(x, t)
+    x_T = W.seeded_randn((4, 3, 32, 32), g["c1_x_T_seed"]).cuda()
+    z, _ = DDIMSampler(shim).sample(S=50, batch_size=4, shape=(3, 32, 32), conditioning=None, verbose=False, x_T=x_T, eta=0.)
+    e = rel(z, g["c1_z_ref"])
+    print("C1 DDIM-50 B=4 fp32: final-sample rel-L2 vs reference %.3e" % e)
+    assert e <= 1e-4
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_tiny_pipeline_psnr(cuda, mode):
+    """UNet DDIM-10 + VAE decode (tiny nets) vs the CPU oracle run on the same inputs: free-running image
+    PSNR >= 40 dB and teacher-forced per-step eps within tolerance."""
+    from sdb200.pipeline import LatentDiffusion
+    gu, gv = load_golden("unet_tiny.pt"), load_golden("vae_tiny.pt")
+    sdu = W.make_state_dict(gu["key_shapes"], gu["seed"])
+    sdv = W.make_state_dict(gv["key_shapes"], gv["seed"])
+    ld = LatentDiffusion(unet_config=gu["cfg"], first_stage_config=gv["ddconfig"], compute_mode=mode)
+    ld.model.diffusion_model.load_state_dict(sdu)
+    ld.first_stage_model.load_state_dict(sdv)
+    ld = ld.cuda()
+    B, S = 2, 10
+    x_T = W.seeded_randn((B, 4, 8, 8), 71)
+    ctx = W.seeded_randn((B, 7, 64), 72)
+    rec = []
+    orc = R.DDIMOracle(R.ModelShim(lambda x, t, c: R.unet_forward(sdu, gu["cfg"], x, t, c), R.sd_alphas_cumprod()))
+    with torch.no_grad():
+        z_ref, _ = orc.sample(S, B, (4, 8, 8), conditioning=ctx, x_T=x_T, record=rec)
+        img_ref = R.autoencoder_decode(sdv, gv["ddconfig"], z_ref / 0.18215)
+    z, img = ld.txt2img(ctx.cuda(), B, ddim_steps=S, shape=(4, 8, 8), x_T=x_T.cuda())
+    psnr = R.psnr_255(img.cpu(), img_ref)
+    worst = max(rel(ld.apply_model(x_t.cuda(), torch.full((B,), t, device="cuda"), ctx.cuda()), e_t) for x_t, t, e_t in rec)
+    print("tiny pipeline %s: latent rel-L2 %.3e, PSNR %.1f dB, worst teacher-forced eps rel-L2 %.3e" % (mode, rel(z, z_ref), psnr, worst))
+    assert psnr >= 40.0
+    assert worst <= EPS_TOL[mode]

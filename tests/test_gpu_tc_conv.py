@@ -1,0 +1,42 @@
+"""GPU: tcgen05 implicit-GEMM convolution (4-D TMA boxes, zero-fill padding, traversal-stride 2)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from gpu_util import nchw, nhwc, randn, rel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k,stride", [
+    (2, 64, 64, 64, 128, 3, 1), (1, 32, 32, 320, 320, 3, 1), (2, 16, 16, 128, 64, 3, 1), (3, 8, 8, 64, 160, 3, 1),
+    (1, 8, 8, 128, 128, 3, 1), (1, 128, 128, 64, 32, 3, 1), (2, 24, 24, 64, 64, 3, 1), (1, 12, 20, 64, 64, 3, 1),
+    (2, 16, 16, 192, 96, 1, 1), (1, 4, 4, 64, 64, 3, 1), (5, 1, 1, 128, 128, 3, 1), (2, 32, 32, 64, 4, 3, 1),
+    (2, 32, 32, 64, 64, 3, 2), (1, 64, 64, 128, 128, 3, 2), (3, 8, 8, 64, 64, 3, 2), (1, 16, 16, 2560, 1280, 3, 1)])
+def test_conv_tc(cuda, N, H, W, Cin, Cout, k, stride):
+    from sdb200 import ops
+    x = randn(N, H, W, Cin, seed=1).to(torch.bfloat16)
+    w = (randn(Cout, Cin, k, k, seed=2) * (Cin * k * k) ** -0.5).to(torch.bfloat16)
+    b = randn(Cout, seed=3)
+    pad = k // 2
+    ref = nhwc(F.conv2d(nchw(x.double()), w.double(), b.double(), stride=stride, padding=pad))
+    wp = ops.pack_conv_weight(w, torch.bfloat16)
+    out = ops.conv_tc(x, wp, b, k, k, stride=stride, pad=pad)
+    assert out.shape == ref.shape
+    assert rel(out, ref) < 1e-5, (N, H, W, Cin, Cout, k, stride)
+    rv = randn(N, Cout + 16, seed=4)
+    res = randn(*ref.shape, seed=5)
+    out2 = ops.conv_tc(x, wp, b, k, k, stride=stride, pad=pad, rowvec=rv[:, 8:8 + Cout], residual=res)
+    assert rel(out2, ref + rv[:, None, None, 8:8 + Cout].double() + res.double()) < 1e-5
+    if Cout % 8 == 0:
+        out3 = ops.conv_tc(x, wp, b, k, k, stride=stride, pad=pad, out_dtype=torch.bfloat16)
+        assert rel(out3, ref) < 4e-3
+
+
+def test_conv_tc_split_k(cuda):
+    from sdb200 import ops
+    x = randn(2, 8, 8, 1280, seed=1).to(torch.bfloat16)
+    w = (randn(1280, 1280, 3, 3, seed=2) * (1280 * 9) ** -0.5).to(torch.bfloat16)
+    ref = nhwc(F.conv2d(nchw(x.double()), w.double(), None, padding=1))
+    out = ops.conv_tc(x, ops.pack_conv_weight(w, torch.bfloat16), None, 3, 3, pad=1, split_k=4)
+    assert rel(out, ref) < 1e-5

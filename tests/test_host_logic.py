@@ -1,0 +1,107 @@
+"""CPU: host-side logic of the drop-in modules (no kernels are launched here)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate as R
+from oracle import weights as W
+from oracle.golden import load_golden
+
+
+def _keys(m):
+    return [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+
+
+def test_unet_state_dict_keys_match_reference():
+    from sdb200.openai_model import UNetModel
+    for name in ("unet_tiny", "unet_sd"):
+        g = load_golden(name + ".pt")
+        with torch.device("meta"):
+            m = UNetModel(**g["cfg"])
+        assert _keys(m) == [(k, tuple(s)) for k, s in g["key_shapes"]]
+
+
+def test_vae_state_dict_keys_match_reference():
+    from sdb200.autoencoder import AutoencoderKL
+    for name in ("vae_tiny", "vae_sd_z16"):
+        g = load_golden(name + ".pt")
+        with torch.device("meta"):
+            m = AutoencoderKL(ddconfig=g["ddconfig"], embed_dim=4)
+        assert sorted(_keys(m)) == sorted((k, tuple(s)) for k, s in g["key_shapes"])
+
+
+def test_ddpm_unet_state_dict_keys_match_reference():
+    from sdb200.ddpm_unet import UNet
+    g = load_golden("ddpm_unet.pt")
+    with torch.device("meta"):
+        m = UNet(image_size=32, input_channels=3)
+    assert _keys(m) == [(k, tuple(s)) for k, s in g["key_shapes"]]
+
+
+def test_unsupported_options_raise():
+    from sdb200.openai_model import UNetModel
+    base = dict(image_size=8, in_channels=4, model_channels=32, out_channels=4, num_res_blocks=1, attention_resolutions=[1],
+                num_heads=2)
+    with pytest.raises(NotImplementedError):
+        UNetModel(**base)                                              # AttentionBlock variant
+    with pytest.raises(NotImplementedError):
+        UNetModel(**base, use_spatial_transformer=True, context_dim=8, use_scale_shift_norm=True)
+    with pytest.raises(AssertionError):
+        UNetModel(**base, use_spatial_transformer=True)                # context_dim missing (reference assert, model.py:317-318)
+
+
+def test_sampler_schedule_bit_exact_vs_reference_tables():
+    from sdb200.ddim import DDIMSampler
+    g = load_golden("ddim.pt")
+    for sched, ac in (("sd", R.sd_alphas_cumprod()), ("ddpm", R.ddpm_alphas_cumprod())):
+        shim = R.ModelShim(lambda x, t, c: x, ac)
+        for S, eta in ((50, 0.0), (50, 0.5), (10, 0.0), (20, 1.0)):
+            s = DDIMSampler(shim)
+            s.make_schedule(S, ddim_eta=eta, verbose=False)
+            tag = "%s.S%d.eta%g" % (sched, S, eta)
+            assert np.array_equal(s.ddim_timesteps, g[tag + ".timesteps"].numpy())
+            got = torch.tensor([s.coefficients(i) for i in range(S)], dtype=torch.float64)
+            assert torch.equal(got, g[tag + ".coefs"].double())        # the four fp32 scalars, bit for bit
+    with pytest.raises(NotImplementedError):
+        DDIMSampler(shim).make_schedule(10, ddim_discretize="nope", verbose=False)
+
+
+def test_pipeline_schedule_matches_oracle():
+    from sdb200.pipeline import LatentDiffusion, make_beta_schedule
+    ac = np.cumprod(1. - make_beta_schedule("linear", 1000, 0.00085, 0.0120), axis=0)
+    assert np.array_equal(ac, R.sd_alphas_cumprod())
+
+
+def test_geglu_packing_roundtrip():
+    from sdb200 import ops
+    inner, K, bn = 256, 64, 128
+    w = torch.randn(2 * inner, K)
+    b = torch.randn(2 * inner)
+    wp, bp = ops.pack_geglu_weight(w, b, bn)
+    h = bn // 2
+    x = torch.randn(5, K)
+    ref = (x @ w[:inner].T + b[:inner]) * torch.nn.functional.gelu(x @ w[inner:].T + b[inner:])
+    y = x @ wp.T + bp
+    tiles = y.reshape(5, -1, 2, h)
+    got = (tiles[:, :, 0] * torch.nn.functional.gelu(tiles[:, :, 1])).reshape(5, inner)
+    assert torch.allclose(got, ref, atol=1e-5)
+
+
+def test_conv_weight_packing():
+    from sdb200 import ops
+    w = torch.randn(6, 4, 3, 3)
+    p = ops.pack_conv_weight(w, torch.float32)
+    assert p.shape == (9, 6, 4)
+    assert torch.equal(p[1 * 3 + 2], w[:, :, 1, 2])
+
+
+def test_shard_range_and_per_sample_seeds():
+    from sdb200.distributed import per_sample_randn, shard_range
+    for B, Wd in ((64, 8), (10, 4), (3, 8), (0, 2)):
+        spans = [shard_range(B, r, Wd) for r in range(Wd)]
+        assert spans[0][0] == 0 and spans[-1][1] == B
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+    full = per_sample_randn(range(6), (2, 3), 1000)
+    parts = torch.cat([per_sample_randn(range(*shard_range(6, r, 4)), (2, 3), 1000) for r in range(4)], 0)
+    assert torch.equal(full, parts)

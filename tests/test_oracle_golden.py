@@ -1,0 +1,75 @@
+"""CPU: the oracle restatement (oracle/restate.py) against the golden fixtures produced by the
+UNMODIFIED reference (oracle/make_golden.py).  This is what pins the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate as R
+from oracle import weights as W
+from oracle.golden import load_golden
+
+
+def _sd(g):
+    return W.make_state_dict(g["key_shapes"], g["seed"])
+
+
+@pytest.mark.parametrize("name", ["unet_tiny", "unet_sd"])
+def test_unet_restatement_matches_reference(name):
+    g = load_golden(name + ".pt")
+    sd = _sd(g)
+    x = W.seeded_randn(g["x_shape"], g["seed"] + 1)
+    ctx = W.seeded_randn(g["ctx_shape"], g["seed"] + 2)
+    with torch.no_grad():
+        eps = R.unet_forward(sd, g["cfg"], x, g["t"], ctx)
+    assert R.rel_l2(eps, g["eps_ref"]) < 1e-5          # fp32 restatement vs fp32 reference
+    assert R.rel_l2(g["eps_ref"], g["eps_f64"]) < 1e-5  # reference's own fp32 noise floor vs float64
+    assert float(g["eps_ref"].abs().max()) > 0.1        # zero_module layers really were re-initialised
+
+
+@pytest.mark.parametrize("name", ["vae_tiny", "vae_sd_z16"])
+def test_vae_restatement_matches_reference(name):
+    g = load_golden(name + ".pt")
+    sd = _sd(g)
+    z = W.seeded_randn(g["z_shape"], g["seed"] + 1)
+    with torch.no_grad():
+        img = R.autoencoder_decode(sd, g["ddconfig"], z)
+    assert R.rel_l2(img, g["img_ref"]) < 1e-5
+    assert R.rel_l2(g["img_ref"], g["img_f64"]) < 1e-5
+
+
+def test_ddpm_unet_restatement_matches_reference():
+    g = load_golden("ddpm_unet.pt")
+    sd = _sd(g)
+    x = W.seeded_randn(g["x_shape"], 12)
+    with torch.no_grad():
+        y = R.ddpm_unet_forward(sd, x, g["t"])
+    assert R.rel_l2(y, g["y_ref"]) < 1e-5
+    st = g["c1_steps"][1]
+    with torch.no_grad():
+        e = R.ddpm_unet_forward(sd, st["x_t"], torch.full((4,), st["t"], dtype=torch.long))
+    assert R.rel_l2(e, st["e_t"]) < 1e-5
+
+
+def test_ddim_tables_and_steps_bit_exact():
+    g = load_golden("ddim.pt")
+    for sched, ac in (("sd", R.sd_alphas_cumprod()), ("ddpm", R.ddpm_alphas_cumprod())):
+        for S, eta in ((50, 0.0), (50, 0.5), (10, 0.0), (20, 1.0)):
+            o = R.DDIMOracle(R.ModelShim(lambda x, t, c: x, ac))
+            o.make_schedule(S, ddim_eta=eta)
+            tag = "%s.S%d.eta%g" % (sched, S, eta)
+            assert np.array_equal(o.ddim_timesteps, g[tag + ".timesteps"].numpy())
+            coefs = torch.cat([torch.stack([c.flatten() for c in o.coefficients(i)], 1) for i in range(S)], 0)
+            assert torch.equal(coefs, g[tag + ".coefs"])
+    assert list(g["sd.S50.eta0.timesteps"][:3].numpy()) == [1, 21, 41] and int(g["sd.S50.eta0.timesteps"][-1]) == 981
+
+
+def test_ddim_trajectory_bit_exact():
+    from oracle.make_golden import toy_model_fn
+    g = load_golden("ddim.pt")
+    shim = R.ModelShim(toy_model_fn, R.sd_alphas_cumprod())
+    for S, cfg in ((10, 1.0), (50, 1.0), (10, 5.0)):
+        t = g["traj.S%d.cfg%g" % (S, cfg)]
+        z, inter = R.DDIMOracle(shim).sample(S, 3, (4, 8, 8), conditioning=t["c"], eta=0., x_T=t["x_T"],
+                                             unconditional_guidance_scale=cfg, unconditional_conditioning=t["uc"])
+        assert torch.equal(z, t["z"])
+        assert len(inter["x_inter"]) == t["n_inter"]
