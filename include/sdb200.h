@@ -61,7 +61,7 @@ int sdb_groupnorm_nhwc(const float* x0, int C0, const float* x1, int C1, int N, 
 
 /* ---- LayerNorm over the last dim ---------------------------------------------------------------
  * Replaces nn.LayerNorm(dim) x3 per BasicTransformerBlock (openai_model/attention.py:216-218,
- * 251-253), eps 1e-5.  x [rows, C] fp32 -> out [rows, C] (out_dtype). C % 4 == 0, C <= 4096. */
+ * 251-253), eps 1e-5.  x [rows, C] fp32 -> out [rows, C] (out_dtype). C % 4 == 0, C <= 2048. */
 int sdb_layernorm(const float* x, int rows, int C, float eps, const float* gamma, const float* beta,
                   void* out, int out_dtype, void* stream);
 
@@ -111,13 +111,16 @@ int sdb_skinny_linear(const float* x, int M, int K, const float* W, const float*
 /* ---- DDIM update ---------------------------------------------------------------------------
  * Replaces p_sample_ddim's arithmetic (ldm/diffusion/ddim.py:175-205 == DDIM/ddim.py):
  *   e = e_uncond + cfg_scale*(e_cond - e_uncond)      (if e_uncond != NULL)
- *   pred_x0 = (x - sqrt_one_minus_at*e) / sqrt(a_t)
- *   x_prev  = sqrt(a_prev)*pred_x0 + sqrt(1 - a_prev - sigma^2)*e + sigma*temperature*noise
+ *   pred_x0 = (x - sqrt_one_minus_at*e) / sqrt_at
+ *   x_prev  = sqrt_aprev*pred_x0 + dir_coef*e + sigma_t*noise*temperature
  * all fp32, every operation individually rounded (no FMA contraction) like the eager reference.
- * noise may be NULL when sigma == 0. n = number of elements. */
+ * The caller passes the derived per-step scalars sqrt_at = a_t.sqrt(), sqrt_aprev = a_prev.sqrt(),
+ * dir_coef = (1 - a_prev - sigma_t**2).sqrt() (ddim.py:197-205) so that it can evaluate them with the
+ * reference's own expressions.  noise may be NULL when sigma_t == 0.  n = number of elements. */
 int sdb_ddim_step(const float* x, const float* e_cond, const float* e_uncond, float cfg_scale,
-                  const float* noise, float a_t, float a_prev, float sigma_t, float sqrt_one_minus_at,
-                  float temperature, float* x_prev, float* pred_x0, long long n, void* stream);
+                  const float* noise, float sqrt_at, float sqrt_aprev, float dir_coef, float sigma_t,
+                  float sqrt_one_minus_at, float temperature, float* x_prev, float* pred_x0, long long n,
+                  void* stream);
 
 /* ---- fp32 SIMT contraction (the fp32 parity mode; also the C_in=4 / tiny layers) --------------
  * One kernel family: out[m, n] = alpha * sum_k A(m,k) * B(n,k) + bias[n] + rowvec[img(m), n]

@@ -90,7 +90,7 @@ SIGNATURES = {
     "sdb_timestep_embedding": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "sdb_gather_rows": (_I, [_P, _P, _I, _I, _P, _P]),
     "sdb_skinny_linear": (_I, [_P, _I, _I, _P, _P, _I, _I, _I, _P, _P]),
-    "sdb_ddim_step": (_I, [_P, _P, _P, _F, _P, _F, _F, _F, _F, _F, _P, _P, _L, _P]),
+    "sdb_ddim_step": (_I, [_P, _P, _P, _F, _P, _F, _F, _F, _F, _F, _F, _P, _P, _L, _P]),
     "sdb_simt_contract": (_I, [C.POINTER(SimtArgs), _P]),
     "sdb_tc_contract": (_I, [C.POINTER(TcArgs), _P]),
     "sdb_attention_fwd": (_I, [C.POINTER(AttnArgs), _P]),

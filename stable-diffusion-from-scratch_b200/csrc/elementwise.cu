@@ -404,17 +404,11 @@ int sdb_skinny_linear(const float* x, int M, int K, const float* W, const float*
 }
 
 int sdb_ddim_step(const float* x, const float* e_cond, const float* e_uncond, float cfg_scale,
-                  const float* noise, float a_t, float a_prev, float sigma_t, float sqrt_one_minus_at,
-                  float temperature, float* x_prev, float* pred_x0, long long n, void* stream) {
+                  const float* noise, float sqrt_at, float sqrt_aprev, float dir_coef, float sigma_t,
+                  float sqrt_one_minus_at, float temperature, float* x_prev, float* pred_x0, long long n,
+                  void* stream) {
     SDB_REQUIRE(x && e_cond && x_prev && pred_x0 && n > 0, "ddim_step: bad args");
     SDB_REQUIRE(noise || sigma_t == 0.0f, "ddim_step: sigma_t != 0 needs a noise tensor");
-    // coefficient arithmetic in fp32, op by op, as the reference does on [B,1,1,1] fp32 tensors
-    // (ldm/diffusion/ddim.py:191-201): a_t.sqrt(), a_prev.sqrt(), (1 - a_prev - sigma^2).sqrt()
-    float sqrt_at = sqrtf(a_t);
-    float sqrt_aprev = sqrtf(a_prev);
-    float s2 = sigma_t * sigma_t;
-    float t1 = 1.0f - a_prev;
-    float dir_coef = sqrtf(t1 - s2);
     ddim_step_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
         x, e_cond, e_uncond, cfg_scale, noise, sqrt_at, sqrt_aprev, dir_coef, sigma_t, sqrt_one_minus_at,
         temperature, x_prev, pred_x0, n);

@@ -28,9 +28,12 @@ static GnGeom gn_geom(int N, int HW, int C) {
     if (g.R > 32) g.R = 32;
     if (g.R > HW) g.R = HW;
     g.threads = g.V * g.R;
+    // The split depends on (HW, C) only, never on N: the summation order of a sample's statistics is
+    // then independent of the batch it is in (sample i of a batch == the same sample run alone, bit for bit).
+    (void)N;
     int by_rows = ceil_div(HW, g.R);                 // at least one row-slot per CTA
-    int want = ceil_div(592, N);                     // >= 4 waves' worth of CTAs over the batch
-    int cap = ceil_div(HW, g.R * 32);                // <= 32 rows per thread
+    int want = 148;                                  // one CTA per SM per sample
+    int cap = ceil_div(HW, g.R * 8);                 // <= 8 rows per thread
     int chunks = want > cap ? want : cap;
     if (chunks > by_rows) chunks = by_rows;
     if (chunks < 1) chunks = 1;
@@ -83,21 +86,30 @@ __global__ void gn_stats_kernel(const float* __restrict__ x0, int C0, const floa
     }
 }
 
-// Pass 2: combine chunk partials -> (mean, rstd) per (sample, group).
-__global__ void gn_finalize_kernel(const double* __restrict__ partial, int chunks, int groups, double count,
+// Pass 2: combine chunk partials -> (mean, rstd) per (sample, group): one warp per (n, g), lanes stride
+// over the chunks, fixed-order fp64 shuffle reduction (deterministic).
+__global__ void gn_finalize_kernel(const double* __restrict__ partial, int chunks, int groups, int total, double count,
                                    float eps, float2* __restrict__ stats) {
-    const int n = blockIdx.x;
-    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-        double S = 0.0, Q = 0.0;
-        for (int ch = 0; ch < chunks; ++ch) {
-            const double* p = partial + (((long long)n * chunks + ch) * groups + g) * 2;
-            S += p[0]; Q += p[1];
-        }
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= total) return;
+    const int n = w / groups, g = w - n * groups;
+    double S = 0.0, Q = 0.0;
+    for (int ch = lane; ch < chunks; ch += 32) {
+        const double* p = partial + (((long long)n * chunks + ch) * groups + g) * 2;
+        S += p[0]; Q += p[1];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        S += __shfl_xor_sync(0xffffffffu, S, o);
+        Q += __shfl_xor_sync(0xffffffffu, Q, o);
+    }
+    if (lane == 0) {
         double mean = S / count;
         double var = Q / count - mean * mean;
         if (var < 0.0) var = 0.0;
         double rstd = 1.0 / sqrt(var + (double)eps);
-        stats[n * groups + g] = make_float2((float)mean, (float)rstd);
+        stats[w] = make_float2((float)mean, (float)rstd);
     }
 }
 
@@ -151,7 +163,7 @@ template <bool OUT_BF16>
 __global__ void layernorm_kernel(const float* __restrict__ x, int rows, int C, float eps,
                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                  void* __restrict__ out) {
-    constexpr int MAXV = 8;   // C <= 4*32*8 = 4096... capped at 1024 floats/lane-set
+    constexpr int MAXV = 16;  // float4 vectors per lane: C <= 4*32*16 = 2048
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= rows) return;
@@ -236,7 +248,8 @@ int sdb_groupnorm_nhwc(const float* x0, int C0, const float* x1, int C1, int N, 
     gn_stats_kernel<<<grid, g.threads, smem, st>>>(x0, C0, x1, C1, HW, groups, g.V, g.R, g.rows_per_chunk, partial);
     int rc = check_launch("gn_stats_kernel");
     if (rc) return rc;
-    gn_finalize_kernel<<<N, 32, 0, st>>>(partial, g.chunks, groups, (double)HW * (C / groups), eps, stats);
+    gn_finalize_kernel<<<ceil_div(N * groups, 8), 256, 0, st>>>(partial, g.chunks, groups, N * groups,
+                                                              (double)HW * (C / groups), eps, stats);
     rc = check_launch("gn_finalize_kernel");
     if (rc) return rc;
 #define LAUNCH_APPLY(BF, EX)                                                                             \
@@ -251,8 +264,8 @@ int sdb_groupnorm_nhwc(const float* x0, int C0, const float* x1, int C1, int N, 
 int sdb_layernorm(const float* x, int rows, int C, float eps, const float* gamma, const float* beta,
                   void* out, int out_dtype, void* stream) {
     SDB_REQUIRE(x && out && gamma && beta, "layernorm: null pointer");
-    SDB_REQUIRE(rows > 0 && C > 0 && C % 4 == 0 && C <= 1024 * 4 / 4 * 4 && C <= 4096, "layernorm: bad shape rows=%d C=%d", rows, C);
-    SDB_REQUIRE(C / 4 <= 32 * 8, "layernorm: C=%d too wide", C);
+    SDB_REQUIRE(rows > 0 && C > 0 && C % 4 == 0, "layernorm: bad shape rows=%d C=%d", rows, C);
+    SDB_REQUIRE(C <= 2048, "layernorm: C=%d too wide (max 2048)", C);
     cudaStream_t st = (cudaStream_t)stream;
     const int threads = 256;
     const int blocks = ceil_div(rows, threads / 32);

@@ -163,6 +163,24 @@ class DDIMSampler(object):
         sigmas = self.model.ddim_sigmas_for_original_num_steps if use_original_steps else self.ddim_sigmas
         return (_f32(alphas[index]), _f32(alphas_prev[index]), _f32(sigmas[index]), _f32(sqrt_one_minus_alphas[index]))
 
+    def derived_coefficients(self, index, use_original_steps=False):
+        """sqrt(a_t), sqrt(a_prev), sqrt(1 - a_prev - sigma^2), sigma_t, sqrt(1-a_t) as the fp32 values the
+        reference's [b,1,1,1] tensors hold (ddim.py:191-205), evaluated with the reference's own torch
+        expressions on host tensors.  (torch's CPU sqrt is not correctly rounded for every input — e.g. 4 of
+        the 50 SD DDIM-50 alphas land 1 ulp off IEEE — so calling the same routine is what keeps the update
+        bit-identical to the CPU-executed reference; cached per (index, schedule).)"""
+        key = (index, use_original_steps)
+        cache = self.__dict__.setdefault("_coef_cache", {})
+        tag = (id(self.ddim_alphas), id(self.ddim_sigmas))
+        if cache.get("tag") != tag:
+            cache.clear()
+            cache["tag"] = tag
+        if key not in cache:
+            a_t, a_prev, sigma_t, s1m = self.coefficients(index, use_original_steps)
+            ta, tp, ts = torch.full((1, 1, 1, 1), a_t), torch.full((1, 1, 1, 1), a_prev), torch.full((1, 1, 1, 1), sigma_t)
+            cache[key] = (float(ta.sqrt()), float(tp.sqrt()), float((1. - tp - ts ** 2).sqrt()), sigma_t, s1m)
+        return cache[key]
+
     @torch.no_grad()
     def p_sample_ddim(self, x, c, t, index, repeat_noise=False, use_original_steps=False, quantize_denoised=False,
                       temperature=1., noise_dropout=0., score_corrector=None, corrector_kwargs=None,
@@ -185,7 +203,7 @@ class DDIMSampler(object):
         if quantize_denoised or noise_dropout > 0.:
             raise NotImplementedError("sdb200 DDIMSampler: quantize_denoised / noise_dropout are outside the hot path")
 
-        a_t, a_prev, sigma_t, s1m = self.coefficients(index, use_original_steps)
+        sqrt_at, sqrt_aprev, dir_coef, sigma_t, s1m = self.derived_coefficients(index, use_original_steps)
 
         noise = None
         if sigma_t != 0.0 or self.consume_rng_like_reference:
@@ -197,7 +215,7 @@ class DDIMSampler(object):
                 noise = None
         xf = x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous()
         ef = e_t if (e_t.dtype == torch.float32 and e_t.is_contiguous()) else e_t.float().contiguous()
-        x_prev, pred_x0 = ops.ddim_step(xf, ef, a_t, a_prev, sigma_t, s1m, e_uncond=e_uncond,
+        x_prev, pred_x0 = ops.ddim_step(xf, ef, sqrt_at, sqrt_aprev, dir_coef, sigma_t, s1m, e_uncond=e_uncond,
                                         cfg_scale=unconditional_guidance_scale, noise=noise, temperature=temperature)
         return x_prev, pred_x0
 

@@ -173,14 +173,16 @@ def skinny_linear(x, W, bias=None, act_in=0, act_out=0):
     return y
 
 
-def ddim_step(x, e_cond, a_t, a_prev, sigma_t, sqrt_one_minus_at, e_uncond=None, cfg_scale=1.0, noise=None, temperature=1.0):
+def ddim_step(x, e_cond, sqrt_at, sqrt_aprev, dir_coef, sigma_t, sqrt_one_minus_at, e_uncond=None, cfg_scale=1.0,
+              noise=None, temperature=1.0):
+    """One fused DDIM update; the five scalars are the fp32 per-step coefficients (see DDIMSampler.derived_coefficients)."""
     require_cuda(x, e_cond, e_uncond, noise)
     assert x.dtype == torch.float32 and e_cond.dtype == torch.float32 and x.is_contiguous() and e_cond.is_contiguous()
     x_prev = torch.empty_like(x)
     pred_x0 = torch.empty_like(x)
-    check(_L().sdb_ddim_step(ptr(x), ptr(e_cond), ptr(e_uncond), float(cfg_scale), ptr(noise), float(a_t), float(a_prev),
-                             float(sigma_t), float(sqrt_one_minus_at), float(temperature), ptr(x_prev), ptr(pred_x0),
-                             x.numel(), stream_ptr()), "ddim_step")
+    check(_L().sdb_ddim_step(ptr(x), ptr(e_cond), ptr(e_uncond), float(cfg_scale), ptr(noise), float(sqrt_at), float(sqrt_aprev),
+                             float(dir_coef), float(sigma_t), float(sqrt_one_minus_at), float(temperature), ptr(x_prev),
+                             ptr(pred_x0), x.numel(), stream_ptr()), "ddim_step")
     return x_prev, pred_x0
 
 

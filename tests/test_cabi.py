@@ -44,7 +44,7 @@ def test_no_cpu_fallback(lib):
     with pytest.raises(_lib.SdbError):
         ops.groupnorm(x, torch.ones(32), torch.zeros(32), 1e-5)
     with pytest.raises(_lib.SdbError):
-        ops.ddim_step(torch.zeros(4), torch.zeros(4), 0.5, 0.6, 0.0, 0.7)
+        ops.ddim_step(torch.zeros(4), torch.zeros(4), 0.5, 0.6, 0.3, 0.0, 0.7)
 
 
 def test_missing_library_is_loud(tmp_path):
@@ -60,5 +60,5 @@ def test_argument_validation_without_gpu(lib):
     assert lib.sdb_groupnorm_ws_bytes(2, 4096, 320, 32) > 0
     rc = lib.sdb_layernorm(None, 4, 320, 1e-5, None, None, None, 0, None)
     assert rc == -1 and b"null" in lib.sdb_last_error_string()
-    rc = lib.sdb_ddim_step(None, None, None, 1.0, None, 0.5, 0.6, 0.0, 0.7, 1.0, None, None, 0, None)
+    rc = lib.sdb_ddim_step(None, None, None, 1.0, None, 0.5, 0.6, 0.3, 0.0, 0.7, 1.0, None, None, 0, None)
     assert rc == -1
