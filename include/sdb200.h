@@ -159,7 +159,8 @@ int sdb_simt_contract(const sdb_simt_args* args /* host */, void* stream);
  * epilogue: + bias[n] + rowvec[img, n] + residual[m, n]; optional GEGLU pairing
  * (openai_model/attention.py:140-141) when geglu != 0 (B rows packed a|gate per BN tile);
  * optional column-group remap (n -> (n / cg)*cgs + n % cg) used to write q/k/v heads padded.
- * split_k > 1 accumulates with red.global.add.f32 into a pre-zeroed fp32 `out`. */
+ * split_k > 1: every K-split writes its fp32 partial tile to the workspace and a second kernel sums
+ * the splits in a fixed order and applies bias / rowvec / residual (deterministic, no atomics). */
 typedef struct sdb_tc_args {
     const void* A; const void* B; void* out;
     const float* bias; const float* rowvec; const float* residual;
@@ -178,8 +179,21 @@ typedef struct sdb_tc_args {
     int cout_pad;                         /* rows of B per tap */
     /* output pixel remap (sub-pixel upsample phases): oh' = oh*out_sh + out_oh etc. */
     int out_sh, out_sw, out_oh, out_ow, OHF, OWF;
+    /* split-K workspace (device, 16-byte aligned) for the per-split partial tiles; may be NULL when
+     * split_k == 1.  split_k == 0 lets the library choose (it only splits when `ws` is given). */
+    void* ws; long long ws_bytes;
+    /* gemm mode: rows of A owned by ONE independent sample (tokens per image), 0 = unknown.  Only used so
+     * that the automatic split-K choice does not depend on the batch size (batch-invariant bit patterns). */
+    int rows_per_item;
 } sdb_tc_args;
+/* bytes of workspace sdb_tc_contract may use for these args (0 = none; -1 = invalid args).  With
+ * split_k == 0 this is what the library's automatic split choice needs. */
+long long sdb_tc_workspace_bytes(const sdb_tc_args* args /* host */);
 int sdb_tc_contract(const sdb_tc_args* args /* host */, void* stream);
+/* Tuning switch (measurement only, same results either way): 1 = CTA-pair persistent kernel
+ * (cta_group::2, 256 x BN tiles) for block_n >= 128 [default], 0 = one-CTA 128 x BN kernel everywhere.
+ * Returns the previous setting. */
+int sdb_tc_set_pair_kernel(int enable);
 
 /* ---- fused attention forward (bf16, tcgen05) ---------------------------------------------------
  * Replaces flash_attn_func(q,k,v, softmax_scale, causal=False) (openai_model/attention.py:106-112).

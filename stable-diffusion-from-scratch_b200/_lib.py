@@ -53,6 +53,8 @@ class TcArgs(C.Structure):
         ("NB", C.c_int), ("IH", C.c_int), ("IW", C.c_int), ("Cin", C.c_int), ("OH", C.c_int), ("OW", C.c_int),
         ("cout_pad", C.c_int),
         ("out_sh", C.c_int), ("out_sw", C.c_int), ("out_oh", C.c_int), ("out_ow", C.c_int), ("OHF", C.c_int), ("OWF", C.c_int),
+        ("ws", C.c_void_p), ("ws_bytes", C.c_longlong),
+        ("rows_per_item", C.c_int),
     ]
 
 
@@ -93,6 +95,8 @@ SIGNATURES = {
     "sdb_ddim_step": (_I, [_P, _P, _P, _F, _P, _F, _F, _F, _F, _F, _F, _P, _P, _L, _P]),
     "sdb_simt_contract": (_I, [C.POINTER(SimtArgs), _P]),
     "sdb_tc_contract": (_I, [C.POINTER(TcArgs), _P]),
+    "sdb_tc_set_pair_kernel": (_I, [_I]),
+    "sdb_tc_workspace_bytes": (_L, [C.POINTER(TcArgs)]),
     "sdb_attention_fwd": (_I, [C.POINTER(AttnArgs), _P]),
 }
 

@@ -159,11 +159,11 @@ __global__ void gn_apply_kernel(const float* __restrict__ x0, int C0, const floa
 }
 
 // ---- LayerNorm: one warp per row, row held in registers (two-pass mean/variance) ----------------
-template <bool OUT_BF16>
-__global__ void layernorm_kernel(const float* __restrict__ x, int rows, int C, float eps,
-                                 const float* __restrict__ gamma, const float* __restrict__ beta,
-                                 void* __restrict__ out) {
-    constexpr int MAXV = 16;  // float4 vectors per lane: C <= 4*32*16 = 2048
+template <bool OUT_BF16, int MAXV>   // MAXV float4 vectors per lane: C <= 128 * MAXV
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, int rows, int C, float eps,
+                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                 void* __restrict__ out) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= rows) return;
@@ -267,11 +267,21 @@ int sdb_layernorm(const float* x, int rows, int C, float eps, const float* gamma
     SDB_REQUIRE(rows > 0 && C > 0 && C % 4 == 0, "layernorm: bad shape rows=%d C=%d", rows, C);
     SDB_REQUIRE(C <= 2048, "layernorm: C=%d too wide (max 2048)", C);
     cudaStream_t st = (cudaStream_t)stream;
+    SDB_REQUIRE(out_dtype == SDB_BF16 || out_dtype == SDB_F32, "layernorm: bad out_dtype");
     const int threads = 256;
     const int blocks = ceil_div(rows, threads / 32);
-    if (out_dtype == SDB_BF16) layernorm_kernel<true><<<blocks, threads, 0, st>>>(x, rows, C, eps, gamma, beta, out);
-    else if (out_dtype == SDB_F32) layernorm_kernel<false><<<blocks, threads, 0, st>>>(x, rows, C, eps, gamma, beta, out);
-    else SDB_REQUIRE(false, "layernorm: bad out_dtype");
+    const int nv = ceil_div(C / 4, 32);      // float4 vectors per lane; the row stays in registers
+#define LAUNCH_LN(NV)                                                                                              \
+    do {                                                                                                           \
+        if (out_dtype == SDB_BF16) layernorm_kernel<true, NV><<<blocks, threads, 0, st>>>(x, rows, C, eps, gamma, beta, out); \
+        else layernorm_kernel<false, NV><<<blocks, threads, 0, st>>>(x, rows, C, eps, gamma, beta, out);           \
+    } while (0)
+    if (nv <= 1) LAUNCH_LN(1);
+    else if (nv <= 3) LAUNCH_LN(3);
+    else if (nv <= 5) LAUNCH_LN(5);
+    else if (nv <= 10) LAUNCH_LN(10);
+    else LAUNCH_LN(16);
+#undef LAUNCH_LN
     return check_launch("layernorm_kernel");
 }
 

@@ -20,6 +20,8 @@
 // mainloop.  Roofline: tensor pipe; algorithmic FLOP = 2*M*N*K*taps.
 #include "common.cuh"
 #include "ptx.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 namespace sdb {
 
@@ -28,6 +30,7 @@ using namespace ptx;
 struct TcP {
     void* out;
     const float* bias; const float* rowvec; const float* residual;
+    float* ws; long long ws_split_stride;   // split-K partial sums: [split_k][M_out][N] fp32
     long long ldc, ldr, ldv;
     int M, N;
     int kblocks;            // total k-blocks = taps * kpt
@@ -36,6 +39,7 @@ struct TcP {
     int col_group, col_group_stride;
     int split_k;
     int tiles_n;
+    int m_pairs;            // pair kernel: number of 256-row tile pairs
     // conv
     int conv;
     int kw, stride, pad_h, pad_w;
@@ -58,41 +62,142 @@ struct TcCfg {
     static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 256 + BN * 4;
 };
 
-__device__ __forceinline__ void store_row_chunk(const TcP& p, long long row_off, int n, const float* v, int cnt, bool atomic) {
-    // v[0..cnt) are consecutive output columns n..n+cnt-1 (cnt multiple of 4 unless at the N edge)
-    if (p.out_bf16) {
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out);
-        for (int j = 0; j < cnt; j += 8) {
-            int nn = n + j;
-            if (nn >= p.N) break;
-            int dn = p.col_group ? (nn / p.col_group) * p.col_group_stride + nn % p.col_group : nn;
-            if (nn + 8 <= p.N && j + 8 <= cnt && ((row_off + dn) & 7) == 0) {
-                uint4 u;
-                u.x = pack_bf16x2(v[j], v[j + 1]); u.y = pack_bf16x2(v[j + 2], v[j + 3]);
-                u.z = pack_bf16x2(v[j + 4], v[j + 5]); u.w = pack_bf16x2(v[j + 6], v[j + 7]);
-                *reinterpret_cast<uint4*>(o + row_off + dn) = u;
-            } else {
-                for (int t = 0; t < 8 && j + t < cnt && nn + t < p.N; ++t) {
-                    int n2 = nn + t;
-                    int d2 = p.col_group ? (n2 / p.col_group) * p.col_group_stride + n2 % p.col_group : n2;
-                    o[row_off + d2] = __float2bfloat16_rn(v[j + t]);
+constexpr int EPI_LD = 36;                        // floats per staged row: 16-B aligned, conflict-free for 128-bit access
+constexpr int EPI_WARP_BYTES = 32 * EPI_LD * 4;   // one 32 x 32 fp32 chunk per epilogue warp
+
+__device__ __forceinline__ float4 ldg_f4_or_zero(const float* p, bool pred) {
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pred) r = __ldg(reinterpret_cast<const float4*>(p));
+    return r;
+}
+
+// Epilogue of one warp = 32 rows (its TMEM lane quarter) x (a subset of) the BN columns of an accumulator.
+// tcgen05.ld gives each lane one ROW (32 consecutive columns per chunk); stores in that layout would
+// touch 32 different 128-B lines per instruction.  The chunk is therefore transposed through a padded
+// smem tile so that 8 lanes cover 32 consecutive columns (128 B) of one row and one warp instruction
+// covers 4 whole rows: bias / time-emb row / residual loads and the output stores are all coalesced,
+// and the residual / time-emb loads of a chunk are issued before its TMEM load so their latency overlaps.
+// `row_pix` = output row index of THIS lane's tile row (or -1 when the row is outside the problem),
+// `row_img` = its image index (conv mode; selects the time-embedding row).  The warp handles the
+// 32-column chunks ch0, ch0 + chstep, ... (two warps can share one lane quarter).
+template <int BN>
+__device__ __forceinline__ void epilogue_warp(const TcP& p, uint32_t taddr, const float* s_bias, float* stage, int lane,
+                                              int n0, int nt, long long row_pix, int row_img, int split, int ch0, int chstep) {
+    // rows this lane stores after the transpose: r_i = 4*i + (lane >> 3), i = 0..7
+    long long rpix[8];
+    int rimg[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int src = 4 * i + (lane >> 3);
+        rpix[i] = __shfl_sync(0xffffffffu, row_pix, src);
+        rimg[i] = __shfl_sync(0xffffffffu, row_img, src);
+    }
+    const int cq = 4 * (lane & 7);                // this lane's 4 columns inside a 32-column chunk
+    const uint32_t stage_a = smem_u32(stage), sbias_a = smem_u32(s_bias);
+    const bool partial = p.split_k > 1;           // write raw partial sums to the split-K workspace
+    float* const ws = partial ? p.ws + (long long)split * p.ws_split_stride : nullptr;
+    const float* const resid = (p.residual && !partial) ? p.residual : nullptr;
+    const float* const rowv = (p.rowvec && !partial && p.conv) ? p.rowvec : nullptr;
+    constexpr int CH = 32;
+    constexpr int NCHUNK = (BN + CH - 1) / CH;
+    const int n_out = p.geglu ? p.N / 2 : p.N;    // stored columns
+    const int nb = p.geglu ? nt * (BN / 2) : n0;  // first stored column of this tile
+    const int cols = p.geglu ? BN / 2 : BN;
+    // vector fast path: whole 4-column groups, every row pitch and base 16-byte aligned (warp-uniform test)
+    const bool vec_ok = (n_out % 4 == 0) && (p.ldc % 4 == 0) && (p.ldr % 4 == 0) && (p.ldv % 4 == 0) &&
+                        ((reinterpret_cast<uintptr_t>(p.out) | reinterpret_cast<uintptr_t>(p.residual) |
+                          reinterpret_cast<uintptr_t>(p.rowvec)) & 15) == 0 &&
+                        (!p.col_group || (p.col_group % 4 == 0 && p.col_group_stride % 4 == 0));
+#pragma unroll 1
+    for (int ch = ch0; ch < NCHUNK; ch += chstep) {
+        const int c0 = ch * CH;
+        if (c0 >= cols || nb + c0 >= n_out) break;                     // warp-uniform
+        const int cn = nb + c0 + cq;                                    // first of this lane's 4 output columns
+        const bool col_ok = cn < n_out;
+        // ---- issue the residual / time-emb loads first (fast path), they land while TMEM is read and transposed
+        float4 addv[8];
+        if (vec_ok) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const bool ok = col_ok && rpix[i] >= 0;
+                addv[i] = ldg_f4_or_zero(resid + rpix[i] * p.ldr + cn, ok && resid != nullptr);
+            }
+            if (rowv) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const bool ok = col_ok && rpix[i] >= 0;
+                    float4 q = ldg_f4_or_zero(rowv + (long long)rimg[i] * p.ldv + cn, ok);
+                    addv[i].x += q.x; addv[i].y += q.y; addv[i].z += q.z; addv[i].w += q.w;
                 }
             }
         }
-    } else {
-        float* o = reinterpret_cast<float*>(p.out);
-        for (int j = 0; j < cnt; j += 4) {
-            int nn = n + j;
-            if (nn >= p.N) break;
-            if (atomic) {
-                for (int t = 0; t < 4 && j + t < cnt && nn + t < p.N; ++t) atomicAdd(o + row_off + nn + t, v[j + t]);
-            } else if (nn + 4 <= p.N && j + 4 <= cnt && ((row_off + nn) & 3) == 0) {
-                *reinterpret_cast<float4*>(o + row_off + nn) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-                for (int t = 0; t < 4 && j + t < cnt && nn + t < p.N; ++t) o[row_off + nn + t] = v[j + t];
+        uint32_t r[32];
+        tmem_ld_x32(taddr + c0, r);
+        if (p.geglu) {
+            // value columns [0, BN/2) | gate columns [BN/2, BN) of the same outputs (weights packed so by the host)
+            uint32_t g[32];
+            tmem_ld_x32(taddr + BN / 2 + c0, g);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float a = __uint_as_float(r[j]) + lds32(sbias_a + 4 * (c0 + j));
+                float gg = __uint_as_float(g[j]) + lds32(sbias_a + 4 * (BN / 2 + c0 + j));
+                r[j] = __float_as_uint(a * gelu_erf_fast(gg));
+            }
+        } else {
+            tmem_ld_wait();
+        }
+        __syncwarp();                                                   // previous chunk's readers are done
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            sts128(stage_a + 4 * (lane * EPI_LD + 4 * q), r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+        __syncwarp();
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!p.geglu && !partial) bias4 = lds128(sbias_a + 4 * (c0 + cq));
+        if (vec_ok) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const long long pix = rpix[i];
+                float4 v = lds128(stage_a + 4 * ((4 * i + (lane >> 3)) * EPI_LD + cq));
+                v.x += bias4.x + addv[i].x; v.y += bias4.y + addv[i].y; v.z += bias4.z + addv[i].z; v.w += bias4.w + addv[i].w;
+                if (!(col_ok && pix >= 0)) continue;
+                if (partial) {
+                    *reinterpret_cast<float4*>(ws + pix * p.N + cn) = v;                      // dense [rows_out, N]
+                } else if (p.out_bf16) {
+                    const int dn = p.col_group ? (cn / p.col_group) * p.col_group_stride + cn % p.col_group : cn;
+                    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.ldc + dn) =
+                        make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+                } else {
+                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.ldc + cn) = v;
+                }
+            }
+        } else {
+            // generic path: any N / pitch / alignment, element by element
+            const int nvalid = n_out - cn < 4 ? n_out - cn : 4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const long long pix = rpix[i];
+                if (pix < 0 || nvalid <= 0) continue;
+                const float4 v4 = lds128(stage_a + 4 * ((4 * i + (lane >> 3)) * EPI_LD + cq));
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    if (t >= nvalid) break;
+                    const int n2 = cn + t;
+                    float v = t == 0 ? v4.x + bias4.x : (t == 1 ? v4.y + bias4.y : (t == 2 ? v4.z + bias4.z : v4.w + bias4.w));
+                    if (rowv) v += __ldg(rowv + (long long)rimg[i] * p.ldv + n2);
+                    if (resid) v += __ldg(resid + pix * p.ldr + n2);
+                    if (partial) {
+                        ws[pix * p.N + n2] = v;
+                    } else {
+                        const int d2 = p.col_group ? (n2 / p.col_group) * p.col_group_stride + n2 % p.col_group : n2;
+                        if (p.out_bf16) reinterpret_cast<__nv_bfloat16*>(p.out)[pix * p.ldc + d2] = __float2bfloat16_rn(v);
+                        else reinterpret_cast<float*>(p.out)[pix * p.ldc + d2] = v;
+                    }
+                }
             }
         }
     }
+    __syncwarp();
 }
 
 template <int BN>
@@ -189,14 +294,13 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int et = threadIdx.x - 64;             // 0..127
         for (int i = et; i < BN; i += 128) {
             int n = n0 + i;
-            s_bias[i] = (p.bias && n < p.N && split == 0) ? p.bias[n] : 0.f;
+            s_bias[i] = (p.bias && n < p.N) ? p.bias[n] : 0.f;
         }
         named_bar_sync(1, 128);
 
         const int lg = warp & 3;                     // TMEM lane group this warp may access
         const int row = lg * 32 + lane;              // row of the 128-row tile
-        bool valid;
-        long long pix;                               // output row index (pixel / token)
+        long long pix;                               // output row index (pixel / token), -1 = outside the problem
         int img = 0;
         if (p.conv) {
             int in_ = row / (p.th * p.tw);
@@ -204,75 +308,17 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             int ih = rem / p.tw, iw = rem - ih * p.tw;
             img = img0 + in_;
             int oh = oh0 + ih, ow = ow0 + iw;
-            valid = (img < p.NB) && (oh < p.OH) && (ow < p.OW);
-            pix = ((long long)img * p.OHF + (oh * p.out_sh + p.out_oh)) * p.OWF + (ow * p.out_sw + p.out_ow);
+            bool valid = (img < p.NB) && (oh < p.OH) && (ow < p.OW);
+            pix = valid ? ((long long)img * p.OHF + (oh * p.out_sh + p.out_oh)) * p.OWF + (ow * p.out_sw + p.out_ow) : -1;
         } else {
-            valid = (m0 + row) < p.M;
-            pix = m0 + row;
+            pix = (m0 + row) < p.M ? m0 + row : -1;
         }
-        const long long out_off = pix * p.ldc;
-        const float* res = (p.residual && split == 0) ? p.residual + pix * p.ldr : nullptr;
-        const float* rv = (p.rowvec && split == 0 && p.conv) ? p.rowvec + (long long)img * p.ldv : nullptr;
-        const bool atomic = p.split_k > 1;
-
         mbar_wait(accum_bar, 0);
         tcgen05_fence_after();
+        // every TMA load has been consumed by now: the A ring doubles as the transpose staging area
+        float* stage = reinterpret_cast<float*>(sA) + (warp - 2) * (EPI_WARP_BYTES / 4);
         const uint32_t taddr = tmem_d + ((uint32_t)(lg * 32) << 16);
-
-        if (!p.geglu) {
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld_x32(taddr + c0, r);
-                tmem_ld_wait();
-                if (valid && n0 + c0 < p.N) {
-                    float v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_bias[c0 + j];
-                    if (rv) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) if (n0 + c0 + j < p.N) v[j] += __ldg(rv + n0 + c0 + j);
-                    }
-                    if (res) {
-                        if (n0 + c0 + 32 <= p.N && ((pix * p.ldr + n0 + c0) & 3) == 0) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                float4 q = __ldg(reinterpret_cast<const float4*>(res + n0 + c0 + j));
-                                v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
-                            }
-                        } else {
-                            for (int j = 0; j < 32; ++j) if (n0 + c0 + j < p.N) v[j] += res[n0 + c0 + j];
-                        }
-                    }
-                    store_row_chunk(p, out_off, n0 + c0, v, 32, atomic);
-                }
-            }
-        } else {
-            // GEGLU: tile columns [0, BN/2) are the value half, [BN/2, BN) the gate half of the same
-            // output columns nt*BN/2 + j  (weights packed that way by the host).
-            constexpr int HALF = BN / 2;
-            const int on0 = nt * HALF;
-            const int NO = p.N / 2;                  // output columns
-#pragma unroll 1
-            for (int c0 = 0; c0 < HALF; c0 += 16) {
-                uint32_t ra[16], rg[16];
-                tmem_ld_x16(taddr + c0, ra);
-                tmem_ld_x16(taddr + HALF + c0, rg);
-                tmem_ld_wait();
-                if (valid && on0 + c0 < NO) {
-                    float v[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float a = __uint_as_float(ra[j]) + s_bias[c0 + j];
-                        float g = __uint_as_float(rg[j]) + s_bias[HALF + c0 + j];
-                        v[j] = a * gelu_erf(g);
-                    }
-                    TcP q = p;
-                    q.N = NO;
-                    store_row_chunk(q, out_off, on0 + c0, v, 16, false);
-                }
-            }
-        }
+        epilogue_warp<BN>(p, taddr, s_bias, stage, lane, n0, nt, pix, img, split, 0, 1);
     }
 
     // ---- teardown ----
@@ -281,6 +327,192 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (warp == 1) {
         tcgen05_fence_after();
         tmem_dealloc(tmem_d, Cfg::TMEM_COLS);
+    }
+}
+
+// ---- CTA-pair persistent kernel ------------------------------------------------------------------
+// A cluster of two CTAs (one per SM of a TPC) owns a 256 x BN output tile: tcgen05.mma.cta_group::2
+// with M = 256, each CTA staging its own 128 rows of A and HALF of the B tile (BN/2 rows), so the
+// bytes pulled from L2 per FLOP drop by 1/3 .. 1/2 against the one-CTA 128 x BN kernel.  The pair is
+// persistent over a strided list of work units (m-pair, n-tile, k-split); the 512-column TMEM holds
+// two accumulators so the epilogue of unit i overlaps the mainloop of unit i+1.
+//   warp 0 : TMA producer for A, warp 3 : TMA producer for B (both CTAs; completion bytes are
+//            signalled on the LEADER's full barrier, which the leader's A-producer arms)
+//   warp 1 : MMA issuer (leader CTA only); tcgen05.commit multicasts "slot free" / "accumulator
+//            ready" to the barriers of both CTAs
+//   warp 2 : TMEM allocator
+//   warps 4..11 : epilogue, two warps per TMEM lane quarter (warp & 3), alternating 32-column chunks
+constexpr int TC2_THREADS = 384;
+constexpr int TC2_EPI_WARPS = 8;
+
+template <int BN>
+struct Tc2Cfg {
+    static constexpr int B_HALF_BYTES = (BN / 2) * TC_BK * 2;
+    static constexpr int STAGE_BYTES = TC_A_BYTES + B_HALF_BYTES;       // per CTA
+    static constexpr int STAGES_RAW = (184 * 1024) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+    static constexpr int ACC_STRIDE = 256;                                // TMEM columns between the two accumulators
+    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 512 + BN * 4 + TC2_EPI_WARPS * EPI_WARP_BYTES;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
+tc_contract_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcP p) {
+    using Cfg = Tc2Cfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * TC_A_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;        // [2] accumulator ready   (arrives: MMA commit, multicast)
+    uint64_t* tempty_bar = tfull_bar + 2;            // [2] accumulator drained (leader's copy is the one waited on)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* s_bias = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 512);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int units = p.m_pairs * p.tiles_n * p.split_k;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 2 * TC2_EPI_WARPS); }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc_pair(tmem_slot, 512);
+        tmem_relinquish_pair();
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+
+    if (warp == 0 || warp == 3) {
+        // ================= TMA producers (both CTAs): warp 0 loads A, warp 3 loads B =================
+        if (lane == 0) {
+            const bool load_a = warp == 0;
+            const uint32_t fb0 = mapa_u32(&full_bar[0], 0);           // leader's full barriers (8 bytes apart)
+            int s = 0; uint32_t ph = 0;
+            for (int u = pair; u < units; u += npairs) {
+                const int split = u % p.split_k, t = u / p.split_k;
+                const int nt = t % p.tiles_n, mt = (t / p.tiles_n) * 2 + (int)rank;
+                const int brow0 = nt * BN + (int)rank * (BN / 2);
+                const int kb0 = (int)((long long)p.kblocks * split / p.split_k);
+                const int kb1 = (int)((long long)p.kblocks * (split + 1) / p.split_k);
+                const int m0 = mt * TC_BM;
+                int cw = 0, chh = 0, img0 = 0;
+                if (p.conv) {
+                    int tww = mt % p.tiles_w;
+                    int thh = (mt / p.tiles_w) % p.tiles_h;
+                    int tnb = mt / (p.tiles_w * p.tiles_h);
+                    cw = tww * p.tw * p.stride - p.pad_w; chh = thh * p.th * p.stride - p.pad_h; img0 = tnb * p.tn;
+                }
+                int tap = kb0 / p.kpt, cs = kb0 - tap * p.kpt;
+                int r = p.conv ? tap / p.kw : 0, sx = p.conv ? tap - r * p.kw : 0;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    const uint32_t fb = fb0 + 8u * (uint32_t)s;
+                    if (load_a) {
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
+                        if (p.conv) tma_load_4d_pair(sA + s * TC_A_BYTES, &tmA, fb, cs * TC_BK, cw + sx, chh + r, img0);
+                        else tma_load_2d_pair(sA + s * TC_A_BYTES, &tmA, fb, cs * TC_BK, m0);
+                    } else {
+                        tma_load_2d_pair(sB + s * Cfg::B_HALF_BYTES, &tmB, fb, cs * TC_BK, tap * p.cout_pad + brow0);
+                    }
+                    if (++cs == p.kpt) { cs = 0; ++tap; if (++sx == p.kw) { sx = 0; ++r; } }
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (leader CTA) =================
+        if (rank == 0 && lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16_m256(BN, false, false);
+            const uint64_t adesc0 = umma_desc_kmajor_sw128(smem_u32(sA));
+            const uint64_t bdesc0 = umma_desc_kmajor_sw128(smem_u32(sB));
+            int s = 0; uint32_t ph = 0;
+            int it = 0;
+            for (int u = pair; u < units; u += npairs, ++it) {
+                const int split = u % p.split_k;
+                const int kb0 = (int)((long long)p.kblocks * split / p.split_k);
+                const int kb1 = (int)((long long)p.kblocks * (split + 1) / p.split_k);
+                const int buf = it & 1;
+                mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);     // both CTAs' epilogues drained this accumulator
+                tcgen05_fence_after();
+                const uint32_t acc = tmem_d + buf * Cfg::ACC_STRIDE;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full_bar[s], ph);
+                    tcgen05_fence_after();
+                    const uint64_t adesc = adesc0 + (uint64_t)(s * (TC_A_BYTES >> 4));
+                    const uint64_t bdesc = bdesc0 + (uint64_t)(s * (Cfg::B_HALF_BYTES >> 4));
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; ++k)
+                        umma_bf16_ss_pair(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    umma_commit_pair(&empty_bar[s], 3);              // slot free in both CTAs
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+                umma_commit_pair(&tfull_bar[buf], 3);                // accumulator ready in both CTAs
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue (warps 4..11 -> TMEM lane quarter warp & 3, chunk parity (warp - 4) >> 2) ====
+        const int et = threadIdx.x - 128;
+        const int lg = warp & 3;
+        const int half = (warp - 4) >> 2;
+        const int row = lg * 32 + lane;
+        const uint32_t tempty_leader0 = mapa_u32(&tempty_bar[0], 0);
+        const uint32_t tempty_leader1 = mapa_u32(&tempty_bar[1], 0);
+        float* stage = s_bias + BN + (warp - 4) * (EPI_WARP_BYTES / 4);
+        int it = 0;
+        for (int u = pair; u < units; u += npairs, ++it) {
+            const int split = u % p.split_k, t = u / p.split_k;
+            const int nt = t % p.tiles_n, mt = (t / p.tiles_n) * 2 + (int)rank;
+            const int n0 = nt * BN;
+            const int buf = it & 1;
+            named_bar_sync(1, 32 * TC2_EPI_WARPS);   // previous unit's readers of s_bias are done
+            for (int i = et; i < BN; i += 32 * TC2_EPI_WARPS) {
+                int n = n0 + i;
+                s_bias[i] = (p.bias && n < p.N) ? p.bias[n] : 0.f;
+            }
+            named_bar_sync(1, 32 * TC2_EPI_WARPS);
+            long long pix;
+            int img = 0;
+            if (p.conv) {
+                int tww = mt % p.tiles_w;
+                int thh = (mt / p.tiles_w) % p.tiles_h;
+                int tnb = mt / (p.tiles_w * p.tiles_h);
+                int in_ = row / (p.th * p.tw);
+                int rem = row - in_ * (p.th * p.tw);
+                int ih = rem / p.tw, iw = rem - ih * p.tw;
+                img = tnb * p.tn + in_;
+                int oh = thh * p.th + ih, ow = tww * p.tw + iw;
+                bool valid = (img < p.NB) && (oh < p.OH) && (ow < p.OW);
+                pix = valid ? ((long long)img * p.OHF + (oh * p.out_sh + p.out_oh)) * p.OWF + (ow * p.out_sw + p.out_ow) : -1;
+            } else {
+                pix = (mt * TC_BM + row) < p.M ? (long long)mt * TC_BM + row : -1;
+            }
+            mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
+            tcgen05_fence_after();
+            const uint32_t taddr = tmem_d + ((uint32_t)(lg * 32) << 16) + buf * Cfg::ACC_STRIDE;
+            epilogue_warp<BN>(p, taddr, s_bias, stage, lane, n0, nt, pix, img, split, half, 2);
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(buf ? tempty_leader1 : tempty_leader0);
+        }
+    }
+
+    // ---- teardown: both CTAs must be done with TMEM and with each other's barriers ----
+    __syncwarp();
+    tcgen05_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc_pair(tmem_d, 512);
     }
 }
 
@@ -356,59 +588,218 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcP& 
     return check_launch("tc_contract_kernel");
 }
 
-}  // namespace sdb
+static int sm_count_cached() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
 
-using namespace sdb;
+template <int BN>
+static int launch_tc_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, TcP& p, int m_tiles, cudaStream_t st) {
+    using Cfg = Tc2Cfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc_contract_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) { set_last_error("tc_contract(pair): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SDB_ERR_CUDA; }
+        attr_set = true;
+    }
+    p.m_pairs = (m_tiles + 1) / 2;
+    long long units = (long long)p.m_pairs * p.tiles_n * p.split_k;
+    int pairs = sm_count_cached() / 2;
+    if (units < pairs) pairs = (int)units;
+    tc_contract_pair_kernel<BN><<<dim3(2 * pairs), TC2_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+    return check_launch("tc_contract_pair_kernel");
+}
 
-extern "C" int sdb_tc_contract(const sdb_tc_args* a, void* stream) {
-    SDB_REQUIRE(a && a->A && a->B && a->out, "tc_contract: null pointer");
-    SDB_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "tc_contract: empty problem");
+// Kernel selection: 1 = CTA-pair persistent kernel for BN >= 128 (default), 0 = one-CTA kernel everywhere.
+// Initialised from SDB200_TC_KERNEL=single|pair, changeable at run time through sdb_tc_set_pair_kernel.
+static int g_pair_kernel = -1;
+static bool pair_kernel_enabled() {
+    if (g_pair_kernel < 0) {
+        const char* e = getenv("SDB200_TC_KERNEL");
+        g_pair_kernel = (e && strcmp(e, "single") == 0) ? 0 : 1;
+    }
+    return g_pair_kernel == 1;
+}
+
+// ---- split-K: deterministic reduction of the per-split partial tiles --------------------------------
+// out[m, n] = sum_s ws[s][m][n] + bias[n] + rowvec[m / rows_per_img][n] + residual[m][n]   (4 columns per thread)
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, long long split_stride, int splits, long long rows, int N,
+                                     const float* __restrict__ bias, const float* __restrict__ rowvec, long long ldv,
+                                     long long rows_per_img, const float* __restrict__ residual, long long ldr,
+                                     void* __restrict__ out, long long ldc, int out_bf16) {
+    const int nq = N >> 2;
+    const long long total = rows * nq;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long m = i / nq;
+        const int n = (int)(i - m * nq) << 2;
+        float4 acc = *reinterpret_cast<const float4*>(ws + m * N + n);
+        for (int s = 1; s < splits; ++s) {
+            float4 q = *reinterpret_cast<const float4*>(ws + s * split_stride + m * N + n);
+            acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+        }
+        if (bias) { acc.x += bias[n]; acc.y += bias[n + 1]; acc.z += bias[n + 2]; acc.w += bias[n + 3]; }
+        if (rowvec) {
+            const float* rp = rowvec + (m / rows_per_img) * ldv + n;
+            acc.x += rp[0]; acc.y += rp[1]; acc.z += rp[2]; acc.w += rp[3];
+        }
+        if (residual) {
+            const float* rp = residual + m * ldr + n;
+            acc.x += rp[0]; acc.y += rp[1]; acc.z += rp[2]; acc.w += rp[3];
+        }
+        if (out_bf16) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + m * ldc + n;
+            o[0] = __float2bfloat16_rn(acc.x); o[1] = __float2bfloat16_rn(acc.y);
+            o[2] = __float2bfloat16_rn(acc.z); o[3] = __float2bfloat16_rn(acc.w);
+        } else {
+            float* o = reinterpret_cast<float*>(out) + m * ldc + n;
+            o[0] = acc.x; o[1] = acc.y; o[2] = acc.z; o[3] = acc.w;
+        }
+    }
+}
+
+// ---- launch plan: tile width, kernel variant, pixel-block decomposition, split-K ---------------------
+struct TcPlan {
+    int bn, use_pair, taps, Kt, kpt, kblocks, tiles_n, m_tiles, split_k;
+    int tw, th, tn, tiles_w, tiles_h;
+    long long rows_out;          // rows of the output / workspace (M, or NB*OHF*OWF for a remapped conv)
+    long long ws_bytes;
+};
+
+static int make_plan(const sdb_tc_args* a, TcPlan* pl) {
+    SDB_REQUIRE(a && a->M > 0 && a->N > 0 && a->K > 0, "tc_contract: empty problem");
+    memset(pl, 0, sizeof(*pl));
     const bool conv = a->taps > 0;
-    const int taps = conv ? a->taps : 1;
-    const int Kt = conv ? a->Cin : a->K;                 // contraction length per tap
-    SDB_REQUIRE(Kt % 8 == 0, "tc_contract: K per tap (%d) must be a multiple of 8", Kt);
-
+    pl->taps = conv ? a->taps : 1;
+    pl->Kt = conv ? a->Cin : a->K;                        // contraction length per tap
+    SDB_REQUIRE(pl->Kt % 8 == 0, "tc_contract: K per tap (%d) must be a multiple of 8", pl->Kt);
     int bn = a->block_n;
     if (bn == 0) {
         if (a->N <= 32) bn = 32;
         else if (a->N <= 64) bn = 64;
+        else if (pair_kernel_enabled()) {
+            // CTA-pair kernel: widest tile that divides N (bytes pulled from L2 per FLOP fall with BN)
+            if (a->N % 256 == 0) bn = 256;
+            else if (a->N % 160 == 0) bn = 160;
+            else bn = a->N > 128 ? 256 : 128;
+        }
         else if (a->N % 160 == 0 && a->N % 128 != 0) bn = 160;
         else if (a->N % 256 == 0 && (long long)a->M * a->N >= 148LL * 2 * 128 * 256) bn = 256;
         else bn = 128;
     }
     SDB_REQUIRE(bn == 32 || bn == 64 || bn == 128 || bn == 160 || bn == 256, "tc_contract: block_n %d unsupported", bn);
-    if (a->geglu) SDB_REQUIRE(a->N % bn == 0 && (bn / 2) % 16 == 0 && !conv, "tc_contract: geglu needs N %% block_n == 0");
+    if (a->geglu) SDB_REQUIRE(a->N % bn == 0 && (bn / 2) % 32 == 0 && !conv, "tc_contract: geglu needs N %% block_n == 0, block_n %% 64 == 0");
+    pl->bn = bn;
+    pl->use_pair = pair_kernel_enabled() && bn >= 128;
+    pl->kpt = ceil_div(pl->Kt, TC_BK);
+    pl->kblocks = pl->taps * pl->kpt;
+    pl->tiles_n = ceil_div(a->N, bn);
+    if (conv) {
+        SDB_REQUIRE(a->kw > 0 && pl->taps % a->kw == 0 && a->stride >= 1 && a->stride <= 2, "tc_contract: bad conv geometry");
+        SDB_REQUIRE(a->NB > 0 && a->IH > 0 && a->IW > 0 && a->OH > 0 && a->OW > 0, "tc_contract: bad conv dims");
+        SDB_REQUIRE(a->M == a->NB * a->OH * a->OW, "tc_contract: M != NB*OH*OW");
+        SDB_REQUIRE(a->cout_pad >= a->N, "tc_contract: cout_pad < N");
+        pick_tile(a->OW, a->OH, a->NB, a->stride, &pl->tw, &pl->th, &pl->tn);
+        pl->tiles_w = ceil_div(a->OW, pl->tw); pl->tiles_h = ceil_div(a->OH, pl->th);
+        pl->m_tiles = pl->tiles_w * pl->tiles_h * ceil_div(a->NB, pl->tn);
+        const long long OHF = a->OHF > 0 ? a->OHF : a->OH, OWF = a->OWF > 0 ? a->OWF : a->OW;
+        pl->rows_out = (long long)a->NB * OHF * OWF;
+    } else {
+        pl->m_tiles = ceil_div(a->M, TC_BM);
+        pl->rows_out = a->M;
+    }
+    // split-K: only when the tile grid leaves most of the machine idle and K is long
+    int sk = a->split_k;
+    const bool splittable = !a->geglu && !a->col_group && a->N % 4 == 0;
+    if (sk == 0) {
+        sk = 1;
+        if (splittable && a->ws) {
+            // The choice must not depend on how many independent samples share the call (sample i of a batch has to
+            // come out bit-identical to the same sample run alone), so the tile count is taken at a nominal batch
+            // of 8 samples whenever the caller says how many rows one sample owns.
+            const long long rpi = conv ? (long long)a->OH * a->OW : (long long)a->rows_per_item;
+            const long long m_ref = rpi > 0 ? 8 * rpi : (long long)a->M;
+            const long long mt_ref = (m_ref + TC_BM - 1) / TC_BM;
+            const long long units = (pl->use_pair ? (mt_ref + 1) / 2 : mt_ref) * pl->tiles_n;
+            const long long slots = pl->use_pair ? sm_count_cached() / 2 : 2LL * sm_count_cached();
+            if (units * 2 <= slots && pl->kblocks >= 16) {
+                long long want = slots / units;
+                if (want > pl->kblocks / 8) want = pl->kblocks / 8;
+                if (want > 16) want = 16;
+                if (want > 1) sk = (int)want;
+            }
+        }
+    }
+    if (sk < 1) sk = 1;
+    if (sk > pl->kblocks) sk = pl->kblocks;
+    SDB_REQUIRE(sk == 1 || splittable, "tc_contract: split_k needs a plain (no GEGLU / column remap) output with N %% 4 == 0");
+    pl->split_k = sk;
+    pl->ws_bytes = sk > 1 ? (long long)sk * pl->rows_out * a->N * 4 : 0;
+    return SDB_OK;
+}
+
+}  // namespace sdb
+
+using namespace sdb;
+
+extern "C" int sdb_tc_set_pair_kernel(int enable) {
+    int prev = pair_kernel_enabled() ? 1 : 0;
+    g_pair_kernel = enable ? 1 : 0;
+    return prev;
+}
+
+extern "C" long long sdb_tc_workspace_bytes(const sdb_tc_args* a) {
+    if (!a) return -1;
+    // what the automatic split choice would need if a workspace were supplied
+    sdb_tc_args t = *a;
+    if (t.split_k == 0 && !t.ws) t.ws = reinterpret_cast<void*>(16);
+    TcPlan pl;
+    if (make_plan(&t, &pl) != SDB_OK) return -1;
+    return pl.ws_bytes;
+}
+
+extern "C" int sdb_tc_contract(const sdb_tc_args* a, void* stream) {
+    SDB_REQUIRE(a && a->A && a->B && a->out, "tc_contract: null pointer");
+    TcPlan pl;
+    int rc = make_plan(a, &pl);
+    if (rc) return rc;
+    const bool conv = a->taps > 0;
+    const int bn = pl.bn;
+    const bool use_pair = pl.use_pair;
 
     TcP p;
     memset(&p, 0, sizeof(p));
     p.out = a->out; p.bias = a->bias; p.rowvec = a->rowvec; p.residual = a->residual;
     p.ldc = a->ldc; p.ldr = a->ldr; p.ldv = a->ldv;
     p.M = a->M; p.N = a->N;
-    p.kpt = ceil_div(Kt, TC_BK);
-    p.kblocks = taps * p.kpt;
+    p.kpt = pl.kpt;
+    p.kblocks = pl.kblocks;
     p.out_bf16 = a->out_dtype == SDB_BF16;
     p.geglu = a->geglu;
     p.col_group = a->col_group; p.col_group_stride = a->col_group_stride;
-    p.split_k = a->split_k > 1 ? a->split_k : 1;
-    if (p.split_k > p.kblocks) p.split_k = p.kblocks;
-    SDB_REQUIRE(p.split_k == 1 || (!p.out_bf16 && !a->geglu), "tc_contract: split_k needs fp32 plain output");
-    p.tiles_n = ceil_div(a->N, bn);
+    p.split_k = pl.split_k;
+    if (p.split_k > 1) {
+        SDB_REQUIRE(a->ws && a->ws_bytes >= pl.ws_bytes, "tc_contract: split_k=%d needs a %lld-byte workspace (got %lld)",
+                    p.split_k, pl.ws_bytes, a->ws ? a->ws_bytes : 0LL);
+        SDB_REQUIRE(((uintptr_t)a->ws & 15) == 0, "tc_contract: workspace must be 16-byte aligned");
+        p.ws = reinterpret_cast<float*>(a->ws);
+        p.ws_split_stride = pl.rows_out * a->N;
+    }
+    p.tiles_n = pl.tiles_n;
     p.conv = conv;
     p.cout_pad = conv ? a->cout_pad : 0;
 
     CUtensorMap tmA, tmB;
-    int m_tiles;
-    int rc;
+    const int m_tiles = pl.m_tiles;
+    const int taps = pl.taps;
     if (conv) {
-        SDB_REQUIRE(a->kw > 0 && taps % a->kw == 0 && a->stride >= 1 && a->stride <= 2, "tc_contract: bad conv geometry");
-        SDB_REQUIRE(a->NB > 0 && a->IH > 0 && a->IW > 0 && a->OH > 0 && a->OW > 0, "tc_contract: bad conv dims");
-        SDB_REQUIRE(a->M == a->NB * a->OH * a->OW, "tc_contract: M != NB*OH*OW");
-        SDB_REQUIRE(a->cout_pad >= a->N, "tc_contract: cout_pad < N");
-        pick_tile(a->OW, a->OH, a->NB, a->stride, &p.tw, &p.th, &p.tn);
+        p.tw = pl.tw; p.th = pl.th; p.tn = pl.tn;
         p.kw = a->kw; p.stride = a->stride; p.pad_h = a->pad_h; p.pad_w = a->pad_w;
         p.NB = a->NB; p.OH = a->OH; p.OW = a->OW;
-        p.tiles_w = ceil_div(a->OW, p.tw); p.tiles_h = ceil_div(a->OH, p.th);
-        m_tiles = p.tiles_w * p.tiles_h * ceil_div(a->NB, p.tn);
+        p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h;
         p.out_sh = a->out_sh > 0 ? a->out_sh : 1; p.out_sw = a->out_sw > 0 ? a->out_sw : 1;
         p.out_oh = a->out_oh; p.out_ow = a->out_ow;
         p.OHF = a->OHF > 0 ? a->OHF : a->OH; p.OWF = a->OWF > 0 ? a->OWF : a->OW;
@@ -421,12 +812,11 @@ extern "C" int sdb_tc_contract(const sdb_tc_args* a, void* stream) {
         if (rc) return rc;
         long long bdims[2] = {a->Cin, (long long)taps * a->cout_pad};
         long long bstr[1] = {a->ldb > 0 ? a->ldb : a->Cin};
-        int bbox[2] = {TC_BK, bn};
+        int bbox[2] = {TC_BK, use_pair ? bn / 2 : bn};
         int bes[2] = {1, 1};
         rc = make_tmap_bf16(&tmB, a->B, 2, bdims, bstr, bbox, bes);
         if (rc) return rc;
     } else {
-        m_tiles = ceil_div(a->M, TC_BM);
         long long dims[2] = {a->K, a->M};
         long long strides[1] = {a->lda};
         int box[2] = {TC_BK, TC_BM};
@@ -435,17 +825,34 @@ extern "C" int sdb_tc_contract(const sdb_tc_args* a, void* stream) {
         if (rc) return rc;
         long long bdims[2] = {a->K, a->N};
         long long bstr[1] = {a->ldb};
-        int bbox[2] = {TC_BK, bn};
+        int bbox[2] = {TC_BK, use_pair ? bn / 2 : bn};
         rc = make_tmap_bf16(&tmB, a->B, 2, bdims, bstr, bbox, es);
         if (rc) return rc;
     }
     SDB_REQUIRE((long long)m_tiles * p.tiles_n < (1LL << 31), "tc_contract: grid too large");
     cudaStream_t st = (cudaStream_t)stream;
-    switch (bn) {
-        case 32: return launch_tc<32>(tmA, tmB, p, m_tiles, st);
-        case 64: return launch_tc<64>(tmA, tmB, p, m_tiles, st);
-        case 128: return launch_tc<128>(tmA, tmB, p, m_tiles, st);
-        case 160: return launch_tc<160>(tmA, tmB, p, m_tiles, st);
-        default: return launch_tc<256>(tmA, tmB, p, m_tiles, st);
+    if (use_pair) {
+        switch (bn) {
+            case 128: rc = launch_tc_pair<128>(tmA, tmB, p, m_tiles, st); break;
+            case 160: rc = launch_tc_pair<160>(tmA, tmB, p, m_tiles, st); break;
+            default: rc = launch_tc_pair<256>(tmA, tmB, p, m_tiles, st); break;
+        }
+    } else {
+        switch (bn) {
+            case 32: rc = launch_tc<32>(tmA, tmB, p, m_tiles, st); break;
+            case 64: rc = launch_tc<64>(tmA, tmB, p, m_tiles, st); break;
+            case 128: rc = launch_tc<128>(tmA, tmB, p, m_tiles, st); break;
+            case 160: rc = launch_tc<160>(tmA, tmB, p, m_tiles, st); break;
+            default: rc = launch_tc<256>(tmA, tmB, p, m_tiles, st); break;
+        }
     }
+    if (rc || p.split_k == 1) return rc;
+    const long long total = pl.rows_out * (a->N / 4);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    const long long rows_per_img = conv ? (long long)p.OHF * p.OWF : 1;
+    splitk_reduce_kernel<<<blocks, 256, 0, st>>>(p.ws, p.ws_split_stride, p.split_k, pl.rows_out, a->N, a->bias,
+                                                 conv ? a->rowvec : nullptr, a->ldv, rows_per_img, a->residual, a->ldr,
+                                                 a->out, a->ldc, p.out_bf16);
+    return check_launch("splitk_reduce_kernel");
 }

@@ -72,13 +72,14 @@ def conv(x, pc, rowvec=None, residual=None, out_dtype=torch.float32, up=1):
                          residual=residual, out_dtype=out_dtype)
 
 
-def linear(x, pl, residual=None, out_dtype=torch.float32, col_group=0, col_group_stride=0):
+def linear(x, pl, residual=None, out_dtype=torch.float32, col_group=0, col_group_stride=0, rows_per_item=0, out=None):
     """x [rows, K] -> [rows, N] (or [rows, N/2] for a GEGLU layer)."""
     rows = x.numel() // x.shape[-1]
     x2 = x.reshape(rows, x.shape[-1])
     if pl.use_tc:
         return ops.gemm_tc(x2, pl.w, pl.bias, residual=residual, out_dtype=out_dtype, geglu=pl.geglu,
-                           col_group=col_group, col_group_stride=col_group_stride, block_n=pl.block_n)
+                           col_group=col_group, col_group_stride=col_group_stride, block_n=pl.block_n,
+                           rows_per_item=rows_per_item, out=out)
     assert col_group == 0
     if pl.geglu:
         h = ops.gemm_simt(x2, pl.w, pl.bias)

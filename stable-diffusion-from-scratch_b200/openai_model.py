@@ -259,12 +259,25 @@ class UNetModel(nn.Module):
         self._packed = {}        # mode -> packed weights
         self._ctx_cache = {}     # (mode, context identity) -> per-layer projected K/V
         self._graphs = {}
+        self._padbufs = {}       # (rows, width, d, dp) -> zero-initialised padded-head projection buffer
 
     # ---- weight packing ---------------------------------------------------------------------------
     def _invalidate(self):
         self._packed = {}
         self._ctx_cache = {}
         self._graphs = {}
+        self._padbufs = {}
+
+    def _padbuf(self, rows, width, d, dp, dev):
+        """Persistent [rows, width] bf16 buffer for q/k/v heads stored padded from d to dp channels.  The GEMM
+        epilogue only ever writes the d real channels of each head, so the pad channels stay zero after the one
+        initial fill; every layer with the same geometry shares the buffer (use is stream-ordered)."""
+        key = (rows, width, d, dp, str(dev))
+        buf = self._padbufs.get(key)
+        if buf is None:
+            buf = torch.zeros((rows, width), dtype=torch.bfloat16, device=dev)
+            self._padbufs[key] = buf
+        return buf
 
     def load_state_dict(self, *a, **k):
         r = super().load_state_dict(*a, **k)
@@ -369,9 +382,9 @@ class UNetModel(nn.Module):
                 cb = ops.cast_concat(context.reshape(1, 1, B * Sk, Cc).contiguous(), None, out_dtype=torch.bfloat16).reshape(B * Sk, Cc)
                 self._ctx_cache[("ctx_bf16", context.data_ptr(), context._version)] = cb
             dp = head_pad(d)
-            kv = engine.linear(cb, P[("kv2", id(blk))], out_dtype=torch.bfloat16, col_group=d, col_group_stride=dp)   # [B*Sk, 2*H*dp]
+            kv = engine.linear(cb, P[("kv2", id(blk))], out_dtype=torch.bfloat16, col_group=d, col_group_stride=dp, rows_per_item=Sk)   # [B*Sk, 2*H*dp]
         else:
-            kv = engine.linear(context.reshape(B * Sk, Cc), P[("kv2", id(blk))])                                      # [B*Sk, 2*H*d]
+            kv = engine.linear(context.reshape(B * Sk, Cc), P[("kv2", id(blk))], rows_per_item=Sk)                                      # [B*Sk, 2*H*d]
         if len(self._ctx_cache) > 256:
             self._ctx_cache.clear()
         self._ctx_cache[key] = kv
@@ -389,28 +402,30 @@ class UNetModel(nn.Module):
             dp = head_pad(d)
             W3 = 3 * H * dp
             a = ops.layernorm(t, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps, out_dtype=odt)
-            qkv = engine.linear(a, P[("qkv1", id(blk))], out_dtype=odt, col_group=d, col_group_stride=dp)    # [B*S, 3*H*dp]
+            qkv = engine.linear(a, P[("qkv1", id(blk))], out_dtype=odt, col_group=d, col_group_stride=dp, rows_per_item=S,
+                                out=self._padbuf(B * S, W3, d, dp, t.device))                                  # [B*S, 3*H*dp]
             o = ops.attention_tc(qkv, qkv[:, H * dp:], qkv[:, 2 * H * dp:], B, H, S, S, d, dp, a1.scale,
                                  (S * W3, W3, dp), (S * W3, W3, dp), (S * W3, W3, dp))
-            t = engine.linear(o.reshape(B * S, Cc), P[("o1", id(blk))], residual=t)
+            t = engine.linear(o.reshape(B * S, Cc), P[("o1", id(blk))], residual=t, rows_per_item=S)
             a = ops.layernorm(t, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps, out_dtype=odt)
-            q = engine.linear(a, P[("q2", id(blk))], out_dtype=odt, col_group=d, col_group_stride=dp)        # [B*S, H*dp]
+            q = engine.linear(a, P[("q2", id(blk))], out_dtype=odt, col_group=d, col_group_stride=dp, rows_per_item=S,
+                              out=self._padbuf(B * S, H * dp, d, dp, t.device))                                # [B*S, H*dp]
             W2 = 2 * H * dp
             o = ops.attention_tc(q, kv, kv[:, H * dp:], B, H, S, Sk, d, dp, a2.scale,
                                  (S * H * dp, H * dp, dp), (Sk * W2, W2, dp), (Sk * W2, W2, dp))
-            t = engine.linear(o.reshape(B * S, Cc), P[("o2", id(blk))], residual=t)
+            t = engine.linear(o.reshape(B * S, Cc), P[("o2", id(blk))], residual=t, rows_per_item=S)
         else:
             a = ops.layernorm(t, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps, out_dtype=odt)
-            qkv = engine.linear(a, P[("qkv1", id(blk))])                                                     # [B*S, 3C]
+            qkv = engine.linear(a, P[("qkv1", id(blk))], rows_per_item=S)                                                     # [B*S, 3C]
             o = self._attn_fp32(qkv, 3 * Cc, 0, qkv, 3 * Cc, Cc, qkv, 3 * Cc, 2 * Cc, B, H, S, S, d, a1.scale)
-            t = engine.linear(o, P[("o1", id(blk))], residual=t)
+            t = engine.linear(o, P[("o1", id(blk))], residual=t, rows_per_item=S)
             a = ops.layernorm(t, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps, out_dtype=odt)
-            q = engine.linear(a, P[("q2", id(blk))])
+            q = engine.linear(a, P[("q2", id(blk))], rows_per_item=S)
             o = self._attn_fp32(q, Cc, 0, kv, 2 * Cc, 0, kv, 2 * Cc, Cc, B, H, S, Sk, d, a2.scale)
-            t = engine.linear(o, P[("o2", id(blk))], residual=t)
+            t = engine.linear(o, P[("o2", id(blk))], residual=t, rows_per_item=S)
         a = ops.layernorm(t, blk.norm3.weight, blk.norm3.bias, blk.norm3.eps, out_dtype=odt)
-        g = engine.linear(a, P[("ff1", id(blk))], out_dtype=odt)          # GEGLU fused (bf16) or gemm + geglu kernel (fp32)
-        t = engine.linear(g, P[("ff2", id(blk))], residual=t)
+        g = engine.linear(a, P[("ff1", id(blk))], out_dtype=odt, rows_per_item=S)          # GEGLU fused (bf16) or gemm + geglu kernel (fp32)
+        t = engine.linear(g, P[("ff2", id(blk))], residual=t, rows_per_item=S)
         return t
 
     @staticmethod

@@ -270,8 +270,21 @@ def gemm_simt(A, B, bias=None, residual=None, alpha=1.0, b_kn=False, out=None, o
 
 
 # ---- tcgen05 contraction -----------------------------------------------------------------------------
+def _tc_launch(a, what):
+    """Give the call its split-K workspace (if the plan splits) and enqueue it."""
+    lib = _L()
+    need = lib.sdb_tc_workspace_bytes(C.byref(a))
+    if need < 0:
+        check(-1, what)
+    ws = None
+    if need > 0:
+        ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+        a.ws, a.ws_bytes = ws.data_ptr(), need
+    check(lib.sdb_tc_contract(C.byref(a), stream_ptr()), what)
+
+
 def conv_tc(x, w_rskc, bias, kh, kw, stride=1, pad=0, rowvec=None, residual=None, out_dtype=torch.float32,
-            split_k=1, block_n=0, out=None, phase=None):
+            split_k=0, block_n=0, out=None, phase=None):
     """x [N,IH,IW,Cin] bf16, w [kh*kw,Cout,Cin] bf16 -> [N,OH,OW,Cout].
 
     phase=(sh, sw, oh, ow, OHF, OWF, pad_h, pad_w) writes this conv's OHxOW result into the strided
@@ -313,14 +326,12 @@ def conv_tc(x, w_rskc, bias, kh, kw, stride=1, pad=0, rowvec=None, residual=None
     a.cout_pad = Cout
     if residual is not None:
         assert residual.dtype == torch.float32 and residual.is_contiguous()
-    if split_k > 1:
-        out.zero_()
-    check(_L().sdb_tc_contract(C.byref(a), stream_ptr()), "tc conv")
+    _tc_launch(a, "tc conv")
     return out
 
 
 def gemm_tc(A, W, bias=None, residual=None, out_dtype=torch.float32, geglu=False, col_group=0, col_group_stride=0,
-            split_k=1, block_n=0, out=None, ldc=None, M=None, lda=None):
+            split_k=0, block_n=0, out=None, ldc=None, M=None, lda=None, rows_per_item=0):
     """out[M,N] = A[M,K] @ W[N,K]^T + bias + residual; A, W bf16 (K contiguous)."""
     require_cuda(A, W, bias, residual, out)
     assert A.dtype == torch.bfloat16 and W.dtype == torch.bfloat16 and W.is_contiguous()
@@ -351,9 +362,8 @@ def gemm_tc(A, W, bias=None, residual=None, out_dtype=torch.float32, geglu=False
     a.split_k = split_k
     a.block_n = block_n
     a.taps = 0
-    if split_k > 1:
-        out.zero_()
-    check(_L().sdb_tc_contract(C.byref(a), stream_ptr()), "tc gemm")
+    a.rows_per_item = int(rows_per_item)
+    _tc_launch(a, "tc gemm")
     return out
 
 
