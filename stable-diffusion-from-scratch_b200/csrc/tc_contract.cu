@@ -82,7 +82,8 @@ __device__ __forceinline__ float4 ldg_f4_or_zero(const float* p, bool pred) {
 // 32-column chunks ch0, ch0 + chstep, ... (two warps can share one lane quarter).
 template <int BN>
 __device__ __forceinline__ void epilogue_warp(const TcP& p, uint32_t taddr, const float* s_bias, float* stage, int lane,
-                                              int n0, int nt, long long row_pix, int row_img, int split, int ch0, int chstep) {
+                                              int n0, int nt, long long row_pix, int row_img, int split, int ch0, int chstep,
+                                              uint64_t* acc_ready, uint32_t acc_parity) {
     // rows this lane stores after the transpose: r_i = 4*i + (lane >> 3), i = 0..7
     long long rpix[8];
     int rimg[8];
@@ -108,29 +109,35 @@ __device__ __forceinline__ void epilogue_warp(const TcP& p, uint32_t taddr, cons
                         ((reinterpret_cast<uintptr_t>(p.out) | reinterpret_cast<uintptr_t>(p.residual) |
                           reinterpret_cast<uintptr_t>(p.rowvec)) & 15) == 0 &&
                         (!p.col_group || (p.col_group % 4 == 0 && p.col_group_stride % 4 == 0));
+    // residual / time-emb addends of a chunk, fetched one chunk ahead (the first one before the accumulator is even
+    // complete) so that their DRAM latency overlaps the MMA tail, the TMEM read and the previous chunk's stores
+    float4 addn[8];
+    auto fetch_addends = [&](int ch, float4 (&dst)[8]) {
+        const int cn_ = nb + ch * CH + cq;
+        const bool live = vec_ok && ch < NCHUNK && ch * CH < cols && cn_ < n_out;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const bool ok = live && rpix[i] >= 0;
+            dst[i] = ldg_f4_or_zero(resid + rpix[i] * p.ldr + cn_, ok && resid != nullptr);
+            if (rowv) {
+                float4 q = ldg_f4_or_zero(rowv + (long long)rimg[i] * p.ldv + cn_, ok);
+                dst[i].x += q.x; dst[i].y += q.y; dst[i].z += q.z; dst[i].w += q.w;
+            }
+        }
+    };
+    fetch_addends(ch0, addn);
+    mbar_wait(acc_ready, acc_parity);
+    tcgen05_fence_after();
 #pragma unroll 1
     for (int ch = ch0; ch < NCHUNK; ch += chstep) {
         const int c0 = ch * CH;
         if (c0 >= cols || nb + c0 >= n_out) break;                     // warp-uniform
         const int cn = nb + c0 + cq;                                    // first of this lane's 4 output columns
         const bool col_ok = cn < n_out;
-        // ---- issue the residual / time-emb loads first (fast path), they land while TMEM is read and transposed
         float4 addv[8];
-        if (vec_ok) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const bool ok = col_ok && rpix[i] >= 0;
-                addv[i] = ldg_f4_or_zero(resid + rpix[i] * p.ldr + cn, ok && resid != nullptr);
-            }
-            if (rowv) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const bool ok = col_ok && rpix[i] >= 0;
-                    float4 q = ldg_f4_or_zero(rowv + (long long)rimg[i] * p.ldv + cn, ok);
-                    addv[i].x += q.x; addv[i].y += q.y; addv[i].z += q.z; addv[i].w += q.w;
-                }
-            }
-        }
+        for (int i = 0; i < 8; ++i) addv[i] = addn[i];
+        fetch_addends(ch + chstep, addn);
         uint32_t r[32];
         tmem_ld_x32(taddr + c0, r);
         if (p.geglu) {
@@ -313,12 +320,10 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         } else {
             pix = (m0 + row) < p.M ? m0 + row : -1;
         }
-        mbar_wait(accum_bar, 0);
-        tcgen05_fence_after();
-        // every TMA load has been consumed by now: the A ring doubles as the transpose staging area
+        // once the accumulator is ready every TMA load has been consumed: the A ring doubles as the transpose staging area
         float* stage = reinterpret_cast<float*>(sA) + (warp - 2) * (EPI_WARP_BYTES / 4);
         const uint32_t taddr = tmem_d + ((uint32_t)(lg * 32) << 16);
-        epilogue_warp<BN>(p, taddr, s_bias, stage, lane, n0, nt, pix, img, split, 0, 1);
+        epilogue_warp<BN>(p, taddr, s_bias, stage, lane, n0, nt, pix, img, split, 0, 1, accum_bar, 0);
     }
 
     // ---- teardown ----
@@ -496,10 +501,8 @@ tc_contract_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             } else {
                 pix = (mt * TC_BM + row) < p.M ? (long long)mt * TC_BM + row : -1;
             }
-            mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
-            tcgen05_fence_after();
             const uint32_t taddr = tmem_d + ((uint32_t)(lg * 32) << 16) + buf * Cfg::ACC_STRIDE;
-            epilogue_warp<BN>(p, taddr, s_bias, stage, lane, n0, nt, pix, img, split, half, 2);
+            epilogue_warp<BN>(p, taddr, s_bias, stage, lane, n0, nt, pix, img, split, half, 2, &tfull_bar[buf], (it >> 1) & 1);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(buf ? tempty_leader1 : tempty_leader0);

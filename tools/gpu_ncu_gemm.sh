@@ -7,7 +7,5 @@ run() { # name args...
   ncu --set full --clock-control none --import-source on -k regex:tc_contract -s 2 -c 1 -f -o gpurun_out/$name python tools/one_gemm.py "$@" > gpurun_out/$name.ncu.log 2>&1
   echo "$name rc=$?"
 }
+run ncu_geglu_pair 32768 2560 320 0 1 1 0 1
 run ncu_smallk_pair 32768 320 320 1 0 1
-run ncu_smallk_single 32768 320 320 1 0 0
-run ncu_bigk_pair160 32768 320 2880 1 0 1
-run ncu_bigk_pair256 32768 1280 5760 0 0 1

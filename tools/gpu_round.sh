@@ -8,8 +8,8 @@ python tools/profile_unet.py --batch 8 > gpurun_out/prof_plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
     --log-file gpurun_out/launches_unet_b8.csv python tools/profile_unet.py --batch 8 > gpurun_out/prof_ncu.log 2>&1
 echo "ncu launches rc=$?"
-for k in tc_contract_kernel tc_attention_kernel gn_ layernorm_kernel; do
-  ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:$k -s 6 -c 3 -f \
+for k in tc_contract tc_attention_kernel gn_ layernorm_kernel; do
+  ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:$k -s 0 -c 3 -f \
       -o gpurun_out/full_$k python tools/profile_unet.py --batch 8 > gpurun_out/full_$k.log 2>&1
   echo "ncu full $k rc=$?"
 done
