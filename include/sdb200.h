@@ -53,11 +53,15 @@ int sdb_nhwc_to_nchw(const float* src, float* dst, int N, int C, int HW, void* s
  * torch.cat([h, hs.pop()], 1) feeding it (openai_model/model.py:586).
  *   x0 [N,HW,C0] fp32, x1 [N,HW,C1] fp32 or NULL (C1 = 0); C = C0 + C1, C % (4*groups)... see .cu
  *   out [N,HW,C] (out_dtype), ws: float/double scratch of sdb_groupnorm_ws_bytes() bytes.
+ *   raw_out: NULL, or [N,HW,C] bf16 receiving the un-normalised concat input as well (the operand
+ *   of the ResBlock's 1x1 skip_connection, openai_model/model.py:207-218,252) from the same read.
+ *   counters: >= N ints, ZERO on entry and left zero on exit (ticket of the CTA that folds the
+ *   per-chunk partial sums of a sample into its mean / rstd); one buffer per stream.
  *   act: 0 = none, 1 = SiLU.  exact != 0 uses expf (fp32 parity mode) instead of __expf. */
 long long sdb_groupnorm_ws_bytes(int N, int HW, int C, int groups);
 int sdb_groupnorm_nhwc(const float* x0, int C0, const float* x1, int C1, int N, int HW, int groups,
                        float eps, const float* gamma, const float* beta, int act, int exact,
-                       void* out, int out_dtype, void* ws, void* stream);
+                       void* out, int out_dtype, void* raw_out, void* ws, int* counters, void* stream);
 
 /* ---- LayerNorm over the last dim ---------------------------------------------------------------
  * Replaces nn.LayerNorm(dim) x3 per BasicTransformerBlock (openai_model/attention.py:216-218,
@@ -185,6 +189,9 @@ typedef struct sdb_tc_args {
     /* gemm mode: rows of A owned by ONE independent sample (tokens per image), 0 = unknown.  Only used so
      * that the automatic split-K choice does not depend on the batch size (batch-invariant bit patterns). */
     int rows_per_item;
+    /* kernel variant: 0 = library default (see sdb_tc_set_pair_kernel), 1 = one-CTA 128 x BN kernel,
+     * 2 = CTA-pair persistent 256 x BN kernel (block_n >= 128).  Same results up to summation order. */
+    int variant;
 } sdb_tc_args;
 /* bytes of workspace sdb_tc_contract may use for these args (0 = none; -1 = invalid args).  With
  * split_k == 0 this is what the library's automatic split choice needs. */

@@ -55,6 +55,7 @@ class TcArgs(C.Structure):
         ("out_sh", C.c_int), ("out_sw", C.c_int), ("out_oh", C.c_int), ("out_ow", C.c_int), ("OHF", C.c_int), ("OWF", C.c_int),
         ("ws", C.c_void_p), ("ws_bytes", C.c_longlong),
         ("rows_per_item", C.c_int),
+        ("variant", C.c_int),
     ]
 
 
@@ -80,7 +81,7 @@ SIGNATURES = {
     "sdb_nchw_to_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "sdb_nhwc_to_nchw": (_I, [_P, _P, _I, _I, _I, _P]),
     "sdb_groupnorm_ws_bytes": (_L, [_I, _I, _I, _I]),
-    "sdb_groupnorm_nhwc": (_I, [_P, _I, _P, _I, _I, _I, _I, _F, _P, _P, _I, _I, _P, _I, _P, _P]),
+    "sdb_groupnorm_nhwc": (_I, [_P, _I, _P, _I, _I, _I, _I, _F, _P, _P, _I, _I, _P, _I, _P, _P, _P, _P]),
     "sdb_layernorm": (_I, [_P, _I, _I, _F, _P, _P, _P, _I, _P]),
     "sdb_cast_concat": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _P, _I, _P]),
     "sdb_upsample_bilinear2x": (_I, [_P, _I, _I, _I, _I, _P, _I, _P]),

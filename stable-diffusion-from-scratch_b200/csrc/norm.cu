@@ -42,13 +42,17 @@ static GnGeom gn_geom(int N, int HW, int C) {
     return g;
 }
 
-// Pass 1: per-(sample, chunk, group) partial sum / sum of squares.
+// Pass 1: per-(sample, chunk, group) partial sum / sum of squares, then the LAST CTA of a sample to finish
+// (atomic ticket on `counters[n]`, which it leaves at zero again) combines the chunk partials of that
+// sample in a fixed order into (mean, rstd) per group: no separate finalize launch, bit-reproducible.
 // Thread t owns vector column v = t % V for rows rr, rr+R, ...: per-channel fp32 partials in
 // registers, reduced over R in smem, then per-group in fp64.
 __global__ void gn_stats_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1,
                                 int HW, int groups, int V, int R, int rows_per_chunk,
-                                double* __restrict__ partial) {
-    extern __shared__ float red[];   // [2][R][C]
+                                double* __restrict__ partial, int* __restrict__ counters, double count, float eps,
+                                float2* __restrict__ stats) {
+    extern __shared__ float red[];   // [2][R][C] floats; reused as [slots][groups] double2 by the finalizing CTA
+    __shared__ int s_last;
     const int C = C0 + C1;
     const int n = blockIdx.y, chunk = blockIdx.x;
     const int v = threadIdx.x % V, rr = threadIdx.x / V;
@@ -62,7 +66,7 @@ __global__ void gn_stats_kernel(const float* __restrict__ x0, int C0, const floa
     if (row1 > HW) row1 = HW;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
     const float* p = src + ((long long)n * HW) * ld + cc;
-#pragma unroll 4
+#pragma unroll 8
     for (int row = row0 + rr; row < row1; row += R) {
         float4 a = __ldg(reinterpret_cast<const float4*>(p + (long long)row * ld));
         s0 += a.x; s1 += a.y; s2 += a.z; s3 += a.w;
@@ -74,6 +78,7 @@ __global__ void gn_stats_kernel(const float* __restrict__ x0, int C0, const floa
     rq[0] = q0; rq[1] = q1; rq[2] = q2; rq[3] = q3;
     __syncthreads();
     const int cpg = C / groups;
+    const int chunks = gridDim.x;
     for (int g = threadIdx.x; g < groups; g += blockDim.x) {
         double S = 0.0, Q = 0.0;
         for (int r = 0; r < R; ++r) {
@@ -81,44 +86,52 @@ __global__ void gn_stats_kernel(const float* __restrict__ x0, int C0, const floa
             const float* b = red + (long long)R * C + (long long)r * C + g * cpg;
             for (int j = 0; j < cpg; ++j) { S += (double)a[j]; Q += (double)b[j]; }
         }
-        double* o = partial + (((long long)n * gridDim.x + chunk) * groups + g) * 2;
+        double* o = partial + (((long long)n * chunks + chunk) * groups + g) * 2;
         o[0] = S; o[1] = Q;
     }
-}
-
-// Pass 2: combine chunk partials -> (mean, rstd) per (sample, group): one warp per (n, g), lanes stride
-// over the chunks, fixed-order fp64 shuffle reduction (deterministic).
-__global__ void gn_finalize_kernel(const double* __restrict__ partial, int chunks, int groups, int total, double count,
-                                   float eps, float2* __restrict__ stats) {
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (w >= total) return;
-    const int n = w / groups, g = w - n * groups;
-    double S = 0.0, Q = 0.0;
-    for (int ch = lane; ch < chunks; ch += 32) {
-        const double* p = partial + (((long long)n * chunks + ch) * groups + g) * 2;
-        S += p[0]; Q += p[1];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&counters[n], 1) == chunks - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // ---- finalize sample n: slot-strided fp64 sums over the chunks, then a fixed-order sum over the slots ----
+    double2* dred = reinterpret_cast<double2*>(red);
+    int nslots = (int)blockDim.x / groups;
+    if (nslots < 1) nslots = 1;
+    if (nslots > chunks) nslots = chunks;
+    for (int item = threadIdx.x; item < groups * nslots; item += blockDim.x) {
+        const int g = item % groups, slot = item / groups;
+        double S = 0.0, Q = 0.0;
+        for (int ch = slot; ch < chunks; ch += nslots) {
+            const double* q = partial + (((long long)n * chunks + ch) * groups + g) * 2;
+            S += __ldcg(q); Q += __ldcg(q + 1);
+        }
+        dred[item] = make_double2(S, Q);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        S += __shfl_xor_sync(0xffffffffu, S, o);
-        Q += __shfl_xor_sync(0xffffffffu, Q, o);
-    }
-    if (lane == 0) {
+    __syncthreads();
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        double S = 0.0, Q = 0.0;
+        for (int slot = 0; slot < nslots; ++slot) { double2 t = dred[slot * groups + g]; S += t.x; Q += t.y; }
         double mean = S / count;
         double var = Q / count - mean * mean;
         if (var < 0.0) var = 0.0;
         double rstd = 1.0 / sqrt(var + (double)eps);
-        stats[w] = make_float2((float)mean, (float)rstd);
+        stats[n * groups + g] = make_float2((float)mean, (float)rstd);
     }
+    if (threadIdx.x == 0) counters[n] = 0;
 }
 
-// Pass 3: normalise + affine (+ SiLU), emit bf16 (tensor-core operand) or fp32.
-template <bool OUT_BF16, bool EXACT>
+// Pass 2: normalise + affine (+ SiLU), emit bf16 (tensor-core operand) or fp32; optionally also the raw
+// (un-normalised) bf16 copy of the concatenated input, which is the operand of a ResBlock's 1x1 skip conv.
+// A thread's <= 8 rows are fetched before the statistics / affine parameters are, so the CTA pays one
+// memory round trip, not two.
+template <bool OUT_BF16, bool EXACT, bool RAW>
 __global__ void gn_apply_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1,
                                 int HW, int groups, int V, int R, int rows_per_chunk,
                                 const float2* __restrict__ stats, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, int act, void* __restrict__ out) {
+                                const float* __restrict__ beta, int act, void* __restrict__ out,
+                                __nv_bfloat16* __restrict__ raw_out) {
     const int C = C0 + C1;
     const int n = blockIdx.y, chunk = blockIdx.x;
     const int v = threadIdx.x % V, rr = threadIdx.x / V;
@@ -128,23 +141,35 @@ __global__ void gn_apply_kernel(const float* __restrict__ x0, int C0, const floa
     int cc;
     if (c < C0) { src = x0; ld = C0; cc = c; } else { src = x1; ld = C1; cc = c - C0; }
     const int cpg = C / groups;
-    float sc[4], sh[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        float2 st = stats[n * groups + (c + j) / cpg];
-        float g = gamma[c + j], b = beta[c + j];
-        sc[j] = st.y * g;
-        sh[j] = b - st.x * st.y * g;
-    }
     const int row0 = chunk * rows_per_chunk;
     int row1 = row0 + rows_per_chunk;
     if (row1 > HW) row1 = HW;
     const float* p = src + ((long long)n * HW) * ld + cc;
-#pragma unroll 4
-    for (int row = row0 + rr; row < row1; row += R) {
-        float4 a = ld_stream_f4(p + (long long)row * ld);
-        float y0 = fmaf(a.x, sc[0], sh[0]), y1 = fmaf(a.y, sc[1], sh[1]);
-        float y2 = fmaf(a.z, sc[2], sh[2]), y3 = fmaf(a.w, sc[3], sh[3]);
+    constexpr int MAXR = 8;          // gn_geom: rows_per_chunk <= 8 * R
+    float4 a[MAXR];
+#pragma unroll
+    for (int i = 0; i < MAXR; ++i) {
+        const int row = row0 + rr + i * R;
+        if (row < row1) a[i] = ld_stream_f4(p + (long long)row * ld);
+    }
+    float sc[4], sh[4];
+    {
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + c));
+        const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 st = __ldcg(stats + n * groups + (c + j) / cpg);
+            sc[j] = st.y * gg[j];
+            sh[j] = bb[j] - st.x * st.y * gg[j];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < MAXR; ++i) {
+        const int row = row0 + rr + i * R;
+        if (row >= row1) continue;
+        float y0 = fmaf(a[i].x, sc[0], sh[0]), y1 = fmaf(a[i].y, sc[1], sh[1]);
+        float y2 = fmaf(a[i].z, sc[2], sh[2]), y3 = fmaf(a[i].w, sc[3], sh[3]);
         if (act == 1) {
             if (EXACT) { y0 = silu_exact(y0); y1 = silu_exact(y1); y2 = silu_exact(y2); y3 = silu_exact(y3); }
             else       { y0 = silu_f(y0);     y1 = silu_f(y1);     y2 = silu_f(y2);     y3 = silu_f(y3); }
@@ -155,6 +180,7 @@ __global__ void gn_apply_kernel(const float* __restrict__ x0, int C0, const floa
         } else {
             st_stream_f4(reinterpret_cast<float*>(out) + o, make_float4(y0, y1, y2, y3));
         }
+        if (RAW) st_stream_u2(raw_out + o, pack_bf16x2(a[i].x, a[i].y), pack_bf16x2(a[i].z, a[i].w));
     }
 }
 
@@ -226,15 +252,16 @@ long long sdb_groupnorm_ws_bytes(int N, int HW, int C, int groups) {
 
 int sdb_groupnorm_nhwc(const float* x0, int C0, const float* x1, int C1, int N, int HW, int groups,
                        float eps, const float* gamma, const float* beta, int act, int exact,
-                       void* out, int out_dtype, void* ws, void* stream) {
+                       void* out, int out_dtype, void* raw_out, void* ws, int* counters, void* stream) {
     const int C = C0 + C1;
-    SDB_REQUIRE(x0 && out && ws && gamma && beta, "groupnorm: null pointer");
+    SDB_REQUIRE(x0 && out && ws && gamma && beta && counters, "groupnorm: null pointer");
     SDB_REQUIRE(N > 0 && HW > 0 && C > 0, "groupnorm: empty tensor N=%d HW=%d C=%d", N, HW, C);
     SDB_REQUIRE(C0 % 4 == 0 && C1 % 4 == 0, "groupnorm: C0=%d C1=%d must be multiples of 4", C0, C1);
     SDB_REQUIRE((C1 == 0) == (x1 == nullptr), "groupnorm: x1/C1 mismatch");
     SDB_REQUIRE(groups > 0 && C % groups == 0, "groupnorm: C=%d not divisible by groups=%d", C, groups);
     SDB_REQUIRE(C / 4 <= 1024, "groupnorm: C=%d too wide", C);
     SDB_REQUIRE(out_dtype == SDB_F32 || out_dtype == SDB_BF16, "groupnorm: bad out_dtype");
+    SDB_REQUIRE((((uintptr_t)gamma | (uintptr_t)beta) & 15) == 0, "groupnorm: gamma/beta must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     GnGeom g = gn_geom(N, HW, C);
     double* partial = reinterpret_cast<double*>(ws);
@@ -242,21 +269,25 @@ int sdb_groupnorm_nhwc(const float* x0, int C0, const float* x1, int C1, int N, 
                                               (long long)N * g.chunks * groups * 2 * sizeof(double));
     dim3 grid(g.chunks, N);
     size_t smem = (size_t)2 * g.R * C * sizeof(float);
+    if (smem < (size_t)groups * sizeof(double2)) smem = (size_t)groups * sizeof(double2);
     if (smem > 48 * 1024) {
         cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
-    gn_stats_kernel<<<grid, g.threads, smem, st>>>(x0, C0, x1, C1, HW, groups, g.V, g.R, g.rows_per_chunk, partial);
+    gn_stats_kernel<<<grid, g.threads, smem, st>>>(x0, C0, x1, C1, HW, groups, g.V, g.R, g.rows_per_chunk, partial,
+                                                   counters, (double)HW * (C / groups), eps, stats);
     int rc = check_launch("gn_stats_kernel");
     if (rc) return rc;
-    gn_finalize_kernel<<<ceil_div(N * groups, 8), 256, 0, st>>>(partial, g.chunks, groups, N * groups,
-                                                              (double)HW * (C / groups), eps, stats);
-    rc = check_launch("gn_finalize_kernel");
-    if (rc) return rc;
-#define LAUNCH_APPLY(BF, EX)                                                                             \
-    gn_apply_kernel<BF, EX><<<grid, g.threads, 0, st>>>(x0, C0, x1, C1, HW, groups, g.V, g.R,          \
-                                                         g.rows_per_chunk, stats, gamma, beta, act, out)
-    if (out_dtype == SDB_BF16) { if (exact) LAUNCH_APPLY(true, true); else LAUNCH_APPLY(true, false); }
-    else                       { if (exact) LAUNCH_APPLY(false, true); else LAUNCH_APPLY(false, false); }
+    __nv_bfloat16* raw = reinterpret_cast<__nv_bfloat16*>(raw_out);
+#define LAUNCH_APPLY(BF, EX, RW)                                                                         \
+    gn_apply_kernel<BF, EX, RW><<<grid, g.threads, 0, st>>>(x0, C0, x1, C1, HW, groups, g.V, g.R,      \
+                                                             g.rows_per_chunk, stats, gamma, beta, act, out, raw)
+    if (raw) {
+        if (out_dtype == SDB_BF16) { if (exact) LAUNCH_APPLY(true, true, true); else LAUNCH_APPLY(true, false, true); }
+        else                       { if (exact) LAUNCH_APPLY(false, true, true); else LAUNCH_APPLY(false, false, true); }
+    } else {
+        if (out_dtype == SDB_BF16) { if (exact) LAUNCH_APPLY(true, true, false); else LAUNCH_APPLY(true, false, false); }
+        else                       { if (exact) LAUNCH_APPLY(false, true, false); else LAUNCH_APPLY(false, false, false); }
+    }
 #undef LAUNCH_APPLY
     return check_launch("gn_apply_kernel");
 }

@@ -679,11 +679,13 @@ static int make_plan(const sdb_tc_args* a, TcPlan* pl) {
     pl->taps = conv ? a->taps : 1;
     pl->Kt = conv ? a->Cin : a->K;                        // contraction length per tap
     SDB_REQUIRE(pl->Kt % 8 == 0, "tc_contract: K per tap (%d) must be a multiple of 8", pl->Kt);
+    SDB_REQUIRE(a->variant >= 0 && a->variant <= 2, "tc_contract: variant %d unknown", a->variant);
+    const bool want_pair = a->variant ? a->variant == 2 : pair_kernel_enabled();
     int bn = a->block_n;
     if (bn == 0) {
         if (a->N <= 32) bn = 32;
         else if (a->N <= 64) bn = 64;
-        else if (pair_kernel_enabled()) {
+        else if (want_pair) {
             // CTA-pair kernel: widest tile that divides N (bytes pulled from L2 per FLOP fall with BN)
             if (a->N % 256 == 0) bn = 256;
             else if (a->N % 160 == 0) bn = 160;
@@ -696,7 +698,7 @@ static int make_plan(const sdb_tc_args* a, TcPlan* pl) {
     SDB_REQUIRE(bn == 32 || bn == 64 || bn == 128 || bn == 160 || bn == 256, "tc_contract: block_n %d unsupported", bn);
     if (a->geglu) SDB_REQUIRE(a->N % bn == 0 && (bn / 2) % 32 == 0 && !conv, "tc_contract: geglu needs N %% block_n == 0, block_n %% 64 == 0");
     pl->bn = bn;
-    pl->use_pair = pair_kernel_enabled() && bn >= 128;
+    pl->use_pair = want_pair && bn >= 128;
     pl->kpt = ceil_div(pl->Kt, TC_BK);
     pl->kblocks = pl->taps * pl->kpt;
     pl->tiles_n = ceil_div(a->N, bn);

@@ -345,22 +345,27 @@ class UNetModel(nn.Module):
 
     # ---- building blocks (all tensors NHWC / [rows, C]) ---------------------------------------------
     @staticmethod
-    def _gn(norm, x, mode, act, x1=None, out_dtype=None):
+    def _gn(norm, x, mode, act, x1=None, out_dtype=None, want_raw=False):
         dt = out_dtype if out_dtype is not None else engine.op_dtype(mode)
         return ops.groupnorm(x, norm.weight, norm.bias, norm.eps, act=act, out_dtype=dt, x1=x1,
-                             groups=norm.num_groups, exact=(mode == "fp32"))
+                             groups=norm.num_groups, exact=(mode == "fp32"), want_raw=want_raw)
 
     def _res(self, rb, P, mode, x, x1, emb_all):
         """ResBlock._forward (openai_model/model.py:232-252); x1 = skip tensor to be channel-concatenated."""
         c1, c2 = P[("c1", id(rb))], P[("c2", id(rb))]
         off, n = P[("emb_off", id(rb))]
         rowvec = emb_all[:, off:off + n]
-        h = self._gn(rb.in_layers[0], x, mode, 1, x1=x1, out_dtype=c1.in_dtype)
+        sk = P.get(("skip", id(rb)))
+        raw = None
+        if sk is not None and sk.in_dtype == torch.bfloat16:
+            # the 1x1 skip conv's bf16 operand (the raw concat) comes out of the same pass as the normalised one
+            h, raw = self._gn(rb.in_layers[0], x, mode, 1, x1=x1, out_dtype=c1.in_dtype, want_raw=True)
+        else:
+            h = self._gn(rb.in_layers[0], x, mode, 1, x1=x1, out_dtype=c1.in_dtype)
         h = engine.conv(h, c1, rowvec=rowvec)                       # conv + bias + emb_out[..., None, None]
         h = self._gn(rb.out_layers[0], h, mode, 1, out_dtype=c2.in_dtype)
-        if ("skip", id(rb)) in P:
-            sk = P[("skip", id(rb))]
-            xs = ops.cast_concat(x, x1, up=1, out_dtype=sk.in_dtype)
+        if sk is not None:
+            xs = raw if raw is not None else ops.cast_concat(x, x1, up=1, out_dtype=sk.in_dtype)
             xs = engine.conv(xs, sk)
         else:
             assert x1 is None
@@ -390,7 +395,7 @@ class UNetModel(nn.Module):
         self._ctx_cache[key] = kv
         return kv
 
-    def _tblock(self, blk, P, mode, t, B, S, context):
+    def _tblock(self, blk, P, mode, t, B, S, context, final_dtype=torch.float32):
         """BasicTransformerBlock._forward (openai_model/attention.py:233-257) on tokens t [B*S, C] fp32."""
         a1, a2 = blk.attn1, blk.attn2
         H, d = a1.heads, a1.dim_head
@@ -425,7 +430,8 @@ class UNetModel(nn.Module):
             t = engine.linear(o, P[("o2", id(blk))], residual=t, rows_per_item=S)
         a = ops.layernorm(t, blk.norm3.weight, blk.norm3.bias, blk.norm3.eps, out_dtype=odt)
         g = engine.linear(a, P[("ff1", id(blk))], out_dtype=odt, rows_per_item=S)          # GEGLU fused (bf16) or gemm + geglu kernel (fp32)
-        t = engine.linear(g, P[("ff2", id(blk))], residual=t, rows_per_item=S)
+        # `final_dtype` bf16: the block's result only feeds proj_out's tensor-core operand, so it is rounded here
+        t = engine.linear(g, P[("ff2", id(blk))], residual=t, rows_per_item=S, out_dtype=final_dtype)
         return t
 
     @staticmethod
@@ -451,12 +457,14 @@ class UNetModel(nn.Module):
         pin, pout = P[("pin", id(st))], P[("pout", id(st))]
         xn = self._gn(st.norm, x, mode, 0, out_dtype=pin.in_dtype)
         t = engine.conv(xn, pin).reshape(B * Hh * Ww, -1)
-        for blk in st.transformer_blocks:
-            t = self._tblock(blk, P, mode, t, B, Hh * Ww, context)
+        nblk = len(st.transformer_blocks)
+        for i, blk in enumerate(st.transformer_blocks):
+            t = self._tblock(blk, P, mode, t, B, Hh * Ww, context,
+                             final_dtype=pout.in_dtype if i == nblk - 1 else torch.float32)
         inner = t.shape[-1]
         tt = t.reshape(B, Hh, Ww, inner)
-        if pout.in_dtype == torch.bfloat16:
-            tt = ops.cast_concat(tt, None, out_dtype=torch.bfloat16)
+        if tt.dtype != pout.in_dtype:
+            tt = ops.cast_concat(tt, None, out_dtype=pout.in_dtype)
         return engine.conv(tt, pout, residual=x)
 
     def _run_block(self, seq, P, mode, h, x1, emb_all, context):

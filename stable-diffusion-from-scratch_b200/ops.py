@@ -37,8 +37,23 @@ def nhwc_to_nchw(x):
 
 
 # ---- normalisation ----------------------------------------------------------------------------------
-def groupnorm(x0, gamma, beta, eps, act=0, out_dtype=torch.float32, x1=None, groups=32, exact=False):
-    """GroupNorm(groups) over the channel-concat of x0 (and x1) [N,H,W,C*], optional SiLU."""
+_gn_counters = {}
+
+
+def _gn_ticket_buffer(dev, n):
+    """Persistent zeroed ticket counters (one int per sample) for the GroupNorm statistics kernel; the kernel
+    leaves them zero again, so one buffer per (device, stream) serves every call."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    buf = _gn_counters.get(key)
+    if buf is None or buf.numel() < n:
+        buf = torch.zeros(max(n, 1024), dtype=torch.int32, device=dev)
+        _gn_counters[key] = buf
+    return buf
+
+
+def groupnorm(x0, gamma, beta, eps, act=0, out_dtype=torch.float32, x1=None, groups=32, exact=False, want_raw=False):
+    """GroupNorm(groups) over the channel-concat of x0 (and x1) [N,H,W,C*], optional SiLU.
+    want_raw=True also returns the un-normalised bf16 concat (written by the same pass)."""
     require_cuda(x0, x1, gamma, beta)
     assert x0.dtype == torch.float32 and x0.is_contiguous()
     N, H, W, C0 = x0.shape
@@ -53,10 +68,12 @@ def groupnorm(x0, gamma, beta, eps, act=0, out_dtype=torch.float32, x1=None, gro
         raise _lib.SdbError("groupnorm: unsupported shape N=%d HW=%d C=%d" % (N, H * W, Ct))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x0.device)
     out = torch.empty((N, H, W, Ct), dtype=out_dtype, device=x0.device)
+    raw = torch.empty((N, H, W, Ct), dtype=torch.bfloat16, device=x0.device) if want_raw else None
     check(lib.sdb_groupnorm_nhwc(ptr(x0), C0, ptr(x1), C1, N, H * W, groups, float(eps), ptr(gamma), ptr(beta),
-                                 int(act), int(bool(exact)), ptr(out), dtype_code(out_dtype), ptr(ws), stream_ptr()),
+                                 int(act), int(bool(exact)), ptr(out), dtype_code(out_dtype), ptr(raw), ptr(ws),
+                                 ptr(_gn_ticket_buffer(x0.device, N)), stream_ptr()),
           "groupnorm")
-    return out
+    return (out, raw) if want_raw else out
 
 
 def layernorm(x, gamma, beta, eps=1e-5, out_dtype=torch.float32):
@@ -284,7 +301,7 @@ def _tc_launch(a, what):
 
 
 def conv_tc(x, w_rskc, bias, kh, kw, stride=1, pad=0, rowvec=None, residual=None, out_dtype=torch.float32,
-            split_k=0, block_n=0, out=None, phase=None):
+            split_k=0, block_n=0, out=None, phase=None, variant=0):
     """x [N,IH,IW,Cin] bf16, w [kh*kw,Cout,Cin] bf16 -> [N,OH,OW,Cout].
 
     phase=(sh, sw, oh, ow, OHF, OWF, pad_h, pad_w) writes this conv's OHxOW result into the strided
@@ -321,6 +338,7 @@ def conv_tc(x, w_rskc, bias, kh, kw, stride=1, pad=0, rowvec=None, residual=None
     a.col_group = a.col_group_stride = 0
     a.split_k = split_k
     a.block_n = block_n
+    a.variant = variant
     a.taps, a.kw, a.stride, a.pad_h, a.pad_w = taps, kw, stride, pad_h, pad_w
     a.NB, a.IH, a.IW, a.Cin, a.OH, a.OW = N, IH, IW, Cin, OH, OW
     a.cout_pad = Cout
@@ -331,7 +349,7 @@ def conv_tc(x, w_rskc, bias, kh, kw, stride=1, pad=0, rowvec=None, residual=None
 
 
 def gemm_tc(A, W, bias=None, residual=None, out_dtype=torch.float32, geglu=False, col_group=0, col_group_stride=0,
-            split_k=0, block_n=0, out=None, ldc=None, M=None, lda=None, rows_per_item=0):
+            split_k=0, block_n=0, out=None, ldc=None, M=None, lda=None, rows_per_item=0, variant=0):
     """out[M,N] = A[M,K] @ W[N,K]^T + bias + residual; A, W bf16 (K contiguous)."""
     require_cuda(A, W, bias, residual, out)
     assert A.dtype == torch.bfloat16 and W.dtype == torch.bfloat16 and W.is_contiguous()
@@ -361,6 +379,7 @@ def gemm_tc(A, W, bias=None, residual=None, out_dtype=torch.float32, geglu=False
     a.col_group, a.col_group_stride = col_group, col_group_stride
     a.split_k = split_k
     a.block_n = block_n
+    a.variant = variant
     a.taps = 0
     a.rows_per_item = int(rows_per_item)
     _tc_launch(a, "tc gemm")
