@@ -1,6 +1,7 @@
 // sdb200 — library-level entry points: version, error string, launch counter.
 #include "common.cuh"
 #include <stdarg.h>
+#include <stdlib.h>
 #include <atomic>
 
 namespace sdb {
@@ -13,6 +14,15 @@ void set_last_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("SDB200_PDL");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
 }
 
 int check_launch(const char* what) {

@@ -21,10 +21,50 @@ int  check_launch(const char* what);   // cudaGetLastError -> sdb code
         }                                                        \
     } while (0)
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------
+// Every kernel of the library is launched with programmatic stream serialization: it may become resident
+// while its predecessor in the stream is still draining, runs its private prologue (barrier init, TMEM
+// allocation, descriptor prefetch) and then blocks in pdl_wait() until the predecessor has completed and
+// its writes are visible.  Rules every kernel follows: pdl_trigger() first (lets the successor in), no
+// global-memory access before pdl_wait(), and pdl_wait() is executed by every thread that touches memory.
+// SDB200_PDL=0 turns the launch attribute off (the device-side instructions are then no-ops).
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface through check_launch()
+}
+
+// same, for a kernel launched as thread-block clusters of `cluster_x` CTAs along x (runtime cluster size)
+template <typename... KArgs, typename... Args>
+static inline void launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
+                                      Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster_x; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 
 // ---- device helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 // exact variants for the fp32 parity mode (expf, not the fast intrinsic)
 __device__ __forceinline__ float silu_exact(float x) { return x / (1.0f + expf(-x)); }

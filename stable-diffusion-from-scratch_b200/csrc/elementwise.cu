@@ -7,6 +7,8 @@ namespace sdb {
 // ---- NCHW <-> NHWC (32x32 smem tile transpose, padded against bank conflicts) -------------------
 template <bool OUT_BF16>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, void* __restrict__ dst, int C, int HW) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float tile[32][33];
     const int n = blockIdx.z;
     const int hw0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -28,6 +30,8 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, void* __restr
 }
 
 __global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int HW) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float tile[32][33];
     const int n = blockIdx.z;
     const int hw0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -49,6 +53,8 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, float* __rest
 template <bool OUT_BF16>
 __global__ void cast_concat_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1,
                                    int H, int W, int up, long long total_vec, void* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     const int C = C0 + C1, V = C >> 2;
     const int OW = W * up;
     const long long OHW = (long long)H * up * OW;
@@ -71,6 +77,8 @@ __global__ void cast_concat_kernel(const float* __restrict__ x0, int C0, const f
 
 template <bool OUT_BF16>
 __global__ void activation_kernel(const float* __restrict__ x, void* __restrict__ out, long long n, int act) {
+    pdl_trigger();
+    pdl_wait();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float v = x[i];
         if (act == 1) v = silu_exact(v);
@@ -82,6 +90,8 @@ __global__ void activation_kernel(const float* __restrict__ x, void* __restrict_
 
 template <bool OUT_BF16>
 __global__ void geglu_kernel(const float* __restrict__ h, int rows, int inner, void* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     const long long total = (long long)rows * inner;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         long long r = i / inner;
@@ -97,6 +107,8 @@ __global__ void geglu_kernel(const float* __restrict__ h, int rows, int inner, v
 template <bool OUT_BF16>
 __global__ void add_rowvec_kernel(const float* __restrict__ x, const float* __restrict__ rv, long long ldv,
                                   long long HW, int C, long long total_vec, void* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     const int V = C >> 2;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
         int v = (int)(i % V);
@@ -110,6 +122,8 @@ __global__ void add_rowvec_kernel(const float* __restrict__ x, const float* __re
 }
 
 __global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long long n) {
+    pdl_trigger();
+    pdl_wait();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         out[i] = a[i] + b[i];
 }
@@ -118,6 +132,8 @@ __global__ void add_kernel(const float* __restrict__ a, const float* __restrict_
 template <bool OUT_BF16>
 __global__ void softmax_rows_kernel(const float* __restrict__ s, int L, long long lds, float scale,
                                     void* __restrict__ out, long long ldo) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float red[32];
     const long long row = blockIdx.x;
     const float* p = s + row * lds;
@@ -156,6 +172,8 @@ __global__ void softmax_rows_kernel(const float* __restrict__ s, int L, long lon
 // ---- timestep embedding (reference openai_model/utils.py:225-245): [cos | sin] ------------------
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, const float* __restrict__ freqs,
                                           int B, int half, int round_fp16, float* __restrict__ emb) {
+    pdl_trigger();
+    pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * half) return;
     int b = i / half, j = i % half;
@@ -168,6 +186,8 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, const flo
 
 __global__ void gather_rows_kernel(const float* __restrict__ table, const long long* __restrict__ idx,
                                    int B, int dim, float* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * dim) return;
     int b = i / dim, j = i % dim;
@@ -179,6 +199,8 @@ template <int MT>
 __global__ void skinny_linear_kernel(const float* __restrict__ x, int M, int K, const float* __restrict__ W,
                                      const float* __restrict__ bias, int N, int act_in, int act_out,
                                      float* __restrict__ y) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float xs[];   // [M][K] activated input
     for (int i = threadIdx.x; i < M * K; i += blockDim.x) {
         float v = x[i];
@@ -226,6 +248,8 @@ __global__ void ddim_step_kernel(const float* __restrict__ x, const float* __res
                                  float sqrt_at, float sqrt_aprev, float dir_coef, float sigma_t,
                                  float sqrt_one_minus_at, float temperature,
                                  float* __restrict__ x_prev, float* __restrict__ pred_x0, long long n) {
+    pdl_trigger();
+    pdl_wait();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float e = e_c[i];
         if (e_u) {
@@ -247,6 +271,8 @@ __global__ void ddim_step_kernel(const float* __restrict__ x, const float* __res
 template <bool OUT_BF16>
 __global__ void upsample_bilinear2x_kernel(const float* __restrict__ x, int H, int W, int C, long long total_vec,
                                            void* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     const int OH = 2 * H, OW = 2 * W, V = C >> 2;
     // PyTorch's area_pixel_compute_scale for align_corners=True: (in - 1) / (out - 1), 0 when out == 1
     const float sh = OH > 1 ? (float)(H - 1) / (float)(OH - 1) : 0.f;
@@ -295,15 +321,15 @@ extern "C" {
 int sdb_nchw_to_nhwc(const float* src, void* dst, int dst_dtype, int N, int C, int HW, void* stream) {
     SDB_REQUIRE(src && dst && N > 0 && C > 0 && HW > 0, "nchw_to_nhwc: bad args");
     dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), N), block(32, 8);
-    if (dst_dtype == SDB_BF16) nchw_to_nhwc_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(src, dst, C, HW);
-    else nchw_to_nhwc_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(src, dst, C, HW);
+    if (dst_dtype == SDB_BF16) launch_pdl(nchw_to_nhwc_kernel<true>, dim3(grid), dim3(block), 0, (cudaStream_t)stream, src, dst, C, HW);
+    else launch_pdl(nchw_to_nhwc_kernel<false>, dim3(grid), dim3(block), 0, (cudaStream_t)stream, src, dst, C, HW);
     return check_launch("nchw_to_nhwc_kernel");
 }
 
 int sdb_nhwc_to_nchw(const float* src, float* dst, int N, int C, int HW, void* stream) {
     SDB_REQUIRE(src && dst && N > 0 && C > 0 && HW > 0, "nhwc_to_nchw: bad args");
     dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), N), block(32, 8);
-    nhwc_to_nchw_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, dst, C, HW);
+    launch_pdl(nhwc_to_nchw_kernel, dim3(grid), dim3(block), 0, (cudaStream_t)stream, src, dst, C, HW);
     return check_launch("nhwc_to_nchw_kernel");
 }
 
@@ -314,8 +340,8 @@ int sdb_cast_concat(const float* x0, int C0, const float* x1, int C1, int N, int
     SDB_REQUIRE(up == 1 || up == 2, "cast_concat: up must be 1 or 2");
     long long total = (long long)N * H * up * W * up * ((C0 + C1) / 4);
     int threads = 256, blocks = grid_for(total, threads);
-    if (out_dtype == SDB_BF16) cast_concat_kernel<true><<<blocks, threads, 0, (cudaStream_t)stream>>>(x0, C0, x1, C1, H, W, up, total, out);
-    else cast_concat_kernel<false><<<blocks, threads, 0, (cudaStream_t)stream>>>(x0, C0, x1, C1, H, W, up, total, out);
+    if (out_dtype == SDB_BF16) launch_pdl(cast_concat_kernel<true>, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, x0, C0, x1, C1, H, W, up, total, out);
+    else launch_pdl(cast_concat_kernel<false>, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, x0, C0, x1, C1, H, W, up, total, out);
     return check_launch("cast_concat_kernel");
 }
 
@@ -323,24 +349,24 @@ int sdb_upsample_bilinear2x(const float* x, int N, int H, int W, int C, void* ou
     SDB_REQUIRE(x && out && N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "upsample_bilinear2x: bad args");
     long long total = (long long)N * 2 * H * 2 * W * (C / 4);
     int threads = 256, blocks = grid_for(total, threads);
-    if (out_dtype == SDB_BF16) upsample_bilinear2x_kernel<true><<<blocks, threads, 0, (cudaStream_t)stream>>>(x, H, W, C, total, out);
-    else upsample_bilinear2x_kernel<false><<<blocks, threads, 0, (cudaStream_t)stream>>>(x, H, W, C, total, out);
+    if (out_dtype == SDB_BF16) launch_pdl(upsample_bilinear2x_kernel<true>, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, x, H, W, C, total, out);
+    else launch_pdl(upsample_bilinear2x_kernel<false>, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, x, H, W, C, total, out);
     return check_launch("upsample_bilinear2x_kernel");
 }
 
 int sdb_activation(const float* x, void* out, int out_dtype, long long n, int act, void* stream) {
     SDB_REQUIRE(x && out && n > 0, "activation: bad args");
     int threads = 256, blocks = grid_for(n, threads);
-    if (out_dtype == SDB_BF16) activation_kernel<true><<<blocks, threads, 0, (cudaStream_t)stream>>>(x, out, n, act);
-    else activation_kernel<false><<<blocks, threads, 0, (cudaStream_t)stream>>>(x, out, n, act);
+    if (out_dtype == SDB_BF16) launch_pdl(activation_kernel<true>, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, x, out, n, act);
+    else launch_pdl(activation_kernel<false>, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, x, out, n, act);
     return check_launch("activation_kernel");
 }
 
 int sdb_geglu(const float* h, int rows, int inner, void* out, int out_dtype, void* stream) {
     SDB_REQUIRE(h && out && rows > 0 && inner > 0, "geglu: bad args");
     int threads = 256, blocks = grid_for((long long)rows * inner, threads);
-    if (out_dtype == SDB_BF16) geglu_kernel<true><<<blocks, threads, 0, (cudaStream_t)stream>>>(h, rows, inner, out);
-    else geglu_kernel<false><<<blocks, threads, 0, (cudaStream_t)stream>>>(h, rows, inner, out);
+    if (out_dtype == SDB_BF16) launch_pdl(geglu_kernel<true>, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, h, rows, inner, out);
+    else launch_pdl(geglu_kernel<false>, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, h, rows, inner, out);
     return check_launch("geglu_kernel");
 }
 
@@ -349,8 +375,8 @@ int sdb_softmax_rows(const float* s, long long rows, int L, long long lds, float
     SDB_REQUIRE(s && out && rows > 0 && L > 0, "softmax_rows: bad args");
     SDB_REQUIRE(rows < (1LL << 31), "softmax_rows: too many rows");
     int threads = L >= 1024 ? 256 : (L >= 256 ? 128 : 32);
-    if (out_dtype == SDB_BF16) softmax_rows_kernel<true><<<(unsigned)rows, threads, 0, (cudaStream_t)stream>>>(s, L, lds, scale, out, ldo);
-    else softmax_rows_kernel<false><<<(unsigned)rows, threads, 0, (cudaStream_t)stream>>>(s, L, lds, scale, out, ldo);
+    if (out_dtype == SDB_BF16) launch_pdl(softmax_rows_kernel<true>, dim3((unsigned)rows), dim3(threads), 0, (cudaStream_t)stream, s, L, lds, scale, out, ldo);
+    else launch_pdl(softmax_rows_kernel<false>, dim3((unsigned)rows), dim3(threads), 0, (cudaStream_t)stream, s, L, lds, scale, out, ldo);
     return check_launch("softmax_rows_kernel");
 }
 
@@ -359,14 +385,14 @@ int sdb_add_rowvec(const float* x, const float* rowvec, long long ldv, int N, lo
     SDB_REQUIRE(x && rowvec && out && N > 0 && HW > 0 && C > 0 && C % 4 == 0, "add_rowvec: bad args");
     long long total = (long long)N * HW * (C / 4);
     int threads = 256, blocks = grid_for(total, threads);
-    if (out_dtype == SDB_BF16) add_rowvec_kernel<true><<<blocks, threads, 0, (cudaStream_t)stream>>>(x, rowvec, ldv, HW, C, total, out);
-    else add_rowvec_kernel<false><<<blocks, threads, 0, (cudaStream_t)stream>>>(x, rowvec, ldv, HW, C, total, out);
+    if (out_dtype == SDB_BF16) launch_pdl(add_rowvec_kernel<true>, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, x, rowvec, ldv, HW, C, total, out);
+    else launch_pdl(add_rowvec_kernel<false>, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, x, rowvec, ldv, HW, C, total, out);
     return check_launch("add_rowvec_kernel");
 }
 
 int sdb_add(const float* a, const float* b, float* out, long long n, void* stream) {
     SDB_REQUIRE(a && b && out && n > 0, "add: bad args");
-    add_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, out, n);
+    launch_pdl(add_kernel, dim3(grid_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, a, b, out, n);
     return check_launch("add_kernel");
 }
 
@@ -374,13 +400,13 @@ int sdb_timestep_embedding(const float* t, const float* freqs, int B, int half, 
                            void* stream) {
     SDB_REQUIRE(t && freqs && emb && B > 0 && half > 0, "timestep_embedding: bad args");
     int n = B * half;
-    timestep_embedding_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(t, freqs, B, half, round_fp16, emb);
+    launch_pdl(timestep_embedding_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, (cudaStream_t)stream, t, freqs, B, half, round_fp16, emb);
     return check_launch("timestep_embedding_kernel");
 }
 
 int sdb_gather_rows(const float* table, const long long* idx, int B, int dim, float* out, void* stream) {
     SDB_REQUIRE(table && idx && out && B > 0 && dim > 0, "gather_rows: bad args");
-    gather_rows_kernel<<<ceil_div(B * dim, 256), 256, 0, (cudaStream_t)stream>>>(table, idx, B, dim, out);
+    launch_pdl(gather_rows_kernel, dim3(ceil_div(B * dim, 256)), dim3(256), 0, (cudaStream_t)stream, table, idx, B, dim, out);
     return check_launch("gather_rows_kernel");
 }
 
@@ -396,7 +422,7 @@ int sdb_skinny_linear(const float* x, int M, int K, const float* W, const float*
 #define SK(MT)                                                                                              \
     do {                                                                                                    \
         if (smem > 48 * 1024) cudaFuncSetAttribute(skinny_linear_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        skinny_linear_kernel<MT><<<blocks, threads, smem, st>>>(x, M, K, W, bias, N, act_in, act_out, y);   \
+        launch_pdl(skinny_linear_kernel<MT>, dim3(blocks), dim3(threads), smem, st, x, M, K, W, bias, N, act_in, act_out, y);   \
     } while (0)
     if (M <= 4) SK(4); else if (M <= 8) SK(8); else if (M <= 16) SK(16); else SK(32);
 #undef SK
@@ -409,7 +435,7 @@ int sdb_ddim_step(const float* x, const float* e_cond, const float* e_uncond, fl
                   void* stream) {
     SDB_REQUIRE(x && e_cond && x_prev && pred_x0 && n > 0, "ddim_step: bad args");
     SDB_REQUIRE(noise || sigma_t == 0.0f, "ddim_step: sigma_t != 0 needs a noise tensor");
-    ddim_step_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+    launch_pdl(ddim_step_kernel, dim3(grid_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, 
         x, e_cond, e_uncond, cfg_scale, noise, sqrt_at, sqrt_aprev, dir_coef, sigma_t, sqrt_one_minus_at,
         temperature, x_prev, pred_x0, n);
     return check_launch("ddim_step_kernel");

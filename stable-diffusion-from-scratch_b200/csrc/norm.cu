@@ -8,6 +8,9 @@
 // Roofline: HBM. Algorithmic bytes/element = 4 (fp32 read) + 2 (bf16 write) [bf16 mode] or 4+4
 // [fp32 mode]; the statistics pass re-reads the tensor (L2-resident for the UNet's <=126 MB maps).
 #include "common.cuh"
+#include "ptx.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 namespace sdb {
 
@@ -51,6 +54,8 @@ __global__ void gn_stats_kernel(const float* __restrict__ x0, int C0, const floa
                                 int HW, int groups, int V, int R, int rows_per_chunk,
                                 double* __restrict__ partial, int* __restrict__ counters, double count, float eps,
                                 float2* __restrict__ stats) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float red[];   // [2][R][C] floats; reused as [slots][groups] double2 by the finalizing CTA
     __shared__ int s_last;
     const int C = C0 + C1;
@@ -132,6 +137,8 @@ __global__ void gn_apply_kernel(const float* __restrict__ x0, int C0, const floa
                                 const float2* __restrict__ stats, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, int act, void* __restrict__ out,
                                 __nv_bfloat16* __restrict__ raw_out) {
+    pdl_trigger();
+    pdl_wait();
     const int C = C0 + C1;
     const int n = blockIdx.y, chunk = blockIdx.x;
     const int v = threadIdx.x % V, rr = threadIdx.x / V;
@@ -184,12 +191,229 @@ __global__ void gn_apply_kernel(const float* __restrict__ x0, int C0, const floa
     }
 }
 
+// ---- GroupNorm as ONE kernel: a thread-block cluster per sample ------------------------------------
+// The CTAs of a cluster (8 or 16, one per SM) split the rows of one sample.  Pass 1 accumulates per-channel
+// sums (fp32 over blocks of <= 8 rows, fp64 across blocks), folds them to per-group partials and all-gathers
+// those through distributed shared memory (every CTA stores its 32 x (S, Q) into every peer's smem, then one
+// cluster barrier); each CTA then sums the ranks' partials in rank order -> (mean, rstd): deterministic, no
+// atomics, no second launch, and a sample's bits do not depend on the batch it is in.  Pass 2 re-reads the
+// CTA's slab (L2-resident: it was read a few microseconds earlier), normalises, applies SiLU and writes the
+// bf16 / fp32 result (and optionally the raw bf16 copy).  Traffic: 4 B/element from HBM + 4 B/element from
+// L2 + 2 B/element written (bf16 out).
+constexpr int GNC_MAX_CS = 16;
+
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+template <bool OUT_BF16, bool EXACT, bool RAW>
+__global__ void __launch_bounds__(1024, 1)
+gn_cluster_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1,
+                  int HW, int groups, int V, int R, int rows_per_cta, int cs, float eps,
+                  const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+                  void* __restrict__ out, __nv_bfloat16* __restrict__ raw_out) {
+    extern __shared__ double gsm[];
+    pdl_trigger();
+    // phase 0 of the cluster barrier: "this CTA is running" (a peer's shared memory may only be written once it is)
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+    const int C = C0 + C1;
+    double* redS = gsm;                                   // [R][C]
+    double* redQ = gsm + (size_t)R * C;                   // [R][C]
+    double2* gpart = reinterpret_cast<double2*>(redQ + (size_t)R * C);          // [cs][groups] (written by every rank)
+    double2* gquart = gpart + (size_t)GNC_MAX_CS * groups;                      // [4][groups]
+    float2* gstat = reinterpret_cast<float2*>(gquart + 4 * (size_t)groups);     // [groups] (mean, rstd)
+    const uint32_t rank = ptx::cluster_ctarank();
+    const int n = blockIdx.y;
+    const int v = threadIdx.x % V, rr = threadIdx.x / V;
+    const int c = v * 4;
+    const float* src;
+    long long ld;
+    int cc;
+    if (c < C0) { src = x0; ld = C0; cc = c; } else { src = x1; ld = C1; cc = c - C0; }
+    const int cpg = C / groups;
+    const int row0 = (int)rank * rows_per_cta;
+    int row1 = row0 + rows_per_cta;
+    if (row1 > HW) row1 = HW;
+    const float* p = src + ((long long)n * HW) * ld + cc;
+    const long long rstep = (long long)R * ld;
+    constexpr int UB = 8;                                 // rows per thread in flight
+    pdl_wait();
+
+    // ---- pass 1: statistics ----
+    double S0 = 0, S1 = 0, S2 = 0, S3 = 0, Q0 = 0, Q1 = 0, Q2 = 0, Q3 = 0;
+    for (int rb = row0 + rr; rb < row1; rb += UB * R) {
+        float4 a[UB];
+        const float* q = p + (long long)rb * ld;
+#pragma unroll
+        for (int i = 0; i < UB; ++i) {
+            a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rb + i * R < row1) a[i] = __ldg(reinterpret_cast<const float4*>(q + i * rstep));
+        }
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+        for (int i = 0; i < UB; ++i) {
+            s0 += a[i].x; s1 += a[i].y; s2 += a[i].z; s3 += a[i].w;
+            q0 = fmaf(a[i].x, a[i].x, q0); q1 = fmaf(a[i].y, a[i].y, q1);
+            q2 = fmaf(a[i].z, a[i].z, q2); q3 = fmaf(a[i].w, a[i].w, q3);
+        }
+        S0 += s0; S1 += s1; S2 += s2; S3 += s3;
+        Q0 += q0; Q1 += q1; Q2 += q2; Q3 += q3;
+    }
+    {
+        double* ps = redS + (size_t)rr * C + c;
+        double* pq = redQ + (size_t)rr * C + c;
+        ps[0] = S0; ps[1] = S1; ps[2] = S2; ps[3] = S3;
+        pq[0] = Q0; pq[1] = Q1; pq[2] = Q2; pq[3] = Q3;
+    }
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {             // fold the R row-slots of every channel (fixed order)
+        double S = 0.0, Q = 0.0;
+        for (int r = 0; r < R; ++r) { S += redS[(size_t)r * C + ch]; Q += redQ[(size_t)r * C + ch]; }
+        redS[ch] = S; redQ[ch] = Q;
+    }
+    __syncthreads();
+    for (int item = threadIdx.x; item < 4 * groups; item += blockDim.x) {   // quarter-group sums
+        const int g = item % groups, part = item / groups;
+        const int lo = g * cpg + (part * cpg) / 4, hi = g * cpg + ((part + 1) * cpg) / 4;
+        double S = 0.0, Q = 0.0;
+        for (int ch = lo; ch < hi; ++ch) { S += redS[ch]; Q += redQ[ch]; }
+        gquart[part * groups + g] = make_double2(S, Q);
+    }
+    __syncthreads();
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");       // every CTA of the cluster has started
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        double S = 0.0, Q = 0.0;
+        for (int part = 0; part < 4; ++part) { double2 t = gquart[part * groups + g]; S += t.x; Q += t.y; }
+        const uint32_t local = ptx::smem_u32(&gpart[(size_t)rank * groups + g]);
+        for (int k = 0; k < cs; ++k) {
+            uint32_t remote;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(k));
+            asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(remote), "d"(S), "d"(Q) : "memory");
+        }
+    }
+    ptx::cluster_sync_all();                                            // release / acquire: every rank's partials have landed
+    const double count = (double)HW * cpg;
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        double S = 0.0, Q = 0.0;
+        for (int k = 0; k < cs; ++k) { double2 t = gpart[(size_t)k * groups + g]; S += t.x; Q += t.y; }
+        double mean = S / count;
+        double var = Q / count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        gstat[g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+    }
+    __syncthreads();
+
+    // ---- pass 2: normalise + affine (+ SiLU) ----
+    float sc[4], sh[4];
+    {
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + c));
+        const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 st = gstat[(c + j) / cpg];
+            sc[j] = st.y * gg[j];
+            sh[j] = bb[j] - st.x * st.y * gg[j];
+        }
+    }
+    const long long obase = ((long long)n * HW) * C + c;
+    for (int rb = row0 + rr; rb < row1; rb += UB * R) {
+        float4 a[UB];
+        const float* q = p + (long long)rb * ld;
+#pragma unroll
+        for (int i = 0; i < UB; ++i)
+            if (rb + i * R < row1) a[i] = ld_stream_f4(q + i * rstep);
+#pragma unroll
+        for (int i = 0; i < UB; ++i) {
+            const int row = rb + i * R;
+            if (row >= row1) break;
+            float y0 = fmaf(a[i].x, sc[0], sh[0]), y1 = fmaf(a[i].y, sc[1], sh[1]);
+            float y2 = fmaf(a[i].z, sc[2], sh[2]), y3 = fmaf(a[i].w, sc[3], sh[3]);
+            if (act == 1) {
+                if (EXACT) { y0 = silu_exact(y0); y1 = silu_exact(y1); y2 = silu_exact(y2); y3 = silu_exact(y3); }
+                else       { y0 = silu_fast(y0);  y1 = silu_fast(y1);  y2 = silu_fast(y2);  y3 = silu_fast(y3); }
+            }
+            const long long o = obase + (long long)row * C;
+            if (OUT_BF16) st_stream_u2(reinterpret_cast<__nv_bfloat16*>(out) + o, pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+            else st_stream_f4(reinterpret_cast<float*>(out) + o, make_float4(y0, y1, y2, y3));
+            if (RAW) st_stream_u2(raw_out + o, pack_bf16x2(a[i].x, a[i].y), pack_bf16x2(a[i].z, a[i].w));
+        }
+    }
+}
+
+// geometry of the cluster kernel: V float4 columns, R row slots (V * R threads <= 1024)
+struct GncGeom { int V, R, threads, cs, rows_per_cta; size_t smem; };
+
+static bool gnc_geom(int HW, int C, int groups, int max_cs, GncGeom* g) {
+    g->V = C / 4;
+    if (g->V < 1 || g->V > 1024 || max_cs < 2) return false;
+    g->R = 1024 / g->V;
+    if (g->R > 32) g->R = 32;
+    if (g->R > HW) g->R = HW;
+    g->threads = g->V * g->R;
+    int cs = max_cs;
+    while (cs > 2 && HW < cs * g->R) cs >>= 1;            // at least one row per thread slot and CTA
+    g->cs = cs;
+    g->rows_per_cta = ceil_div(HW, cs);
+    g->smem = (size_t)2 * g->R * C * sizeof(double) + (size_t)(GNC_MAX_CS + 4) * groups * sizeof(double2) +
+              (size_t)groups * sizeof(float2) + 16;
+    return g->smem <= 200 * 1024;
+}
+
+template <bool BF, bool EX, bool RW>
+static int gnc_max_cluster() {
+    // largest cluster size (16, 8, ...) the device can co-schedule for this instantiation; 0 = cluster path unusable
+    static int cached = -1;
+    if (cached >= 0) return cached;
+    cached = 0;
+    auto k = gn_cluster_kernel<BF, EX, RW>;
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); }
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) { cudaGetLastError(); return cached; }
+    for (int cs = GNC_MAX_CS; cs >= 2; cs >>= 1) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(cs, 1, 1); cfg.blockDim = dim3(1024, 1, 1); cfg.dynamicSmemBytes = 72 * 1024;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int nclusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, k, &cfg) == cudaSuccess && nclusters >= 1) { cached = cs; break; }
+        cudaGetLastError();
+    }
+    return cached;
+}
+
+template <bool BF, bool EX, bool RW>
+static int launch_gn_cluster(const float* x0, int C0, const float* x1, int C1, int N, int HW, int groups, float eps,
+                             const float* gamma, const float* beta, int act, void* out, __nv_bfloat16* raw, cudaStream_t st,
+                             bool* launched) {
+    *launched = false;
+    const int max_cs = gnc_max_cluster<BF, EX, RW>();
+    GncGeom g;
+    if (max_cs < 2 || !gnc_geom(HW, C0 + C1, groups, max_cs, &g)) return SDB_OK;
+    launch_pdl_cluster(gn_cluster_kernel<BF, EX, RW>, dim3(g.cs, N), dim3(g.threads), g.smem, st, g.cs,
+                       x0, C0, x1, C1, HW, groups, g.V, g.R, g.rows_per_cta, g.cs, eps, gamma, beta, act, out, raw);
+    *launched = true;
+    return check_launch("gn_cluster_kernel");
+}
+
+// SDB200_GN=split forces the two-kernel (statistics + apply) path; measurement only
+static bool gn_cluster_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("SDB200_GN");
+        on = (e && strcmp(e, "split") == 0) ? 0 : 1;
+    }
+    return on == 1;
+}
+
 // ---- LayerNorm: one warp per row, row held in registers (two-pass mean/variance) ----------------
 template <bool OUT_BF16, int MAXV>   // MAXV float4 vectors per lane: C <= 128 * MAXV
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int rows, int C, float eps,
                  const float* __restrict__ gamma, const float* __restrict__ beta,
                  void* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= rows) return;
@@ -263,6 +487,21 @@ int sdb_groupnorm_nhwc(const float* x0, int C0, const float* x1, int C1, int N, 
     SDB_REQUIRE(out_dtype == SDB_F32 || out_dtype == SDB_BF16, "groupnorm: bad out_dtype");
     SDB_REQUIRE((((uintptr_t)gamma | (uintptr_t)beta) & 15) == 0, "groupnorm: gamma/beta must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
+    __nv_bfloat16* raw = reinterpret_cast<__nv_bfloat16*>(raw_out);
+    if (gn_cluster_enabled() && N <= 65535) {
+        bool launched = false;
+        int rc = SDB_OK;
+#define TRY_CLUSTER(BF, EX, RW) rc = launch_gn_cluster<BF, EX, RW>(x0, C0, x1, C1, N, HW, groups, eps, gamma, beta, act, out, raw, st, &launched)
+        if (raw) {
+            if (out_dtype == SDB_BF16) { if (exact) TRY_CLUSTER(true, true, true); else TRY_CLUSTER(true, false, true); }
+            else                       { if (exact) TRY_CLUSTER(false, true, true); else TRY_CLUSTER(false, false, true); }
+        } else {
+            if (out_dtype == SDB_BF16) { if (exact) TRY_CLUSTER(true, true, false); else TRY_CLUSTER(true, false, false); }
+            else                       { if (exact) TRY_CLUSTER(false, true, false); else TRY_CLUSTER(false, false, false); }
+        }
+#undef TRY_CLUSTER
+        if (rc || launched) return rc;
+    }
     GnGeom g = gn_geom(N, HW, C);
     double* partial = reinterpret_cast<double*>(ws);
     float2* stats = reinterpret_cast<float2*>(reinterpret_cast<char*>(ws) +
@@ -273,13 +512,12 @@ int sdb_groupnorm_nhwc(const float* x0, int C0, const float* x1, int C1, int N, 
     if (smem > 48 * 1024) {
         cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
-    gn_stats_kernel<<<grid, g.threads, smem, st>>>(x0, C0, x1, C1, HW, groups, g.V, g.R, g.rows_per_chunk, partial,
+    launch_pdl(gn_stats_kernel, dim3(grid), dim3(g.threads), smem, st, x0, C0, x1, C1, HW, groups, g.V, g.R, g.rows_per_chunk, partial,
                                                    counters, (double)HW * (C / groups), eps, stats);
     int rc = check_launch("gn_stats_kernel");
     if (rc) return rc;
-    __nv_bfloat16* raw = reinterpret_cast<__nv_bfloat16*>(raw_out);
 #define LAUNCH_APPLY(BF, EX, RW)                                                                         \
-    gn_apply_kernel<BF, EX, RW><<<grid, g.threads, 0, st>>>(x0, C0, x1, C1, HW, groups, g.V, g.R,      \
+    launch_pdl(gn_apply_kernel<BF, EX, RW>, dim3(grid), dim3(g.threads), 0, st, x0, C0, x1, C1, HW, groups, g.V, g.R,      \
                                                              g.rows_per_chunk, stats, gamma, beta, act, out, raw)
     if (raw) {
         if (out_dtype == SDB_BF16) { if (exact) LAUNCH_APPLY(true, true, true); else LAUNCH_APPLY(true, false, true); }
@@ -304,8 +542,8 @@ int sdb_layernorm(const float* x, int rows, int C, float eps, const float* gamma
     const int nv = ceil_div(C / 4, 32);      // float4 vectors per lane; the row stays in registers
 #define LAUNCH_LN(NV)                                                                                              \
     do {                                                                                                           \
-        if (out_dtype == SDB_BF16) layernorm_kernel<true, NV><<<blocks, threads, 0, st>>>(x, rows, C, eps, gamma, beta, out); \
-        else layernorm_kernel<false, NV><<<blocks, threads, 0, st>>>(x, rows, C, eps, gamma, beta, out);           \
+        if (out_dtype == SDB_BF16) launch_pdl(layernorm_kernel<true, NV>, dim3(blocks), dim3(threads), 0, st, x, rows, C, eps, gamma, beta, out); \
+        else launch_pdl(layernorm_kernel<false, NV>, dim3(blocks), dim3(threads), 0, st, x, rows, C, eps, gamma, beta, out);           \
     } while (0)
     if (nv <= 1) LAUNCH_LN(1);
     else if (nv <= 3) LAUNCH_LN(3);

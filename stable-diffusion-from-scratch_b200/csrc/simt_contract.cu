@@ -33,6 +33,8 @@ struct SimtP {
 
 template <bool CONV>
 __global__ void __launch_bounds__(256) simt_contract_kernel(const SimtP p) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ __align__(16) float As[SBK][SBM + 4];
     __shared__ __align__(16) float Bs[SBK][SBN + 4];
 
@@ -239,7 +241,7 @@ extern "C" int sdb_simt_contract(const sdb_simt_args* a, void* stream) {
     }
     dim3 grid(ceil_div(a->M, SBM), ceil_div(a->N, SBN), nb1 * p.nb2);
     SDB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "simt_contract: grid too large");
-    if (conv) simt_contract_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
-    else simt_contract_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    if (conv) launch_pdl(simt_contract_kernel<true>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, p);
+    else launch_pdl(simt_contract_kernel<false>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, p);
     return check_launch("simt_contract_kernel");
 }

@@ -90,6 +90,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint64_t* pv_done = p_full + G;     // G   O_g += P_g V retired (P_g and O_g free)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + G);
 
+    pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * (128 * G), h = blockIdx.y, b = blockIdx.z;
     const int ntiles = (p.Sk + 127) / 128;
@@ -115,6 +116,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_wait();                                      // q / k / v written by the preceding projection are visible
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -332,7 +334,7 @@ static int launch_attn(const sdb_attn_args* a, cudaStream_t st) {
     p.Sq = a->Sq; p.Sk = a->Sk; p.d = a->d; p.H = a->H;
     p.scale_log2 = a->scale * 1.4426950408889634f;
     dim3 grid((unsigned)ceil_div(a->Sq, 128 * Cfg::G), (unsigned)a->H, (unsigned)a->B);
-    tc_attention_kernel<DPAD><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
+    launch_pdl(tc_attention_kernel<DPAD>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, tmQ, tmK, tmV, p);
     return check_launch("tc_attention_kernel");
 }
 

@@ -5,6 +5,7 @@ torch is used for allocation (`torch.empty`) and pointers only.  Activations are
 images [N, H, W, C], tokens [rows, C].
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -287,6 +288,35 @@ def gemm_simt(A, B, bias=None, residual=None, alpha=1.0, b_kn=False, out=None, o
 
 
 # ---- tcgen05 contraction -----------------------------------------------------------------------------
+def _plan_table():
+    if os.environ.get("SDB200_TC_PLANS", "1") == "0":
+        return {}
+    from .tc_plans import PLANS
+    return PLANS
+
+
+_PLANS = None
+
+
+def _apply_plan(a, kind, rows_per_sample):
+    """Fill (variant, block_n, split_k) from the measured plan table when the caller left all three on auto.
+    Keyed by the per-sample geometry only, so the plan (and a sample's bits) is independent of the batch size."""
+    global _PLANS
+    if a.split_k or a.variant or (a.block_n and not a.geglu):
+        return
+    if _PLANS is None:
+        _PLANS = _plan_table()
+    key = (kind, int(rows_per_sample), a.N, a.K, a.taps, a.stride if a.taps else 0, a.geglu, int(bool(a.residual)),
+           a.out_dtype, a.col_group)
+    hit = _PLANS.get(key)
+    if hit is not None:
+        if a.geglu:                      # the tile width is baked into the packed GEGLU weights
+            if hit[1] == a.block_n:
+                a.variant = hit[0]
+        else:
+            a.variant, a.block_n, a.split_k = hit[0], hit[1], hit[2]
+
+
 def _tc_launch(a, what):
     """Give the call its split-K workspace (if the plan splits) and enqueue it."""
     lib = _L()
@@ -344,6 +374,7 @@ def conv_tc(x, w_rskc, bias, kh, kw, stride=1, pad=0, rowvec=None, residual=None
     a.cout_pad = Cout
     if residual is not None:
         assert residual.dtype == torch.float32 and residual.is_contiguous()
+    _apply_plan(a, "conv", OH * OW)
     _tc_launch(a, "tc conv")
     return out
 
@@ -382,6 +413,8 @@ def gemm_tc(A, W, bias=None, residual=None, out_dtype=torch.float32, geglu=False
     a.variant = variant
     a.taps = 0
     a.rows_per_item = int(rows_per_item)
+    if rows_per_item:
+        _apply_plan(a, "gemm", rows_per_item)
     _tc_launch(a, "tc gemm")
     return out
 
