@@ -63,6 +63,15 @@ int sdb_groupnorm_nhwc(const float* x0, int C0, const float* x1, int C1, int N, 
                        float eps, const float* gamma, const float* beta, int act, int exact,
                        void* out, int out_dtype, void* raw_out, void* ws, int* counters, void* stream);
 
+/* Same GroupNorm, statistics taken from the column sums the producing tcgen05 convs wrote (sdb_tc_args.colstats:
+ * cs = fp32 [2][slots][C*], `slots_per_item` consecutive 32-row slots per sample), so the tensor is read once.
+ * ws: >= N*groups*8 bytes.  Other arguments as sdb_groupnorm_nhwc. */
+int sdb_groupnorm_from_colstats(const float* x0, int C0, const float* cs0, long long slots0,
+                                const float* x1, int C1, const float* cs1, long long slots1,
+                                long long slots_per_item, int N, int HW, int groups, float eps,
+                                const float* gamma, const float* beta, int act, int exact,
+                                void* out, int out_dtype, void* raw_out, void* ws, void* stream);
+
 /* ---- LayerNorm over the last dim ---------------------------------------------------------------
  * Replaces nn.LayerNorm(dim) x3 per BasicTransformerBlock (openai_model/attention.py:216-218,
  * 251-253), eps 1e-5.  x [rows, C] fp32 -> out [rows, C] (out_dtype). C % 4 == 0, C <= 2048. */
@@ -192,7 +201,15 @@ typedef struct sdb_tc_args {
     /* kernel variant: 0 = library default (see sdb_tc_set_pair_kernel), 1 = one-CTA 128 x BN kernel,
      * 2 = CTA-pair persistent 256 x BN kernel (block_n >= 128).  Same results up to summation order. */
     int variant;
+    /* optional, conv mode: fp32 [2][colstats_slots][N] receiving, for every 32-row slot of the output (4 per 128-row
+     * m-tile, slot = 4*tile + row/32) and every column, the sum and the sum of squares of the values this call stores
+     * — the statistics pass of the GroupNorm that consumes the output (openai_model/utils.py:15-22) comes for free.
+     * Size it with sdb_tc_colstats_layout(); NULL = off. */
+    float* colstats; long long colstats_slots;
 } sdb_tc_args;
+/* slots the column statistics of these args occupy and how many consecutive slots belong to one sample (both 0 when
+ * the plan cannot produce them: split-K, several samples per tile, bf16 / remapped output). */
+int sdb_tc_colstats_layout(const sdb_tc_args* args /* host */, long long* slots, long long* slots_per_item);
 /* bytes of workspace sdb_tc_contract may use for these args (0 = none; -1 = invalid args).  With
  * split_k == 0 this is what the library's automatic split choice needs. */
 long long sdb_tc_workspace_bytes(const sdb_tc_args* args /* host */);

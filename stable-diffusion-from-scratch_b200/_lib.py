@@ -56,6 +56,7 @@ class TcArgs(C.Structure):
         ("ws", C.c_void_p), ("ws_bytes", C.c_longlong),
         ("rows_per_item", C.c_int),
         ("variant", C.c_int),
+        ("colstats", C.c_void_p), ("colstats_slots", C.c_longlong),
     ]
 
 
@@ -82,6 +83,7 @@ SIGNATURES = {
     "sdb_nhwc_to_nchw": (_I, [_P, _P, _I, _I, _I, _P]),
     "sdb_groupnorm_ws_bytes": (_L, [_I, _I, _I, _I]),
     "sdb_groupnorm_nhwc": (_I, [_P, _I, _P, _I, _I, _I, _I, _F, _P, _P, _I, _I, _P, _I, _P, _P, _P, _P]),
+    "sdb_groupnorm_from_colstats": (_I, [_P, _I, _P, _L, _P, _I, _P, _L, _L, _I, _I, _I, _F, _P, _P, _I, _I, _P, _I, _P, _P, _P]),
     "sdb_layernorm": (_I, [_P, _I, _I, _F, _P, _P, _P, _I, _P]),
     "sdb_cast_concat": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _P, _I, _P]),
     "sdb_upsample_bilinear2x": (_I, [_P, _I, _I, _I, _I, _P, _I, _P]),
@@ -98,6 +100,7 @@ SIGNATURES = {
     "sdb_tc_contract": (_I, [C.POINTER(TcArgs), _P]),
     "sdb_tc_set_pair_kernel": (_I, [_I]),
     "sdb_tc_workspace_bytes": (_L, [C.POINTER(TcArgs)]),
+    "sdb_tc_colstats_layout": (_I, [C.POINTER(TcArgs), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "sdb_attention_fwd": (_I, [C.POINTER(AttnArgs), _P]),
 }
 

@@ -45,6 +45,50 @@ static GnGeom gn_geom(int N, int HW, int C) {
     return g;
 }
 
+// SiLU for the bf16 tensor-core path: ex2.approx + rcp.approx (2 MUFU + 3 FMA-pipe instructions; the IEEE division of
+// x / (1 + e^-x) costs ~10 and made the apply pass instruction-bound)
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+// Statistics from the producer: the tcgen05 conv that wrote the tensor also wrote, per 32-row slot and channel, the sum
+// and sum of squares of what it stored (sdb_tc_args.colstats).  One warp per (sample, group) folds its slots x channels
+// in fp64 in a fixed order -> (mean, rstd); the tensor itself is not read.  Two sources = the channel concat.
+__global__ void gn_colstats_finalize_kernel(const float* __restrict__ cs0, int C0, long long slots0,
+                                            const float* __restrict__ cs1, int C1, long long slots1,
+                                            long long slots_per_item, int groups, int total, double count, float eps,
+                                            float2* __restrict__ stats) {
+    pdl_trigger();
+    pdl_wait();
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= total) return;
+    const int n = w / groups, g = w - n * groups;
+    const int C = C0 + C1, cpg = C / groups;
+    double S = 0.0, Q = 0.0;
+    for (long long sl = lane; sl < slots_per_item; sl += 32) {
+        const long long s = (long long)n * slots_per_item + sl;
+        const float* a0 = cs0 + s * C0;
+        const float* q0 = a0 + slots0 * C0;
+        const float* a1 = cs1 ? cs1 + s * C1 : nullptr;
+        const float* q1 = cs1 ? a1 + slots1 * C1 : nullptr;
+        for (int j = 0; j < cpg; ++j) {
+            const int c = g * cpg + j;
+            if (c < C0) { S += (double)__ldcg(a0 + c); Q += (double)__ldcg(q0 + c); }
+            else        { S += (double)__ldcg(a1 + (c - C0)); Q += (double)__ldcg(q1 + (c - C0)); }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        S += __shfl_xor_sync(0xffffffffu, S, o);
+        Q += __shfl_xor_sync(0xffffffffu, Q, o);
+    }
+    if (lane == 0) {
+        double mean = S / count;
+        double var = Q / count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        stats[w] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+    }
+}
+
 // Pass 1: per-(sample, chunk, group) partial sum / sum of squares, then the LAST CTA of a sample to finish
 // (atomic ticket on `counters[n]`, which it leaves at zero again) combines the chunk partials of that
 // sample in a fixed order into (mean, rstd) per group: no separate finalize launch, bit-reproducible.
@@ -179,7 +223,7 @@ __global__ void gn_apply_kernel(const float* __restrict__ x0, int C0, const floa
         float y2 = fmaf(a[i].z, sc[2], sh[2]), y3 = fmaf(a[i].w, sc[3], sh[3]);
         if (act == 1) {
             if (EXACT) { y0 = silu_exact(y0); y1 = silu_exact(y1); y2 = silu_exact(y2); y3 = silu_exact(y3); }
-            else       { y0 = silu_f(y0);     y1 = silu_f(y1);     y2 = silu_f(y2);     y3 = silu_f(y3); }
+            else       { y0 = silu_fast(y0);  y1 = silu_fast(y1);  y2 = silu_fast(y2);  y3 = silu_fast(y3); }
         }
         long long o = ((long long)n * HW + row) * C + c;
         if (OUT_BF16) {
@@ -201,8 +245,6 @@ __global__ void gn_apply_kernel(const float* __restrict__ x0, int C0, const floa
 // bf16 / fp32 result (and optionally the raw bf16 copy).  Traffic: 4 B/element from HBM + 4 B/element from
 // L2 + 2 B/element written (bf16 out).
 constexpr int GNC_MAX_CS = 16;
-
-__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 template <bool OUT_BF16, bool EXACT, bool RAW>
 __global__ void __launch_bounds__(1024, 1)
@@ -367,7 +409,9 @@ static int gnc_max_cluster() {
     auto k = gn_cluster_kernel<BF, EX, RW>;
     if (cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); }
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) { cudaGetLastError(); return cached; }
-    for (int cs = GNC_MAX_CS; cs >= 2; cs >>= 1) {
+    int cs_cap = GNC_MAX_CS;
+    if (const char* e = getenv("SDB200_GN_CS")) { int v = atoi(e); if (v >= 2 && v <= GNC_MAX_CS) cs_cap = v; }   // measurement only
+    for (int cs = cs_cap; cs >= 2; cs >>= 1) {
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3(cs, 1, 1); cfg.blockDim = dim3(1024, 1, 1); cfg.dynamicSmemBytes = 72 * 1024;
@@ -407,6 +451,10 @@ static bool gn_cluster_enabled() {
 }
 
 // ---- LayerNorm: one warp per row, row held in registers (two-pass mean/variance) ----------------
+// A warp normalises LN_ROWS consecutive rows: all their loads are issued before the first reduction (LN_ROWS * MAXV
+// 16-byte loads in flight per lane) and gamma / beta are fetched once per warp, not once per row.
+constexpr int LN_ROWS = 4;
+
 template <bool OUT_BF16, int MAXV>   // MAXV float4 vectors per lane: C <= 128 * MAXV
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int rows, int C, float eps,
@@ -414,53 +462,75 @@ layernorm_kernel(const float* __restrict__ x, int rows, int C, float eps,
                  void* __restrict__ out) {
     pdl_trigger();
     pdl_wait();
+    constexpr int NR = (MAXV <= 3) ? LN_ROWS : (MAXV <= 5 ? 2 : 1);   // rows per warp (register budget)
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (warp >= rows) return;
+    const int row0 = warp * NR;
+    if (row0 >= rows) return;
     const int V = C >> 2;
-    const float* p = x + (long long)warp * C;
-    float4 r[MAXV];
-    float s = 0.f;
+    float4 r[NR][MAXV];
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-        int v = lane + 32 * i;
-        if (v < V) {
-            r[i] = ld_stream_f4(p + 4 * v);
-            s += (r[i].x + r[i].y) + (r[i].z + r[i].w);
+    for (int j = 0; j < NR; ++j) {
+        const float* p = x + (long long)(row0 + j) * C;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int v = lane + 32 * i;
+            r[j][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (v < V && row0 + j < rows) r[j][i] = ld_stream_f4(p + 4 * v);
         }
     }
-    s = warp_sum(s);
-    const float mean = s / (float)C;
-    float q = 0.f;
+    constexpr int NG = NR > 1 ? MAXV : 1;                 // gamma / beta stay in registers only when they are reused
+    float4 g[NG], b[NG];
+    if (NR > 1) {
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-        int v = lane + 32 * i;
-        if (v < V) {
-            float a = r[i].x - mean, b = r[i].y - mean, c = r[i].z - mean, d = r[i].w - mean;
-            q += (a * a + b * b) + (c * c + d * d);
+        for (int i = 0; i < NG; ++i) {
+            const int v = lane + 32 * i;
+            if (v < V) {
+                g[i] = __ldg(reinterpret_cast<const float4*>(gamma) + v);
+                b[i] = __ldg(reinterpret_cast<const float4*>(beta) + v);
+            }
         }
     }
-    q = warp_sum(q);
-    const float rstd = rsqrtf(q / (float)C + eps);
+    const float invC = 1.0f / (float)C;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-        int v = lane + 32 * i;
-        if (v < V) {
-            float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + v);
-            float4 b = __ldg(reinterpret_cast<const float4*>(beta) + v);
-            float y0 = (r[i].x - mean) * rstd * g.x + b.x;
-            float y1 = (r[i].y - mean) * rstd * g.y + b.y;
-            float y2 = (r[i].z - mean) * rstd * g.z + b.z;
-            float y3 = (r[i].w - mean) * rstd * g.w + b.w;
-            long long o = (long long)warp * C + 4 * v;
-            if (OUT_BF16) {
-                st_stream_u2(reinterpret_cast<__nv_bfloat16*>(out) + o, pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
-            } else {
-                st_stream_f4(reinterpret_cast<float*>(out) + o, make_float4(y0, y1, y2, y3));
+    for (int j = 0; j < NR; ++j) {
+        if (row0 + j >= rows) break;                       // warp-uniform
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) s += (r[j][i].x + r[j][i].y) + (r[j][i].z + r[j][i].w);   // padding lanes hold zeros
+        s = warp_sum(s);
+        const float mean = s * invC;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int v = lane + 32 * i;
+            if (v < V) {
+                float a = r[j][i].x - mean, bb = r[j][i].y - mean, c = r[j][i].z - mean, d = r[j][i].w - mean;
+                q += (a * a + bb * bb) + (c * c + d * d);
+            }
+        }
+        q = warp_sum(q);
+        const float rstd = rsqrtf(q * invC + eps);
+        const long long obase = (long long)(row0 + j) * C;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int v = lane + 32 * i;
+            if (v < V) {
+                const float4 gi = NR > 1 ? g[NR > 1 ? i : 0] : __ldg(reinterpret_cast<const float4*>(gamma) + v);
+                const float4 bi = NR > 1 ? b[NR > 1 ? i : 0] : __ldg(reinterpret_cast<const float4*>(beta) + v);
+                float y0 = (r[j][i].x - mean) * rstd * gi.x + bi.x;
+                float y1 = (r[j][i].y - mean) * rstd * gi.y + bi.y;
+                float y2 = (r[j][i].z - mean) * rstd * gi.z + bi.z;
+                float y3 = (r[j][i].w - mean) * rstd * gi.w + bi.w;
+                const long long o = obase + 4 * v;
+                if (OUT_BF16) st_stream_u2(reinterpret_cast<__nv_bfloat16*>(out) + o, pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+                else st_stream_f4(reinterpret_cast<float*>(out) + o, make_float4(y0, y1, y2, y3));
             }
         }
     }
 }
+
+static inline int ln_rows_per_warp(int nv) { return nv <= 3 ? LN_ROWS : (nv <= 5 ? 2 : 1); }
 
 }  // namespace sdb
 
@@ -530,6 +600,45 @@ int sdb_groupnorm_nhwc(const float* x0, int C0, const float* x1, int C1, int N, 
     return check_launch("gn_apply_kernel");
 }
 
+int sdb_groupnorm_from_colstats(const float* x0, int C0, const float* cs0, long long slots0,
+                                const float* x1, int C1, const float* cs1, long long slots1,
+                                long long slots_per_item, int N, int HW, int groups, float eps,
+                                const float* gamma, const float* beta, int act, int exact,
+                                void* out, int out_dtype, void* raw_out, void* ws, void* stream) {
+    const int C = C0 + C1;
+    SDB_REQUIRE(x0 && cs0 && out && ws && gamma && beta, "groupnorm_from_colstats: null pointer");
+    SDB_REQUIRE(N > 0 && HW > 0 && C > 0 && slots_per_item > 0, "groupnorm_from_colstats: empty tensor");
+    SDB_REQUIRE(C0 % 4 == 0 && C1 % 4 == 0 && (C1 == 0) == (x1 == nullptr) && (C1 == 0) == (cs1 == nullptr),
+                "groupnorm_from_colstats: bad channel split %d + %d", C0, C1);
+    SDB_REQUIRE(groups > 0 && C % groups == 0 && C / 4 <= 1024, "groupnorm_from_colstats: C=%d groups=%d unsupported", C, groups);
+    SDB_REQUIRE(slots0 >= (long long)N * slots_per_item && (!cs1 || slots1 >= (long long)N * slots_per_item),
+                "groupnorm_from_colstats: statistics buffers too small");
+    SDB_REQUIRE(out_dtype == SDB_F32 || out_dtype == SDB_BF16, "groupnorm_from_colstats: bad out_dtype");
+    SDB_REQUIRE((((uintptr_t)gamma | (uintptr_t)beta) & 15) == 0, "groupnorm_from_colstats: gamma/beta must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    float2* stats = reinterpret_cast<float2*>(ws);                 // [N][groups]
+    const int total = N * groups;
+    launch_pdl(gn_colstats_finalize_kernel, dim3(ceil_div(total, 8)), dim3(256), 0, st, cs0, C0, slots0, cs1, C1, slots1,
+               slots_per_item, groups, total, (double)HW * (C / groups), eps, stats);
+    int rc = check_launch("gn_colstats_finalize_kernel");
+    if (rc) return rc;
+    GnGeom g = gn_geom(N, HW, C);
+    dim3 grid(g.chunks, N);
+    __nv_bfloat16* raw = reinterpret_cast<__nv_bfloat16*>(raw_out);
+#define LAUNCH_APPLY(BF, EX, RW)                                                                         \
+    launch_pdl(gn_apply_kernel<BF, EX, RW>, dim3(grid), dim3(g.threads), 0, st, x0, C0, x1, C1, HW, groups, g.V, g.R, \
+               g.rows_per_chunk, stats, gamma, beta, act, out, raw)
+    if (raw) {
+        if (out_dtype == SDB_BF16) { if (exact) LAUNCH_APPLY(true, true, true); else LAUNCH_APPLY(true, false, true); }
+        else                       { if (exact) LAUNCH_APPLY(false, true, true); else LAUNCH_APPLY(false, false, true); }
+    } else {
+        if (out_dtype == SDB_BF16) { if (exact) LAUNCH_APPLY(true, true, false); else LAUNCH_APPLY(true, false, false); }
+        else                       { if (exact) LAUNCH_APPLY(false, true, false); else LAUNCH_APPLY(false, false, false); }
+    }
+#undef LAUNCH_APPLY
+    return check_launch("gn_apply_kernel");
+}
+
 int sdb_layernorm(const float* x, int rows, int C, float eps, const float* gamma, const float* beta,
                   void* out, int out_dtype, void* stream) {
     SDB_REQUIRE(x && out && gamma && beta, "layernorm: null pointer");
@@ -538,8 +647,9 @@ int sdb_layernorm(const float* x, int rows, int C, float eps, const float* gamma
     cudaStream_t st = (cudaStream_t)stream;
     SDB_REQUIRE(out_dtype == SDB_BF16 || out_dtype == SDB_F32, "layernorm: bad out_dtype");
     const int threads = 256;
-    const int blocks = ceil_div(rows, threads / 32);
-    const int nv = ceil_div(C / 4, 32);      // float4 vectors per lane; the row stays in registers
+    const int nv = ceil_div(C / 4, 32);      // float4 vectors per lane; the rows stay in registers
+    const int nvt = nv <= 1 ? 1 : (nv <= 3 ? 3 : (nv <= 5 ? 5 : (nv <= 10 ? 10 : 16)));   // template instance used below
+    const int blocks = ceil_div(ceil_div(rows, ln_rows_per_warp(nvt)), threads / 32);
 #define LAUNCH_LN(NV)                                                                                              \
     do {                                                                                                           \
         if (out_dtype == SDB_BF16) launch_pdl(layernorm_kernel<true, NV>, dim3(blocks), dim3(threads), 0, st, x, rows, C, eps, gamma, beta, out); \

@@ -31,6 +31,7 @@ struct TcP {
     void* out;
     const float* bias; const float* rowvec; const float* residual;
     float* ws; long long ws_split_stride;   // split-K partial sums: [split_k][M_out][N] fp32
+    float* colstats; long long colstats_sq; // per-(32-row slot, column) sum / sum of squares of the stored values: [2][slots][N]
     long long ldc, ldr, ldv;
     int M, N;
     int kblocks;            // total k-blocks = taps * kpt
@@ -98,7 +99,7 @@ __device__ __forceinline__ void prefetch_residual_row(const TcP& p, long long pi
 template <int BN>
 __device__ __forceinline__ void epilogue_warp(const TcP& p, uint32_t taddr, const float* s_bias, float* stage, int lane,
                                               int n0, int nt, long long row_pix, int row_img, int split, int ch0, int chstep,
-                                              uint64_t* acc_ready, uint32_t acc_parity) {
+                                              uint64_t* acc_ready, uint32_t acc_parity, int slot) {
     // rows this lane stores after the transpose: r_i = 4*i + (lane >> 3), i = 0..7
     long long rpix[8];
     int rimg[8];
@@ -177,12 +178,20 @@ __device__ __forceinline__ void epilogue_warp(const TcP& p, uint32_t taddr, cons
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (!p.geglu && !partial) bias4 = lds128(sbias_a + 4 * (c0 + cq));
         if (vec_ok) {
+            // column statistics of the stored tile (GroupNorm of the consumer, see sdb_tc_args.colstats)
+            const bool want_cs = p.colstats != nullptr && !partial;
+            float4 cs_s = make_float4(0.f, 0.f, 0.f, 0.f), cs_q = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const long long pix = rpix[i];
                 float4 v = lds128(stage_a + 4 * ((4 * i + (lane >> 3)) * EPI_LD + cq));
                 v.x += bias4.x + addv[i].x; v.y += bias4.y + addv[i].y; v.z += bias4.z + addv[i].z; v.w += bias4.w + addv[i].w;
                 if (!(col_ok && pix >= 0)) continue;
+                if (want_cs) {
+                    cs_s.x += v.x; cs_s.y += v.y; cs_s.z += v.z; cs_s.w += v.w;
+                    cs_q.x = fmaf(v.x, v.x, cs_q.x); cs_q.y = fmaf(v.y, v.y, cs_q.y);
+                    cs_q.z = fmaf(v.z, v.z, cs_q.z); cs_q.w = fmaf(v.w, v.w, cs_q.w);
+                }
                 if (partial) {
                     *reinterpret_cast<float4*>(ws + pix * p.N + cn) = v;                      // dense [rows_out, N]
                 } else if (p.out_bf16) {
@@ -191,6 +200,21 @@ __device__ __forceinline__ void epilogue_warp(const TcP& p, uint32_t taddr, cons
                         make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
                 } else {
                     *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.ldc + cn) = v;
+                }
+            }
+            if (want_cs) {
+                // rows 4i + (lane >> 3) live in this lane: fold the 4 lanes that share a column quad (fixed order)
+#pragma unroll
+                for (int o = 8; o <= 16; o <<= 1) {
+                    cs_s.x += __shfl_xor_sync(0xffffffffu, cs_s.x, o); cs_s.y += __shfl_xor_sync(0xffffffffu, cs_s.y, o);
+                    cs_s.z += __shfl_xor_sync(0xffffffffu, cs_s.z, o); cs_s.w += __shfl_xor_sync(0xffffffffu, cs_s.w, o);
+                    cs_q.x += __shfl_xor_sync(0xffffffffu, cs_q.x, o); cs_q.y += __shfl_xor_sync(0xffffffffu, cs_q.y, o);
+                    cs_q.z += __shfl_xor_sync(0xffffffffu, cs_q.z, o); cs_q.w += __shfl_xor_sync(0xffffffffu, cs_q.w, o);
+                }
+                if (lane < 8 && col_ok) {
+                    float* dst = p.colstats + (long long)slot * p.N + cn;
+                    *reinterpret_cast<float4*>(dst) = cs_s;
+                    *reinterpret_cast<float4*>(dst + p.colstats_sq) = cs_q;
                 }
             }
         } else {
@@ -341,7 +365,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // once the accumulator is ready every TMA load has been consumed: the A ring doubles as the transpose staging area
         float* stage = reinterpret_cast<float*>(sA) + (warp - 2) * (EPI_WARP_BYTES / 4);
         const uint32_t taddr = tmem_d + ((uint32_t)(lg * 32) << 16);
-        epilogue_warp<BN>(p, taddr, s_bias, stage, lane, n0, nt, pix, img, split, 0, 1, accum_bar, 0);
+        epilogue_warp<BN>(p, taddr, s_bias, stage, lane, n0, nt, pix, img, split, 0, 1, accum_bar, 0, mt * 4 + lg);
     }
 
     // ---- teardown ----
@@ -534,7 +558,8 @@ tc_contract_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             int img = 0;
             const long long pix = row_of(mt, img);
             const uint32_t taddr = tmem_d + ((uint32_t)(lg * 32) << 16) + buf * Cfg::ACC_STRIDE;
-            epilogue_warp<BN>(p, taddr, s_bias, stage, lane, n0, nt, pix, img, split, half, 2, &tfull_bar[buf], (it >> 1) & 1);
+            epilogue_warp<BN>(p, taddr, s_bias, stage, lane, n0, nt, pix, img, split, half, 2, &tfull_bar[buf], (it >> 1) & 1,
+                              mt * 4 + lg);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(buf ? tempty_leader1 : tempty_leader0);
@@ -800,11 +825,40 @@ extern "C" long long sdb_tc_workspace_bytes(const sdb_tc_args* a) {
     return pl.ws_bytes;
 }
 
+// column-statistics layout of a plan: 4 slots (32-row lane quarters) per 128-row m-tile; only for plans whose tiles
+// never straddle two samples and that store their final values themselves (no split-K)
+static bool colstats_supported(const sdb_tc_args* a, const TcPlan& pl) {
+    return a->taps > 0 && pl.tn == 1 && pl.split_k == 1 && !a->geglu && !a->col_group && a->out_dtype == SDB_F32 &&
+           a->N % 4 == 0 && a->ldc % 4 == 0 && (a->out_sh <= 1 && a->out_sw <= 1 && a->out_oh == 0 && a->out_ow == 0);
+}
+
+extern "C" int sdb_tc_colstats_layout(const sdb_tc_args* a, long long* slots, long long* slots_per_item) {
+    if (!a || !slots || !slots_per_item) return SDB_ERR_INVALID;
+    *slots = 0; *slots_per_item = 0;
+    sdb_tc_args t = *a;
+    if (t.split_k == 0 && !t.ws) t.ws = reinterpret_cast<void*>(16);
+    TcPlan pl;
+    int rc = make_plan(&t, &pl);
+    if (rc) return rc;
+    if (!colstats_supported(a, pl)) return SDB_OK;
+    const long long mt = pl.use_pair ? 2LL * ((pl.m_tiles + 1) / 2) : pl.m_tiles;
+    *slots = 4 * mt;
+    *slots_per_item = 4LL * pl.tiles_w * pl.tiles_h;
+    return SDB_OK;
+}
+
 extern "C" int sdb_tc_contract(const sdb_tc_args* a, void* stream) {
     SDB_REQUIRE(a && a->A && a->B && a->out, "tc_contract: null pointer");
     TcPlan pl;
     int rc = make_plan(a, &pl);
     if (rc) return rc;
+    if (a->colstats) {
+        SDB_REQUIRE(colstats_supported(a, pl), "tc_contract: column statistics need a conv plan with one sample per tile, no split-K, fp32 output");
+        const long long mt = pl.use_pair ? 2LL * ((pl.m_tiles + 1) / 2) : pl.m_tiles;
+        SDB_REQUIRE(a->colstats_slots >= 4 * mt, "tc_contract: colstats buffer has %lld slots, needs %lld", a->colstats_slots, 4 * mt);
+        SDB_REQUIRE(((uintptr_t)a->colstats & 15) == 0 && ((uintptr_t)a->out & 15) == 0 && (!a->residual || (((uintptr_t)a->residual & 15) == 0 && a->ldr % 4 == 0)) &&
+                    (!a->rowvec || (((uintptr_t)a->rowvec & 15) == 0 && a->ldv % 4 == 0)), "tc_contract: column statistics need 16-byte aligned operands");
+    }
     const bool conv = a->taps > 0;
     const int bn = pl.bn;
     const bool use_pair = pl.use_pair;
@@ -827,6 +881,8 @@ extern "C" int sdb_tc_contract(const sdb_tc_args* a, void* stream) {
         p.ws = reinterpret_cast<float*>(a->ws);
         p.ws_split_stride = pl.rows_out * a->N;
     }
+    p.colstats = a->colstats;
+    p.colstats_sq = a->colstats ? a->colstats_slots * (long long)a->N : 0;
     p.tiles_n = pl.tiles_n;
     p.conv = conv;
     p.cout_pad = conv ? a->cout_pad : 0;

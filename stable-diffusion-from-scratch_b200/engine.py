@@ -62,12 +62,13 @@ class PackedLinear:
         self.bias = None if b is None else b.contiguous()
 
 
-def conv(x, pc, rowvec=None, residual=None, out_dtype=torch.float32, up=1):
-    """x [N,H,W,Cin] in pc.in_dtype (fp32 for the SIMT path, bf16 for tcgen05) -> [N,OH,OW,Cout]."""
+def conv(x, pc, rowvec=None, residual=None, out_dtype=torch.float32, up=1, want_stats=False):
+    """x [N,H,W,Cin] in pc.in_dtype (fp32 for the SIMT path, bf16 for tcgen05) -> [N,OH,OW,Cout].
+    want_stats: the output feeds a GroupNorm — let the tcgen05 epilogue also emit its column statistics."""
     if pc.use_tc:
         assert up == 1
         return ops.conv_tc(x, pc.w, pc.bias, pc.kh, pc.kw, stride=pc.stride, pad=pc.pad, rowvec=rowvec,
-                           residual=residual, out_dtype=out_dtype)
+                           residual=residual, out_dtype=out_dtype, want_stats=want_stats)
     return ops.conv_simt(x, pc.w, pc.bias, pc.kh, pc.kw, stride=pc.stride, pad=pc.pad, up=up, rowvec=rowvec,
                          residual=residual, out_dtype=out_dtype)
 

@@ -362,7 +362,7 @@ class UNetModel(nn.Module):
             h, raw = self._gn(rb.in_layers[0], x, mode, 1, x1=x1, out_dtype=c1.in_dtype, want_raw=True)
         else:
             h = self._gn(rb.in_layers[0], x, mode, 1, x1=x1, out_dtype=c1.in_dtype)
-        h = engine.conv(h, c1, rowvec=rowvec)                       # conv + bias + emb_out[..., None, None]
+        h = engine.conv(h, c1, rowvec=rowvec, want_stats=True)      # conv + bias + emb_out[..., None, None]
         h = self._gn(rb.out_layers[0], h, mode, 1, out_dtype=c2.in_dtype)
         if sk is not None:
             xs = raw if raw is not None else ops.cast_concat(x, x1, up=1, out_dtype=sk.in_dtype)
@@ -370,7 +370,7 @@ class UNetModel(nn.Module):
         else:
             assert x1 is None
             xs = x
-        return engine.conv(h, c2, residual=xs)                      # conv + bias + skip_connection(x)
+        return engine.conv(h, c2, residual=xs, want_stats=True)     # conv + bias + skip_connection(x)
 
     def _kv_context(self, blk, P, mode, context):
         """to_k / to_v of the (step-invariant) context, cached per context tensor."""
@@ -465,7 +465,7 @@ class UNetModel(nn.Module):
         tt = t.reshape(B, Hh, Ww, inner)
         if tt.dtype != pout.in_dtype:
             tt = ops.cast_concat(tt, None, out_dtype=pout.in_dtype)
-        return engine.conv(tt, pout, residual=x)
+        return engine.conv(tt, pout, residual=x, want_stats=True)
 
     def _run_block(self, seq, P, mode, h, x1, emb_all, context):
         for layer in seq:
@@ -477,11 +477,11 @@ class UNetModel(nn.Module):
             elif isinstance(layer, Downsample):
                 pc = P[("op", id(layer))]
                 hx = ops.cast_concat(h, None, out_dtype=pc.in_dtype) if pc.in_dtype == torch.bfloat16 else h
-                h = engine.conv(hx, pc)
+                h = engine.conv(hx, pc, want_stats=True)
             elif isinstance(layer, Upsample):
                 pc = P[("conv", id(layer))]
                 if pc.use_tc:
-                    h = engine.conv(ops.cast_concat(h, None, up=2, out_dtype=torch.bfloat16), pc)
+                    h = engine.conv(ops.cast_concat(h, None, up=2, out_dtype=torch.bfloat16), pc, want_stats=True)
                 else:
                     h = engine.conv(h, pc, up=2)
             elif isinstance(layer, nn.Conv2d):

@@ -39,6 +39,7 @@ def nhwc_to_nchw(x):
 
 # ---- normalisation ----------------------------------------------------------------------------------
 _gn_counters = {}
+_USE_COLSTATS = os.environ.get("SDB200_COLSTATS", "1") != "0"     # measurement switch
 
 
 def _gn_ticket_buffer(dev, n):
@@ -64,6 +65,18 @@ def groupnorm(x0, gamma, beta, eps, act=0, out_dtype=torch.float32, x1=None, gro
         C1 = x1.shape[3]
     Ct = C0 + C1
     lib = _L()
+    cs0 = getattr(x0, "_sdb_cs", None)
+    cs1 = getattr(x1, "_sdb_cs", None) if x1 is not None else None
+    if cs0 is not None and (x1 is None or (cs1 is not None and cs1[2] == cs0[2])) and _USE_COLSTATS:
+        # statistics were produced by the conv(s) that wrote x0 / x1: finalize them and make ONE pass over the tensor
+        ws = torch.empty(N * groups * 8 + 256, dtype=torch.uint8, device=x0.device)
+        out = torch.empty((N, H, W, Ct), dtype=out_dtype, device=x0.device)
+        raw = torch.empty((N, H, W, Ct), dtype=torch.bfloat16, device=x0.device) if want_raw else None
+        check(lib.sdb_groupnorm_from_colstats(ptr(x0), C0, ptr(cs0[0]), cs0[1], ptr(x1), C1, ptr(cs1[0]) if cs1 else 0,
+                                              cs1[1] if cs1 else 0, cs0[2], N, H * W, groups, float(eps), ptr(gamma), ptr(beta),
+                                              int(act), int(bool(exact)), ptr(out), dtype_code(out_dtype), ptr(raw), ptr(ws),
+                                              stream_ptr()), "groupnorm_from_colstats")
+        return (out, raw) if want_raw else out
     ws_bytes = lib.sdb_groupnorm_ws_bytes(N, H * W, Ct, groups)
     if ws_bytes < 0:
         raise _lib.SdbError("groupnorm: unsupported shape N=%d HW=%d C=%d" % (N, H * W, Ct))
@@ -331,7 +344,7 @@ def _tc_launch(a, what):
 
 
 def conv_tc(x, w_rskc, bias, kh, kw, stride=1, pad=0, rowvec=None, residual=None, out_dtype=torch.float32,
-            split_k=0, block_n=0, out=None, phase=None, variant=0):
+            split_k=0, block_n=0, out=None, phase=None, variant=0, want_stats=False):
     """x [N,IH,IW,Cin] bf16, w [kh*kw,Cout,Cin] bf16 -> [N,OH,OW,Cout].
 
     phase=(sh, sw, oh, ow, OHF, OWF, pad_h, pad_w) writes this conv's OHxOW result into the strided
@@ -375,7 +388,18 @@ def conv_tc(x, w_rskc, bias, kh, kw, stride=1, pad=0, rowvec=None, residual=None
     if residual is not None:
         assert residual.dtype == torch.float32 and residual.is_contiguous()
     _apply_plan(a, "conv", OH * OW)
+    cs = None
+    if want_stats and phase is None and out.dtype == torch.float32:
+        # per-(32-row slot, channel) sums of the stored values, written by the epilogue: the statistics pass of the
+        # GroupNorm that reads `out` next (ops.groupnorm picks them up from the tensor)
+        slots, spi = C.c_longlong(0), C.c_longlong(0)
+        check(_L().sdb_tc_colstats_layout(C.byref(a), C.byref(slots), C.byref(spi)), "tc colstats layout")
+        if slots.value > 0:
+            cs = torch.empty((2, slots.value, Cout), dtype=torch.float32, device=x.device)
+            a.colstats, a.colstats_slots = cs.data_ptr(), slots.value
     _tc_launch(a, "tc conv")
+    if cs is not None:
+        out._sdb_cs = (cs, slots.value, spi.value)
     return out
 
 

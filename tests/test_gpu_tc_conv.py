@@ -42,3 +42,39 @@ def test_conv_tc_split_k(cuda):
     ref = nhwc(F.conv2d(nchw(x.double()), w.double(), None, padding=1))
     out = ops.conv_tc(x, ops.pack_conv_weight(w, torch.bfloat16), None, 3, 3, pad=1, split_k=4)
     assert rel(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k,variant,bn", [
+    (2, 32, 32, 64, 320, 3, 1, 160), (2, 32, 32, 64, 320, 3, 2, 160), (3, 16, 16, 128, 640, 1, 2, 256),
+    (1, 64, 64, 64, 96, 3, 1, 0), (3, 24, 20, 64, 128, 3, 2, 128), (2, 16, 16, 64, 1280, 3, 0, 0)])
+def test_conv_tc_column_statistics_feed_groupnorm(cuda, N, H, W, Cin, Cout, k, variant, bn):
+    """The conv epilogue's per-slot column sums equal the sums of what it stored, and GroupNorm computed from them
+    (one pass over the tensor) matches GroupNorm computed from the tensor — alone and as one half of a channel concat."""
+    from sdb200 import ops
+    x = randn(N, H, W, Cin, seed=1).to(torch.bfloat16)
+    w = (randn(Cout, Cin, k, k, seed=2) * (Cin * k * k) ** -0.5).to(torch.bfloat16)
+    b = randn(Cout, seed=3)
+    res = randn(N, H, W, Cout, seed=5)
+    wp = ops.pack_conv_weight(w, torch.bfloat16)
+    out = ops.conv_tc(x, wp, b, k, k, pad=k // 2, residual=res, want_stats=True, variant=variant, block_n=bn)
+    plain = ops.conv_tc(x, wp, b, k, k, pad=k // 2, residual=res, variant=variant, block_n=bn)
+    assert torch.equal(out, plain)
+    cs, slots, spi = out._sdb_cs
+    assert cs.shape == (2, slots, Cout) and slots >= N * spi
+    per_sample = cs[:, :N * spi].double().reshape(2, N, spi, Cout).sum(2)
+    o = out.double().reshape(N, H * W, Cout)
+    assert rel(per_sample[0], o.sum(1)) < 1e-5
+    assert rel(per_sample[1], (o * o).sum(1)) < 1e-5
+    g, be = randn(Cout, seed=6) * 0.1 + 1, randn(Cout, seed=7) * 0.1
+    ref = nhwc(F.silu(F.group_norm(nchw(out).double(), 32, g.double(), be.double(), 1e-5)))
+    got = ops.groupnorm(out, g, be, 1e-5, act=1, out_dtype=torch.float32, exact=True)
+    assert rel(got, ref) < 2e-6
+    got16, raw = ops.groupnorm(out, g, be, 1e-5, act=1, out_dtype=torch.bfloat16, want_raw=True)
+    assert rel(got16, ref) < 4e-3 and torch.equal(raw, out.to(torch.bfloat16))
+    # concat with a second producer's output (different channel count)
+    w2 = (randn(64, Cin, k, k, seed=8) * (Cin * k * k) ** -0.5).to(torch.bfloat16)
+    out2 = ops.conv_tc(x, ops.pack_conv_weight(w2, torch.bfloat16), None, k, k, pad=k // 2, want_stats=True)
+    C = Cout + 64
+    g2, be2 = randn(C, seed=9) * 0.1 + 1, randn(C, seed=10) * 0.1
+    ref2 = nhwc(F.group_norm(nchw(torch.cat([out, out2], -1)).double(), 32, g2.double(), be2.double(), 1e-6))
+    assert rel(ops.groupnorm(out, g2, be2, 1e-6, out_dtype=torch.float32, x1=out2, exact=True), ref2) < 2e-6

@@ -45,6 +45,11 @@ elif kind == "gn":
     x = torch.randn(N, HW, 1, Cc, device=dev)
     g, b = torch.randn(Cc, device=dev), torch.randn(Cc, device=dev)
     fn = lambda: ops.groupnorm(x, g, b, 1e-5, act=act, out_dtype=torch.bfloat16)
+elif kind == "ln":
+    rows, Cc = v[:2]
+    x = torch.randn(rows, Cc, device=dev)
+    g, b = torch.randn(Cc, device=dev), torch.randn(Cc, device=dev)
+    fn = lambda: ops.layernorm(x, g, b, 1e-5, out_dtype=torch.bfloat16)
 else:
     raise SystemExit("unknown kind")
 for _ in range(4):
