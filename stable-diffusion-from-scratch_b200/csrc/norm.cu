@@ -52,38 +52,46 @@ __device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f 
 // Statistics from the producer: the tcgen05 conv that wrote the tensor also wrote, per 32-row slot and channel, the sum
 // and sum of squares of what it stored (sdb_tc_args.colstats).  One warp per (sample, group) folds its slots x channels
 // in fp64 in a fixed order -> (mean, rstd); the tensor itself is not read.  Two sources = the channel concat.
-__global__ void gn_colstats_finalize_kernel(const float* __restrict__ cs0, int C0, long long slots0,
-                                            const float* __restrict__ cs1, int C1, long long slots1,
-                                            long long slots_per_item, int groups, int total, double count, float eps,
-                                            float2* __restrict__ stats) {
+__global__ void __launch_bounds__(128)
+gn_colstats_finalize_kernel(const float* __restrict__ cs0, int C0, long long slots0,
+                            const float* __restrict__ cs1, int C1, long long slots1,
+                            long long slots_per_item, int groups, double count, float eps,
+                            float2* __restrict__ stats) {
     pdl_trigger();
     pdl_wait();
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (w >= total) return;
+    __shared__ double redS[128], redQ[128];
+    const int w = blockIdx.x;                       // (sample, group)
     const int n = w / groups, g = w - n * groups;
     const int C = C0 + C1, cpg = C / groups;
+    const long long items = slots_per_item * cpg;
+    const long long sbase = (long long)n * slots_per_item;
     double S = 0.0, Q = 0.0;
-    for (long long sl = lane; sl < slots_per_item; sl += 32) {
-        const long long s = (long long)n * slots_per_item + sl;
-        const float* a0 = cs0 + s * C0;
-        const float* q0 = a0 + slots0 * C0;
-        const float* a1 = cs1 ? cs1 + s * C1 : nullptr;
-        const float* q1 = cs1 ? a1 + slots1 * C1 : nullptr;
-        for (int j = 0; j < cpg; ++j) {
-            const int c = g * cpg + j;
-            if (c < C0) { S += (double)__ldcg(a0 + c); Q += (double)__ldcg(q0 + c); }
-            else        { S += (double)__ldcg(a1 + (c - C0)); Q += (double)__ldcg(q1 + (c - C0)); }
-        }
-    }
+    // item = (slot, channel-in-group); 4 items (8 loads) in flight per thread, summed in index order
+    for (long long i0 = threadIdx.x; i0 < items; i0 += 4 * 128) {
+        float a[4], q[4];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        S += __shfl_xor_sync(0xffffffffu, S, o);
-        Q += __shfl_xor_sync(0xffffffffu, Q, o);
+        for (int u = 0; u < 4; ++u) {
+            const long long i = i0 + u * 128;
+            a[u] = 0.f; q[u] = 0.f;
+            if (i < items) {
+                const long long sl = sbase + i / cpg;
+                const int c = g * cpg + (int)(i % cpg);
+                if (c < C0) { a[u] = __ldcg(cs0 + sl * C0 + c); q[u] = __ldcg(cs0 + (slots0 + sl) * C0 + c); }
+                else        { a[u] = __ldcg(cs1 + sl * C1 + (c - C0)); q[u] = __ldcg(cs1 + (slots1 + sl) * C1 + (c - C0)); }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { S += (double)a[u]; Q += (double)q[u]; }
     }
-    if (lane == 0) {
-        double mean = S / count;
-        double var = Q / count - mean * mean;
+    redS[threadIdx.x] = S; redQ[threadIdx.x] = Q;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { redS[threadIdx.x] += redS[threadIdx.x + o]; redQ[threadIdx.x] += redQ[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double mean = redS[0] / count;
+        double var = redQ[0] / count - mean * mean;
         if (var < 0.0) var = 0.0;
         stats[w] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
     }
@@ -173,16 +181,18 @@ __global__ void gn_stats_kernel(const float* __restrict__ x0, int C0, const floa
 
 // Pass 2: normalise + affine (+ SiLU), emit bf16 (tensor-core operand) or fp32; optionally also the raw
 // (un-normalised) bf16 copy of the concatenated input, which is the operand of a ResBlock's 1x1 skip conv.
-// A thread's <= 8 rows are fetched before the statistics / affine parameters are, so the CTA pays one
-// memory round trip, not two.
+// One wave of CTAs (2 per SM); a thread streams its rows in blocks of 4 with the next block's loads issued before
+// the current block is processed, so every SM keeps ~100 KB of loads in flight from the first to the last row.
+constexpr int GNA_UB = 4;
+
 template <bool OUT_BF16, bool EXACT, bool RAW>
-__global__ void gn_apply_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1,
-                                int HW, int groups, int V, int R, int rows_per_chunk,
-                                const float2* __restrict__ stats, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, int act, void* __restrict__ out,
-                                __nv_bfloat16* __restrict__ raw_out) {
+__global__ void __launch_bounds__(512, 2)
+gn_apply_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1,
+                int HW, int groups, int V, int R, int rows_per_chunk,
+                const float2* __restrict__ stats, const float* __restrict__ gamma,
+                const float* __restrict__ beta, int act, void* __restrict__ out,
+                __nv_bfloat16* __restrict__ raw_out) {
     pdl_trigger();
-    pdl_wait();
     const int C = C0 + C1;
     const int n = blockIdx.y, chunk = blockIdx.x;
     const int v = threadIdx.x % V, rr = threadIdx.x / V;
@@ -196,12 +206,15 @@ __global__ void gn_apply_kernel(const float* __restrict__ x0, int C0, const floa
     int row1 = row0 + rows_per_chunk;
     if (row1 > HW) row1 = HW;
     const float* p = src + ((long long)n * HW) * ld + cc;
-    constexpr int MAXR = 8;          // gn_geom: rows_per_chunk <= 8 * R
-    float4 a[MAXR];
+    const long long rstep = (long long)R * ld;
+    constexpr int UB = GNA_UB;
+    pdl_wait();
+    float4 cur[UB], nxt[UB];
+    int rb = row0 + rr;
 #pragma unroll
-    for (int i = 0; i < MAXR; ++i) {
-        const int row = row0 + rr + i * R;
-        if (row < row1) a[i] = ld_stream_f4(p + (long long)row * ld);
+    for (int i = 0; i < UB; ++i) {
+        cur[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rb + i * R < row1) cur[i] = ld_stream_f4(p + (long long)rb * ld + i * rstep);
     }
     float sc[4], sh[4];
     {
@@ -215,24 +228,52 @@ __global__ void gn_apply_kernel(const float* __restrict__ x0, int C0, const floa
             sh[j] = bb[j] - st.x * st.y * gg[j];
         }
     }
+    const long long obase = ((long long)n * HW) * C + c;
+    for (; rb < row1; rb += UB * R) {
+        const int rn = rb + UB * R;
 #pragma unroll
-    for (int i = 0; i < MAXR; ++i) {
-        const int row = row0 + rr + i * R;
-        if (row >= row1) continue;
-        float y0 = fmaf(a[i].x, sc[0], sh[0]), y1 = fmaf(a[i].y, sc[1], sh[1]);
-        float y2 = fmaf(a[i].z, sc[2], sh[2]), y3 = fmaf(a[i].w, sc[3], sh[3]);
-        if (act == 1) {
-            if (EXACT) { y0 = silu_exact(y0); y1 = silu_exact(y1); y2 = silu_exact(y2); y3 = silu_exact(y3); }
-            else       { y0 = silu_fast(y0);  y1 = silu_fast(y1);  y2 = silu_fast(y2);  y3 = silu_fast(y3); }
+        for (int i = 0; i < UB; ++i) {
+            nxt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rn + i * R < row1) nxt[i] = ld_stream_f4(p + (long long)rn * ld + i * rstep);
         }
-        long long o = ((long long)n * HW + row) * C + c;
-        if (OUT_BF16) {
-            st_stream_u2(reinterpret_cast<__nv_bfloat16*>(out) + o, pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
-        } else {
-            st_stream_f4(reinterpret_cast<float*>(out) + o, make_float4(y0, y1, y2, y3));
+#pragma unroll
+        for (int i = 0; i < UB; ++i) {
+            const int row = rb + i * R;
+            if (row < row1) {
+                float y0 = fmaf(cur[i].x, sc[0], sh[0]), y1 = fmaf(cur[i].y, sc[1], sh[1]);
+                float y2 = fmaf(cur[i].z, sc[2], sh[2]), y3 = fmaf(cur[i].w, sc[3], sh[3]);
+                if (act == 1) {
+                    if (EXACT) { y0 = silu_exact(y0); y1 = silu_exact(y1); y2 = silu_exact(y2); y3 = silu_exact(y3); }
+                    else       { y0 = silu_fast(y0);  y1 = silu_fast(y1);  y2 = silu_fast(y2);  y3 = silu_fast(y3); }
+                }
+                const long long o = obase + (long long)row * C;
+                if (OUT_BF16) st_stream_u2(reinterpret_cast<__nv_bfloat16*>(out) + o, pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+                else st_stream_f4(reinterpret_cast<float*>(out) + o, make_float4(y0, y1, y2, y3));
+                if (RAW) st_stream_u2(raw_out + o, pack_bf16x2(cur[i].x, cur[i].y), pack_bf16x2(cur[i].z, cur[i].w));
+            }
         }
-        if (RAW) st_stream_u2(raw_out + o, pack_bf16x2(a[i].x, a[i].y), pack_bf16x2(a[i].z, a[i].w));
+#pragma unroll
+        for (int i = 0; i < UB; ++i) cur[i] = nxt[i];
     }
+}
+
+// apply-pass geometry: elementwise given the statistics, so (unlike the statistics pass) it may depend on the batch:
+// ~2 CTAs per SM in one wave
+static GnGeom gn_apply_geom(int N, int HW, int C) {
+    GnGeom g;
+    g.V = C / 4;
+    g.R = 512 / g.V;
+    if (g.R < 1) g.R = 1;
+    if (g.R > 32) g.R = 32;
+    if (g.R > HW) g.R = HW;
+    g.threads = g.V * g.R;
+    int want = ceil_div(2 * 148, N);
+    int by_rows = ceil_div(HW, g.R);
+    if (want > by_rows) want = by_rows;
+    if (want < 1) want = 1;
+    g.rows_per_chunk = ceil_div(HW, want);
+    g.chunks = ceil_div(HW, g.rows_per_chunk);
+    return g;
 }
 
 // ---- GroupNorm as ONE kernel: a thread-block cluster per sample ------------------------------------
@@ -409,7 +450,9 @@ static int gnc_max_cluster() {
     auto k = gn_cluster_kernel<BF, EX, RW>;
     if (cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); }
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) { cudaGetLastError(); return cached; }
-    int cs_cap = GNC_MAX_CS;
+    // 16-CTA clusters fit only 7 at a time on a B200 (launch__cluster_max_active), i.e. two waves for 8 samples: the
+    // portable size 8 (one wave) is faster at every UNet shape (profiles/r01_gn_cluster_sizes.txt)
+    int cs_cap = 8;
     if (const char* e = getenv("SDB200_GN_CS")) { int v = atoi(e); if (v >= 2 && v <= GNC_MAX_CS) cs_cap = v; }   // measurement only
     for (int cs = cs_cap; cs >= 2; cs >>= 1) {
         cudaLaunchConfig_t cfg;
@@ -586,9 +629,11 @@ int sdb_groupnorm_nhwc(const float* x0, int C0, const float* x1, int C1, int N, 
                                                    counters, (double)HW * (C / groups), eps, stats);
     int rc = check_launch("gn_stats_kernel");
     if (rc) return rc;
+    const GnGeom ga = gn_apply_geom(N, HW, C);
+    const dim3 grid_a(ga.chunks, N);
 #define LAUNCH_APPLY(BF, EX, RW)                                                                         \
-    launch_pdl(gn_apply_kernel<BF, EX, RW>, dim3(grid), dim3(g.threads), 0, st, x0, C0, x1, C1, HW, groups, g.V, g.R,      \
-                                                             g.rows_per_chunk, stats, gamma, beta, act, out, raw)
+    launch_pdl(gn_apply_kernel<BF, EX, RW>, dim3(grid_a), dim3(ga.threads), 0, st, x0, C0, x1, C1, HW, groups, ga.V, ga.R, \
+                                                             ga.rows_per_chunk, stats, gamma, beta, act, out, raw)
     if (raw) {
         if (out_dtype == SDB_BF16) { if (exact) LAUNCH_APPLY(true, true, true); else LAUNCH_APPLY(true, false, true); }
         else                       { if (exact) LAUNCH_APPLY(false, true, true); else LAUNCH_APPLY(false, false, true); }
@@ -618,11 +663,11 @@ int sdb_groupnorm_from_colstats(const float* x0, int C0, const float* cs0, long 
     cudaStream_t st = (cudaStream_t)stream;
     float2* stats = reinterpret_cast<float2*>(ws);                 // [N][groups]
     const int total = N * groups;
-    launch_pdl(gn_colstats_finalize_kernel, dim3(ceil_div(total, 8)), dim3(256), 0, st, cs0, C0, slots0, cs1, C1, slots1,
-               slots_per_item, groups, total, (double)HW * (C / groups), eps, stats);
+    launch_pdl(gn_colstats_finalize_kernel, dim3(total), dim3(128), 0, st, cs0, C0, slots0, cs1, C1, slots1,
+               slots_per_item, groups, (double)HW * (C / groups), eps, stats);
     int rc = check_launch("gn_colstats_finalize_kernel");
     if (rc) return rc;
-    GnGeom g = gn_geom(N, HW, C);
+    GnGeom g = gn_apply_geom(N, HW, C);
     dim3 grid(g.chunks, N);
     __nv_bfloat16* raw = reinterpret_cast<__nv_bfloat16*>(raw_out);
 #define LAUNCH_APPLY(BF, EX, RW)                                                                         \

@@ -37,8 +37,8 @@ else:
     z = torch.randn(a.batch, 4, a.latent, a.latent, device=dev)
     run = lambda: net.decode(z)
 
-NAMES = ["sdb_tc_contract", "sdb_attention_fwd", "sdb_groupnorm_nhwc", "sdb_layernorm", "sdb_cast_concat", "sdb_simt_contract",
-         "sdb_skinny_linear"]
+NAMES = ["sdb_tc_contract", "sdb_attention_fwd", "sdb_groupnorm_nhwc", "sdb_groupnorm_from_colstats", "sdb_layernorm", "sdb_cast_concat",
+         "sdb_simt_contract", "sdb_skinny_linear"]
 
 
 def describe(name, args):
@@ -51,6 +51,8 @@ def describe(name, args):
         return "attn B=%d H=%d Sq=%d Sk=%d d=%d" % (o.B, o.H, o.Sq, o.Sk, o.d), 4.0 * o.B * o.H * o.Sq * o.Sk * o.d
     if name == "sdb_groupnorm_nhwc":
         return "groupnorm N=%d HW=%d C=%d" % (args[4], args[5], args[1] + args[3]), 0.0
+    if name == "sdb_groupnorm_from_colstats":
+        return "groupnorm(colstats) N=%d HW=%d C=%d" % (args[9], args[10], args[1] + args[5]), 0.0
     if name == "sdb_layernorm":
         return "layernorm rows=%d C=%d" % (args[1], args[2]), 0.0
     if name == "sdb_cast_concat":
