@@ -186,7 +186,7 @@ __global__ void gn_stats_kernel(const float* __restrict__ x0, int C0, const floa
 constexpr int GNA_UB = 4;
 
 template <bool OUT_BF16, bool EXACT, bool RAW>
-__global__ void __launch_bounds__(512, 2)
+__global__ void __launch_bounds__(1024, 1)      // <= 64 registers: two ~480-thread CTAs per SM; C up to 4096 in one CTA row
 gn_apply_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1,
                 int HW, int groups, int V, int R, int rows_per_chunk,
                 const float2* __restrict__ stats, const float* __restrict__ gamma,

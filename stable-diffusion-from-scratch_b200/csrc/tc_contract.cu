@@ -48,7 +48,21 @@ struct TcP {
     int tw, th, tn, tiles_w, tiles_h;
     int cout_pad;
     int out_sh, out_sw, out_oh, out_ow, OHF, OWF;
+#ifdef SDB_TC_TRACE
+    long long* trace;       // [pair][64 units][8] SM clock stamps (measurement build only, tools/trace_pair.py)
+#endif
 };
+
+#ifdef SDB_TC_TRACE
+#define TC_TRACE(slot, it_)                                                                              \
+    do {                                                                                                 \
+        if (p.trace && rank == 0 && (it_) < 64) p.trace[((long long)pair * 64 + (it_)) * 8 + (slot)] = clock64(); \
+    } while (0)
+static long long* g_trace_ptr = nullptr;
+extern "C" void sdb_tc_set_trace(long long* ptr) { g_trace_ptr = ptr; }
+#else
+#define TC_TRACE(slot, it_) do { } while (0)
+#endif
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
@@ -97,7 +111,7 @@ __device__ __forceinline__ void prefetch_residual_row(const TcP& p, long long pi
 // `row_img` = its image index (conv mode; selects the time-embedding row).  The warp handles the
 // 32-column chunks ch0, ch0 + chstep, ... (two warps can share one lane quarter).
 template <int BN>
-__device__ __forceinline__ void epilogue_warp(const TcP& p, uint32_t taddr, const float* s_bias, float* stage, int lane,
+__device__ __noinline__ void epilogue_generic(const TcP p /* by value: a reference would force the kernel's parameter block into local memory */, uint32_t taddr, const float* s_bias, float* stage, int lane,
                                               int n0, int nt, long long row_pix, int row_img, int split, int ch0, int chstep,
                                               uint64_t* acc_ready, uint32_t acc_parity, int slot) {
     // rows this lane stores after the transpose: r_i = 4*i + (lane >> 3), i = 0..7
@@ -244,6 +258,179 @@ __device__ __forceinline__ void epilogue_warp(const TcP& p, uint32_t taddr, cons
         }
     }
     __syncwarp();
+}
+
+// ---- fast epilogue -------------------------------------------------------------------------------------
+// Same data flow as epilogue_generic (TMEM row-per-lane -> padded smem transpose -> 4 full 128-B row segments per
+// store instruction) for the layouts the models actually use (16-byte aligned, N % 4 == 0, residual pitch == output
+// pitch), with everything that does not change inside a work unit hoisted out of the chunk loop: the eight row
+// offsets and their validity mask, the column-group remap, the uniform time-embedding row; stores are predicated,
+// not branched around, and the output kind is a template parameter.  The generic version spent ~900 warp
+// instructions per 32x32 chunk on index arithmetic and divergence bookkeeping (profiles/r01_pair_timeline.txt: the
+// epilogue, not the MMA, paced every K <= 1280 layer); this one needs ~200.
+enum { EPI_F32 = 0, EPI_BF16 = 1, EPI_PARTIAL = 2, EPI_GEGLU = 3 };
+
+template <int BN, int MODE, bool HAS_ADD>
+__device__ __forceinline__ void epilogue_fast(const TcP& p, uint32_t taddr, const float* s_bias, float* stage, int lane,
+                                              int n0, int nt, long long row_pix, int row_img, int split, int ch0, int chstep,
+                                              uint64_t* acc_ready, uint32_t acc_parity, int slot) {
+    constexpr int CH = 32;
+    constexpr bool GEGLU = MODE == EPI_GEGLU;
+    constexpr int COLS = GEGLU ? BN / 2 : BN;
+    constexpr int NCHUNK = (COLS + CH - 1) / CH;
+    const int n_out = GEGLU ? p.N / 2 : p.N;
+    const int nb = GEGLU ? nt * (BN / 2) : n0;
+    const int cq = 4 * (lane & 7);
+    const int rsel = lane >> 3;
+    const uint32_t stage_a = smem_u32(stage), sbias_a = smem_u32(s_bias);
+    const long long ldo = MODE == EPI_PARTIAL ? (long long)p.N : p.ldc;
+    // rows this lane stores after the transpose: 4*i + rsel
+    long long roff[8];
+    uint32_t mask = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const long long px = __shfl_sync(0xffffffffu, row_pix, 4 * i + rsel);
+        if (px >= 0) mask |= 1u << i;
+        roff[i] = px * ldo;
+    }
+    const float* const resid = (HAS_ADD && p.residual) ? p.residual : nullptr;
+    const float* rowv = (HAS_ADD && p.rowvec && p.conv) ? p.rowvec : nullptr;
+    const int img0 = __shfl_sync(0xffffffffu, row_img, 0);
+    const bool rv_uniform = __all_sync(0xffffffffu, row_img == img0);
+    int rimg[8];
+    if (HAS_ADD && rowv && !rv_uniform) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rimg[i] = __shfl_sync(0xffffffffu, row_img, 4 * i + rsel);
+    }
+    float* const ws = MODE == EPI_PARTIAL ? p.ws + (long long)split * p.ws_split_stride : nullptr;
+    const bool want_cs = MODE == EPI_F32 && p.colstats != nullptr;
+
+    float4 addn[8];
+    auto fetch_residual = [&](int ch, float4 (&dst)[8]) {
+        const int cn_ = nb + ch * CH + cq;
+        const bool live = resid != nullptr && ch < NCHUNK && cn_ < n_out;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dst[i] = ldg_f4_or_zero(resid + roff[i] + cn_, live && ((mask >> i) & 1u));
+    };
+    if (HAS_ADD) fetch_residual(ch0, addn);
+    mbar_wait(acc_ready, acc_parity);
+    tcgen05_fence_after();
+#pragma unroll 1
+    for (int ch = ch0; ch < NCHUNK; ch += chstep) {
+        const int c0 = ch * CH;
+        if (nb + c0 >= n_out) break;                                    // warp-uniform
+        const int cn = nb + c0 + cq;
+        const bool col_ok = cn < n_out;
+        float4 addv[8];
+        if (HAS_ADD) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) addv[i] = addn[i];
+            fetch_residual(ch + chstep, addn);
+        }
+        float4 cadd = make_float4(0.f, 0.f, 0.f, 0.f);                  // per-column addend: bias (+ uniform time-emb row)
+        if (HAS_ADD && rowv && rv_uniform) cadd = ldg_f4_or_zero(rowv + (long long)img0 * p.ldv + cn, col_ok);
+        uint32_t r[32];
+        tmem_ld_x32(taddr + c0, r);
+        if (GEGLU) {
+            uint32_t g[32];
+            tmem_ld_x32(taddr + BN / 2 + c0, g);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 bv = lds128(sbias_a + 4 * (c0 + 4 * q));
+                const float4 bg = lds128(sbias_a + 4 * (BN / 2 + c0 + 4 * q));
+                r[4 * q + 0] = __float_as_uint((__uint_as_float(r[4 * q + 0]) + bv.x) * gelu_erf_fast(__uint_as_float(g[4 * q + 0]) + bg.x));
+                r[4 * q + 1] = __float_as_uint((__uint_as_float(r[4 * q + 1]) + bv.y) * gelu_erf_fast(__uint_as_float(g[4 * q + 1]) + bg.y));
+                r[4 * q + 2] = __float_as_uint((__uint_as_float(r[4 * q + 2]) + bv.z) * gelu_erf_fast(__uint_as_float(g[4 * q + 2]) + bg.z));
+                r[4 * q + 3] = __float_as_uint((__uint_as_float(r[4 * q + 3]) + bv.w) * gelu_erf_fast(__uint_as_float(g[4 * q + 3]) + bg.w));
+            }
+        } else {
+            tmem_ld_wait();
+        }
+        __syncwarp();                                                   // previous chunk's readers are done
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            sts128(stage_a + 4 * (lane * EPI_LD + 4 * q), r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+        __syncwarp();
+        if (MODE == EPI_F32 || MODE == EPI_BF16) {
+            const float4 b4 = lds128(sbias_a + 4 * (c0 + cq));
+            cadd.x += b4.x; cadd.y += b4.y; cadd.z += b4.z; cadd.w += b4.w;
+        }
+        int dn = cn;                                                    // destination column (q/k/v head padding remap)
+        if (MODE == EPI_BF16 && p.col_group) dn = (cn / p.col_group) * p.col_group_stride + cn % p.col_group;
+        float4 cs_s = make_float4(0.f, 0.f, 0.f, 0.f), cs_q = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float4 v = lds128(stage_a + 4 * ((4 * i + rsel) * EPI_LD + cq));
+            v.x += cadd.x; v.y += cadd.y; v.z += cadd.z; v.w += cadd.w;
+            if (HAS_ADD) {
+                v.x += addv[i].x; v.y += addv[i].y; v.z += addv[i].z; v.w += addv[i].w;
+                if (rowv && !rv_uniform) {
+                    const float4 q4 = ldg_f4_or_zero(rowv + (long long)rimg[i] * p.ldv + cn, col_ok && ((mask >> i) & 1u));
+                    v.x += q4.x; v.y += q4.y; v.z += q4.z; v.w += q4.w;
+                }
+            }
+            const bool ok = col_ok && ((mask >> i) & 1u);
+            if (MODE == EPI_F32) {
+                if (want_cs && ok) {
+                    cs_s.x += v.x; cs_s.y += v.y; cs_s.z += v.z; cs_s.w += v.w;
+                    cs_q.x = fmaf(v.x, v.x, cs_q.x); cs_q.y = fmaf(v.y, v.y, cs_q.y);
+                    cs_q.z = fmaf(v.z, v.z, cs_q.z); cs_q.w = fmaf(v.w, v.w, cs_q.w);
+                }
+                if (ok) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + roff[i] + cn) = v;
+            } else if (MODE == EPI_PARTIAL) {
+                if (ok) *reinterpret_cast<float4*>(ws + roff[i] + cn) = v;
+            } else if (MODE == EPI_BF16 || p.out_bf16) {
+                if (ok) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + roff[i] + dn) =
+                            make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+            } else {
+                if (ok) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + roff[i] + cn) = v;
+            }
+        }
+        if (want_cs) {
+            // rows 4i + rsel live in this lane: fold the 4 lanes that share a column quad (fixed order)
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) {
+                cs_s.x += __shfl_xor_sync(0xffffffffu, cs_s.x, o); cs_s.y += __shfl_xor_sync(0xffffffffu, cs_s.y, o);
+                cs_s.z += __shfl_xor_sync(0xffffffffu, cs_s.z, o); cs_s.w += __shfl_xor_sync(0xffffffffu, cs_s.w, o);
+                cs_q.x += __shfl_xor_sync(0xffffffffu, cs_q.x, o); cs_q.y += __shfl_xor_sync(0xffffffffu, cs_q.y, o);
+                cs_q.z += __shfl_xor_sync(0xffffffffu, cs_q.z, o); cs_q.w += __shfl_xor_sync(0xffffffffu, cs_q.w, o);
+            }
+            if (lane < 8 && col_ok) {
+                float* dst = p.colstats + (long long)slot * p.N + cn;
+                *reinterpret_cast<float4*>(dst) = cs_s;
+                *reinterpret_cast<float4*>(dst + p.colstats_sq) = cs_q;
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// picks the epilogue for this launch (warp-uniform): the fast one whenever the layout allows
+template <int BN>
+__device__ __forceinline__ void epilogue_warp(const TcP& p, uint32_t taddr, const float* s_bias, float* stage, int lane,
+                                              int n0, int nt, long long row_pix, int row_img, int split, int ch0, int chstep,
+                                              uint64_t* acc_ready, uint32_t acc_parity, int slot) {
+    const int n_out = p.geglu ? p.N / 2 : p.N;
+    const bool partial = p.split_k > 1;
+    const bool fast_ok = (n_out % 4 == 0) && (p.ldc % 4 == 0) && (p.ldv % 4 == 0) &&
+                         ((reinterpret_cast<uintptr_t>(p.out) | reinterpret_cast<uintptr_t>(p.residual) |
+                           reinterpret_cast<uintptr_t>(p.rowvec) | reinterpret_cast<uintptr_t>(p.ws)) & 15) == 0 &&
+                         (!p.col_group || (p.col_group % 4 == 0 && p.col_group_stride % 4 == 0)) &&
+                         (p.residual == nullptr || partial || p.ldr == p.ldc) && !(p.geglu && partial);
+#define SDB_EPI(MODE, ADD) epilogue_fast<BN, MODE, ADD>(p, taddr, s_bias, stage, lane, n0, nt, row_pix, row_img, split, ch0, chstep, acc_ready, acc_parity, slot)
+    if (!fast_ok) {
+        epilogue_generic<BN>(p, taddr, s_bias, stage, lane, n0, nt, row_pix, row_img, split, ch0, chstep, acc_ready, acc_parity, slot);
+    } else if (p.geglu) {
+        SDB_EPI(EPI_GEGLU, false);
+    } else if (partial) {
+        SDB_EPI(EPI_PARTIAL, false);
+    } else {
+        const bool has_add = p.residual != nullptr || (p.rowvec != nullptr && p.conv);
+        if (p.out_bf16) { if (has_add) SDB_EPI(EPI_BF16, true); else SDB_EPI(EPI_BF16, false); }
+        else            { if (has_add) SDB_EPI(EPI_F32, true);  else SDB_EPI(EPI_F32, false); }
+    }
+#undef SDB_EPI
 }
 
 template <int BN>
@@ -465,6 +652,8 @@ tc_contract_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                 int r = p.conv ? tap / p.kw : 0, sx = p.conv ? tap - r * p.kw : 0;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[s], ph ^ 1);
+                    if (load_a && kb == kb0) TC_TRACE(6, (u - pair) / npairs);
+                    if (load_a && kb == kb1 - 1) TC_TRACE(7, (u - pair) / npairs);
                     const uint32_t fb = fb0 + 8u * (uint32_t)s;
                     if (load_a) {
                         if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
@@ -491,12 +680,15 @@ tc_contract_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                 const int kb0 = (int)((long long)p.kblocks * split / p.split_k);
                 const int kb1 = (int)((long long)p.kblocks * (split + 1) / p.split_k);
                 const int buf = it & 1;
+                TC_TRACE(5, it);
                 mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);     // both CTAs' epilogues drained this accumulator
                 tcgen05_fence_after();
+                TC_TRACE(0, it);
                 const uint32_t acc = tmem_d + buf * Cfg::ACC_STRIDE;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full_bar[s], ph);
                     tcgen05_fence_after();
+                    if (kb == kb0) TC_TRACE(1, it);
                     const uint64_t adesc = adesc0 + (uint64_t)(s * (TC_A_BYTES >> 4));
                     const uint64_t bdesc = bdesc0 + (uint64_t)(s * (Cfg::B_HALF_BYTES >> 4));
 #pragma unroll
@@ -506,6 +698,7 @@ tc_contract_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
                 umma_commit_pair(&tfull_bar[buf], 3);                // accumulator ready in both CTAs
+                TC_TRACE(2, it);
             }
         }
     } else if (warp >= 4) {
@@ -558,8 +751,10 @@ tc_contract_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             int img = 0;
             const long long pix = row_of(mt, img);
             const uint32_t taddr = tmem_d + ((uint32_t)(lg * 32) << 16) + buf * Cfg::ACC_STRIDE;
+            if (warp == 4 && lane == 0) TC_TRACE(3, it);
             epilogue_warp<BN>(p, taddr, s_bias, stage, lane, n0, nt, pix, img, split, half, 2, &tfull_bar[buf], (it >> 1) & 1,
                               mt * 4 + lg);
+            if (warp == 4 && lane == 0) TC_TRACE(4, it);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(buf ? tempty_leader1 : tempty_leader0);
@@ -883,6 +1078,9 @@ extern "C" int sdb_tc_contract(const sdb_tc_args* a, void* stream) {
     }
     p.colstats = a->colstats;
     p.colstats_sq = a->colstats ? a->colstats_slots * (long long)a->N : 0;
+#ifdef SDB_TC_TRACE
+    p.trace = g_trace_ptr;
+#endif
     p.tiles_n = pl.tiles_n;
     p.conv = conv;
     p.cout_pad = conv ? a->cout_pad : 0;

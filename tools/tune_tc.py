@@ -58,17 +58,25 @@ torch.cuda.empty_cache()
 print("distinct contractions:", len(shapes), flush=True)
 
 
-def timed(fn, nrot, iters):
+def timed(fn, nrot, iters, warm=None):
+    """Mean device time of fn(i) bracketed by events, one launch at a time.  `warm(i)` (untimed) re-writes the A operand first,
+    so that it sits in L2 as it does in the real step (it was just produced by the preceding norm kernel) while the
+    rotated weights / residual / output come from DRAM."""
     for i in range(2):
         fn(i % nrot)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    evs = []
     for i in range(iters):
+        if warm is not None:
+            warm(i % nrot)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         fn(i % nrot)
-    e1.record()
+        e1.record()
+        evs.append((e0, e1))
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters * 1e3
+    ts = sorted(a.elapsed_time(b) for a, b in evs)
+    return ts[len(ts) // 2] * 1e3                      # median, us
 
 
 out_f = open(a.out, "w")
@@ -90,6 +98,9 @@ for key, count in sorted(shapes.items(), key=lambda kv: -kv[0][0] * kv[0][1] * k
         A = [torch.randn(M, K, device=dev).to(torch.bfloat16) for _ in range(nrot)]
         W = [(torch.randn(N, K, device=dev) / K ** 0.5).to(torch.bfloat16) for _ in range(nrot)]
         oshape = (M, width)
+    Asrc = A[0].clone()
+    warm = (lambda i: A[i].copy_(Asrc)) if A[0].numel() * 2 <= 48e6 else None
+    stats = conv and not obf
     bias = torch.randn(N, device=dev) if has_bias else None
     R = [torch.randn(oshape, device=dev) for _ in range(nrot)] if has_res else None
     rowvec = torch.randn(d["NB"], N, device=dev) if has_rowvec else None
@@ -109,13 +120,13 @@ for key, count in sorted(shapes.items(), key=lambda kv: -kv[0][0] * kv[0][1] * k
                 def fn(i):
                     if conv:
                         ops.conv_tc(A[i], W[i], bias, d["taps"] // d["kw"], d["kw"], stride=d["stride"], pad=d["pad_h"], rowvec=rowvec,
-                                    residual=R[i] if R else None, out=O[i], split_k=sk, block_n=bn, variant=variant)
+                                    residual=R[i] if R else None, out=O[i], split_k=sk, block_n=bn, variant=variant, want_stats=stats and sk == 1)
                     else:
                         ops.gemm_tc(A[i], W[i], bias, residual=R[i] if R else None, geglu=bool(d["geglu"]), col_group=d["col_group"],
                                     col_group_stride=d["col_group_stride"], split_k=sk, block_n=bn, out=O[i],
                                     rows_per_item=d["rows_per_item"], variant=variant)
                 try:
-                    us = timed(fn, nrot, a.iters)
+                    us = timed(fn, nrot, a.iters, warm)
                     res.append((variant, bn, sk, round(us, 2)))
                 except Exception as e:
                     res.append((variant, bn, sk, None))
@@ -123,11 +134,11 @@ for key, count in sorted(shapes.items(), key=lambda kv: -kv[0][0] * kv[0][1] * k
     def fn0(i):
         if conv:
             ops.conv_tc(A[i], W[i], bias, d["taps"] // d["kw"], d["kw"], stride=d["stride"], pad=d["pad_h"], rowvec=rowvec,
-                        residual=R[i] if R else None, out=O[i], block_n=d["block_n"])
+                        residual=R[i] if R else None, out=O[i], block_n=d["block_n"], want_stats=stats)
         else:
             ops.gemm_tc(A[i], W[i], bias, residual=R[i] if R else None, geglu=bool(d["geglu"]), col_group=d["col_group"],
                         col_group_stride=d["col_group_stride"], block_n=d["block_n"], out=O[i], rows_per_item=d["rows_per_item"])
-    auto_us = timed(fn0, nrot, a.iters)
+    auto_us = timed(fn0, nrot, a.iters, warm)
     ok = [r for r in res if r[3] is not None]
     best = min(ok, key=lambda r: r[3])
     rec = {"shape": d, "res": has_res, "rowvec": has_rowvec, "count": count, "auto_us": round(auto_us, 2), "best": best, "all": res,
