@@ -327,8 +327,11 @@ __device__ __forceinline__ void epilogue_fast(const TcP& p, uint32_t taddr, cons
             for (int i = 0; i < 8; ++i) addv[i] = addn[i];
             fetch_residual(ch + chstep, addn);
         }
-        float4 cadd = make_float4(0.f, 0.f, 0.f, 0.f);                  // per-column addend: bias (+ uniform time-emb row)
-        if (HAS_ADD && rowv && rv_uniform) cadd = ldg_f4_or_zero(rowv + (long long)img0 * p.ldv + cn, col_ok);
+        float4 cadd = make_float4(0.f, 0.f, 0.f, 0.f);                  // per-column addend: bias
+        // time-embedding row: one load per chunk when the whole tile belongs to one image, else one per row; it is added
+        // LAST in both cases, so a sample's bits do not depend on whether its tile is shared with another sample
+        float4 rv4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (HAS_ADD && rowv && rv_uniform) rv4 = ldg_f4_or_zero(rowv + (long long)img0 * p.ldv + cn, col_ok);
         uint32_t r[32];
         tmem_ld_x32(taddr + c0, r);
         if (GEGLU) {
@@ -365,10 +368,9 @@ __device__ __forceinline__ void epilogue_fast(const TcP& p, uint32_t taddr, cons
             v.x += cadd.x; v.y += cadd.y; v.z += cadd.z; v.w += cadd.w;
             if (HAS_ADD) {
                 v.x += addv[i].x; v.y += addv[i].y; v.z += addv[i].z; v.w += addv[i].w;
-                if (rowv && !rv_uniform) {
-                    const float4 q4 = ldg_f4_or_zero(rowv + (long long)rimg[i] * p.ldv + cn, col_ok && ((mask >> i) & 1u));
-                    v.x += q4.x; v.y += q4.y; v.z += q4.z; v.w += q4.w;
-                }
+                float4 q4 = rv4;
+                if (rowv && !rv_uniform) q4 = ldg_f4_or_zero(rowv + (long long)rimg[i] * p.ldv + cn, col_ok && ((mask >> i) & 1u));
+                v.x += q4.x; v.y += q4.y; v.z += q4.z; v.w += q4.w;
             }
             const bool ok = col_ok && ((mask >> i) & 1u);
             if (MODE == EPI_F32) {
