@@ -32,7 +32,22 @@ using namespace ptx;
 int make_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const long long* dims, const long long* strides_elems,
                    const int* box, const int* estr);
 
+#ifdef SDB_ATTN_TRACE
+static long long* g_attn_trace = nullptr;
+extern "C" void sdb_attn_set_trace(long long* ptr) { g_attn_trace = ptr; }
+#define AT_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && t < 32) \
+    p.trace[((warp - 4) * 32 + t) * 8 + (slot)] = clock64(); } while (0)
+#define AT_TRACE_MMA(slot) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && t < 32) \
+    p.trace[(8 * 32 + t) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define AT_TRACE(slot) do { } while (0)
+#define AT_TRACE_MMA(slot) do { } while (0)
+#endif
+
 struct AttnP {
+#ifdef SDB_ATTN_TRACE
+    long long* trace;
+#endif
     void* out;
     long long o_bs, o_ss, o_hs;
     int Sq, Sk, d, H;
@@ -44,9 +59,12 @@ struct AttnCfg {
     static constexpr int G = (256 + 2 * DPAD <= 512) ? 2 : 1;   // query tiles per CTA (TMEM: G * (128 + DPAD) columns)
     static constexpr int NBLK = DPAD / 64;                      // 64-wide column blocks per operand tile
     static constexpr int TILE_BYTES = 128 * DPAD * 2;           // one Q / K / V tile
-    static constexpr int STAGES = DPAD == 64 ? 3 : 1;
+    static constexpr int STAGES = DPAD == 64 ? 2 : 1;
     static constexpr int P_BYTES = 128 * 128 * 2;
-    static constexpr int SMEM_BYTES = 1024 + TILE_BYTES * (G + 2 * STAGES) + G * P_BYTES + 512;
+    // d <= 64: two P buffers per query tile, so the softmax of key tile t never waits for P_{t-1} V to retire (that
+    // wait left the MUFU pipe idle ~40 % of the time, profiles/r01_ncu_full_summary.txt); larger heads have no smem for it
+    static constexpr int PBUF = DPAD == 64 ? 2 : 1;
+    static constexpr int SMEM_BYTES = 1024 + TILE_BYTES * (G + 2 * STAGES) + G * PBUF * P_BYTES + 512;
     static constexpr int TMEM_COLS = 512;
     static constexpr int THREADS = 128 + 128 * G;
     __host__ __device__ static constexpr int s_col(int g) { return g * 128; }
@@ -58,10 +76,27 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+#ifndef SDB_ATTN_VARIANT
+#define SDB_ATTN_VARIANT 0      // measurement builds: bit 0 = 2-input max, bit 1 = integer bf16 pack (tools/attn_variants.sh)
+#endif
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
+#if SDB_ATTN_VARIANT & 1
+    return fmaxf(fmaxf(a, b), c);
+#else
     float y;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
     return y;
+#endif
+}
+// two non-negative fp32 -> packed bf16x2 (lo in the low half), round-to-nearest
+__device__ __forceinline__ uint32_t pack_p_bf16x2(float lo, float hi) {
+#if SDB_ATTN_VARIANT & 2
+    // integer rounding (half away from zero on the magnitude; the inputs are probabilities in [0, 1]): 2 IADD + 1 PRMT
+    const uint32_t a = __float_as_uint(lo) + 0x8000u, b = __float_as_uint(hi) + 0x8000u;
+    return __byte_perm(a, b, 0x7632);
+#else
+    return pack_bf16x2(lo, hi);
+#endif
 }
 
 template <int DPAD>
@@ -72,13 +107,15 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     constexpr int ST = Cfg::STAGES;
     constexpr int NBLK = Cfg::NBLK;
     constexpr int G = Cfg::G;
+    constexpr int PB = Cfg::PBUF;
+    constexpr int NI = (G == 2 && DPAD == 64) ? 2 : 1;      // MMA-issuing threads
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sQ = smem;                                   // [G] tiles
     uint8_t* sK = sQ + G * Cfg::TILE_BYTES;               // [ST]
     uint8_t* sV = sK + ST * Cfg::TILE_BYTES;              // [ST]
-    uint8_t* sP = sV + ST * Cfg::TILE_BYTES;              // [G] 128 x 128 bf16
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + G * Cfg::P_BYTES);
+    uint8_t* sP = sV + ST * Cfg::TILE_BYTES;              // [G][PB] 128 x 128 bf16
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + G * PB * Cfg::P_BYTES);
     uint64_t* q_full = bars;            // 1
     uint64_t* k_full = bars + 1;        // ST
     uint64_t* k_empty = k_full + ST;    // ST
@@ -86,9 +123,9 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint64_t* v_empty = v_full + ST;    // ST
     uint64_t* s_full = v_empty + ST;    // G   S_g written by the MMA
     uint64_t* s_empty = s_full + G;     // G   S_g copied to registers by its 128 softmax threads
-    uint64_t* p_full = s_empty + G;     // G   P_g written to smem
-    uint64_t* pv_done = p_full + G;     // G   O_g += P_g V retired (P_g and O_g free)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + G);
+    uint64_t* p_full = s_empty + G;     // G*PB  P_g (buffer b) written to smem
+    uint64_t* pv_done = p_full + G * PB;   // G*PB  O_g += P_g[b] V retired (that P buffer is free; with PB = 1 also O_g)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + G * PB);
 
     pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -99,13 +136,11 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
         mbar_init(q_full, 1);
         for (int s = 0; s < ST; ++s) {
-            mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
-            mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+            mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], NI);   // every MMA issuer releases the slot
+            mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], NI);
         }
-        for (int g = 0; g < G; ++g) {
-            mbar_init(&s_full[g], 1); mbar_init(&s_empty[g], 128);
-            mbar_init(&p_full[g], 128); mbar_init(&pv_done[g], 1);
-        }
+        for (int g = 0; g < G; ++g) { mbar_init(&s_full[g], 1); mbar_init(&s_empty[g], 128); }
+        for (int i = 0; i < G * PB; ++i) { mbar_init(&p_full[i], 128); mbar_init(&pv_done[i], 1); }
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -140,52 +175,71 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 if (++s == ST) { s = 0; ph ^= 1; }
             }
         }
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
+    } else if (warp == 1 || (NI == 2 && warp == 3)) {
+        // ================= MMA issuers: one elected thread per issuer =================
+        // A single thread issuing both tiles' 22 small MMAs per key tile (3 x QK^T, 8 x PV each, d = 40) took ~3000 cycles
+        // per key tile (profiles/r01_attn_timeline.txt) — longer than the exponentials; the tensor pipe sat idle behind
+        // the issue thread.  For d <= 64 two issuers (warp 1 -> tile 0, warp 3 -> tile 1) halve that chain and decouple the
+        // tiles; descriptors are built once and every MMA just adds an offset.
         if (lane == 0) {
+            const int g_lo = (NI == 2 && warp == 3) ? 1 : 0;
+            const int g_hi = NI == 2 ? g_lo + 1 : G;
             const uint32_t idesc_s = umma_idesc_bf16(128, false, false);     // S = Q K^T : N = 128 keys
             const uint32_t idesc_o = umma_idesc_bf16(DPAD, false, true);     // O = P V   : B (V) is MN-major
             const int ksteps_qk = (p.d + 15) / 16;
+            constexpr uint32_t TILE16 = Cfg::TILE_BYTES >> 4;                // descriptor address units are 16 bytes
+            const uint64_t qdesc0 = umma_desc_kmajor_sw128(smem_u32(sQ));
+            const uint64_t kdesc0 = umma_desc_kmajor_sw128(smem_u32(sK));
+            const uint64_t vdesc0 = umma_desc_mnmajor_sw128(smem_u32(sV), 16384);
+            const uint64_t pdesc0 = umma_desc_kmajor_sw128(smem_u32(sP));
             mbar_wait(q_full, 0);
             int s = 0; uint32_t ph = 0;        // K ring
             int sv = 0; uint32_t phv = 0;      // V ring (lags by one tile)
             for (int t = 0; t <= ntiles; ++t) {
                 if (t < ntiles) {
+                    if (g_lo == 0) AT_TRACE_MMA(0);
                     mbar_wait(&k_full[s], ph);
-                    const uint32_t ka = smem_u32(sK + s * Cfg::TILE_BYTES);
-#pragma unroll
-                    for (int g = 0; g < G; ++g) {
+                    if (g_lo == 0) AT_TRACE_MMA(1);
+                    const uint64_t kdesc = kdesc0 + (uint64_t)(s * TILE16);
+                    for (int g = g_lo; g < g_hi; ++g) {
                         mbar_wait(&s_empty[g], (t & 1) ^ 1);       // softmax g holds S_g(t-1) in registers
                         tcgen05_fence_after();
-                        const uint32_t qa = smem_u32(sQ + g * Cfg::TILE_BYTES);
-                        for (int k = 0; k < ksteps_qk; ++k) {
-                            const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
-                            umma_bf16_ss(tmem + Cfg::s_col(g), umma_desc_kmajor_sw128(qa + off),
-                                         umma_desc_kmajor_sw128(ka + off), idesc_s, k > 0 ? 1u : 0u);
+                        if (g == 0) AT_TRACE_MMA(2);
+                        const uint64_t qdesc = qdesc0 + (uint64_t)(g * TILE16);
+#pragma unroll
+                        for (int k = 0; k < DPAD / 16; ++k) {
+                            if (k < ksteps_qk) {                   // (k >> 2) * 16 KB column block + (k & 3) * 32 B inside the swizzle row
+                                const uint64_t off = (uint64_t)((k >> 2) * 1024 + (k & 3) * 2);
+                                umma_bf16_ss(tmem + Cfg::s_col(g), qdesc + off, kdesc + off, idesc_s, k > 0 ? 1u : 0u);
+                            }
                         }
                         umma_commit(&s_full[g]);
                     }
-                    umma_commit(&k_empty[s]);
+                    umma_commit(&k_empty[s]);                      // one arrival per issuer
+                    if (g_lo == 0) AT_TRACE_MMA(3);
                     if (++s == ST) { s = 0; ph ^= 1; }
                 }
                 if (t >= 1) {
                     const int tp = t - 1;
+                    if (g_lo == 0) AT_TRACE_MMA(4);
                     mbar_wait(&v_full[sv], phv);
-                    const uint32_t va = smem_u32(sV + sv * Cfg::TILE_BYTES);
-#pragma unroll
-                    for (int g = 0; g < G; ++g) {
-                        mbar_wait(&p_full[g], tp & 1);
+                    if (g_lo == 0) AT_TRACE_MMA(5);
+                    const int pb = PB == 2 ? (tp & 1) : 0;         // P buffer of key tile tp
+                    const uint64_t vdesc = vdesc0 + (uint64_t)(sv * TILE16);
+                    for (int g = g_lo; g < g_hi; ++g) {
+                        mbar_wait(&p_full[g * PB + pb], PB == 2 ? ((tp >> 1) & 1) : (tp & 1));
                         tcgen05_fence_after();
-                        const uint32_t pa = smem_u32(sP + g * Cfg::P_BYTES);
+                        if (g == 0) AT_TRACE_MMA(6);
+                        const uint64_t pdesc = pdesc0 + (uint64_t)((g * PB + pb) * (Cfg::P_BYTES >> 4));
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {      // 128 keys = 8 x K16
-                            const uint64_t adesc = umma_desc_kmajor_sw128(pa + (k >> 2) * 16384 + (k & 3) * 32);
-                            const uint64_t bdesc = umma_desc_mnmajor_sw128(va + k * 2048, 16384);
-                            umma_bf16_ss(tmem + Cfg::o_col(g), adesc, bdesc, idesc_o, (tp > 0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < 8; ++k) {              // 128 keys = 8 x K16
+                            umma_bf16_ss(tmem + Cfg::o_col(g), pdesc + (uint64_t)((k >> 2) * 1024 + (k & 3) * 2), vdesc + (uint64_t)(k * 128),
+                                         idesc_o, (tp > 0 || k > 0) ? 1u : 0u);
                         }
-                        umma_commit(&pv_done[g]);
+                        umma_commit(&pv_done[g * PB + pb]);
                     }
-                    umma_commit(&v_empty[sv]);
+                    umma_commit(&v_empty[sv]);                     // one arrival per issuer
+                    if (g_lo == 0) AT_TRACE_MMA(7);
                     if (++sv == ST) { sv = 0; phv ^= 1; }
                 }
             }
@@ -198,13 +252,21 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const uint32_t lane_addr = tmem + ((uint32_t)(lg * 32) << 16);
         const uint32_t s_addr = lane_addr + Cfg::s_col(g);
         const uint32_t o_addr = lane_addr + Cfg::o_col(g);
-        const uint32_t prow = smem_u32(sP + g * Cfg::P_BYTES) + row * 128;
+        const uint32_t prow0 = smem_u32(sP + g * PB * Cfg::P_BYTES) + row * 128;
         float m_used = -INFINITY, l = 0.f;
         const float c = p.scale_log2;
+        // Exponential phase ping-pong (G == 2): the two softmax warps of one SM sub-partition share its MUFU unit and its
+        // TMEM read port.  Left alone they run in lockstep — both reading S, then both in ex2 at half rate — and the MUFU
+        // pipe idles ~40 % of the time.  A pair of named barriers per lane quarter hands the ex2 phase back and forth, so
+        // one warp's TMEM read + row max always runs under the other's exponentials.
+        const uint32_t bar_mine = 2 + 4 * g + lg, bar_other = 2 + 4 * (g ^ 1) + lg;
+        if (G == 2 && g == 1) asm volatile("bar.arrive %0, 64;" ::"r"(bar_other) : "memory");   // tile 0 goes first
         for (int t = 0; t < ntiles; ++t) {
             const int kvalid = p.Sk - t * 128;          // keys >= kvalid are padding
+            AT_TRACE(0);
             mbar_wait(&s_full[g], t & 1);
             tcgen05_fence_after();
+            AT_TRACE(1);
             // the whole score row -> registers, then S_g is free for the next Q K^T
             uint32_t r[128];
             tmem_ld_x32(s_addr, r);
@@ -212,6 +274,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             tmem_ld_x32(s_addr + 64, r + 64);
             tmem_ld_x32(s_addr + 96, r + 96);
             tmem_ld_wait();
+            AT_TRACE(2);
             tcgen05_fence_before();
             mbar_arrive(&s_empty[g]);
             if (kvalid < 128) {
@@ -229,9 +292,18 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             float alpha = 1.0f;
             if (need) { alpha = ex2_approx(m_used - mx); m_used = mx; }
             const bool any_need = __any_sync(0xffffffffu, need);
-            // O_g and the P_g buffer are free once PV_g(t-1) has retired
-            if (t > 0) {
-                mbar_wait(&pv_done[g], (t - 1) & 1);
+            AT_TRACE(3);
+            const int pb = PB == 2 ? (t & 1) : 0;
+            const uint32_t prow = prow0 + pb * Cfg::P_BYTES;
+            if (PB == 2) {
+                // this P buffer was last read by P_{t-2} V: almost always retired long ago
+                if (t >= 2) mbar_wait(&pv_done[g * PB + pb], ((t >> 1) - 1) & 1);
+            }
+            // PB == 1: O_g and the single P_g buffer are free once PV_g(t-1) has retired;
+            // PB == 2: only a rescale of O_g (rare) has to wait for P_{t-1} V
+            if (t > 0 && (PB == 1 || any_need)) {
+                if (PB == 2) mbar_wait(&pv_done[g * PB + ((t - 1) & 1)], ((t - 1) >> 1) & 1);
+                else mbar_wait(&pv_done[g], (t - 1) & 1);
                 tcgen05_fence_after();
                 if (any_need) {
 #pragma unroll 1
@@ -247,6 +319,9 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 }
             }
             l *= alpha;
+            AT_TRACE(4);
+            if (G == 2) asm volatile("bar.sync %0, 64;" ::"r"(bar_mine) : "memory");              // my turn on the MUFU
+            AT_TRACE(5);
             // p = exp2(s*c - m), row sum, P_g (bf16, K-major SW128: two [128 x 64] blocks)
             float sum0 = 0.f, sum1 = 0.f;
             const float nm = -m_used;
@@ -259,15 +334,19 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 sum1 += (e[4] + e[5]) + (e[6] + e[7]);
                 const int chunk = (c0 & 63) >> 3;
                 sts128(prow + (c0 >> 6) * 16384 + ((chunk ^ (row & 7)) << 4),
-                       pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
+                       pack_p_bf16x2(e[0], e[1]), pack_p_bf16x2(e[2], e[3]), pack_p_bf16x2(e[4], e[5]), pack_p_bf16x2(e[6], e[7]));
             }
             l += sum0 + sum1;
+            AT_TRACE(6);
+            if (G == 2) asm volatile("bar.arrive %0, 64;" ::"r"(bar_other) : "memory");           // hand the MUFU over
             tcgen05_fence_before();
             fence_proxy_async_smem();               // P visible to the tensor core (async proxy)
-            mbar_arrive(&p_full[g]);
+            mbar_arrive(&p_full[g * PB + pb]);
+            AT_TRACE(7);
         }
         // ---- epilogue: O / l -> bf16 -> out[b, q, h, 0..d) ----
-        mbar_wait(&pv_done[g], (ntiles - 1) & 1);
+        if (PB == 2) mbar_wait(&pv_done[g * PB + ((ntiles - 1) & 1)], ((ntiles - 1) >> 1) & 1);   // in-order pipe: the last PV retires last
+        else mbar_wait(&pv_done[g], (ntiles - 1) & 1);
         tcgen05_fence_after();
         const float inv = 1.0f / l;
         const int q = q0 + g * 128 + row;
@@ -330,6 +409,9 @@ static int launch_attn(const sdb_attn_args* a, cudaStream_t st) {
         attr_set = true;
     }
     AttnP p;
+#ifdef SDB_ATTN_TRACE
+    p.trace = g_attn_trace;
+#endif
     p.out = a->out; p.o_bs = a->o_bs; p.o_ss = a->o_ss; p.o_hs = a->o_hs;
     p.Sq = a->Sq; p.Sk = a->Sk; p.d = a->d; p.H = a->H;
     p.scale_log2 = a->scale * 1.4426950408889634f;
