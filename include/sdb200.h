@@ -43,7 +43,9 @@ unsigned long long sdb_launch_count(void);
 /* ---- layout ------------------------------------------------------------------------------- */
 /* NCHW fp32 <-> NHWC fp32/bf16.  Replaces nothing arithmetic: the reference computes in NCHW
  * (openai_model/model.py:572-595); the kernels compute in NHWC, this is the boundary transpose. */
-int sdb_nchw_to_nhwc(const float* src, void* dst, int dst_dtype, int N, int C, int HW, void* stream);
+/* dst_C (0 = C): channel count of dst; channels C..dst_C-1 are written as zeros (the 4-channel latent is padded to 32
+ * bf16 channels so that conv_in, openai_model/model.py:365, runs on the tensor cores). */
+int sdb_nchw_to_nhwc(const float* src, void* dst, int dst_dtype, int N, int C, int dst_C, int HW, void* stream);
 int sdb_nhwc_to_nchw(const float* src, float* dst, int N, int C, int HW, void* stream);
 
 /* ---- GroupNorm(32) [+ SiLU] over NHWC, optional two-source channel concat -------------------

@@ -6,7 +6,7 @@ namespace sdb {
 
 // ---- NCHW <-> NHWC (32x32 smem tile transpose, padded against bank conflicts) -------------------
 template <bool OUT_BF16>
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, void* __restrict__ dst, int C, int HW) {
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, void* __restrict__ dst, int C, int Cd, int HW) {
     pdl_trigger();
     pdl_wait();
     __shared__ float tile[32][33];
@@ -15,13 +15,13 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, void* __restr
     const float* s = src + (long long)n * C * HW;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         int c = c0 + i, hw = hw0 + threadIdx.x;
-        tile[i][threadIdx.x] = (c < C && hw < HW) ? s[(long long)c * HW + hw] : 0.f;
+        tile[i][threadIdx.x] = (c < C && hw < HW) ? s[(long long)c * HW + hw] : 0.f;     // channels C..Cd-1 are zero padding
     }
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         int hw = hw0 + i, c = c0 + threadIdx.x;
-        if (hw < HW && c < C) {
-            long long o = ((long long)n * HW + hw) * C + c;
+        if (hw < HW && c < Cd) {
+            long long o = ((long long)n * HW + hw) * Cd + c;
             float v = tile[threadIdx.x][i];
             if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(dst)[o] = __float2bfloat16_rn(v);
             else reinterpret_cast<float*>(dst)[o] = v;
@@ -215,13 +215,27 @@ __global__ void skinny_linear_kernel(const float* __restrict__ x, int M, int K, 
 #pragma unroll
         for (int m = 0; m < MT; ++m) acc[m] = 0.f;
         const float* w = W + (long long)n * K;
-        for (int k = lane * 4; k < K; k += 128) {
-            float4 wv = ld_stream_f4(w + k);
+        // the weight row is streamed once: issue up to KU 16-byte loads per lane before the first FMA (one load in flight
+        // per lane made this kernel latency-bound at ~1 TB/s on the 113 MB ResBlock time-embedding matrix)
+        constexpr int KU = 10;
+        for (int k0 = lane * 4; k0 < K; k0 += 128 * KU) {
+            float4 wv[KU];
 #pragma unroll
-            for (int m = 0; m < MT; ++m) {
-                if (m < M) {
-                    const float* xr = xs + m * K + k;
-                    acc[m] += wv.x * xr[0] + wv.y * xr[1] + wv.z * xr[2] + wv.w * xr[3];
+            for (int u = 0; u < KU; ++u) {
+                wv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (k0 + 128 * u < K) wv[u] = ld_stream_f4(w + k0 + 128 * u);
+            }
+#pragma unroll
+            for (int u = 0; u < KU; ++u) {
+                const int k = k0 + 128 * u;
+                if (k < K) {
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) {
+                        if (m < M) {
+                            const float4 xr = *reinterpret_cast<const float4*>(xs + m * K + k);
+                            acc[m] += wv[u].x * xr.x + wv[u].y * xr.y + wv[u].z * xr.z + wv[u].w * xr.w;
+                        }
+                    }
                 }
             }
         }
@@ -318,11 +332,13 @@ using namespace sdb;
 
 extern "C" {
 
-int sdb_nchw_to_nhwc(const float* src, void* dst, int dst_dtype, int N, int C, int HW, void* stream) {
+int sdb_nchw_to_nhwc(const float* src, void* dst, int dst_dtype, int N, int C, int dst_C, int HW, void* stream) {
     SDB_REQUIRE(src && dst && N > 0 && C > 0 && HW > 0, "nchw_to_nhwc: bad args");
-    dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), N), block(32, 8);
-    if (dst_dtype == SDB_BF16) launch_pdl(nchw_to_nhwc_kernel<true>, dim3(grid), dim3(block), 0, (cudaStream_t)stream, src, dst, C, HW);
-    else launch_pdl(nchw_to_nhwc_kernel<false>, dim3(grid), dim3(block), 0, (cudaStream_t)stream, src, dst, C, HW);
+    const int Cd = dst_C > 0 ? dst_C : C;
+    SDB_REQUIRE(Cd >= C, "nchw_to_nhwc: dst_C=%d < C=%d", Cd, C);
+    dim3 grid(ceil_div(HW, 32), ceil_div(Cd, 32), N), block(32, 8);
+    if (dst_dtype == SDB_BF16) launch_pdl(nchw_to_nhwc_kernel<true>, dim3(grid), dim3(block), 0, (cudaStream_t)stream, src, dst, C, Cd, HW);
+    else launch_pdl(nchw_to_nhwc_kernel<false>, dim3(grid), dim3(block), 0, (cudaStream_t)stream, src, dst, C, Cd, HW);
     return check_launch("nchw_to_nhwc_kernel");
 }
 

@@ -494,9 +494,9 @@ static bool gn_cluster_enabled() {
 }
 
 // ---- LayerNorm: one warp per row, row held in registers (two-pass mean/variance) ----------------
-// A warp normalises LN_ROWS consecutive rows: all their loads are issued before the first reduction (LN_ROWS * MAXV
-// 16-byte loads in flight per lane) and gamma / beta are fetched once per warp, not once per row.
-constexpr int LN_ROWS = 4;
+// One row per warp measured fastest: several rows per warp (more loads in flight per lane, fewer resident warps) and a
+// bulk-async shared-memory ring with 8-24 consumer warps were both 20-60 % slower at the UNet shapes — the kernel is
+// bound by its two dependent shuffle reductions per row, which only more resident warps hide.
 
 template <bool OUT_BF16, int MAXV>   // MAXV float4 vectors per lane: C <= 128 * MAXV
 __global__ void __launch_bounds__(256)
@@ -505,7 +505,7 @@ layernorm_kernel(const float* __restrict__ x, int rows, int C, float eps,
                  void* __restrict__ out) {
     pdl_trigger();
     pdl_wait();
-    constexpr int NR = (MAXV <= 3) ? LN_ROWS : (MAXV <= 5 ? 2 : 1);   // rows per warp (register budget)
+    constexpr int NR = 1;   // rows per warp: 1 measured fastest (more rows per warp = fewer resident warps, profiles/r01_layers_unet_b8.txt)
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const int row0 = warp * NR;
@@ -573,7 +573,7 @@ layernorm_kernel(const float* __restrict__ x, int rows, int C, float eps,
     }
 }
 
-static inline int ln_rows_per_warp(int nv) { return nv <= 3 ? LN_ROWS : (nv <= 5 ? 2 : 1); }
+static inline int ln_rows_per_warp(int nv) { (void)nv; return 1; }
 
 }  // namespace sdb
 

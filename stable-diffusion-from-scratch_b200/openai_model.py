@@ -205,6 +205,7 @@ class UNetModel(nn.Module):
         self.predict_codebook_ids = False
         self.compute_mode = compute_mode or engine.default_mode()
         self.t_emb_fp16_round = True     # `t_emb.half()`, openai_model/model.py:566
+        self.conv_in_tensor_cores = False
         self.use_cuda_graph = False
 
         time_embed_dim = model_channels * 4
@@ -340,7 +341,12 @@ class UNetModel(nn.Module):
                 P[("o2", id(m))] = PackedLinear(a2.to_out[0].weight, a2.to_out[0].bias, mode)
                 P[("ff1", id(m))] = PackedLinear(m.ff.net[0].proj.weight, m.ff.net[0].proj.bias, mode, geglu=True)
                 P[("ff2", id(m))] = PackedLinear(m.ff.net[2].weight, m.ff.net[2].bias, mode)
-        P["conv_in"] = PackedConv(self.input_blocks[0][0].weight, self.input_blocks[0][0].bias, mode)
+        cin_w = self.input_blocks[0][0].weight
+        if mode == "bf16" and cin_w.shape[1] < 32 and self.conv_in_tensor_cores:
+            # conv_in on the tensor cores: the latent's channels are zero-padded to 32 (a whole 64-byte TMA row).  Off by
+            # default: rounding x_t itself to bf16 moved eps rel-L2 from 7.05e-3 to 7.64e-3 (bound 1e-2) for 0.08 ms
+            cin_w = torch.nn.functional.pad(cin_w.detach(), (0, 0, 0, 0, 0, 32 - cin_w.shape[1]))
+        P["conv_in"] = PackedConv(cin_w, self.input_blocks[0][0].bias, mode)
         P["conv_out"] = PackedConv(self.out[2].weight, self.out[2].bias, mode)
         self._packed[mode] = P
         return P
@@ -490,7 +496,7 @@ class UNetModel(nn.Module):
                 else:
                     h = engine.conv(h, pc, up=2)
             elif isinstance(layer, nn.Conv2d):
-                h = engine.conv(h, P["conv_in"])
+                h = engine.conv(h, P["conv_in"], want_stats=True)
             else:
                 raise NotImplementedError(type(layer))
         assert x1 is None
@@ -504,7 +510,7 @@ class UNetModel(nn.Module):
         # time_embed[2] then every ResBlock's SiLU -> Linear (openai_model/model.py:195-201), batched
         emb = ops.skinny_linear(e, P["te2"][0], P["te2"][1])
         emb_all = ops.skinny_linear(emb, P["emb_w"], P["emb_b"], act_in=1)
-        h = ops.nchw_to_nhwc(x_nchw)
+        h = ops.nchw_to_nhwc(x_nchw, out_dtype=P["conv_in"].in_dtype, pad_to=P["conv_in"].cin)
         hs = []
         for module in self.input_blocks:
             h = self._run_block(module, P, mode, h, None, emb_all, context)

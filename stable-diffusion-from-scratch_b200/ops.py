@@ -18,13 +18,14 @@ def _L():
 
 
 # ---- layout ---------------------------------------------------------------------------------------
-def nchw_to_nhwc(x, out_dtype=torch.float32):
-    """[N,C,H,W] fp32 -> [N,H,W,C]."""
+def nchw_to_nhwc(x, out_dtype=torch.float32, pad_to=0):
+    """[N,C,H,W] fp32 -> [N,H,W,C] (or [N,H,W,pad_to] with zero channels appended)."""
     require_cuda(x)
     assert x.dtype == torch.float32 and x.is_contiguous()
     N, Cc, H, W = x.shape
-    out = torch.empty((N, H, W, Cc), dtype=out_dtype, device=x.device)
-    check(_L().sdb_nchw_to_nhwc(ptr(x), ptr(out), dtype_code(out_dtype), N, Cc, H * W, stream_ptr()), "nchw_to_nhwc")
+    Cd = max(Cc, pad_to)
+    out = torch.empty((N, H, W, Cd), dtype=out_dtype, device=x.device)
+    check(_L().sdb_nchw_to_nhwc(ptr(x), ptr(out), dtype_code(out_dtype), N, Cc, Cd, H * W, stream_ptr()), "nchw_to_nhwc")
     return out
 
 

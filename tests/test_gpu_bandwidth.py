@@ -77,6 +77,9 @@ def test_small_elementwise(cuda):
     assert torch.equal(ops.nchw_to_nhwc(xi), nhwc(xi))
     assert torch.equal(ops.nhwc_to_nchw(nhwc(xi)), xi)
     assert torch.equal(ops.nchw_to_nhwc(xi, out_dtype=torch.bfloat16), nhwc(xi).to(torch.bfloat16))
+    padded = ops.nchw_to_nhwc(xi, out_dtype=torch.bfloat16, pad_to=32)          # latent -> 32-channel tensor-core operand
+    assert padded.shape == (3, 6, 7, 32) and torch.equal(padded[..., :5], nhwc(xi).to(torch.bfloat16))
+    assert float(padded[..., 5:].abs().max()) == 0.0
 
 
 def test_timestep_embedding_and_skinny(cuda):
