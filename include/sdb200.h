@@ -66,11 +66,12 @@ int sdb_groupnorm_nhwc(const float* x0, int C0, const float* x1, int C1, int N, 
                        void* out, int out_dtype, void* raw_out, void* ws, int* counters, void* stream);
 
 /* Same GroupNorm, statistics taken from the column sums the producing tcgen05 convs wrote (sdb_tc_args.colstats:
- * cs = fp32 [2][slots][C*], `slots_per_item` consecutive 32-row slots per sample), so the tensor is read once.
- * ws: >= N*groups*8 bytes.  Other arguments as sdb_groupnorm_nhwc. */
-int sdb_groupnorm_from_colstats(const float* x0, int C0, const float* cs0, long long slots0,
-                                const float* x1, int C1, const float* cs1, long long slots1,
-                                long long slots_per_item, int N, int HW, int groups, float eps,
+ * cs = fp32 [2][slots][C*]), so the tensor is read once.  layout (host, 4 values per source) = {slots, consecutive 32-row
+ * slots per sample, regions, slots between regions}: regions > 1 is the output of a sub-pixel upsampling conv, whose four
+ * phase convolutions each filled one region.  ws: >= N*groups*8 bytes.  Other arguments as sdb_groupnorm_nhwc. */
+int sdb_groupnorm_from_colstats(const float* x0, int C0, const float* cs0, const long long* layout0 /* host */,
+                                const float* x1, int C1, const float* cs1, const long long* layout1 /* host */,
+                                int N, int HW, int groups, float eps,
                                 const float* gamma, const float* beta, int act, int exact,
                                 void* out, int out_dtype, void* raw_out, void* ws, void* stream);
 

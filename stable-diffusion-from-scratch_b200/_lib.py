@@ -83,7 +83,8 @@ SIGNATURES = {
     "sdb_nhwc_to_nchw": (_I, [_P, _P, _I, _I, _I, _P]),
     "sdb_groupnorm_ws_bytes": (_L, [_I, _I, _I, _I]),
     "sdb_groupnorm_nhwc": (_I, [_P, _I, _P, _I, _I, _I, _I, _F, _P, _P, _I, _I, _P, _I, _P, _P, _P, _P]),
-    "sdb_groupnorm_from_colstats": (_I, [_P, _I, _P, _L, _P, _I, _P, _L, _L, _I, _I, _I, _F, _P, _P, _I, _I, _P, _I, _P, _P, _P]),
+    "sdb_groupnorm_from_colstats": (_I, [_P, _I, _P, C.POINTER(C.c_longlong), _P, _I, _P, C.POINTER(C.c_longlong), _I, _I, _I, _F,
+                                         _P, _P, _I, _I, _P, _I, _P, _P, _P]),
     "sdb_layernorm": (_I, [_P, _I, _I, _F, _P, _P, _P, _I, _P]),
     "sdb_cast_concat": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _P, _I, _P]),
     "sdb_upsample_bilinear2x": (_I, [_P, _I, _I, _I, _I, _P, _I, _P]),

@@ -153,29 +153,34 @@ class Decoder(nn.Module):
                 P[("v", id(m))] = PackedLinear(m.v.weight.reshape(Cc, Cc), None, mode)
                 P[("vb", id(m))] = m.v.bias.detach().float().contiguous()
             elif isinstance(m, Upsample):
-                P[("up", id(m))] = PackedConv(m.conv.weight, m.conv.bias, mode)
+                P[("up", id(m))] = PackedConv(m.conv.weight, m.conv.bias, mode, up2=True)
         P["conv_in"] = PackedConv(self.conv_in.weight, self.conv_in.bias, mode)
         P["conv_out"] = PackedConv(self.conv_out.weight, self.conv_out.bias, mode)
         self._packed[mode] = P
         return P
 
     @staticmethod
-    def _gn(norm, x, mode, act, out_dtype):
+    def _gn(norm, x, mode, act, out_dtype, want_raw=False):
         return ops.groupnorm(x, norm.weight, norm.bias, norm.eps, act=act, out_dtype=out_dtype,
-                             groups=norm.num_groups, exact=(mode == "fp32"))
+                             groups=norm.num_groups, exact=(mode == "fp32"), want_raw=want_raw)
 
     def _resnet(self, rb, P, mode, x):
-        """ResnetBlock.forward with temb=None (model.py:123-143)."""
+        """ResnetBlock.forward with temb=None (model.py:123-143).  Every conv whose output feeds a GroupNorm also emits
+        that GroupNorm's column statistics (want_stats), and the 1x1 nin_shortcut's bf16 operand comes out of norm1's pass."""
         c1, c2 = P[("c1", id(rb))], P[("c2", id(rb))]
-        h = engine.conv(self._gn(rb.norm1, x, mode, 1, c1.in_dtype), c1)
+        sc = P.get(("sc", id(rb)))
+        raw = None
+        if sc is not None and sc.in_dtype == torch.bfloat16:
+            hn, raw = self._gn(rb.norm1, x, mode, 1, c1.in_dtype, want_raw=True)
+        else:
+            hn = self._gn(rb.norm1, x, mode, 1, c1.in_dtype)
+        h = engine.conv(hn, c1, want_stats=True)
         h = self._gn(rb.norm2, h, mode, 1, c2.in_dtype)
-        if ("sc", id(rb)) in P:
-            sc = P[("sc", id(rb))]
-            xs = ops.cast_concat(x, None, out_dtype=sc.in_dtype) if sc.in_dtype == torch.bfloat16 else x
-            xs = engine.conv(xs, sc)
+        if sc is not None:
+            xs = engine.conv(raw if raw is not None else x, sc)
         else:
             xs = x
-        return engine.conv(h, c2, residual=xs)
+        return engine.conv(h, c2, residual=xs, want_stats=True)
 
     def _attn(self, ab, P, mode, x):
         """AttnBlock.forward (model.py:180-204): single head, d = C, scores materialised per image
@@ -206,7 +211,7 @@ class Decoder(nn.Module):
 
     def _forward_nhwc(self, z, mode):
         P = self._pack(mode)
-        h = engine.conv(z, P["conv_in"])
+        h = engine.conv(z, P["conv_in"], want_stats=True)
         h = self._resnet(self.mid.block_1, P, mode, h)
         if isinstance(self.mid.attn_1, AttnBlock):
             h = self._attn(self.mid.attn_1, P, mode, h)
@@ -219,7 +224,7 @@ class Decoder(nn.Module):
             if i_level != 0:
                 pc = P[("up", id(self.up[i_level].upsample))]
                 if pc.use_tc:
-                    h = engine.conv(ops.cast_concat(h, None, up=2, out_dtype=torch.bfloat16), pc)
+                    h = engine.conv_up2(ops.cast_concat(h, None, out_dtype=torch.bfloat16), pc, want_stats=True)
                 else:
                     h = engine.conv(h, pc, up=2)
         co = P["conv_out"]

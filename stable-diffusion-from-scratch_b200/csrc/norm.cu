@@ -52,21 +52,33 @@ __device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f 
 // Statistics from the producer: the tcgen05 conv that wrote the tensor also wrote, per 32-row slot and channel, the sum
 // and sum of squares of what it stored (sdb_tc_args.colstats).  One warp per (sample, group) folds its slots x channels
 // in fp64 in a fixed order -> (mean, rstd); the tensor itself is not read.  Two sources = the channel concat.
+// layout of one source's statistics: cs = fp32 [2][slots][C]; a sample owns `spi` consecutive slots in each of `regions`
+// regions that start `rstride` slots apart (regions > 1: the sub-pixel phases of an upsampling conv, one region each)
+struct CsSrc {
+    const float* cs;
+    int C;
+    long long slots, spi, rstride;
+    int regions;
+};
+
 __global__ void __launch_bounds__(128)
-gn_colstats_finalize_kernel(const float* __restrict__ cs0, int C0, long long slots0,
-                            const float* __restrict__ cs1, int C1, long long slots1,
-                            long long slots_per_item, int groups, double count, float eps,
-                            float2* __restrict__ stats) {
+gn_colstats_finalize_kernel(const CsSrc s0, const CsSrc s1, int groups, double count, float eps, float2* __restrict__ stats) {
     pdl_trigger();
     pdl_wait();
     __shared__ double redS[128], redQ[128];
     const int w = blockIdx.x;                       // (sample, group)
     const int n = w / groups, g = w - n * groups;
-    const int C = C0 + C1, cpg = C / groups;
-    const long long items = slots_per_item * cpg;
-    const long long sbase = (long long)n * slots_per_item;
+    const int C = s0.C + s1.C, cpg = C / groups;
+    // channels of this group inside each source
+    const int c_lo = g * cpg, c_hi = c_lo + cpg;
+    const int a_lo = c_lo < s0.C ? c_lo : s0.C, a_hi = c_hi < s0.C ? c_hi : s0.C;              // [a_lo, a_hi) in source 0
+    const int b_lo = (c_lo > s0.C ? c_lo : s0.C) - s0.C, b_hi = (c_hi > s0.C ? c_hi : s0.C) - s0.C;   // [b_lo, b_hi) in source 1
+    const int na = a_hi - a_lo, nb = b_hi - b_lo;
+    const long long items0 = (long long)s0.regions * s0.spi * na;
+    const long long items1 = s1.cs ? (long long)s1.regions * s1.spi * nb : 0;
+    const long long items = items0 + items1;
     double S = 0.0, Q = 0.0;
-    // item = (slot, channel-in-group); 4 items (8 loads) in flight per thread, summed in index order
+    // item = (region, slot, channel); 4 items (8 loads) in flight per thread, summed in index order
     for (long long i0 = threadIdx.x; i0 < items; i0 += 4 * 128) {
         float a[4], q[4];
 #pragma unroll
@@ -74,10 +86,16 @@ gn_colstats_finalize_kernel(const float* __restrict__ cs0, int C0, long long slo
             const long long i = i0 + u * 128;
             a[u] = 0.f; q[u] = 0.f;
             if (i < items) {
-                const long long sl = sbase + i / cpg;
-                const int c = g * cpg + (int)(i % cpg);
-                if (c < C0) { a[u] = __ldcg(cs0 + sl * C0 + c); q[u] = __ldcg(cs0 + (slots0 + sl) * C0 + c); }
-                else        { a[u] = __ldcg(cs1 + sl * C1 + (c - C0)); q[u] = __ldcg(cs1 + (slots1 + sl) * C1 + (c - C0)); }
+                const bool first = i < items0;
+                const CsSrc& s = first ? s0 : s1;
+                const long long k = first ? i : i - items0;
+                const int nch = first ? na : nb;
+                const long long qd = k / nch;
+                const int c = (first ? a_lo : b_lo) + (int)(k - qd * nch);
+                const long long region = qd / s.spi, sl = qd - region * s.spi;
+                const long long slot = region * s.rstride + (long long)n * s.spi + sl;
+                a[u] = __ldcg(s.cs + slot * s.C + c);
+                q[u] = __ldcg(s.cs + (s.slots + slot) * s.C + c);
             }
         }
 #pragma unroll
@@ -645,26 +663,35 @@ int sdb_groupnorm_nhwc(const float* x0, int C0, const float* x1, int C1, int N, 
     return check_launch("gn_apply_kernel");
 }
 
-int sdb_groupnorm_from_colstats(const float* x0, int C0, const float* cs0, long long slots0,
-                                const float* x1, int C1, const float* cs1, long long slots1,
-                                long long slots_per_item, int N, int HW, int groups, float eps,
+int sdb_groupnorm_from_colstats(const float* x0, int C0, const float* cs0, const long long* layout0,
+                                const float* x1, int C1, const float* cs1, const long long* layout1,
+                                int N, int HW, int groups, float eps,
                                 const float* gamma, const float* beta, int act, int exact,
                                 void* out, int out_dtype, void* raw_out, void* ws, void* stream) {
     const int C = C0 + C1;
     SDB_REQUIRE(x0 && cs0 && out && ws && gamma && beta, "groupnorm_from_colstats: null pointer");
-    SDB_REQUIRE(N > 0 && HW > 0 && C > 0 && slots_per_item > 0, "groupnorm_from_colstats: empty tensor");
+    SDB_REQUIRE(N > 0 && HW > 0 && C > 0 && layout0, "groupnorm_from_colstats: empty tensor");
     SDB_REQUIRE(C0 % 4 == 0 && C1 % 4 == 0 && (C1 == 0) == (x1 == nullptr) && (C1 == 0) == (cs1 == nullptr),
                 "groupnorm_from_colstats: bad channel split %d + %d", C0, C1);
     SDB_REQUIRE(groups > 0 && C % groups == 0 && C / 4 <= 1024, "groupnorm_from_colstats: C=%d groups=%d unsupported", C, groups);
-    SDB_REQUIRE(slots0 >= (long long)N * slots_per_item && (!cs1 || slots1 >= (long long)N * slots_per_item),
-                "groupnorm_from_colstats: statistics buffers too small");
+    // layout = {slots, slots per sample (per region), regions, region stride}
+    CsSrc s0, s1;
+    memset(&s1, 0, sizeof(s1));
+    s0.cs = cs0; s0.C = C0; s0.slots = layout0[0]; s0.spi = layout0[1]; s0.regions = (int)layout0[2]; s0.rstride = layout0[3];
+    if (cs1) {
+        SDB_REQUIRE(layout1, "groupnorm_from_colstats: second source has no layout");
+        s1.cs = cs1; s1.C = C1; s1.slots = layout1[0]; s1.spi = layout1[1]; s1.regions = (int)layout1[2]; s1.rstride = layout1[3];
+    }
+    SDB_REQUIRE(s0.spi > 0 && s0.regions >= 1 && (s0.regions - 1) * s0.rstride + (long long)N * s0.spi <= s0.slots,
+                "groupnorm_from_colstats: statistics buffer of source 0 too small");
+    SDB_REQUIRE(!cs1 || (s1.spi > 0 && s1.regions >= 1 && (s1.regions - 1) * s1.rstride + (long long)N * s1.spi <= s1.slots),
+                "groupnorm_from_colstats: statistics buffer of source 1 too small");
     SDB_REQUIRE(out_dtype == SDB_F32 || out_dtype == SDB_BF16, "groupnorm_from_colstats: bad out_dtype");
     SDB_REQUIRE((((uintptr_t)gamma | (uintptr_t)beta) & 15) == 0, "groupnorm_from_colstats: gamma/beta must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     float2* stats = reinterpret_cast<float2*>(ws);                 // [N][groups]
     const int total = N * groups;
-    launch_pdl(gn_colstats_finalize_kernel, dim3(total), dim3(128), 0, st, cs0, C0, slots0, cs1, C1, slots1,
-               slots_per_item, groups, (double)HW * (C / groups), eps, stats);
+    launch_pdl(gn_colstats_finalize_kernel, dim3(total), dim3(128), 0, st, s0, s1, groups, (double)HW * (C / groups), eps, stats);
     int rc = check_launch("gn_colstats_finalize_kernel");
     if (rc) return rc;
     GnGeom g = gn_apply_geom(N, HW, C);

@@ -12,6 +12,20 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 // ---- mbarrier -----------------------------------------------------------------------------------
+// true in exactly one lane of a fully converged warp.  Issuing tcgen05 / TMA instructions under `if (elect_one())` inside
+// warp-uniform control flow (instead of a long `if (lane == 0)` region) lets the compiler keep descriptors and barrier
+// addresses in uniform registers: no per-instruction R2UR traffic in front of every MMA.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }

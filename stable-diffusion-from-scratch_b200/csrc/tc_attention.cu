@@ -37,11 +37,14 @@ static long long* g_attn_trace = nullptr;
 extern "C" void sdb_attn_set_trace(long long* ptr) { g_attn_trace = ptr; }
 #define AT_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && t < 32) \
     p.trace[((warp - 4) * 32 + t) * 8 + (slot)] = clock64(); } while (0)
-#define AT_TRACE_MMA(slot) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && t < 32) \
+#define AT_TRACE_MMA(slot) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && t < 32 && lane == 0) \
     p.trace[(8 * 32 + t) * 8 + (slot)] = clock64(); } while (0)
+#define AT_TRACE_ISS(slot) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && t < 32 && g_lo == 0 && lane == 0) \
+    p.trace[(9 * 32 + t) * 8 + (slot)] = clock64(); } while (0)
 #else
 #define AT_TRACE(slot) do { } while (0)
 #define AT_TRACE_MMA(slot) do { } while (0)
+#define AT_TRACE_ISS(slot) do { } while (0)
 #endif
 
 struct AttnP {
@@ -181,7 +184,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         // per key tile (profiles/r01_attn_timeline.txt) — longer than the exponentials; the tensor pipe sat idle behind
         // the issue thread.  For d <= 64 two issuers (warp 1 -> tile 0, warp 3 -> tile 1) halve that chain and decouple the
         // tiles; descriptors are built once and every MMA just adds an offset.
-        if (lane == 0) {
+        {   // the whole warp runs this loop (uniform control flow); one elected lane issues
             const int g_lo = (NI == 2 && warp == 3) ? 1 : 0;
             const int g_hi = NI == 2 ? g_lo + 1 : G;
             const uint32_t idesc_s = umma_idesc_bf16(128, false, false);     // S = Q K^T : N = 128 keys
@@ -210,12 +213,12 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                         for (int k = 0; k < DPAD / 16; ++k) {
                             if (k < ksteps_qk) {                   // (k >> 2) * 16 KB column block + (k & 3) * 32 B inside the swizzle row
                                 const uint64_t off = (uint64_t)((k >> 2) * 1024 + (k & 3) * 2);
-                                umma_bf16_ss(tmem + Cfg::s_col(g), qdesc + off, kdesc + off, idesc_s, k > 0 ? 1u : 0u);
+                                if (elect_one()) umma_bf16_ss(tmem + Cfg::s_col(g), qdesc + off, kdesc + off, idesc_s, k > 0 ? 1u : 0u);
                             }
                         }
-                        umma_commit(&s_full[g]);
+                        if (elect_one()) umma_commit(&s_full[g]);
                     }
-                    umma_commit(&k_empty[s]);                      // one arrival per issuer
+                    if (elect_one()) umma_commit(&k_empty[s]);     // one arrival per issuer
                     if (g_lo == 0) AT_TRACE_MMA(3);
                     if (++s == ST) { s = 0; ph ^= 1; }
                 }
@@ -231,14 +234,21 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                         tcgen05_fence_after();
                         if (g == 0) AT_TRACE_MMA(6);
                         const uint64_t pdesc = pdesc0 + (uint64_t)((g * PB + pb) * (Cfg::P_BYTES >> 4));
+                        AT_TRACE_ISS(0);
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {              // 128 keys = 8 x K16
-                            umma_bf16_ss(tmem + Cfg::o_col(g), pdesc + (uint64_t)((k >> 2) * 1024 + (k & 3) * 2), vdesc + (uint64_t)(k * 128),
-                                         idesc_o, (tp > 0 || k > 0) ? 1u : 0u);
+                            if (elect_one())
+                                umma_bf16_ss(tmem + Cfg::o_col(g), pdesc + (uint64_t)((k >> 2) * 1024 + (k & 3) * 2), vdesc + (uint64_t)(k * 128),
+                                             idesc_o, (tp > 0 || k > 0) ? 1u : 0u);
+                            if (k == 0) AT_TRACE_ISS(1);
+                            if (k == 3) AT_TRACE_ISS(2);
                         }
-                        umma_commit(&pv_done[g * PB + pb]);
+                        AT_TRACE_ISS(3);
+                        if (elect_one()) umma_commit(&pv_done[g * PB + pb]);
+                        AT_TRACE_ISS(4);
                     }
-                    umma_commit(&v_empty[sv]);                     // one arrival per issuer
+                    if (elect_one()) umma_commit(&v_empty[sv]);    // one arrival per issuer
+                    AT_TRACE_ISS(5);
                     if (g_lo == 0) AT_TRACE_MMA(7);
                     if (++sv == ST) { sv = 0; phv ^= 1; }
                 }

@@ -1025,8 +1025,9 @@ extern "C" long long sdb_tc_workspace_bytes(const sdb_tc_args* a) {
 // column-statistics layout of a plan: 4 slots (32-row lane quarters) per 128-row m-tile; only for plans whose tiles
 // never straddle two samples and that store their final values themselves (no split-K)
 static bool colstats_supported(const sdb_tc_args* a, const TcPlan& pl) {
+    // (an output remap — sub-pixel phase of an upsampling conv — is fine: the caller gives every phase its own slot region)
     return a->taps > 0 && pl.tn == 1 && pl.split_k == 1 && !a->geglu && !a->col_group && a->out_dtype == SDB_F32 &&
-           a->N % 4 == 0 && a->ldc % 4 == 0 && (a->out_sh <= 1 && a->out_sw <= 1 && a->out_oh == 0 && a->out_ow == 0);
+           a->N % 4 == 0 && a->ldc % 4 == 0;
 }
 
 extern "C" int sdb_tc_colstats_layout(const sdb_tc_args* a, long long* slots, long long* slots_per_item) {

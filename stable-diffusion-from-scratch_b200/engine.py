@@ -31,7 +31,7 @@ def head_pad(d):
 class PackedConv:
     """A conv layer's weights repacked tap-major [kh*kw, Cout, Cin] for one compute mode."""
 
-    def __init__(self, weight, bias, mode, stride=1, pad=None):
+    def __init__(self, weight, bias, mode, stride=1, pad=None, up2=False):
         Cout, Cin, kh, kw = weight.shape
         self.cout, self.cin, self.kh, self.kw = Cout, Cin, kh, kw
         self.stride = stride
@@ -41,6 +41,8 @@ class PackedConv:
         dt = torch.bfloat16 if self.use_tc else torch.float32
         self.w = ops.pack_conv_weight(weight, dt)
         self.bias = None if bias is None else bias.detach().float().contiguous()
+        # conv that follows a nearest-2x upsampling: folded sub-pixel weights (tensor-core path only)
+        self.w_up2 = ops.fold_upsample_weights(weight, dt) if (up2 and self.use_tc and kh == 3 and kw == 3 and stride == 1) else None
 
     @property
     def in_dtype(self):
@@ -71,6 +73,13 @@ def conv(x, pc, rowvec=None, residual=None, out_dtype=torch.float32, up=1, want_
                            residual=residual, out_dtype=out_dtype, want_stats=want_stats)
     return ops.conv_simt(x, pc.w, pc.bias, pc.kh, pc.kw, stride=pc.stride, pad=pc.pad, up=up, rowvec=rowvec,
                          residual=residual, out_dtype=out_dtype)
+
+
+def conv_up2(x, pc, want_stats=False):
+    """conv `pc` applied to the nearest-2x upsampling of x [N,H,W,Cin] (bf16 on the tensor-core path)."""
+    if pc.w_up2 is not None:
+        return ops.conv_up2_tc(x, pc.w_up2, pc.bias, want_stats=want_stats)
+    return conv(x, pc, up=2)
 
 
 def linear(x, pl, residual=None, out_dtype=torch.float32, col_group=0, col_group_stride=0, rows_per_item=0, out=None):

@@ -328,7 +328,7 @@ class UNetModel(nn.Module):
             elif isinstance(m, Downsample):
                 P[("op", id(m))] = PackedConv(m.op.weight, m.op.bias, mode, stride=2, pad=1)
             elif isinstance(m, Upsample):
-                P[("conv", id(m))] = PackedConv(m.conv.weight, m.conv.bias, mode)
+                P[("conv", id(m))] = PackedConv(m.conv.weight, m.conv.bias, mode, up2=True)
             elif isinstance(m, SpatialTransformer):
                 P[("pin", id(m))] = PackedConv(m.proj_in.weight, m.proj_in.bias, mode)
                 P[("pout", id(m))] = PackedConv(m.proj_out.weight, m.proj_out.bias, mode)
@@ -491,8 +491,8 @@ class UNetModel(nn.Module):
                 h = engine.conv(hx, pc, want_stats=True)
             elif isinstance(layer, Upsample):
                 pc = P[("conv", id(layer))]
-                if pc.use_tc:
-                    h = engine.conv(ops.cast_concat(h, None, up=2, out_dtype=torch.bfloat16), pc, want_stats=True)
+                if pc.use_tc:      # sub-pixel form: four 2x2 convs on the low-resolution tensor, no 4x intermediate
+                    h = engine.conv_up2(ops.cast_concat(h, None, out_dtype=torch.bfloat16), pc, want_stats=True)
                 else:
                     h = engine.conv(h, pc, up=2)
             elif isinstance(layer, nn.Conv2d):

@@ -68,13 +68,15 @@ def groupnorm(x0, gamma, beta, eps, act=0, out_dtype=torch.float32, x1=None, gro
     lib = _L()
     cs0 = getattr(x0, "_sdb_cs", None)
     cs1 = getattr(x1, "_sdb_cs", None) if x1 is not None else None
-    if cs0 is not None and (x1 is None or (cs1 is not None and cs1[2] == cs0[2])) and _USE_COLSTATS:
+    if cs0 is not None and (x1 is None or cs1 is not None) and _USE_COLSTATS:
         # statistics were produced by the conv(s) that wrote x0 / x1: finalize them and make ONE pass over the tensor
         ws = torch.empty(N * groups * 8 + 256, dtype=torch.uint8, device=x0.device)
         out = torch.empty((N, H, W, Ct), dtype=out_dtype, device=x0.device)
         raw = torch.empty((N, H, W, Ct), dtype=torch.bfloat16, device=x0.device) if want_raw else None
-        check(lib.sdb_groupnorm_from_colstats(ptr(x0), C0, ptr(cs0[0]), cs0[1], ptr(x1), C1, ptr(cs1[0]) if cs1 else 0,
-                                              cs1[1] if cs1 else 0, cs0[2], N, H * W, groups, float(eps), ptr(gamma), ptr(beta),
+        lay0 = (C.c_longlong * 4)(*cs0[1:5])
+        lay1 = (C.c_longlong * 4)(*cs1[1:5]) if cs1 else None
+        check(lib.sdb_groupnorm_from_colstats(ptr(x0), C0, ptr(cs0[0]), lay0, ptr(x1), C1, ptr(cs1[0]) if cs1 else 0, lay1,
+                                              N, H * W, groups, float(eps), ptr(gamma), ptr(beta),
                                               int(act), int(bool(exact)), ptr(out), dtype_code(out_dtype), ptr(raw), ptr(ws),
                                               stream_ptr()), "groupnorm_from_colstats")
         return (out, raw) if want_raw else out
@@ -345,7 +347,7 @@ def _tc_launch(a, what):
 
 
 def conv_tc(x, w_rskc, bias, kh, kw, stride=1, pad=0, rowvec=None, residual=None, out_dtype=torch.float32,
-            split_k=0, block_n=0, out=None, phase=None, variant=0, want_stats=False):
+            split_k=0, block_n=0, out=None, phase=None, variant=0, want_stats=False, stats_into=None):
     """x [N,IH,IW,Cin] bf16, w [kh*kw,Cout,Cin] bf16 -> [N,OH,OW,Cout].
 
     phase=(sh, sw, oh, ow, OHF, OWF, pad_h, pad_w) writes this conv's OHxOW result into the strided
@@ -390,18 +392,90 @@ def conv_tc(x, w_rskc, bias, kh, kw, stride=1, pad=0, rowvec=None, residual=None
         assert residual.dtype == torch.float32 and residual.is_contiguous()
     _apply_plan(a, "conv", OH * OW)
     cs = None
-    if want_stats and phase is None and out.dtype == torch.float32:
+    if stats_into is not None:
+        # one phase of an upsampling conv: its slot region inside the caller's statistics buffer (see conv_up2_tc)
+        cs_t, total_slots, first_slot = stats_into
+        a.colstats, a.colstats_slots = cs_t.data_ptr() + 4 * first_slot * Cout, total_slots
+    elif want_stats and phase is None and out.dtype == torch.float32:
         # per-(32-row slot, channel) sums of the stored values, written by the epilogue: the statistics pass of the
         # GroupNorm that reads `out` next (ops.groupnorm picks them up from the tensor)
-        slots, spi = C.c_longlong(0), C.c_longlong(0)
-        check(_L().sdb_tc_colstats_layout(C.byref(a), C.byref(slots), C.byref(spi)), "tc colstats layout")
-        if slots.value > 0:
-            cs = torch.empty((2, slots.value, Cout), dtype=torch.float32, device=x.device)
-            a.colstats, a.colstats_slots = cs.data_ptr(), slots.value
+        slots, spi = tc_colstats_layout(a)
+        if slots > 0:
+            cs = torch.empty((2, slots, Cout), dtype=torch.float32, device=x.device)
+            a.colstats, a.colstats_slots = cs.data_ptr(), slots
     _tc_launch(a, "tc conv")
     if cs is not None:
-        out._sdb_cs = (cs, slots.value, spi.value)
+        out._sdb_cs = (cs, slots, spi, 1, 0)          # (buffer, slots, slots per sample, regions, region stride)
     return out
+
+
+def tc_colstats_layout(a):
+    slots, spi = C.c_longlong(0), C.c_longlong(0)
+    check(_L().sdb_tc_colstats_layout(C.byref(a), C.byref(slots), C.byref(spi)), "tc colstats layout")
+    return slots.value, spi.value
+
+
+UP2_PHASES = ((0, 0), (0, 1), (1, 0), (1, 1))
+
+
+def fold_upsample_weights(w, dtype):
+    """Nearest-2x upsampling followed by a 3x3 / pad 1 conv (openai_model/model.py:119-131; ldm/.../model.py:44-59) equals,
+    for each output phase (py, px), a 2x2 conv over the LOW-resolution input whose taps are sums of the 3x3 taps that land
+    on the same source pixel: 4/9 of the multiply-adds and no 4x intermediate.  w [Cout,Cin,3,3] -> 4 x [4, Cout, Cin]."""
+    rows = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}      # phase -> 3x3 taps hitting source offset (-1 + phase) and (0 + phase)
+    wf = w.detach().float()
+    out = []
+    for py, px in UP2_PHASES:
+        taps = []
+        for a_ in (0, 1):
+            for b_ in (0, 1):
+                acc = None
+                for ky in rows[py][a_]:
+                    for kx in rows[px][b_]:
+                        acc = wf[:, :, ky, kx] if acc is None else acc + wf[:, :, ky, kx]
+                taps.append(acc)
+        out.append(torch.stack(taps, 0).to(dtype).contiguous())
+    return out
+
+
+def conv_up2_tc(x, w_phases, bias, want_stats=False):
+    """conv3x3(pad 1) of the nearest-2x upsampling of x [N,H,W,Cin] bf16 as four sub-pixel 2x2 convs -> [N,2H,2W,Cout] fp32."""
+    require_cuda(x, bias)
+    N, H, W, Cin = x.shape
+    Cout = w_phases[0].shape[1]
+    out = torch.empty((N, 2 * H, 2 * W, Cout), dtype=torch.float32, device=x.device)
+    cs = None
+    for p, (py, px) in enumerate(UP2_PHASES):
+        ph = (2, 2, py, px, 2 * H, 2 * W, 1 - py, 1 - px)
+        if want_stats and p == 0:
+            # probe the layout of one phase (all four share it), then give each phase its own slot region
+            probe = TcArgs()
+            _fill_conv_args(probe, x, w_phases[0], bias, out, 2, 2, 1, ph)
+            _apply_plan(probe, "conv", H * W)
+            slots, spi = tc_colstats_layout(probe)
+            if slots > 0:
+                cs = torch.empty((2, 4 * slots, Cout), dtype=torch.float32, device=x.device)
+        conv_tc(x, w_phases[p], bias, 2, 2, stride=1, pad=0, out=out, phase=ph,
+                stats_into=(cs, 4 * slots, p * slots) if cs is not None else None)
+    if cs is not None:
+        out._sdb_cs = (cs, 4 * slots, spi, 4, slots)
+    return out
+
+
+def _fill_conv_args(a, x, w_rskc, bias, out, kh, kw, stride, phase):
+    """Geometry part of conv_tc's argument block (enough for plan / layout queries)."""
+    N, IH, IW, Cin = x.shape
+    taps, Cout, _ = w_rskc.shape
+    sh, sw, o_h, o_w, OHF, OWF, pad_h, pad_w = phase
+    a.out_sh, a.out_sw, a.out_oh, a.out_ow, a.OHF, a.OWF = sh, sw, o_h, o_w, OHF, OWF
+    a.A, a.B, a.out = ptr(x), ptr(w_rskc), ptr(out)
+    a.bias = ptr(bias)
+    a.lda, a.ldb, a.ldc, a.ldr = Cin, Cin, Cout, Cout
+    a.M, a.N, a.K = N * IH * IW, Cout, taps * Cin
+    a.out_dtype = dtype_code(out.dtype)
+    a.taps, a.kw, a.stride, a.pad_h, a.pad_w = taps, kw, stride, pad_h, pad_w
+    a.NB, a.IH, a.IW, a.Cin, a.OH, a.OW = N, IH, IW, Cin, IH, IW
+    a.cout_pad = Cout
 
 
 def gemm_tc(A, W, bias=None, residual=None, out_dtype=torch.float32, geglu=False, col_group=0, col_group_stride=0,

@@ -59,7 +59,7 @@ def test_conv_tc_column_statistics_feed_groupnorm(cuda, N, H, W, Cin, Cout, k, v
     out = ops.conv_tc(x, wp, b, k, k, pad=k // 2, residual=res, want_stats=True, variant=variant, block_n=bn)
     plain = ops.conv_tc(x, wp, b, k, k, pad=k // 2, residual=res, variant=variant, block_n=bn)
     assert torch.equal(out, plain)
-    cs, slots, spi = out._sdb_cs
+    cs, slots, spi = out._sdb_cs[:3]
     assert cs.shape == (2, slots, Cout) and slots >= N * spi
     per_sample = cs[:, :N * spi].double().reshape(2, N, spi, Cout).sum(2)
     o = out.double().reshape(N, H * W, Cout)
@@ -78,3 +78,39 @@ def test_conv_tc_column_statistics_feed_groupnorm(cuda, N, H, W, Cin, Cout, k, v
     g2, be2 = randn(C, seed=9) * 0.1 + 1, randn(C, seed=10) * 0.1
     ref2 = nhwc(F.group_norm(nchw(torch.cat([out, out2], -1)).double(), 32, g2.double(), be2.double(), 1e-6))
     assert rel(ops.groupnorm(out, g2, be2, 1e-6, out_dtype=torch.float32, x1=out2, exact=True), ref2) < 2e-6
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout", [(2, 16, 16, 64, 128), (1, 32, 32, 128, 64), (3, 8, 8, 64, 96), (2, 24, 20, 64, 320)])
+def test_conv_up2_subpixel(cuda, N, H, W, Cin, Cout):
+    """nearest-2x upsample + conv3x3 as four folded 2x2 phase convs == the direct form; its per-phase column statistics
+    feed GroupNorm (alone and concatenated with an ordinary conv's output)."""
+    from sdb200 import ops
+    x = randn(N, H, W, Cin, seed=1).to(torch.bfloat16)
+    w = randn(Cout, Cin, 3, 3, seed=2) * (Cin * 9) ** -0.5
+    b = randn(Cout, seed=3)
+    up = F.interpolate(nchw(x.double()), scale_factor=2, mode="nearest")
+    ref = nhwc(F.conv2d(up, w.double(), b.double(), padding=1))
+    out = ops.conv_up2_tc(x, ops.fold_upsample_weights(w, torch.bfloat16), b, want_stats=True)
+    assert out.shape == ref.shape
+    # folded taps are sums of up to four fp32 weights rounded once to bf16 (the direct form rounds each tap): ~2^-9 relative
+    assert rel(out, ref) < 4e-3
+    # exactness of the decomposition itself: same folded bf16 weights applied by the reference
+    wf = ops.fold_upsample_weights(w, torch.bfloat16)
+    chk = torch.zeros_like(ref)
+    xp = F.pad(nchw(x.double()), (1, 1, 1, 1))
+    for p_, (py, px) in enumerate(ops.UP2_PHASES):
+        k = wf[p_].double().reshape(2, 2, Cout, Cin).permute(2, 3, 0, 1)
+        y = F.conv2d(xp[:, :, py:py + H + 1, px:px + W + 1], k)
+        chk[:, py::2, px::2, :] = nhwc(y) + b.double()
+    assert rel(out, chk) < 1e-5
+    if getattr(out, "_sdb_cs", None) is not None:
+        g, be = randn(Cout, seed=6) * 0.1 + 1, randn(Cout, seed=7) * 0.1
+        refn = nhwc(F.silu(F.group_norm(nchw(out).double(), 32, g.double(), be.double(), 1e-5)))
+        assert rel(ops.groupnorm(out, g, be, 1e-5, act=1, out_dtype=torch.float32, exact=True), refn) < 2e-6
+        x2 = randn(N, 2 * H, 2 * W, 64, seed=8).to(torch.bfloat16)
+        w2 = (randn(64, 64, 3, 3, seed=9) * (64 * 9) ** -0.5).to(torch.bfloat16)
+        o2 = ops.conv_tc(x2, ops.pack_conv_weight(w2, torch.bfloat16), None, 3, 3, pad=1, want_stats=True)
+        C = Cout + 64
+        g2, be2 = randn(C, seed=10) * 0.1 + 1, randn(C, seed=11) * 0.1
+        ref2 = nhwc(F.group_norm(nchw(torch.cat([o2, out], -1)).double(), 32, g2.double(), be2.double(), 1e-6))
+        assert rel(ops.groupnorm(o2, g2, be2, 1e-6, out_dtype=torch.float32, x1=out, exact=True), ref2) < 2e-6

@@ -27,13 +27,13 @@ v = torch.zeros(B, Sk, H, dp, device=dev, dtype=torch.bfloat16); v[..., :d] = to
 fn = lambda: ops.attention_tc(q, k, v, B, H, Sq, Sk, d, dp, d ** -0.5, (Sq * H * dp, H * dp, dp), (Sk * H * dp, H * dp, dp), (Sk * H * dp, H * dp, dp))
 for _ in range(3):
     fn()
-trace = torch.zeros(9 * 32 * 8, dtype=torch.int64, device=dev)
+trace = torch.zeros(10 * 32 * 8, dtype=torch.int64, device=dev)
 lib.sdb_attn_set_trace.argtypes = [C.c_void_p]
 lib.sdb_attn_set_trace(trace.data_ptr())
 fn()
 torch.cuda.synchronize()
 lib.sdb_attn_set_trace(None)
-t = trace.cpu().reshape(9, 32, 8)
+t = trace.cpu().reshape(10, 32, 8)
 base = int(t[t > 0].min())
 print("args", sys.argv[1:])
 print("MMA issuer of tile 0: iter | reach Kfull Sempty QKissued | PVreach Vfull Pfull PVissued")
@@ -42,6 +42,12 @@ for u in range(32):
     if int(r.max()) == 0:
         break
     print("  %2d | %s" % (u, " ".join(("%7d" % (int(x) - base)) if int(x) else "      -" for x in r)))
+print("PV issue of tile 0 (deltas, cycles): iter | MMA0 MMA1-3 MMA4-7 commit(pv_done) commit(v_empty)")
+for u in range(1, 32):
+    r = [int(x) for x in t[9, u]]
+    if max(r) == 0:
+        break
+    print("  %2d | %5d %5d %5d %5d %5d" % (u, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[5] - r[4]))
 for w in (0, 4):
     print("softmax warp %d (query tile %d, lane quarter %d): tile | reach Sready Sregs max free turn expdone pub | step" % (w + 4, w // 4, w % 4))
     prev = None
