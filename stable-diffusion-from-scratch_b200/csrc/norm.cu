@@ -61,11 +61,13 @@ struct CsSrc {
     int regions;
 };
 
-__global__ void __launch_bounds__(128)
+constexpr int GNF_THREADS = 256, GNF_UNROLL = 8;
+
+__global__ void __launch_bounds__(GNF_THREADS)
 gn_colstats_finalize_kernel(const CsSrc s0, const CsSrc s1, int groups, double count, float eps, float2* __restrict__ stats) {
     pdl_trigger();
     pdl_wait();
-    __shared__ double redS[128], redQ[128];
+    __shared__ double redS[GNF_THREADS], redQ[GNF_THREADS];
     const int w = blockIdx.x;                       // (sample, group)
     const int n = w / groups, g = w - n * groups;
     const int C = s0.C + s1.C, cpg = C / groups;
@@ -74,36 +76,38 @@ gn_colstats_finalize_kernel(const CsSrc s0, const CsSrc s1, int groups, double c
     const int a_lo = c_lo < s0.C ? c_lo : s0.C, a_hi = c_hi < s0.C ? c_hi : s0.C;              // [a_lo, a_hi) in source 0
     const int b_lo = (c_lo > s0.C ? c_lo : s0.C) - s0.C, b_hi = (c_hi > s0.C ? c_hi : s0.C) - s0.C;   // [b_lo, b_hi) in source 1
     const int na = a_hi - a_lo, nb = b_hi - b_lo;
-    const long long items0 = (long long)s0.regions * s0.spi * na;
-    const long long items1 = s1.cs ? (long long)s1.regions * s1.spi * nb : 0;
-    const long long items = items0 + items1;
+    // item = (source, region, slot, channel), 32-bit indices (the host checks the counts); GNF_UNROLL items (2 loads each) in flight per
+    // thread, summed in index order
+    const uint32_t items0 = (uint32_t)(s0.regions * s0.spi * na);
+    const uint32_t items1 = s1.cs ? (uint32_t)(s1.regions * s1.spi * nb) : 0u;
+    const uint32_t items = items0 + items1;
+    const uint32_t spi0 = (uint32_t)s0.spi, spi1 = (uint32_t)s1.spi;
     double S = 0.0, Q = 0.0;
-    // item = (region, slot, channel); 4 items (8 loads) in flight per thread, summed in index order
-    for (long long i0 = threadIdx.x; i0 < items; i0 += 4 * 128) {
-        float a[4], q[4];
+    for (uint32_t i0 = threadIdx.x; i0 < items; i0 += GNF_UNROLL * GNF_THREADS) {
+        float a[GNF_UNROLL], q[GNF_UNROLL];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const long long i = i0 + u * 128;
+        for (int u = 0; u < GNF_UNROLL; ++u) {
+            const uint32_t i = i0 + u * GNF_THREADS;
             a[u] = 0.f; q[u] = 0.f;
             if (i < items) {
                 const bool first = i < items0;
                 const CsSrc& s = first ? s0 : s1;
-                const long long k = first ? i : i - items0;
-                const int nch = first ? na : nb;
-                const long long qd = k / nch;
+                const uint32_t k = first ? i : i - items0;
+                const uint32_t nch = first ? (uint32_t)na : (uint32_t)nb, spi = first ? spi0 : spi1;
+                const uint32_t qd = k / nch;
                 const int c = (first ? a_lo : b_lo) + (int)(k - qd * nch);
-                const long long region = qd / s.spi, sl = qd - region * s.spi;
-                const long long slot = region * s.rstride + (long long)n * s.spi + sl;
+                const uint32_t region = s.regions > 1 ? qd / spi : 0u, sl = qd - region * spi;
+                const long long slot = (long long)region * s.rstride + (long long)n * s.spi + sl;
                 a[u] = __ldcg(s.cs + slot * s.C + c);
                 q[u] = __ldcg(s.cs + (s.slots + slot) * s.C + c);
             }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { S += (double)a[u]; Q += (double)q[u]; }
+        for (int u = 0; u < GNF_UNROLL; ++u) { S += (double)a[u]; Q += (double)q[u]; }
     }
     redS[threadIdx.x] = S; redQ[threadIdx.x] = Q;
     __syncthreads();
-    for (int o = 64; o > 0; o >>= 1) {
+    for (int o = GNF_THREADS / 2; o > 0; o >>= 1) {
         if (threadIdx.x < o) { redS[threadIdx.x] += redS[threadIdx.x + o]; redQ[threadIdx.x] += redQ[threadIdx.x + o]; }
         __syncthreads();
     }
@@ -523,70 +527,69 @@ layernorm_kernel(const float* __restrict__ x, int rows, int C, float eps,
                  void* __restrict__ out) {
     pdl_trigger();
     pdl_wait();
-    constexpr int NR = 1;   // rows per warp: 1 measured fastest (more rows per warp = fewer resident warps, profiles/r01_layers_unet_b8.txt)
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    const int row0 = warp * NR;
-    if (row0 >= rows) return;
+    if (row >= rows) return;
     const int V = C >> 2;
-    float4 r[NR][MAXV];
+    const float* p = x + (long long)row * C;
+    float4 r[MAXV];
 #pragma unroll
-    for (int j = 0; j < NR; ++j) {
-        const float* p = x + (long long)(row0 + j) * C;
-#pragma unroll
-        for (int i = 0; i < MAXV; ++i) {
-            const int v = lane + 32 * i;
-            r[j][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (v < V && row0 + j < rows) r[j][i] = ld_stream_f4(p + 4 * v);
-        }
-    }
-    constexpr int NG = NR > 1 ? MAXV : 1;                 // gamma / beta stay in registers only when they are reused
-    float4 g[NG], b[NG];
-    if (NR > 1) {
-#pragma unroll
-        for (int i = 0; i < NG; ++i) {
-            const int v = lane + 32 * i;
-            if (v < V) {
-                g[i] = __ldg(reinterpret_cast<const float4*>(gamma) + v);
-                b[i] = __ldg(reinterpret_cast<const float4*>(beta) + v);
-            }
-        }
+    for (int i = 0; i < MAXV; ++i) {
+        const int v = lane + 32 * i;
+        r[i] = make_float4(0.f, 0.f, 0.f, 0.f);            // padding lanes hold zeros
+        if (v < V) r[i] = ld_stream_f4(p + 4 * v);
     }
     const float invC = 1.0f / (float)C;
+    float mean, rstd;
+    if (OUT_BF16) {
+        // tensor-core operand: sum and sum of squares reduced together (ONE dependent shuffle chain per row instead of
+        // two); E[x^2] - mean^2 in fp32 is far inside the bf16 rounding of the result
+        float s = 0.f, q = 0.f;
 #pragma unroll
-    for (int j = 0; j < NR; ++j) {
-        if (row0 + j >= rows) break;                       // warp-uniform
+        for (int i = 0; i < MAXV; ++i) {
+            s += (r[i].x + r[i].y) + (r[i].z + r[i].w);
+            q += (r[i].x * r[i].x + r[i].y * r[i].y) + (r[i].z * r[i].z + r[i].w * r[i].w);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        mean = s * invC;
+        rstd = rsqrtf(fmaxf(q * invC - mean * mean, 0.f) + eps);
+    } else {
+        // fp32 parity mode: centred two-pass variance
         float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < MAXV; ++i) s += (r[j][i].x + r[j][i].y) + (r[j][i].z + r[j][i].w);   // padding lanes hold zeros
+        for (int i = 0; i < MAXV; ++i) s += (r[i].x + r[i].y) + (r[i].z + r[i].w);
         s = warp_sum(s);
-        const float mean = s * invC;
+        mean = s * invC;
         float q = 0.f;
 #pragma unroll
         for (int i = 0; i < MAXV; ++i) {
             const int v = lane + 32 * i;
             if (v < V) {
-                float a = r[j][i].x - mean, bb = r[j][i].y - mean, c = r[j][i].z - mean, d = r[j][i].w - mean;
+                float a = r[i].x - mean, bb = r[i].y - mean, c = r[i].z - mean, d = r[i].w - mean;
                 q += (a * a + bb * bb) + (c * c + d * d);
             }
         }
         q = warp_sum(q);
-        const float rstd = rsqrtf(q * invC + eps);
-        const long long obase = (long long)(row0 + j) * C;
+        rstd = rsqrtf(q * invC + eps);
+    }
+    const long long obase = (long long)row * C;
 #pragma unroll
-        for (int i = 0; i < MAXV; ++i) {
-            const int v = lane + 32 * i;
-            if (v < V) {
-                const float4 gi = NR > 1 ? g[NR > 1 ? i : 0] : __ldg(reinterpret_cast<const float4*>(gamma) + v);
-                const float4 bi = NR > 1 ? b[NR > 1 ? i : 0] : __ldg(reinterpret_cast<const float4*>(beta) + v);
-                float y0 = (r[j][i].x - mean) * rstd * gi.x + bi.x;
-                float y1 = (r[j][i].y - mean) * rstd * gi.y + bi.y;
-                float y2 = (r[j][i].z - mean) * rstd * gi.z + bi.z;
-                float y3 = (r[j][i].w - mean) * rstd * gi.w + bi.w;
-                const long long o = obase + 4 * v;
-                if (OUT_BF16) st_stream_u2(reinterpret_cast<__nv_bfloat16*>(out) + o, pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
-                else st_stream_f4(reinterpret_cast<float*>(out) + o, make_float4(y0, y1, y2, y3));
-            }
+    for (int i = 0; i < MAXV; ++i) {
+        const int v = lane + 32 * i;
+        if (v < V) {
+            const float4 gi = __ldg(reinterpret_cast<const float4*>(gamma) + v);
+            const float4 bi = __ldg(reinterpret_cast<const float4*>(beta) + v);
+            float y0 = (r[i].x - mean) * rstd * gi.x + bi.x;
+            float y1 = (r[i].y - mean) * rstd * gi.y + bi.y;
+            float y2 = (r[i].z - mean) * rstd * gi.z + bi.z;
+            float y3 = (r[i].w - mean) * rstd * gi.w + bi.w;
+            const long long o = obase + 4 * v;
+            if (OUT_BF16) st_stream_u2(reinterpret_cast<__nv_bfloat16*>(out) + o, pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+            else st_stream_f4(reinterpret_cast<float*>(out) + o, make_float4(y0, y1, y2, y3));
         }
     }
 }
@@ -682,6 +685,8 @@ int sdb_groupnorm_from_colstats(const float* x0, int C0, const float* cs0, const
         SDB_REQUIRE(layout1, "groupnorm_from_colstats: second source has no layout");
         s1.cs = cs1; s1.C = C1; s1.slots = layout1[0]; s1.spi = layout1[1]; s1.regions = (int)layout1[2]; s1.rstride = layout1[3];
     }
+    SDB_REQUIRE((long long)s0.regions * s0.spi * C + (long long)s1.regions * s1.spi * C < (1LL << 31),
+                "groupnorm_from_colstats: too many statistics slots per sample");
     SDB_REQUIRE(s0.spi > 0 && s0.regions >= 1 && (s0.regions - 1) * s0.rstride + (long long)N * s0.spi <= s0.slots,
                 "groupnorm_from_colstats: statistics buffer of source 0 too small");
     SDB_REQUIRE(!cs1 || (s1.spi > 0 && s1.regions >= 1 && (s1.regions - 1) * s1.rstride + (long long)N * s1.spi <= s1.slots),
@@ -691,7 +696,7 @@ int sdb_groupnorm_from_colstats(const float* x0, int C0, const float* cs0, const
     cudaStream_t st = (cudaStream_t)stream;
     float2* stats = reinterpret_cast<float2*>(ws);                 // [N][groups]
     const int total = N * groups;
-    launch_pdl(gn_colstats_finalize_kernel, dim3(total), dim3(128), 0, st, s0, s1, groups, (double)HW * (C / groups), eps, stats);
+    launch_pdl(gn_colstats_finalize_kernel, dim3(total), dim3(GNF_THREADS), 0, st, s0, s1, groups, (double)HW * (C / groups), eps, stats);
     int rc = check_launch("gn_colstats_finalize_kernel");
     if (rc) return rc;
     GnGeom g = gn_apply_geom(N, HW, C);

@@ -53,6 +53,16 @@ def test_unet_batch_invariance_and_graph(cuda):
     g1 = net(x, t, ctx)
     g2 = net(x, t, ctx)
     assert torch.equal(g1, full) and torch.equal(g2, full)
+    # the context's K / V projections live in their own graph, replayed only for new conditioning: a different context,
+    # an in-place update of the same tensor, and a return to the first one must all give the eager result
+    ctx2 = W.seeded_randn((B, 77, 768), 7).cuda()
+    net.use_cuda_graph = False
+    full2 = net(x, t, ctx2)
+    net.use_cuda_graph = True
+    assert torch.equal(net(x, t, ctx2), full2)
+    assert torch.equal(net(x, t, ctx), full)
+    ctx.copy_(ctx2)
+    assert torch.equal(net(x, t, ctx), full2)
 
 
 @pytest.mark.parametrize("name", ["vae_tiny", "vae_sd_z16"])

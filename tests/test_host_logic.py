@@ -106,3 +106,32 @@ def test_shard_range_and_per_sample_seeds():
     full = per_sample_randn(range(6), (2, 3), 1000)
     parts = torch.cat([per_sample_randn(range(*shard_range(6, r, 4)), (2, 3), 1000) for r in range(4)], 0)
     assert torch.equal(full, parts)
+
+
+def test_upsample_weight_folding_is_exact():
+    """nearest-2x upsample + conv3x3(pad 1) == four 2x2 phase convs with the folded taps (ops.fold_upsample_weights);
+    checked in float64 on the CPU (no kernels involved: this is the host-side weight transform)."""
+    import torch.nn.functional as F
+    from sdb200 import ops
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 5, 6, 7, generator=g, dtype=torch.float64)
+    w = torch.randn(4, 5, 3, 3, generator=g, dtype=torch.float64)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, padding=1)
+    wf = ops.fold_upsample_weights(w, torch.float64)
+    out = torch.zeros_like(ref)
+    xp = F.pad(x, (1, 1, 1, 1))
+    H, W = x.shape[2:]
+    for p_, (py, px) in enumerate(ops.UP2_PHASES):
+        k = wf[p_].reshape(2, 2, 4, 5).permute(2, 3, 0, 1)
+        out[:, :, py::2, px::2] = F.conv2d(xp[:, :, py:py + H + 1, px:px + W + 1], k)
+    assert float((out - ref).abs().max()) < 1e-5      # the fold itself runs in fp32
+
+
+def test_launch_plan_table_is_well_formed():
+    from sdb200.tc_plans import PLANS
+    assert len(PLANS) > 10
+    for key, (variant, bn, sk, best_us, auto_us) in PLANS.items():
+        assert key[0] in ("conv", "gemm") and len(key) == 10
+        assert variant in (1, 2) and bn in (32, 64, 128, 160, 256) and 1 <= sk <= 16
+        assert not (variant == 2 and bn < 128)
+        assert best_us <= auto_us

@@ -52,7 +52,7 @@ def describe(name, args):
     if name == "sdb_groupnorm_nhwc":
         return "groupnorm N=%d HW=%d C=%d" % (args[4], args[5], args[1] + args[3]), 0.0
     if name == "sdb_groupnorm_from_colstats":
-        return "groupnorm(colstats) N=%d HW=%d C=%d" % (args[9], args[10], args[1] + args[5]), 0.0
+        return "groupnorm(colstats) N=%d HW=%d C=%d" % (args[8], args[9], args[1] + args[5]), 0.0
     if name == "sdb_layernorm":
         return "layernorm rows=%d C=%d" % (args[1], args[2]), 0.0
     if name == "sdb_cast_concat":

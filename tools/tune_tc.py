@@ -37,7 +37,7 @@ else:
     run = lambda: net.decode(z)
 
 FIELDS = ["M", "N", "K", "out_dtype", "geglu", "col_group", "col_group_stride", "taps", "kw", "stride", "pad_h", "pad_w",
-          "NB", "IH", "IW", "Cin", "OH", "OW", "cout_pad", "rows_per_item", "block_n"]
+          "NB", "IH", "IW", "Cin", "OH", "OW", "cout_pad", "rows_per_item", "block_n", "out_sh", "out_sw", "out_oh", "out_ow", "OHF", "OWF"]
 shapes = {}
 orig = lib.sdb_tc_contract
 
@@ -93,7 +93,8 @@ for key, count in sorted(shapes.items(), key=lambda kv: -kv[0][0] * kv[0][1] * k
     if conv:
         A = [torch.randn(d["NB"], d["IH"], d["IW"], d["Cin"], device=dev).to(torch.bfloat16) for _ in range(nrot)]
         W = [(torch.randn(d["taps"], N, d["Cin"], device=dev) / K ** 0.5).to(torch.bfloat16) for _ in range(nrot)]
-        oshape = (d["NB"], d["OH"], d["OW"], N)
+        phase = (d["out_sh"], d["out_sw"], d["out_oh"], d["out_ow"], d["OHF"], d["OWF"], d["pad_h"], d["pad_w"]) if d["out_sh"] > 1 else None
+        oshape = (d["NB"], d["OHF"], d["OWF"], N) if phase else (d["NB"], d["OH"], d["OW"], N)
     else:
         A = [torch.randn(M, K, device=dev).to(torch.bfloat16) for _ in range(nrot)]
         W = [(torch.randn(N, K, device=dev) / K ** 0.5).to(torch.bfloat16) for _ in range(nrot)]
@@ -120,7 +121,7 @@ for key, count in sorted(shapes.items(), key=lambda kv: -kv[0][0] * kv[0][1] * k
                 def fn(i):
                     if conv:
                         ops.conv_tc(A[i], W[i], bias, d["taps"] // d["kw"], d["kw"], stride=d["stride"], pad=d["pad_h"], rowvec=rowvec,
-                                    residual=R[i] if R else None, out=O[i], split_k=sk, block_n=bn, variant=variant, want_stats=stats and sk == 1)
+                                    residual=R[i] if R else None, out=O[i], split_k=sk, block_n=bn, variant=variant, want_stats=stats and sk == 1 and not phase, phase=phase)
                     else:
                         ops.gemm_tc(A[i], W[i], bias, residual=R[i] if R else None, geglu=bool(d["geglu"]), col_group=d["col_group"],
                                     col_group_stride=d["col_group_stride"], split_k=sk, block_n=bn, out=O[i],
@@ -134,7 +135,7 @@ for key, count in sorted(shapes.items(), key=lambda kv: -kv[0][0] * kv[0][1] * k
     def fn0(i):
         if conv:
             ops.conv_tc(A[i], W[i], bias, d["taps"] // d["kw"], d["kw"], stride=d["stride"], pad=d["pad_h"], rowvec=rowvec,
-                        residual=R[i] if R else None, out=O[i], block_n=d["block_n"], want_stats=stats)
+                        residual=R[i] if R else None, out=O[i], block_n=d["block_n"], want_stats=stats and not phase, phase=phase)
         else:
             ops.gemm_tc(A[i], W[i], bias, residual=R[i] if R else None, geglu=bool(d["geglu"]), col_group=d["col_group"],
                         col_group_stride=d["col_group_stride"], block_n=d["block_n"], out=O[i], rows_per_item=d["rows_per_item"])
