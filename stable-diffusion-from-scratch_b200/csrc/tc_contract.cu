@@ -60,8 +60,16 @@ struct TcP {
     } while (0)
 static long long* g_trace_ptr = nullptr;
 extern "C" void sdb_tc_set_trace(long long* ptr) { g_trace_ptr = ptr; }
+#define TC1_TRACE(slot)                                                                                  \
+    do {                                                                                                 \
+        if (p.trace && blockIdx.x < 2048 && blockIdx.y == 0) {                                           \
+            if ((slot) == 7) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); p.trace[(long long)blockIdx.x * 8 + 7] = sm; } \
+            else p.trace[(long long)blockIdx.x * 8 + (slot)] = (long long)globaltimer_ns();               \
+        }                                                                                                \
+    } while (0)
 #else
 #define TC_TRACE(slot, it_) do { } while (0)
+#define TC1_TRACE(slot) do { } while (0)
 #endif
 
 constexpr int TC_BM = 128;
@@ -439,6 +447,7 @@ template <int BN>
 __global__ void __launch_bounds__(192, 2)
 tc_contract_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcP p) {
     pdl_trigger();
+    if (threadIdx.x == 0) { TC1_TRACE(0); TC1_TRACE(7); }
     using Cfg = TcCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -485,7 +494,9 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_d = *tmem_slot;
+    if (threadIdx.x == 0) TC1_TRACE(1);
     pdl_wait();                                      // predecessor's outputs (A, residual, ...) are complete and visible
+    if (threadIdx.x == 0) TC1_TRACE(2);
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -525,6 +536,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 if (++s == STAGES) { s = 0; ph ^= 1; }
             }
             umma_commit(accum_bar);                  // accumulator complete
+            TC1_TRACE(3);
         }
     } else {
         // ================= epilogue (warps 2..5 -> TMEM lane groups 2,3,0,1) =================
@@ -554,7 +566,9 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // once the accumulator is ready every TMA load has been consumed: the A ring doubles as the transpose staging area
         float* stage = reinterpret_cast<float*>(sA) + (warp - 2) * (EPI_WARP_BYTES / 4);
         const uint32_t taddr = tmem_d + ((uint32_t)(lg * 32) << 16);
+        if (warp == 2 && lane == 0) TC1_TRACE(4);
         epilogue_warp<BN>(p, taddr, s_bias, stage, lane, n0, nt, pix, img, split, 0, 1, accum_bar, 0, mt * 4 + lg);
+        if (warp == 2 && lane == 0) TC1_TRACE(5);
     }
 
     // ---- teardown ----
