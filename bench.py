@@ -316,8 +316,15 @@ def roofline_pass(unet, x, t, ctx, mode):
     ms = sum(r[1].elapsed_time(r[2]) for r in recs)
     tf_peak, _, which = peaks()
     ach = flop / (ms / 1000.0) / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_tc_traffic.json")      # ncu dram bytes per launch of the same kernels (tools/gpu_round.sh)
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp))["dram_bytes_per_launch"]
+        except Exception:
+            traffic = None
     return ({"bound": "tensor", "kernel": "tc_contract_kernel (tcgen05 implicit-GEMM conv + GEMM)", "achieved": ach,
-             "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": None, "launches": len(recs),
+             "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": traffic, "launches": len(recs),
              "sum_ms": ms, "algorithmic_gflop": flop / 1e9, "peak_source": which + " (sustained cuBLAS bf16)"}, launches)
 
 

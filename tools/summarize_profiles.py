@@ -60,6 +60,29 @@ with open(os.path.join(P, "%s_ncu_full_summary.txt" % tag), "w") as f:
             top = sorted(st.items(), key=lambda kv: -float(kv[1] or 0))[:5]
             f.write("    top stalls: %s\n" % ", ".join("%s=%s" % (k.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""), v) for k, v in top))
 
+# 2b. DRAM traffic of every tcgen05 contraction launch of one eager UNet call (ncu dram__bytes_read/write)
+src = os.path.join(G, "traffic_tc_unet_b8.csv")
+if os.path.exists(src):
+    rows = list(csv.reader(open(src)))
+    hdr, per_id = None, collections.OrderedDict()
+    for r in rows:
+        if r and r[0] == "ID":
+            hdr = r
+            continue
+        if hdr and len(r) == len(hdr):
+            d = dict(zip(hdr, r))
+            if d.get("Metric Name") not in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                continue
+            v = float(d["Metric Value"].replace(",", ""))
+            mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(d["Metric Unit"], 1.0)
+            per_id[d["ID"]] = per_id.get(d["ID"], 0.0) + v * mult
+    if per_id:
+        tot = sum(per_id.values())
+        json.dump({"kernel": "tc_contract_kernel / tc_contract_pair_kernel", "launches": len(per_id), "dram_bytes_total": tot,
+                   "dram_bytes_per_launch": tot / len(per_id),
+                   "how": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum over one eager SD-1.x UNet call, batch 8 (cold-cache replay per launch)"},
+                  open(os.path.join(P, "%s_tc_traffic.json" % tag), "w"))
+
 # 3. bench lines + per-layer table
 for name in ("bench_full.log", "bench_ref.log"):
     p = os.path.join(G, name)
@@ -67,7 +90,8 @@ for name in ("bench_full.log", "bench_ref.log"):
         lines = [l for l in open(p) if l.startswith("{")]
         if lines:
             open(os.path.join(P, "%s_%s.json" % (tag, name[:-4])), "w").write(lines[-1])
-p = os.path.join(G, "layers_unet_b8.log")
-if os.path.exists(p):
-    open(os.path.join(P, "%s_layers_unet_b8.txt" % tag), "w").write(open(p).read())
+for nm in ("layers_unet_b8", "layers_vae_b8"):
+    p = os.path.join(G, nm + ".log")
+    if os.path.exists(p):
+        open(os.path.join(P, "%s_%s.txt" % (tag, nm)), "w").write(open(p).read())
 print("wrote", sorted(os.listdir(P)))
