@@ -138,6 +138,19 @@ int sdb_ddim_step(const float* x, const float* e_cond, const float* e_uncond, fl
                   float sqrt_one_minus_at, float temperature, float* x_prev, float* pred_x0, long long n,
                   void* stream);
 
+/* ---- VAE posterior and img2img entry ('next' row f3) ------------------------------------------
+ * sdb_diag_gaussian replaces DiagonalGaussianDistribution.__init__ / .sample
+ * (ldm/modules/distributions/distributions.py:24-37): moments [N,2C,HW] fp32 (NCHW, the quant_conv output)
+ * -> mean, logvar = clamp(., -30, 20), std = exp(0.5 logvar), var = exp(logvar), and, when noise != NULL,
+ * sample = mean + std * noise; every output [N,C,HW] fp32.
+ * sdb_q_sample replaces DDIMSampler.stochastic_encode's arithmetic (ldm/diffusion/ddim.py:218-222):
+ * out[b, :] = a[b] * x0[b, :] + c[b] * noise[b, :], a / c device vectors of B per-sample coefficients,
+ * per = elements per sample; individually rounded fp32 operations like the eager reference. */
+int sdb_diag_gaussian(const float* moments, const float* noise, int N, int C, long long HW, float* mean, float* logvar,
+                      float* stdv, float* var, float* sample, void* stream);
+int sdb_q_sample(const float* x0, const float* noise, const float* a, const float* c, int B, long long per, float* out,
+                 void* stream);
+
 /* ---- fp32 SIMT contraction (the fp32 parity mode; also the C_in=4 / tiny layers) --------------
  * One kernel family: out[m, n] = alpha * sum_k A(m,k) * B(n,k) + bias[n] + rowvec[img(m), n]
  *                                + residual[m, n]

@@ -94,6 +94,53 @@ def gen_vae(name, ddconfig, B, zres, seed, with_f64):
     save(name + ".pt", out)
 
 
+def gen_vae_enc(name, ddconfig, B, res, seed):
+    """Encoder + quant_conv + DiagonalGaussianDistribution of the reference, and the img2img entry
+    DDIMSampler.stochastic_encode / decode on the resulting latent ('next' row f3)."""
+    enc = RH.build_encoder(ddconfig)
+    ks_enc = W.key_shapes_of(enc)
+    zc = ddconfig["z_channels"]
+    ks = [("encoder." + k, s) for k, s in ks_enc] + [("quant_conv.weight", (2 * zc, 2 * zc, 1, 1)), ("quant_conv.bias", (2 * zc,))]
+    sd = W.make_state_dict(ks, seed)
+    enc.load_state_dict({k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}, strict=True)
+    x = W.seeded_randn((B, ddconfig["in_channels"], res, res), seed + 1)
+    DG = RH.gaussian_distribution_class()
+    with torch.no_grad(), RH.quiet():
+        moments = torch.nn.functional.conv2d(enc(x), sd["quant_conv.weight"], sd["quant_conv.bias"])   # autoencoder.py:331-334
+        post = DG(moments)
+        torch.manual_seed(seed + 2)
+        z_ref = post.sample()
+        mean_or, logvar_or, std_or = R.autoencoder_encode(sd, ddconfig, x)
+    torch.manual_seed(seed + 2)
+    noise = torch.randn(post.mean.shape)                 # the draw sample() makes (distributions.py:36)
+    assert torch.equal(z_ref, post.mean + post.std * noise)
+    err = R.rel_l2(torch.cat([mean_or, logvar_or], 1), torch.cat([post.mean, post.logvar], 1))
+    print("%s: encoder restatement vs reference rel-L2 = %.3e (moments std %.3f)" % (name, err, float(moments.std())))
+    assert err < 2e-5, err
+    assert R.rel_l2(std_or, post.std) < 2e-5
+    with torch.no_grad():
+        m64, lv64, _ = R.autoencoder_encode({k: v.double() for k, v in sd.items()}, ddconfig, x.double())
+    print("   fp32 reference vs f64 restatement rel-L2 = %.3e" % R.rel_l2(torch.cat([post.mean, post.logvar], 1), torch.cat([m64, lv64], 1)))
+    out = dict(ddconfig=ddconfig, seed=seed, key_shapes=ks, x_shape=tuple(x.shape), mean_ref=post.mean.clone(),
+               logvar_ref=post.logvar.clone(), std_ref=post.std.clone(), noise=noise, z_ref=z_ref.clone(),
+               mean_f64=m64.clone(), logvar_f64=lv64.clone(), kl_ref=post.kl().clone(), restate_err=err)
+    # img2img entry on that latent: stochastic_encode with the reference sampler (toy eps-model, SD schedule)
+    shim = R.ModelShim(toy_model_fn, R.sd_alphas_cumprod())
+    ref = RH.make_cpu_sampler(shim)
+    with RH.quiet():
+        ref.make_schedule(ddim_num_steps=20, ddim_eta=0.0, verbose=False)
+    t_enc = 12
+    n2 = W.seeded_randn(tuple(z_ref.shape), seed + 3)
+    ts = torch.full((B,), t_enc, dtype=torch.long)
+    with RH.quiet():
+        zt_ref = ref.stochastic_encode(z_ref, ts, noise=n2)
+        zdec_ref = ref.decode(zt_ref, None, t_enc)
+    zt_or = R.q_sample_ddim(z_ref, n2, ref.ddim_alphas, ref.ddim_sqrt_one_minus_alphas, ts)
+    assert torch.equal(zt_or, zt_ref), "stochastic_encode restatement is not bit-exact"
+    out.update(t_enc=t_enc, enc_noise=n2, zt_ref=zt_ref.clone(), zdec_ref=zdec_ref.clone())
+    save(name + ".pt", out)
+
+
 def toy_model_fn(x, t, c):
     """A cheap analytic eps-model so that sampler goldens do not depend on any network."""
     s = torch.sin(t.float() * 0.01).view(-1, 1, 1, 1)
@@ -227,6 +274,8 @@ def main():
     if a.part in ("all", "vae"):
         gen_vae("vae_tiny", TINY_VAE_DDCONFIG, B=2, zres=8, seed=41, with_f64=True)
         gen_vae("vae_sd_z16", R.SD_VAE_DDCONFIG, B=1, zres=16, seed=51, with_f64=True)
+    if a.part in ("all", "vae_enc"):
+        gen_vae_enc("vae_enc_tiny", TINY_VAE_DDCONFIG, B=2, res=32, seed=61)
     if a.part == "ddpm":
         gen_ddpm()
     if a.part == "all":   # the DDPM tree's top-level `models` package clashes with ldm's aliases

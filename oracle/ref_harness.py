@@ -81,6 +81,17 @@ def run_unet(net, x, t, ctx):
 
 def build_decoder(ddconfig, state_dict=None, dtype=torch.float32):
     """Construct ldm.modules.diffusionmodules.model.Decoder under shim S-5."""
+    build_decoder_module()
+    with quiet():
+        dec = sys.modules["modules.diffusionmodules.model"].Decoder(**ddconfig)
+    dec = dec.to(dtype).eval()
+    if state_dict is not None:
+        dec.load_state_dict({k: v.to(dtype) for k, v in state_dict.items()}, strict=True)
+    return dec
+
+
+def build_decoder_module():
+    """Shim S-5: import the `ldm` tree under both of the package spellings its files use."""
     for pth in (REF, os.path.join(REF, "ldm")):
         if pth not in sys.path:
             sys.path.insert(0, pth)
@@ -88,12 +99,22 @@ def build_decoder(ddconfig, state_dict=None, dtype=torch.float32):
                  "modules.distributions", "modules.distributions.distributions", "modules.diffusionmodules.model"]:
         if name not in sys.modules:
             sys.modules[name] = importlib.import_module("ldm." + name)
+
+
+def build_encoder(ddconfig, state_dict=None, dtype=torch.float32):
+    """Construct ldm.modules.diffusionmodules.model.Encoder (same shim as build_decoder)."""
+    build_decoder_module()
     with quiet():
-        dec = sys.modules["modules.diffusionmodules.model"].Decoder(**ddconfig)
-    dec = dec.to(dtype).eval()
+        enc = sys.modules["modules.diffusionmodules.model"].Encoder(**ddconfig)
+    enc = enc.to(dtype).eval()
     if state_dict is not None:
-        dec.load_state_dict({k: v.to(dtype) for k, v in state_dict.items()}, strict=True)
-    return dec
+        enc.load_state_dict({k: v.to(dtype) for k, v in state_dict.items()}, strict=True)
+    return enc
+
+
+def gaussian_distribution_class():
+    build_decoder_module()
+    return sys.modules["modules.distributions.distributions"].DiagonalGaussianDistribution
 
 
 def ddim_module():

@@ -291,6 +291,51 @@ def autoencoder_decode(sd, ddconfig, z):
     return decoder_forward(sd, ddconfig, _conv(sd, "post_quant_conv", z), prefix="decoder.")
 
 
+def encoder_forward(sd, ddconfig, x, prefix=""):
+    """Encoder.forward, ldm/modules/diffusionmodules/model.py:434-465 (Downsample.forward :74-81: zero pad (0,1,0,1),
+    then a stride-2 3x3 conv without padding)."""
+    ch_mult = tuple(ddconfig["ch_mult"])
+    nres = len(ch_mult)
+    nrb = ddconfig["num_res_blocks"]
+    attn_resolutions = list(ddconfig.get("attn_resolutions", []))
+    curr_res = ddconfig["resolution"]
+    p = prefix
+    h = _conv(sd, p + "conv_in", x, padding=1)
+    for i_level in range(nres):
+        for i_block in range(nrb):
+            h = vae_resnet_block(sd, "%sdown.%d.block.%d" % (p, i_level, i_block), h)
+            if curr_res in attn_resolutions:
+                h = vae_attn_block(sd, "%sdown.%d.attn.%d" % (p, i_level, i_block), h)
+        if i_level != nres - 1:
+            h = F.pad(h, (0, 1, 0, 1), mode="constant", value=0)
+            h = _conv(sd, "%sdown.%d.downsample.conv" % (p, i_level), h, stride=2, padding=0)
+            curr_res //= 2
+    h = vae_resnet_block(sd, p + "mid.block_1", h)
+    h = vae_attn_block(sd, p + "mid.attn_1", h)
+    h = vae_resnet_block(sd, p + "mid.block_2", h)
+    h = _swish(_gn(sd, p + "norm_out", h, 1e-6))
+    return _conv(sd, p + "conv_out", h, padding=1)
+
+
+def autoencoder_encode(sd, ddconfig, x):
+    """AutoencoderKL.encode, ldm/models/autoencoder.py:331-335: Encoder, quant_conv (1x1), then the moments of a
+    DiagonalGaussianDistribution (ldm/modules/distributions/distributions.py:24-35): returns (mean, logvar clamped
+    to [-30, 20], std)."""
+    moments = _conv(sd, "quant_conv", encoder_forward(sd, ddconfig, x, prefix="encoder."))
+    mean, logvar = torch.chunk(moments, 2, dim=1)
+    logvar = torch.clamp(logvar, -30.0, 20.0)
+    return mean, logvar, torch.exp(0.5 * logvar)
+
+
+def q_sample_ddim(x0, noise, ddim_alphas, ddim_sqrt_one_minus_alphas, t):
+    """DDIMSampler.stochastic_encode, ldm/diffusion/ddim.py:208-222 (use_original_steps=False): extract_into_tensor of
+    sqrt(ddim_alphas) and ddim_sqrt_one_minus_alphas at index t, then sa * x0 + sb * noise."""
+    sa = torch.sqrt(torch.as_tensor(ddim_alphas)).to(torch.float32 if x0.dtype != torch.float64 else torch.float64)
+    sb = torch.as_tensor(ddim_sqrt_one_minus_alphas).to(sa.dtype)
+    shape = (-1,) + (1,) * (x0.dim() - 1)
+    return sa.gather(-1, t).reshape(shape) * x0 + sb.gather(-1, t).reshape(shape) * noise
+
+
 # ----------------------------------------------------------------------------------------------------
 # DDIM sampler
 # ----------------------------------------------------------------------------------------------------
@@ -425,6 +470,23 @@ class DDIMOracle:
                 inter["x_inter"].append(img)
                 inter["pred_x0"].append(pred_x0)
         return img, inter
+
+
+    def stochastic_encode(self, x0, t, noise):
+        """ddim.py:208-222 with the current (make_schedule) tables."""
+        return q_sample_ddim(x0, noise, self.ddim_alphas, self.ddim_sqrt_one_minus_alphas, t)
+
+    def decode(self, x_latent, cond, t_start, unconditional_guidance_scale=1., unconditional_conditioning=None):
+        """ddim.py:224-243: DDIM steps t_start-1 ... 0 starting from x_latent."""
+        timesteps = self.ddim_timesteps[:t_start]
+        total = timesteps.shape[0]
+        x_dec = x_latent
+        for i, step in enumerate(np.flip(timesteps)):
+            index = total - i - 1
+            ts = torch.full((x_latent.shape[0],), int(step), dtype=torch.long)
+            x_dec, _, _ = self.p_sample_ddim(x_dec, cond, ts, index, unconditional_guidance_scale=unconditional_guidance_scale,
+                                             unconditional_conditioning=unconditional_conditioning)
+        return x_dec
 
 
 # ----------------------------------------------------------------------------------------------------

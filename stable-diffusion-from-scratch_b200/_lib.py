@@ -97,6 +97,8 @@ SIGNATURES = {
     "sdb_gather_rows": (_I, [_P, _P, _I, _I, _P, _P]),
     "sdb_skinny_linear": (_I, [_P, _I, _I, _P, _P, _I, _I, _I, _P, _P]),
     "sdb_ddim_step": (_I, [_P, _P, _P, _F, _P, _F, _F, _F, _F, _F, _F, _P, _P, _L, _P]),
+    "sdb_diag_gaussian": (_I, [_P, _P, _I, _I, _L, _P, _P, _P, _P, _P, _P]),
+    "sdb_q_sample": (_I, [_P, _P, _P, _P, _I, _L, _P, _P]),
     "sdb_simt_contract": (_I, [C.POINTER(SimtArgs), _P]),
     "sdb_tc_contract": (_I, [C.POINTER(TcArgs), _P]),
     "sdb_tc_set_pair_kernel": (_I, [_I]),

@@ -1,5 +1,7 @@
 """Drop-in VAE `Decoder` / `AutoencoderKL.decode` (reference: ldm/modules/diffusionmodules/model.py:
-468-574 and ldm/models/autoencoder.py:293-340) running on libsdb200.so.
+468-574 and ldm/models/autoencoder.py:293-340) running on libsdb200.so, plus the 'next' row f3 of SURVEY.md §8:
+`Encoder` (model.py:370-465), `AutoencoderKL.encode` (autoencoder.py:331-335) and `DiagonalGaussianDistribution`
+(ldm/modules/distributions/distributions.py:24-65) built from the same kernels.
 
 Same constructor kwargs and state-dict keys (`decoder.conv_in`, `decoder.mid.block_1.norm1`,
 `decoder.up.L.block.K.conv1`, `decoder.up.L.upsample.conv`, `decoder.norm_out`, `decoder.conv_out`,
@@ -26,6 +28,17 @@ class Upsample(nn.Module):
             raise NotImplementedError("sdb200 VAE Upsample: resamp_with_conv=False is outside the hot path")
         self.with_conv = with_conv
         self.conv = nn.Conv2d(in_channels, in_channels, kernel_size=3, stride=1, padding=1)
+
+
+class Downsample(nn.Module):
+    """ldm/modules/diffusionmodules/model.py:62-81: zero pad (0,1,0,1) then conv3x3 stride 2 without padding."""
+
+    def __init__(self, in_channels, with_conv):
+        super().__init__()
+        if not with_conv:
+            raise NotImplementedError("sdb200 VAE Downsample: resamp_with_conv=False (avg_pool2d) is not built")
+        self.with_conv = with_conv
+        self.conv = nn.Conv2d(in_channels, in_channels, kernel_size=3, stride=2, padding=0)
 
 
 class ResnetBlock(nn.Module):
@@ -69,54 +82,8 @@ def make_attn(in_channels, attn_type="vanilla"):
     raise NotImplementedError("sdb200 VAE: linear attention is outside the hot path")
 
 
-class Decoder(nn.Module):
-    """ldm/modules/diffusionmodules/model.py:468-574."""
-
-    def __init__(self, *, ch, out_ch, ch_mult=(1, 2, 4, 8), num_res_blocks, attn_resolutions, dropout=0.0,
-                 resamp_with_conv=True, in_channels, resolution, z_channels, give_pre_end=False, tanh_out=False,
-                 use_linear_attn=False, attn_type="vanilla", compute_mode=None, **ignorekwargs):
-        super().__init__()
-        if use_linear_attn:
-            attn_type = "linear"
-        if tanh_out or give_pre_end:
-            raise NotImplementedError("sdb200 Decoder: tanh_out / give_pre_end are outside the hot path")
-        self.ch = ch
-        self.temb_ch = 0
-        self.num_resolutions = len(ch_mult)
-        self.num_res_blocks = num_res_blocks
-        self.resolution = resolution
-        self.in_channels = in_channels
-        self.give_pre_end = give_pre_end
-        self.tanh_out = tanh_out
-        self.compute_mode = compute_mode or engine.default_mode()
-        block_in = ch * ch_mult[self.num_resolutions - 1]
-        curr_res = resolution // 2 ** (self.num_resolutions - 1)
-        self.z_shape = (1, z_channels, curr_res, curr_res)
-        self.conv_in = nn.Conv2d(z_channels, block_in, kernel_size=3, stride=1, padding=1)
-        self.mid = nn.Module()
-        self.mid.block_1 = ResnetBlock(in_channels=block_in, out_channels=block_in, temb_channels=self.temb_ch, dropout=dropout)
-        self.mid.attn_1 = make_attn(block_in, attn_type=attn_type)
-        self.mid.block_2 = ResnetBlock(in_channels=block_in, out_channels=block_in, temb_channels=self.temb_ch, dropout=dropout)
-        self.up = nn.ModuleList()
-        for i_level in reversed(range(self.num_resolutions)):
-            block = nn.ModuleList()
-            attn = nn.ModuleList()
-            block_out = ch * ch_mult[i_level]
-            for i_block in range(self.num_res_blocks + 1):
-                block.append(ResnetBlock(in_channels=block_in, out_channels=block_out, temb_channels=self.temb_ch, dropout=dropout))
-                block_in = block_out
-                if curr_res in attn_resolutions:
-                    attn.append(make_attn(block_in, attn_type=attn_type))
-            up = nn.Module()
-            up.block = block
-            up.attn = attn
-            if i_level != 0:
-                up.upsample = Upsample(block_in, resamp_with_conv)
-                curr_res = curr_res * 2
-            self.up.insert(0, up)
-        self.norm_out = Normalize(block_in)
-        self.conv_out = nn.Conv2d(block_in, out_ch, kernel_size=3, stride=1, padding=1)
-        self._packed = {}
+class _VaeNet(nn.Module):
+    """Packing and block execution shared by Encoder and Decoder."""
 
     def _invalidate(self):
         self._packed = {}
@@ -154,6 +121,8 @@ class Decoder(nn.Module):
                 P[("vb", id(m))] = m.v.bias.detach().float().contiguous()
             elif isinstance(m, Upsample):
                 P[("up", id(m))] = PackedConv(m.conv.weight, m.conv.bias, mode, up2=True)
+            elif isinstance(m, Downsample):
+                P[("down", id(m))] = PackedConv(m.conv.weight, m.conv.bias, mode, stride=2, pad=0, pad_hi=1)
         P["conv_in"] = PackedConv(self.conv_in.weight, self.conv_in.bias, mode)
         P["conv_out"] = PackedConv(self.conv_out.weight, self.conv_out.bias, mode)
         self._packed[mode] = P
@@ -209,6 +178,172 @@ class Decoder(nn.Module):
         out = engine.linear(o, P[("proj_out", id(ab))], residual=x.reshape(B * S, Cc))
         return out.reshape(B, Hh, Ww, Cc)
 
+
+class Encoder(_VaeNet):
+    """ldm/modules/diffusionmodules/model.py:370-465 — same constructor kwargs and state-dict keys
+    (`conv_in`, `down.L.block.K.*`, `down.L.attn.K.*`, `down.L.downsample.conv`, `mid.*`, `norm_out`, `conv_out`)."""
+
+    def __init__(self, *, ch, out_ch, ch_mult=(1, 2, 4, 8), num_res_blocks, attn_resolutions, dropout=0.0,
+                 resamp_with_conv=True, in_channels, resolution, z_channels, double_z=True, use_linear_attn=False,
+                 attn_type="vanilla", compute_mode=None, **ignore_kwargs):
+        super().__init__()
+        if use_linear_attn:
+            attn_type = "linear"
+        self.ch = ch
+        self.temb_ch = 0
+        self.num_resolutions = len(ch_mult)
+        self.num_res_blocks = num_res_blocks
+        self.resolution = resolution
+        self.in_channels = in_channels
+        self.compute_mode = compute_mode or engine.default_mode()
+        self.conv_in = nn.Conv2d(in_channels, self.ch, kernel_size=3, stride=1, padding=1)
+        curr_res = resolution
+        in_ch_mult = (1,) + tuple(ch_mult)
+        self.in_ch_mult = in_ch_mult
+        self.down = nn.ModuleList()
+        for i_level in range(self.num_resolutions):
+            block = nn.ModuleList()
+            attn = nn.ModuleList()
+            block_in = ch * in_ch_mult[i_level]
+            block_out = ch * ch_mult[i_level]
+            for i_block in range(self.num_res_blocks):
+                block.append(ResnetBlock(in_channels=block_in, out_channels=block_out, temb_channels=self.temb_ch, dropout=dropout))
+                block_in = block_out
+                if curr_res in attn_resolutions:
+                    attn.append(make_attn(block_in, attn_type=attn_type))
+            down = nn.Module()
+            down.block = block
+            down.attn = attn
+            if i_level != self.num_resolutions - 1:
+                down.downsample = Downsample(block_in, resamp_with_conv)
+                curr_res = curr_res // 2
+            self.down.append(down)
+        self.mid = nn.Module()
+        self.mid.block_1 = ResnetBlock(in_channels=block_in, out_channels=block_in, temb_channels=self.temb_ch, dropout=dropout)
+        self.mid.attn_1 = make_attn(block_in, attn_type=attn_type)
+        self.mid.block_2 = ResnetBlock(in_channels=block_in, out_channels=block_in, temb_channels=self.temb_ch, dropout=dropout)
+        self.norm_out = Normalize(block_in)
+        self.conv_out = nn.Conv2d(block_in, 2 * z_channels if double_z else z_channels, kernel_size=3, stride=1, padding=1)
+        self._packed = {}
+
+    def _forward_nhwc(self, x, mode):
+        """x [N,H,W,in_channels] fp32 -> [N,H/2^(L-1),W/2^(L-1),2*z_channels] fp32 (Encoder.forward, model.py:434-465)."""
+        P = self._pack(mode)
+        ci = P["conv_in"]
+        h = engine.conv(x if ci.in_dtype == torch.float32 else ops.cast_concat(x, None, out_dtype=torch.bfloat16), ci, want_stats=True)
+        for i_level in range(self.num_resolutions):
+            for i_block in range(self.num_res_blocks):
+                h = self._resnet(self.down[i_level].block[i_block], P, mode, h)
+                if len(self.down[i_level].attn) > 0:
+                    h = self._attn(self.down[i_level].attn[i_block], P, mode, h)
+            if i_level != self.num_resolutions - 1:
+                pc = P[("down", id(self.down[i_level].downsample))]
+                hin = h if pc.in_dtype == torch.float32 else ops.cast_concat(h, None, out_dtype=torch.bfloat16)
+                h = engine.conv(hin, pc, want_stats=True)
+        h = self._resnet(self.mid.block_1, P, mode, h)
+        if isinstance(self.mid.attn_1, AttnBlock):
+            h = self._attn(self.mid.attn_1, P, mode, h)
+        h = self._resnet(self.mid.block_2, P, mode, h)
+        co = P["conv_out"]
+        h = self._gn(self.norm_out, h, mode, 1, co.in_dtype)
+        return engine.conv(h, co)
+
+    @torch.no_grad()
+    def forward(self, x):
+        """x [N, in_channels, H, W] -> [N, 2*z_channels, h, w] (fp32 in, fp32 out)."""
+        from ._lib import require_cuda
+        require_cuda(x)
+        h = ops.nchw_to_nhwc(x.float().contiguous())
+        out = ops.nhwc_to_nchw(self._forward_nhwc(h, self.compute_mode))
+        return out if x.dtype == torch.float32 else out.to(x.dtype)
+
+
+class DiagonalGaussianDistribution(object):
+    """ldm/modules/distributions/distributions.py:24-65; mean / logvar / std / var / sample come out of one kernel."""
+
+    def __init__(self, parameters, deterministic=False):
+        self.parameters = parameters
+        self.deterministic = deterministic
+        self._moments = parameters.float().contiguous()
+        self.mean, self.logvar, self.std, self.var, _ = ops.diag_gaussian(self._moments)
+        if self.deterministic:
+            self.var = self.std = torch.zeros_like(self.mean)
+
+    def sample(self, noise=None):
+        """mean + std * randn (distributions.py:35-37); `noise` lets a caller supply the draw (tests, per-sample seeds)."""
+        if noise is None:
+            noise = torch.randn(self.mean.shape, device=self.mean.device)
+        if self.deterministic:
+            return self.mean.clone()
+        return ops.diag_gaussian(self._moments, noise.float().contiguous())[4]
+
+    def kl(self, other=None):
+        if self.deterministic:
+            return torch.Tensor([0.])
+        if other is None:
+            return 0.5 * torch.sum(torch.pow(self.mean, 2) + self.var - 1.0 - self.logvar, dim=[1, 2, 3])
+        return 0.5 * torch.sum(torch.pow(self.mean - other.mean, 2) / other.var + self.var / other.var - 1.0
+                               - self.logvar + other.logvar, dim=[1, 2, 3])
+
+    def nll(self, sample, dims=[1, 2, 3]):
+        if self.deterministic:
+            return torch.Tensor([0.])
+        logtwopi = 1.8378770664093453
+        return 0.5 * torch.sum(logtwopi + self.logvar + torch.pow(sample - self.mean, 2) / self.var, dim=dims)
+
+    def mode(self):
+        return self.mean
+
+
+class Decoder(_VaeNet):
+    """ldm/modules/diffusionmodules/model.py:468-574."""
+
+    def __init__(self, *, ch, out_ch, ch_mult=(1, 2, 4, 8), num_res_blocks, attn_resolutions, dropout=0.0,
+                 resamp_with_conv=True, in_channels, resolution, z_channels, give_pre_end=False, tanh_out=False,
+                 use_linear_attn=False, attn_type="vanilla", compute_mode=None, **ignorekwargs):
+        super().__init__()
+        if use_linear_attn:
+            attn_type = "linear"
+        if tanh_out or give_pre_end:
+            raise NotImplementedError("sdb200 Decoder: tanh_out / give_pre_end are outside the hot path")
+        self.ch = ch
+        self.temb_ch = 0
+        self.num_resolutions = len(ch_mult)
+        self.num_res_blocks = num_res_blocks
+        self.resolution = resolution
+        self.in_channels = in_channels
+        self.give_pre_end = give_pre_end
+        self.tanh_out = tanh_out
+        self.compute_mode = compute_mode or engine.default_mode()
+        block_in = ch * ch_mult[self.num_resolutions - 1]
+        curr_res = resolution // 2 ** (self.num_resolutions - 1)
+        self.z_shape = (1, z_channels, curr_res, curr_res)
+        self.conv_in = nn.Conv2d(z_channels, block_in, kernel_size=3, stride=1, padding=1)
+        self.mid = nn.Module()
+        self.mid.block_1 = ResnetBlock(in_channels=block_in, out_channels=block_in, temb_channels=self.temb_ch, dropout=dropout)
+        self.mid.attn_1 = make_attn(block_in, attn_type=attn_type)
+        self.mid.block_2 = ResnetBlock(in_channels=block_in, out_channels=block_in, temb_channels=self.temb_ch, dropout=dropout)
+        self.up = nn.ModuleList()
+        for i_level in reversed(range(self.num_resolutions)):
+            block = nn.ModuleList()
+            attn = nn.ModuleList()
+            block_out = ch * ch_mult[i_level]
+            for i_block in range(self.num_res_blocks + 1):
+                block.append(ResnetBlock(in_channels=block_in, out_channels=block_out, temb_channels=self.temb_ch, dropout=dropout))
+                block_in = block_out
+                if curr_res in attn_resolutions:
+                    attn.append(make_attn(block_in, attn_type=attn_type))
+            up = nn.Module()
+            up.block = block
+            up.attn = attn
+            if i_level != 0:
+                up.upsample = Upsample(block_in, resamp_with_conv)
+                curr_res = curr_res * 2
+            self.up.insert(0, up)
+        self.norm_out = Normalize(block_in)
+        self.conv_out = nn.Conv2d(block_in, out_ch, kernel_size=3, stride=1, padding=1)
+        self._packed = {}
+
     def _forward_nhwc(self, z, mode):
         P = self._pack(mode)
         h = engine.conv(z, P["conv_in"], want_stats=True)
@@ -243,15 +378,17 @@ class Decoder(nn.Module):
 
 
 class AutoencoderKL(nn.Module):
-    """Decode side of ldm/models/autoencoder.py:292-340.  The encoder / loss / Lightning training hooks
-    are out of scope; their state-dict keys are tolerated with strict=False."""
+    """ldm/models/autoencoder.py:292-350: decode (hot path), encode and forward ('next' row f3).  The loss / Lightning
+    training hooks are out of scope; their state-dict keys are tolerated with strict=False."""
 
     def __init__(self, ddconfig, lossconfig=None, embed_dim=4, ckpt_path=None, ignore_keys=[], image_key="image",
                  colorize_nlabels=None, monitor=None, compute_mode=None, micro_batch=8):
         super().__init__()
         self.image_key = image_key
+        self.encoder = Encoder(**ddconfig, compute_mode=compute_mode)
         self.decoder = Decoder(**ddconfig, compute_mode=compute_mode)
         assert ddconfig["double_z"]
+        self.quant_conv = nn.Conv2d(2 * ddconfig["z_channels"], 2 * embed_dim, 1)
         self.post_quant_conv = nn.Conv2d(embed_dim, ddconfig["z_channels"], 1)
         self.embed_dim = embed_dim
         self.micro_batch = micro_batch
@@ -267,6 +404,7 @@ class AutoencoderKL(nn.Module):
     @compute_mode.setter
     def compute_mode(self, m):
         self.decoder.compute_mode = m
+        self.encoder.compute_mode = m
 
     def init_from_ckpt(self, path, ignore_keys=list()):
         sd = torch.load(path, map_location="cpu")["state_dict"]
@@ -279,10 +417,30 @@ class AutoencoderKL(nn.Module):
     def load_state_dict(self, *a, **k):
         r = super().load_state_dict(*a, **k)
         self.decoder._invalidate()
+        self.encoder._invalidate()
         self._pq = None
+        self._q = None
         return r
 
     _pq = None
+    _q = None
+
+    @torch.no_grad()
+    def encode(self, x):
+        """AutoencoderKL.encode (autoencoder.py:331-335): Encoder, quant_conv (1x1, 8->8), posterior.
+        x [N,3,H,W] in [-1,1] -> DiagonalGaussianDistribution over [N,embed_dim,H/8,W/8]."""
+        from ._lib import require_cuda
+        require_cuda(x)
+        mode = self.encoder.compute_mode
+        if self._q is None:
+            self._q = PackedConv(self.quant_conv.weight, self.quant_conv.bias, "fp32")     # C_in = 8: SIMT fp32 kernel in both modes
+        xf = x.float().contiguous()
+        outs = []
+        for i in range(0, xf.shape[0], self.micro_batch):
+            h = self.encoder._forward_nhwc(ops.nchw_to_nhwc(xf[i:i + self.micro_batch].contiguous()), mode)
+            outs.append(ops.nhwc_to_nchw(engine.conv(h, self._q)))
+        moments = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+        return DiagonalGaussianDistribution(moments)
 
     @torch.no_grad()
     def decode(self, z):
@@ -306,8 +464,11 @@ class AutoencoderKL(nn.Module):
         out = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
         return out if z.dtype == torch.float32 else out.to(z.dtype)
 
-    def forward(self, z):
-        return self.decode(z)
+    def forward(self, input, sample_posterior=True):
+        """autoencoder.py:342-349: (reconstruction, posterior)."""
+        posterior = self.encode(input)
+        z = posterior.sample() if sample_posterior else posterior.mode()
+        return self.decode(z), posterior
 
 
 AutoEncoderKL = AutoencoderKL   # VAE/autoencoder.py spells it with a capital E

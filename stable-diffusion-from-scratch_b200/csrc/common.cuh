@@ -70,19 +70,22 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)
 __device__ __forceinline__ float silu_exact(float x) { return x / (1.0f + expf(-x)); }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-// GELU(erf) for the bf16 tensor-core path: erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the
-// bf16 rounding of the stored product), 2 MUFU + ~12 FMA-pipe instructions and no divergent branches; the
-// fp32 parity mode keeps erff (gelu_erf above).
+// GELU(erf) for the bf16 tensor-core path.  erfc(z) = 2^(-z P(z)) with a quartic P fitted on [0, 4.2] (|erf error| <= 6e-7;
+// beyond 4.2 both sides are 0 in fp32), z = |x| / sqrt(2) folded into the coefficients, so
+//   gelu(x) = max(x, 0) - 0.5 |x| erfc(|x| / sqrt 2) = max(x, 0) - 0.5 |x 2^(|x| Q(|x|))|.
+// ONE MUFU (ex2) and 8 FMA/ALU-pipe instructions, no branches; max |error| 1.2e-6 over [-12, 12] (checked against
+// float64 erf), far below the bf16 rounding of the stored product.  The previous form (Abramowitz-Stegun 7.1.26:
+// rcp + exp + ~17 FMA-pipe instructions) made the GEGLU epilogue, not the MMA, pace the K <= 640 feed-forward layers
+// (profiles/r01_pair_timeline.txt).  The fp32 parity mode keeps erff (gelu_erf above).
 __device__ __forceinline__ float gelu_erf_fast(float x) {
-    const float z = fabsf(x) * 0.70710678118654752440f;
-    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-    float poly = fmaf(1.061405429f, t, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    const float e = poly * t * __expf(-z * z);          // 1 - erf(z), z >= 0
-    const float erf_abs = 1.0f - e;
-    return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+    const float a = fabsf(x);
+    float q = fmaf(-0.0005204587f, a, 0.007397511f);
+    q = fmaf(q, a, -0.05256124f);
+    q = fmaf(q, a, -0.45925468f);
+    q = fmaf(q, a, -1.1510913f);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a * q));
+    return fmaf(-0.5f, fabsf(x * e), fmaxf(x, 0.0f));
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -281,6 +281,41 @@ __global__ void ddim_step_kernel(const float* __restrict__ x, const float* __res
     }
 }
 
+// ---- posterior of the VAE encoder: DiagonalGaussianDistribution (ldm/modules/distributions/distributions.py:24-37) ----
+// moments [N, 2C, HW] fp32 (NCHW) -> mean, logvar (clamped to [-30, 20]), std = exp(0.5 logvar), var = exp(logvar),
+// sample = mean + std * noise (when noise != NULL), each [N, C, HW].
+__global__ void diag_gaussian_kernel(const float* __restrict__ moments, const float* __restrict__ noise, int C, long long HW,
+                                     long long n, float* __restrict__ mean, float* __restrict__ logvar,
+                                     float* __restrict__ stdv, float* __restrict__ var, float* __restrict__ sample) {
+    pdl_trigger();
+    pdl_wait();
+    const long long per = (long long)C * HW;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long img = i / per, r = i - img * per;
+        const float m = moments[img * 2 * per + r];
+        float lv = moments[img * 2 * per + per + r];
+        lv = fminf(fmaxf(lv, -30.0f), 20.0f);
+        const float sd = expf(__fmul_rn(0.5f, lv));
+        mean[i] = m;
+        logvar[i] = lv;
+        stdv[i] = sd;
+        var[i] = expf(lv);
+        if (sample) sample[i] = __fadd_rn(m, __fmul_rn(sd, noise[i]));
+    }
+}
+
+// ---- q_sample with per-sample coefficients: out = a[b] * x0 + c[b] * noise (DDIMSampler.stochastic_encode,
+// ldm/diffusion/ddim.py:208-222; separately rounded fp32 operations like the eager reference) ----
+__global__ void q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ noise, const float* __restrict__ a,
+                                const float* __restrict__ c, long long per, long long n, float* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / per;
+        out[i] = __fadd_rn(__fmul_rn(a[b], x0[i]), __fmul_rn(c[b], noise[i]));
+    }
+}
+
 // ---- bilinear x2 upsample, align_corners=True (DDPM/models/layers.py:68-72), NHWC ----------------
 template <bool OUT_BF16>
 __global__ void upsample_bilinear2x_kernel(const float* __restrict__ x, int H, int W, int C, long long total_vec,
@@ -455,6 +490,26 @@ int sdb_ddim_step(const float* x, const float* e_cond, const float* e_uncond, fl
         x, e_cond, e_uncond, cfg_scale, noise, sqrt_at, sqrt_aprev, dir_coef, sigma_t, sqrt_one_minus_at,
         temperature, x_prev, pred_x0, n);
     return check_launch("ddim_step_kernel");
+}
+
+int sdb_diag_gaussian(const float* moments, const float* noise, int N, int C, long long HW, float* mean, float* logvar,
+                      float* stdv, float* var, float* sample, void* stream) {
+    SDB_REQUIRE(moments && mean && logvar && stdv && var, "diag_gaussian: null pointer");
+    SDB_REQUIRE(N > 0 && C > 0 && HW > 0, "diag_gaussian: empty problem");
+    SDB_REQUIRE((sample == nullptr) == (noise == nullptr), "diag_gaussian: sample and noise go together");
+    const long long n = (long long)N * C * HW;
+    launch_pdl(diag_gaussian_kernel, dim3(grid_for(n, 256)), dim3(256), 0, (cudaStream_t)stream,
+        moments, noise, C, HW, n, mean, logvar, stdv, var, sample);
+    return check_launch("diag_gaussian_kernel");
+}
+
+int sdb_q_sample(const float* x0, const float* noise, const float* a, const float* c, int B, long long per, float* out,
+                 void* stream) {
+    SDB_REQUIRE(x0 && noise && a && c && out, "q_sample: null pointer");
+    SDB_REQUIRE(B > 0 && per > 0, "q_sample: empty problem");
+    const long long n = (long long)B * per;
+    launch_pdl(q_sample_kernel, dim3(grid_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, x0, noise, a, c, per, n, out);
+    return check_launch("q_sample_kernel");
 }
 
 }  // extern "C"

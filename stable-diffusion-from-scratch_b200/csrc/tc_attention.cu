@@ -91,6 +91,26 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
     return y;
 #endif
 }
+#ifndef SDB_ATTN_POLY
+#define SDB_ATTN_POLY 0         // exponentials out of every 8 evaluated on the FMA pipe instead of MUFU.EX2
+#endif
+// 2^x on the FMA pipe: x = n + f with n = round(x), f in [-0.5, 0.5]; cubic for 2^f (relative error 1.0e-4, 20x below the
+// bf16 rounding of P), exponent added with integer arithmetic.  x <= 8 here (lazy rescale), clamped at -125 from below.
+__device__ __forceinline__ float ex2_fma(float x) {
+    x = fmaxf(x, -125.0f);
+    const float t = x + 12582912.0f;                 // 1.5 * 2^23: the low mantissa bits now hold round(x)
+    const float f = x - (t - 12582912.0f);
+    float q = fmaf(0.05583828315138817f, f, 0.2426394820213318f);
+    q = fmaf(q, f, 0.6931367516517639f);
+    q = fmaf(q, f, 0.9999245405197144f);
+    return __int_as_float(__float_as_int(q) + (__float_as_int(t) << 23));
+}
+template <int J>
+__device__ __forceinline__ float ex2_sel(float x) {
+    constexpr bool poly = (SDB_ATTN_POLY == 1 && J == 7) || (SDB_ATTN_POLY == 2 && (J == 3 || J == 7)) ||
+                          (SDB_ATTN_POLY == 3 && (J == 2 || J == 5 || J == 7)) || (SDB_ATTN_POLY == 4 && (J & 1));
+    return poly ? ex2_fma(x) : ex2_approx(x);
+}
 // two non-negative fp32 -> packed bf16x2 (lo in the low half), round-to-nearest
 __device__ __forceinline__ uint32_t pack_p_bf16x2(float lo, float hi) {
 #if SDB_ATTN_VARIANT & 2
@@ -338,8 +358,9 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
             for (int c0 = 0; c0 < 128; c0 += 8) {
                 float e[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) e[j] = ex2_approx(fmaf(__uint_as_float(r[c0 + j]), c, nm));
+#define SDB_E(j) e[j] = ex2_sel<j>(fmaf(__uint_as_float(r[c0 + j]), c, nm))
+                SDB_E(0); SDB_E(1); SDB_E(2); SDB_E(3); SDB_E(4); SDB_E(5); SDB_E(6); SDB_E(7);
+#undef SDB_E
                 sum0 += (e[0] + e[1]) + (e[2] + e[3]);
                 sum1 += (e[4] + e[5]) + (e[6] + e[7]);
                 const int chunk = (c0 & 63) >> 3;

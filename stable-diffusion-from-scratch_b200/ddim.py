@@ -221,18 +221,21 @@ class DDIMSampler(object):
 
     @torch.no_grad()
     def stochastic_encode(self, x0, t, use_original_steps=False, noise=None):
-        """ddim.py:208-222 (img2img entry; 'next' row f3 — host-side torch arithmetic, not a hot-path kernel)."""
+        """ddim.py:208-222 (img2img entry): x_t = sqrt(a_t) x0 + sqrt(1 - a_t) noise with the per-sample
+        coefficients gathered at t, one fused kernel (individually rounded fp32 ops: bit-exact vs the eager reference)."""
         if use_original_steps:
             sqrt_alphas_cumprod = self.sqrt_alphas_cumprod
             sqrt_one_minus_alphas_cumprod = self.sqrt_one_minus_alphas_cumprod
         else:
-            sqrt_alphas_cumprod = torch.sqrt(torch.as_tensor(self.ddim_alphas)).to(x0.device)
-            sqrt_one_minus_alphas_cumprod = torch.as_tensor(self.ddim_sqrt_one_minus_alphas).to(x0.device)
+            sqrt_alphas_cumprod = torch.sqrt(torch.as_tensor(self.ddim_alphas))
+            sqrt_one_minus_alphas_cumprod = torch.as_tensor(self.ddim_sqrt_one_minus_alphas)
         if noise is None:
             noise = torch.randn_like(x0)
-        sa = sqrt_alphas_cumprod.gather(-1, t).reshape(-1, *((1,) * (x0.dim() - 1)))
-        sb = sqrt_one_minus_alphas_cumprod.gather(-1, t).reshape(-1, *((1,) * (x0.dim() - 1)))
-        return sa * x0 + sb * noise
+        dev = x0.device
+        t = t.to(dev)
+        sa = sqrt_alphas_cumprod.to(dev).gather(-1, t).float().contiguous()
+        sb = sqrt_one_minus_alphas_cumprod.to(dev).gather(-1, t).float().contiguous()
+        return ops.q_sample(x0.float().contiguous(), noise.float().contiguous(), sa, sb)
 
     @torch.no_grad()
     def decode(self, x_latent, cond, t_start, unconditional_guidance_scale=1.0, unconditional_conditioning=None,

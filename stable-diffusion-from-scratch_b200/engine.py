@@ -31,11 +31,12 @@ def head_pad(d):
 class PackedConv:
     """A conv layer's weights repacked tap-major [kh*kw, Cout, Cin] for one compute mode."""
 
-    def __init__(self, weight, bias, mode, stride=1, pad=None, up2=False):
+    def __init__(self, weight, bias, mode, stride=1, pad=None, up2=False, pad_hi=None):
         Cout, Cin, kh, kw = weight.shape
         self.cout, self.cin, self.kh, self.kw = Cout, Cin, kh, kw
         self.stride = stride
         self.pad = (kh // 2) if pad is None else pad
+        self.pad_hi = self.pad if pad_hi is None else pad_hi      # bottom/right padding (asymmetric for the VAE Downsample)
         # the tensor-core path needs whole 16-byte channel rows; tiny-C layers stay on the SIMT kernel
         self.use_tc = (mode == "bf16") and (Cin % 8 == 0) and (Cin >= 32)
         dt = torch.bfloat16 if self.use_tc else torch.float32
@@ -70,9 +71,9 @@ def conv(x, pc, rowvec=None, residual=None, out_dtype=torch.float32, up=1, want_
     if pc.use_tc:
         assert up == 1
         return ops.conv_tc(x, pc.w, pc.bias, pc.kh, pc.kw, stride=pc.stride, pad=pc.pad, rowvec=rowvec,
-                           residual=residual, out_dtype=out_dtype, want_stats=want_stats)
+                           residual=residual, out_dtype=out_dtype, want_stats=want_stats, pad_hi=pc.pad_hi)
     return ops.conv_simt(x, pc.w, pc.bias, pc.kh, pc.kw, stride=pc.stride, pad=pc.pad, up=up, rowvec=rowvec,
-                         residual=residual, out_dtype=out_dtype)
+                         residual=residual, out_dtype=out_dtype, pad_hi=pc.pad_hi)
 
 
 def conv_up2(x, pc, want_stats=False):

@@ -220,6 +220,35 @@ def ddim_step(x, e_cond, sqrt_at, sqrt_aprev, dir_coef, sigma_t, sqrt_one_minus_
     return x_prev, pred_x0
 
 
+def diag_gaussian(moments, noise=None):
+    """moments [N,2C,H,W] fp32 -> (mean, logvar, std, var, sample or None), each [N,C,H,W]
+    (DiagonalGaussianDistribution, ldm/modules/distributions/distributions.py:24-37)."""
+    require_cuda(moments, noise)
+    assert moments.dtype == torch.float32 and moments.is_contiguous() and moments.shape[1] % 2 == 0
+    N, C2, H, W = moments.shape
+    shape = (N, C2 // 2, H, W)
+    outs = [torch.empty(shape, dtype=torch.float32, device=moments.device) for _ in range(4)]
+    sample = None
+    if noise is not None:
+        assert noise.dtype == torch.float32 and noise.is_contiguous() and tuple(noise.shape) == shape
+        sample = torch.empty(shape, dtype=torch.float32, device=moments.device)
+    check(_L().sdb_diag_gaussian(ptr(moments), ptr(noise), N, C2 // 2, H * W, ptr(outs[0]), ptr(outs[1]), ptr(outs[2]),
+                                 ptr(outs[3]), ptr(sample), stream_ptr()), "diag_gaussian")
+    return outs[0], outs[1], outs[2], outs[3], sample
+
+
+def q_sample(x0, noise, a, c):
+    """out[b] = a[b] * x0[b] + c[b] * noise[b] (fp32; DDIMSampler.stochastic_encode, ldm/diffusion/ddim.py:218-222)."""
+    require_cuda(x0, noise, a, c)
+    for t in (x0, noise, a, c):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    B = x0.shape[0]
+    assert noise.shape == x0.shape and a.numel() == B and c.numel() == B
+    out = torch.empty_like(x0)
+    check(_L().sdb_q_sample(ptr(x0), ptr(noise), ptr(a), ptr(c), B, x0.numel() // B, ptr(out), stream_ptr()), "q_sample")
+    return out
+
+
 # ---- weight packing (host side, once per load) ----------------------------------------------------------
 def pack_conv_weight(w, dtype):
     """OIHW [Cout,Cin,kh,kw] -> tap-major [kh*kw, Cout, Cin] contiguous ("RSKC")."""
@@ -241,15 +270,16 @@ def pack_geglu_weight(w, b, block_n):
 
 
 # ---- fp32 SIMT contraction ----------------------------------------------------------------------------
-def conv_simt(x, w_rskc, bias, kh, kw, stride=1, pad=0, up=1, rowvec=None, residual=None, out_dtype=torch.float32):
+def conv_simt(x, w_rskc, bias, kh, kw, stride=1, pad=0, up=1, rowvec=None, residual=None, out_dtype=torch.float32, pad_hi=None):
     """x [N,IH,IW,Cin] fp32 (logical input is the nearest-`up`x upsampling of x), w [kh*kw,Cout,Cin] fp32."""
     require_cuda(x, w_rskc, bias, rowvec, residual)
     assert x.dtype == torch.float32 and w_rskc.dtype == torch.float32 and x.is_contiguous() and w_rskc.is_contiguous()
     N, IH, IW, Cin = x.shape
     taps, Cout, Cin2 = w_rskc.shape
     assert Cin2 == Cin and taps == kh * kw
-    OH = (IH * up + 2 * pad - kh) // stride + 1
-    OW = (IW * up + 2 * pad - kw) // stride + 1
+    pad_hi = pad if pad_hi is None else pad_hi          # bottom/right zero padding (VAE Downsample pads (0,1,0,1))
+    OH = (IH * up + pad + pad_hi - kh) // stride + 1
+    OW = (IW * up + pad + pad_hi - kw) // stride + 1
     out = torch.empty((N, OH, OW, Cout), dtype=out_dtype, device=x.device)
     a = SimtArgs()
     a.A, a.B, a.out = ptr(x), ptr(w_rskc), ptr(out)
@@ -347,7 +377,7 @@ def _tc_launch(a, what):
 
 
 def conv_tc(x, w_rskc, bias, kh, kw, stride=1, pad=0, rowvec=None, residual=None, out_dtype=torch.float32,
-            split_k=0, block_n=0, out=None, phase=None, variant=0, want_stats=False, stats_into=None):
+            split_k=0, block_n=0, out=None, phase=None, variant=0, want_stats=False, stats_into=None, pad_hi=None):
     """x [N,IH,IW,Cin] bf16, w [kh*kw,Cout,Cin] bf16 -> [N,OH,OW,Cout].
 
     phase=(sh, sw, oh, ow, OHF, OWF, pad_h, pad_w) writes this conv's OHxOW result into the strided
@@ -360,8 +390,9 @@ def conv_tc(x, w_rskc, bias, kh, kw, stride=1, pad=0, rowvec=None, residual=None
     assert Cin2 == Cin and taps == kh * kw
     a = TcArgs()
     if phase is None:
-        OH = (IH + 2 * pad - kh) // stride + 1
-        OW = (IW + 2 * pad - kw) // stride + 1
+        pad_hi = pad if pad_hi is None else pad_hi      # bottom/right padding: TMA zero-fills whatever lies past the image
+        OH = (IH + pad + pad_hi - kh) // stride + 1
+        OW = (IW + pad + pad_hi - kw) // stride + 1
         pad_h = pad_w = pad
         if out is None:
             out = torch.empty((N, OH, OW, Cout), dtype=out_dtype, device=x.device)

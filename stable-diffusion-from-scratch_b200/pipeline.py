@@ -94,6 +94,38 @@ class LatentDiffusion(nn.Module):
         return self.first_stage_model.decode(z)
 
     @torch.no_grad()
+    def encode_first_stage(self, x):
+        """ldm/diffusion/ddpm.py `encode_first_stage`: first_stage_model.encode(x) -> posterior."""
+        return self.first_stage_model.encode(x)
+
+    @torch.no_grad()
+    def get_first_stage_encoding(self, encoder_posterior, noise=None):
+        """ldm/diffusion/ddpm.py `get_first_stage_encoding`: scale_factor * posterior.sample()."""
+        if hasattr(encoder_posterior, "sample"):
+            z = encoder_posterior.sample() if noise is None else encoder_posterior.sample(noise)
+        elif isinstance(encoder_posterior, torch.Tensor):
+            z = encoder_posterior
+        else:
+            raise NotImplementedError(f"encoder_posterior of type '{type(encoder_posterior)}' not yet implemented")
+        return self.scale_factor * z
+
+    @torch.no_grad()
+    def img2img(self, image, cond, strength=0.75, ddim_steps=50, eta=0.0, unconditional_guidance_scale=1.0,
+                unconditional_conditioning=None, noise=None, posterior_noise=None):
+        """Encode -> DDIMSampler.stochastic_encode to step t_enc = strength * ddim_steps -> DDIMSampler.decode -> VAE
+        decode (the mask-free img2img use of ldm/diffusion/ddim.py:208-243): latents and [-1,1] images.
+        `posterior_noise` / `noise`: optional pre-drawn N(0,1) tensors for the posterior sample and the forward noising."""
+        sampler = DDIMSampler(self)
+        sampler.make_schedule(ddim_num_steps=ddim_steps, ddim_eta=eta, verbose=False)
+        t_enc = max(1, min(ddim_steps, int(strength * ddim_steps)))
+        z0 = self.get_first_stage_encoding(self.encode_first_stage(image), noise=posterior_noise)
+        ts = torch.full((z0.shape[0],), t_enc - 1, device=z0.device, dtype=torch.long)
+        zt = sampler.stochastic_encode(z0, ts, noise=noise)
+        z = sampler.decode(zt, cond, t_enc, unconditional_guidance_scale=unconditional_guidance_scale,
+                           unconditional_conditioning=unconditional_conditioning)
+        return z, self.decode_first_stage(z)
+
+    @torch.no_grad()
     def sample_log(self, cond, batch_size, ddim=True, ddim_steps=50, shape=(4, 64, 64), **kwargs):
         """ldm/diffusion/ddpm.py:1814-1826 (DDIM branch)."""
         assert ddim, "only the DDIM branch is on the hot path"

@@ -71,7 +71,8 @@ def test_vae_decode_parity(cuda, name, mode):
     from sdb200.autoencoder import AutoencoderKL
     g = load_golden(name + ".pt")
     vae = AutoencoderKL(ddconfig=g["ddconfig"], embed_dim=4, compute_mode=mode)
-    missing = vae.load_state_dict(W.make_state_dict(g["key_shapes"], g["seed"]), strict=True)
+    missing = vae.load_state_dict(W.make_state_dict(g["key_shapes"], g["seed"]), strict=False)
+    assert not missing.unexpected_keys and all(k.startswith(("encoder.", "quant_conv.")) for k in missing.missing_keys)
     vae = vae.cuda()
     z = W.seeded_randn(g["z_shape"], g["seed"] + 1).cuda()
     img = vae.decode(z)
@@ -84,6 +85,44 @@ def test_vae_decode_parity(cuda, name, mode):
     if name == "vae_tiny":    # micro-batching must not change anything
         vae.micro_batch = 1
         assert torch.equal(vae.decode(z), img)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_vae_encode_parity(cuda, mode):
+    """'next' row f3: AutoencoderKL.encode (Encoder with the asymmetric-pad stride-2 convs, quant_conv, posterior)
+    and the img2img entry DDIMSampler.stochastic_encode / decode against the reference's outputs."""
+    from sdb200.autoencoder import AutoencoderKL
+    from sdb200.ddim import DDIMSampler
+    from oracle.make_golden import toy_model_fn
+    g = load_golden("vae_enc_tiny.pt")
+    vae = AutoencoderKL(ddconfig=g["ddconfig"], embed_dim=4, compute_mode=mode)
+    r = vae.load_state_dict(W.make_state_dict(g["key_shapes"], g["seed"]), strict=False)
+    assert not r.unexpected_keys and all(k.startswith(("decoder.", "post_quant_conv.")) for k in r.missing_keys)
+    vae = vae.cuda()
+    x = W.seeded_randn(g["x_shape"], g["seed"] + 1).cuda()
+    post = vae.encode(x)
+    tol = 1e-5 if mode == "fp32" else 2e-2
+    em, el, es = rel(post.mean, g["mean_ref"]), rel(post.logvar, g["logvar_ref"]), rel(post.std, g["std_ref"])
+    print("vae_enc_tiny %s: mean %.3e logvar %.3e std %.3e" % (mode, em, el, es))
+    assert post.mean.shape == g["mean_ref"].shape
+    assert em <= tol and el <= tol and es <= tol
+    assert rel(post.var, g["std_ref"] ** 2) <= 2 * tol
+    assert rel(post.sample(g["noise"].cuda()), g["z_ref"]) <= tol
+    assert torch.equal(post.mode(), post.mean)
+    assert rel(post.kl(), g["kl_ref"]) <= 10 * tol
+    vae.micro_batch = 1
+    assert torch.equal(vae.encode(x).mean, post.mean)
+    if mode == "fp32":
+        # img2img entry on the reference's latent: stochastic_encode is bit-exact, decode follows the reference trajectory
+        shim = R.ModelShim(toy_model_fn, R.sd_alphas_cumprod(), device="cuda")
+        shim.betas = shim.betas.cuda()
+        smp = DDIMSampler(shim)
+        smp.make_schedule(20, ddim_eta=0.0, verbose=False)
+        ts = torch.full((x.shape[0],), g["t_enc"], device="cuda", dtype=torch.long)
+        zt = smp.stochastic_encode(g["z_ref"].cuda(), ts, noise=g["enc_noise"].cuda())
+        assert torch.equal(zt.cpu(), g["zt_ref"])
+        zdec = smp.decode(zt, None, g["t_enc"])
+        assert rel(zdec, g["zdec_ref"]) <= 1e-5
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
@@ -126,12 +165,13 @@ def test_tiny_pipeline_psnr(cuda, mode):
     """UNet DDIM-10 + VAE decode (tiny nets) vs the CPU oracle run on the same inputs: free-running image
     PSNR >= 40 dB and teacher-forced per-step eps within tolerance."""
     from sdb200.pipeline import LatentDiffusion
-    gu, gv = load_golden("unet_tiny.pt"), load_golden("vae_tiny.pt")
+    gu, gv, ge = load_golden("unet_tiny.pt"), load_golden("vae_tiny.pt"), load_golden("vae_enc_tiny.pt")
     sdu = W.make_state_dict(gu["key_shapes"], gu["seed"])
     sdv = W.make_state_dict(gv["key_shapes"], gv["seed"])
+    sdv.update(W.make_state_dict(ge["key_shapes"], ge["seed"]))     # encoder + quant_conv: the whole reference AutoencoderKL key set
     ld = LatentDiffusion(unet_config=gu["cfg"], first_stage_config=gv["ddconfig"], compute_mode=mode)
     ld.model.diffusion_model.load_state_dict(sdu)
-    ld.first_stage_model.load_state_dict(sdv)
+    ld.first_stage_model.load_state_dict(sdv, strict=True)
     ld = ld.cuda()
     B, S = 2, 10
     x_T = W.seeded_randn((B, 4, 8, 8), 71)
@@ -147,3 +187,21 @@ def test_tiny_pipeline_psnr(cuda, mode):
     print("tiny pipeline %s: latent rel-L2 %.3e, PSNR %.1f dB, worst teacher-forced eps rel-L2 %.3e" % (mode, rel(z, z_ref), psnr, worst))
     assert psnr >= 40.0
     assert worst <= EPS_TOL[mode]
+    # img2img ('next' row f3): encode the oracle's image, noise it to step t_enc, denoise, decode — vs the oracle doing the same
+    n_post, n_enc = W.seeded_randn((B, 4, 8, 8), 73), W.seeded_randn((B, 4, 8, 8), 74)
+    t_enc = 6
+    with torch.no_grad():
+        mean, _, std = R.autoencoder_encode(sdv, gv["ddconfig"], img_ref)
+        z0 = 0.18215 * (mean + std * n_post)
+        orc.make_schedule(S, ddim_eta=0.0)
+        zt = orc.stochastic_encode(z0, torch.full((B,), t_enc - 1, dtype=torch.long), n_enc)
+        z2_ref = orc.decode(zt, ctx, t_enc)
+        img2_ref = R.autoencoder_decode(sdv, gv["ddconfig"], z2_ref / 0.18215)
+    post = ld.encode_first_stage(img_ref.cuda())
+    z0_gpu = ld.get_first_stage_encoding(post, noise=n_post.cuda())
+    assert rel(z0_gpu, z0) <= (1e-5 if mode == "fp32" else 2e-2)
+    z2, img2 = ld.img2img(img_ref.cuda(), ctx.cuda(), strength=t_enc / S, ddim_steps=S, noise=n_enc.cuda(),
+                          posterior_noise=n_post.cuda())
+    psnr2 = R.psnr_255(img2.cpu(), img2_ref)
+    print("tiny img2img %s: latent rel-L2 %.3e, PSNR %.1f dB" % (mode, rel(z2, z2_ref), psnr2))
+    assert psnr2 >= 40.0

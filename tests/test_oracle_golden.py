@@ -37,6 +37,23 @@ def test_vae_restatement_matches_reference(name):
     assert R.rel_l2(g["img_ref"], g["img_f64"]) < 1e-5
 
 
+def test_vae_encoder_restatement_matches_reference():
+    """'next' row f3: Encoder + quant_conv + posterior moments, and stochastic_encode, against the reference's outputs."""
+    g = load_golden("vae_enc_tiny.pt")
+    sd = _sd(g)
+    x = W.seeded_randn(g["x_shape"], g["seed"] + 1)
+    with torch.no_grad():
+        mean, logvar, std = R.autoencoder_encode(sd, g["ddconfig"], x)
+    assert R.rel_l2(mean, g["mean_ref"]) < 1e-5 and R.rel_l2(logvar, g["logvar_ref"]) < 1e-5 and R.rel_l2(std, g["std_ref"]) < 1e-5
+    assert R.rel_l2(g["mean_ref"], g["mean_f64"]) < 1e-5
+    assert torch.allclose(mean + std * g["noise"], g["z_ref"], rtol=1e-5, atol=1e-6)
+    o = R.DDIMOracle(R.ModelShim(lambda x, t, c: x, R.sd_alphas_cumprod()))
+    o.make_schedule(20, ddim_eta=0.0)
+    ts = torch.full((x.shape[0],), g["t_enc"], dtype=torch.long)
+    zt = R.q_sample_ddim(g["z_ref"], g["enc_noise"], o.ddim_alphas, o.ddim_sqrt_one_minus_alphas, ts)
+    assert torch.equal(zt, g["zt_ref"])
+
+
 def test_ddpm_unet_restatement_matches_reference():
     g = load_golden("ddpm_unet.pt")
     sd = _sd(g)

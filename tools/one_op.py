@@ -61,4 +61,9 @@ for _ in range(20):
     out = fn()
 e1.record()
 torch.cuda.synchronize()
+if kind == "attn":      # accuracy of (batch 0, head 0) against fp64 softmax(q k^T) v on the same bf16 inputs
+    qd, kd, vd = q[0, :, 0, :d].double(), k[0, :, 0, :d].double(), vv[0, :, 0, :d].double()
+    ref = torch.softmax(qd @ kd.T * d ** -0.5, -1) @ vd
+    got = out.view(B, Sq, H, d)[0, :, 0].double()
+    print("rel-L2 vs fp64: %.3e" % float((got - ref).norm() / ref.norm()))
 print("ok %s %s: %.2f us/call, mean|out| %.4f" % (kind, v, e0.elapsed_time(e1) / 20 * 1e3, float(out.float().abs().mean())))
