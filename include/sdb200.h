@@ -59,11 +59,19 @@ int sdb_nhwc_to_nchw(const float* src, float* dst, int N, int C, int HW, void* s
  *   of the ResBlock's 1x1 skip_connection, openai_model/model.py:207-218,252) from the same read.
  *   counters: >= N ints, ZERO on entry and left zero on exit (ticket of the CTA that folds the
  *   per-chunk partial sums of a sample into its mean / rstd); one buffer per stream.
- *   act: 0 = none, 1 = SiLU.  exact != 0 uses expf (fp32 parity mode) instead of __expf. */
+ *   act: 0 = none, 1 = SiLU.  exact != 0 uses expf (fp32 parity mode) instead of __expf.
+ *   gb_stride: 0 = one gamma / beta row [C] shared by the batch; otherwise gamma / beta are [N, gb_stride]
+ *   per-sample rows — how `out_norm(h) * (1 + scale) + shift` of the use_scale_shift_norm ResBlock
+ *   (openai_model/model.py:244-248) is served: sdb_scale_shift_affine folds scale / shift into them. */
 long long sdb_groupnorm_ws_bytes(int N, int HW, int C, int groups);
 int sdb_groupnorm_nhwc(const float* x0, int C0, const float* x1, int C1, int N, int HW, int groups,
-                       float eps, const float* gamma, const float* beta, int act, int exact,
+                       float eps, const float* gamma, const float* beta, long long gb_stride, int act, int exact,
                        void* out, int out_dtype, void* raw_out, void* ws, int* counters, void* stream);
+/* gamma_out[n, c] = gamma[c] * (1 + ss[n, c]),  beta_out[n, c] = beta[c] * (1 + ss[n, c]) + ss[n, C + c];
+ * ss [N, >= 2C] fp32 with row stride ld_ss = the (scale | shift) halves torch.chunk takes from emb_out
+ * (openai_model/model.py:246).  gamma_out / beta_out [N, C]. */
+int sdb_scale_shift_affine(const float* gamma, const float* beta, const float* ss, long long ld_ss, int N, int C,
+                           float* gamma_out, float* beta_out, void* stream);
 
 /* Same GroupNorm, statistics taken from the column sums the producing tcgen05 convs wrote (sdb_tc_args.colstats:
  * cs = fp32 [2][slots][C*]), so the tensor is read once.  layout (host, 4 values per source) = {slots, consecutive 32-row
@@ -72,7 +80,7 @@ int sdb_groupnorm_nhwc(const float* x0, int C0, const float* x1, int C1, int N, 
 int sdb_groupnorm_from_colstats(const float* x0, int C0, const float* cs0, const long long* layout0 /* host */,
                                 const float* x1, int C1, const float* cs1, const long long* layout1 /* host */,
                                 int N, int HW, int groups, float eps,
-                                const float* gamma, const float* beta, int act, int exact,
+                                const float* gamma, const float* beta, long long gb_stride, int act, int exact,
                                 void* out, int out_dtype, void* raw_out, void* ws, void* stream);
 
 /* ---- LayerNorm over the last dim ---------------------------------------------------------------
@@ -89,6 +97,9 @@ int sdb_layernorm(const float* x, int rows, int C, float eps, const float* gamma
 int sdb_cast_concat(const float* x0, int C0, const float* x1, int C1, int N, int H, int W, int up,
                     void* out, int out_dtype, void* stream);
 /* bilinear x2 upsampling with align_corners=True (DDPM/models/layers.py:68-72); x [N,H,W,C] fp32. */
+/* 2x2 average pooling, stride 2 (Downsample(use_conv=False).op = avg_pool2d, openai_model/model.py:88-93; used by
+ * ResBlock(down=True), :184-189): x [N,H,W,C] fp32 -> out [N,H/2,W/2,C] (out_dtype).  H, W even, C % 4 == 0. */
+int sdb_avgpool2x2(const float* x, int N, int H, int W, int C, void* out, int out_dtype, void* stream);
 int sdb_upsample_bilinear2x(const float* x, int N, int H, int W, int C, void* out, int out_dtype, void* stream);
 /* out = act(x) (+ optional cast); act 0 none, 1 SiLU (emb_layers' nn.SiLU, model.py:195-196),
  * 2 GELU-erf (DDPM/models/unet.py:29). n elements. */

@@ -70,6 +70,39 @@ def gen_unet(name, cfg, B, HW, S_ctx, seed, t_values, with_f64):
     save(name + ".pt", out)
 
 
+VARIANT_UNET_CFGS = {   # 'next' row f4: the non-transformer UNetModel variants (cf. the __main__ demo, openai_model/model.py:604-622)
+    "unet_var_legacy": dict(image_size=16, in_channels=4, out_channels=4, model_channels=64, attention_resolutions=[1, 2],
+                            num_res_blocks=1, channel_mult=(1, 2), num_head_channels=32, use_spatial_transformer=False,
+                            use_scale_shift_norm=True, resblock_updown=True, num_classes=10, use_new_attention_order=False,
+                            use_checkpoint=False, legacy=True),
+    "unet_var_neworder": dict(image_size=16, in_channels=4, out_channels=4, model_channels=64, attention_resolutions=[2],
+                              num_res_blocks=1, channel_mult=(1, 2), num_heads=2, use_spatial_transformer=False,
+                              use_scale_shift_norm=False, resblock_updown=False, num_classes=None, use_new_attention_order=True,
+                              use_checkpoint=False, legacy=True),
+}
+
+
+def gen_unet_variant(name, cfg, seed):
+    net = RH.build_unet(cfg)
+    ks = W.key_shapes_of(net)
+    sd = W.make_state_dict(ks, seed)
+    net.load_state_dict(sd, strict=True)
+    B = 2
+    x = W.seeded_randn((B, cfg["in_channels"], 16, 16), seed + 1)
+    t = torch.tensor([981, 1], dtype=torch.long)
+    y = torch.tensor([3, 7], dtype=torch.long) if cfg.get("num_classes") is not None else None
+    eps_ref = RH.run_unet(net, x, t, None, y)
+    with torch.no_grad():
+        eps_or = R.unet_forward(sd, cfg, x, t, None, y=y)
+        eps64 = R.unet_forward({k: v.double() for k, v in sd.items()}, cfg, x.double(), t, None, y=y)
+    err = R.rel_l2(eps_or, eps_ref)
+    print("%s: restatement vs reference rel-L2 = %.3e (eps std %.3f); fp32 reference vs f64 %.3e"
+          % (name, err, float(eps_ref.std()), R.rel_l2(eps_ref, eps64)))
+    assert err < 2e-5, err
+    save(name + ".pt", dict(cfg=cfg, seed=seed, key_shapes=ks, x_shape=tuple(x.shape), t=t, y=y, eps_ref=eps_ref.clone(),
+                            eps_f64=eps64.clone(), restate_err=err))
+
+
 def gen_vae(name, ddconfig, B, zres, seed, with_f64):
     dec = RH.build_decoder(ddconfig)
     ks_dec = W.key_shapes_of(dec)
@@ -274,6 +307,9 @@ def main():
     if a.part in ("all", "vae"):
         gen_vae("vae_tiny", TINY_VAE_DDCONFIG, B=2, zres=8, seed=41, with_f64=True)
         gen_vae("vae_sd_z16", R.SD_VAE_DDCONFIG, B=1, zres=16, seed=51, with_f64=True)
+    if a.part in ("all", "unet_var"):
+        for i, (name, cfg) in enumerate(VARIANT_UNET_CFGS.items()):
+            gen_unet_variant(name, cfg, seed=81 + 10 * i)
     if a.part in ("all", "vae_enc"):
         gen_vae_enc("vae_enc_tiny", TINY_VAE_DDCONFIG, B=2, res=32, seed=61)
     if a.part == "ddpm":

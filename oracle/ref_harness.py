@@ -55,6 +55,11 @@ def _sdpa_adapter(q, k, v, dropout_p=0.0, softmax_scale=None, causal=False):
                                           scale=softmax_scale).transpose(1, 2)
 
 
+def _sdpa_qkvpacked_adapter(qkv, dropout_p=0.0, softmax_scale=None, causal=False):
+    q, k, v = qkv.unbind(2)                                     # [B,S,3,H,D] -> three [B,S,H,D]
+    return _sdpa_adapter(q, k, v, softmax_scale=softmax_scale)
+
+
 def build_unet(cfg, state_dict=None, dtype=torch.float32):
     """Construct the reference UNetModel under shims S-1..S-4; optionally load `state_dict`."""
     if REF not in sys.path:
@@ -64,6 +69,7 @@ def build_unet(cfg, state_dict=None, dtype=torch.float32):
     import openai_model.attention as oa
     import openai_model.model as om
     oa.flash_attn_func = _sdpa_adapter
+    oa.flash_attn_qkvpacked_func = _sdpa_qkvpacked_adapter      # AttentionBlock variants (attention.py:387,514)
     with quiet():
         net = om.UNetModel(**cfg)
     net = net.to(dtype).eval()
@@ -74,9 +80,9 @@ def build_unet(cfg, state_dict=None, dtype=torch.float32):
     return net
 
 
-def run_unet(net, x, t, ctx):
+def run_unet(net, x, t, ctx, y=None):
     with torch.no_grad(), quiet():
-        return net(x, t, ctx)
+        return net(x, t, ctx, y) if y is not None else net(x, t, ctx)
 
 
 def build_decoder(ddconfig, state_dict=None, dtype=torch.float32):

@@ -58,7 +58,8 @@ def unet_layout(cfg):
     """Block structure produced by UNetModel.__init__ (openai_model/model.py:362-532).
 
     Returns (input_blocks, middle_block, output_blocks): lists of layer lists; each layer is a tuple
-    ("conv", cin, cout) | ("res", cin, cout) | ("st", ch, heads, dim_head) | ("down", ch) | ("up", ch).
+    ("conv", cin, cout) | ("res", cin, cout, updown) | ("st", ch, heads, dim_head) | ("attn", ch, heads, new_order)
+    | ("down", ch) | ("up", ch); updown in (None, "up", "down") (resblock_updown, model.py:421-436,505-520).
     """
     mc = cfg["model_channels"]
     mult = tuple(cfg.get("channel_mult", (1, 2, 4, 8)))
@@ -66,62 +67,109 @@ def unet_layout(cfg):
     attn_res = list(cfg["attention_resolutions"])
     num_heads = cfg.get("num_heads", -1)
     num_head_channels = cfg.get("num_head_channels", -1)
+    num_heads_upsample = cfg.get("num_heads_upsample", -1)
+    if num_heads_upsample == -1:
+        num_heads_upsample = num_heads
     legacy = cfg.get("legacy", True)
-    assert cfg.get("use_spatial_transformer", False), "oracle restates the SpatialTransformer variant only"
+    use_st = cfg.get("use_spatial_transformer", False)
+    new_order = cfg.get("use_new_attention_order", False)
+    updown = cfg.get("resblock_updown", False)
 
-    def heads_for(ch):
+    def attn_layer(ch, heads_arg):
+        # model.py:388-408 — `num_heads` itself is reassigned when num_head_channels is given
+        nonlocal num_heads
         if num_head_channels == -1:
-            nh, dh = num_heads, ch // num_heads
+            dh = ch // num_heads
         else:
-            nh, dh = ch // num_head_channels, num_head_channels
+            num_heads = ch // num_head_channels
+            dh = num_head_channels
         if legacy:
-            dh = ch // nh   # use_spatial_transformer branch of model.py:393-395
-        return nh, dh
+            dh = ch // num_heads if use_st else num_head_channels
+        if use_st:
+            return ("st", ch, num_heads, dh)
+        # AttentionBlock.__init__, attention.py:559-574: num_head_channels == -1 -> the given head count
+        h_arg = num_heads if heads_arg is None else heads_arg
+        nh = h_arg if dh == -1 else ch // dh
+        return ("attn", ch, nh, new_order)
 
     inputs = [[("conv", cfg["in_channels"], mc)]]
     chans = [mc]
     ch, ds = mc, 1
     for level, m in enumerate(mult):
         for _ in range(nrb):
-            layers = [("res", ch, m * mc)]
+            layers = [("res", ch, m * mc, None)]
             ch = m * mc
             if ds in attn_res:
-                layers.append(("st", ch) + heads_for(ch))
+                layers.append(attn_layer(ch, None))
             inputs.append(layers)
             chans.append(ch)
         if level != len(mult) - 1:
-            inputs.append([("down", ch)])
+            inputs.append([("res", ch, ch, "down")] if updown else [("down", ch)])
             chans.append(ch)
             ds *= 2
-    middle = [("res", ch, ch), ("st", ch) + heads_for(ch), ("res", ch, ch)]
+    middle = [("res", ch, ch, None), attn_layer(ch, None), ("res", ch, ch, None)]
     outputs = []
     for level, m in list(enumerate(mult))[::-1]:
         for i in range(nrb + 1):
             ich = chans.pop()
-            layers = [("res", ch + ich, mc * m)]
+            layers = [("res", ch + ich, mc * m, None)]
             ch = mc * m
             if ds in attn_res:
-                layers.append(("st", ch) + heads_for(ch))
+                layers.append(attn_layer(ch, num_heads_upsample))
             if level and i == nrb:
-                layers.append(("up", ch))
+                layers.append(("res", ch, ch, "up") if updown else ("up", ch))
                 ds //= 2
             outputs.append(layers)
     return inputs, middle, outputs
 
 
-def resblock(sd, p, x, emb):
-    """ResBlock._forward, openai_model/model.py:232-252 (no updown, no scale-shift)."""
-    h = _gn(sd, p + ".in_layers.0", x, 1e-5)
-    h = F.silu(h)
+def resblock(sd, p, x, emb, scale_shift=False, updown=None):
+    """ResBlock._forward, openai_model/model.py:232-252, including the up/down (h_upd / x_upd = nearest x2 or
+    avg_pool2d(2), :184-191) and use_scale_shift_norm (:244-248) branches."""
+    h = F.silu(_gn(sd, p + ".in_layers.0", x, 1e-5))
+    if updown == "up":
+        h = F.interpolate(h, scale_factor=2, mode="nearest")
+        x = F.interpolate(x, scale_factor=2, mode="nearest")
+    elif updown == "down":
+        h = F.avg_pool2d(h, kernel_size=2, stride=2)
+        x = F.avg_pool2d(x, kernel_size=2, stride=2)
     h = _conv(sd, p + ".in_layers.2", h, padding=1)
-    emb_out = _lin(sd, p + ".emb_layers.1", F.silu(emb)).type(h.dtype)
-    h = h + emb_out[..., None, None]
-    h = _gn(sd, p + ".out_layers.0", h, 1e-5)
-    h = F.silu(h)
+    emb_out = _lin(sd, p + ".emb_layers.1", F.silu(emb)).type(h.dtype)[..., None, None]
+    if scale_shift:
+        scale, shift = torch.chunk(emb_out, 2, dim=1)
+        h = _gn(sd, p + ".out_layers.0", h, 1e-5) * (1 + scale) + shift
+        h = F.silu(h)
+    else:
+        h = h + emb_out
+        h = F.silu(_gn(sd, p + ".out_layers.0", h, 1e-5))
     h = _conv(sd, p + ".out_layers.3", h, padding=1)
     if (p + ".skip_connection.weight") in sd:
         x = _conv(sd, p + ".skip_connection", x)
     return x + h
+
+
+def attention_block(sd, p, x, heads, new_order):
+    """AttentionBlock._forward (openai_model/attention.py:588-599) as the reference executes it:
+    both attention classes view the qkv conv output as [N, T, 3, H, ch] (channel = s*H*ch + h*ch + c);
+    QKVAttentionLegacy (:497-523) passes softmax_scale = ch**-0.25 to flash_attn_qkvpacked_func,
+    FlashAttention (:372-399) passes ch**-0.5 and then permutes the [N,T,H,ch] result to [N,H,T,ch]
+    BEFORE reshaping it to [N,T,H*ch] (so tokens and heads are interleaved) — restated as executed."""
+    b, c = x.shape[:2]
+    xf = x.reshape(b, c, -1)
+    T = xf.shape[-1]
+    hn = F.group_norm(xf, 32, sd[p + ".norm.weight"], sd[p + ".norm.bias"], 1e-5)
+    qkv = F.conv1d(hn, sd[p + ".qkv.weight"], sd[p + ".qkv.bias"])
+    ch = c // heads
+    q, k, v = qkv.permute(0, 2, 1).reshape(b, T, 3, heads, ch).unbind(2)            # each [N,T,H,ch]
+    scale = ch ** -0.5 if new_order else 1 / math.sqrt(math.sqrt(ch))
+    w = torch.softmax(torch.einsum("bthc,bshc->bhts", q, k) * scale, dim=-1)
+    out = torch.einsum("bhts,bshc->bthc", w, v)                                      # [N,T,H,ch]
+    if new_order:
+        out = out.permute(0, 2, 1, 3).reshape(b, T, heads * ch).permute(0, 2, 1)
+    else:
+        out = out.reshape(b, T, -1).permute(0, 2, 1)
+    h = F.conv1d(out, sd[p + ".proj_out.weight"], sd[p + ".proj_out.bias"])
+    return (xf + h).reshape(x.shape)
 
 
 def cross_attention(sd, p, x, context, heads):
@@ -172,16 +220,18 @@ def spatial_transformer(sd, p, x, context, heads, depth=1):
     return x + x_in
 
 
-def _run_layers(sd, prefix, layers, h, emb, context, depth):
+def _run_layers(sd, prefix, layers, h, emb, context, depth, scale_shift=False):
     for j, layer in enumerate(layers):
         p = "%s.%d" % (prefix, j)
         kind = layer[0]
         if kind == "conv":
             h = _conv(sd, p, h, padding=1)
         elif kind == "res":
-            h = resblock(sd, p, h, emb)
+            h = resblock(sd, p, h, emb, scale_shift=scale_shift, updown=layer[3])
         elif kind == "st":
             h = spatial_transformer(sd, p, h, context, layer[2], depth)
+        elif kind == "attn":
+            h = attention_block(sd, p, h, layer[2], layer[3])
         elif kind == "down":   # Downsample.forward, model.py:95-97: conv3x3 stride 2 pad 1
             h = _conv(sd, p + ".op", h, stride=2, padding=1)
         elif kind == "up":     # Upsample.forward, model.py:119-131: nearest x2 then conv3x3
@@ -190,7 +240,7 @@ def _run_layers(sd, prefix, layers, h, emb, context, depth):
     return h
 
 
-def unet_forward(sd, cfg, x, timesteps, context, taps=None):
+def unet_forward(sd, cfg, x, timesteps, context, taps=None, y=None):
     """UNetModel.forward, openai_model/model.py:550-595.  `emb = self.time_embed(t_emb.half())`
     (:566) rounds the sinusoidal embedding through fp16 before the MLP; harness shim S-3 only casts it
     back to the weights' dtype, so that rounding IS part of the reference's result and is restated
@@ -200,20 +250,23 @@ def unet_forward(sd, cfg, x, timesteps, context, taps=None):
     dt = sd["time_embed.0.weight"].dtype
     t_emb = timestep_embedding(timesteps, cfg["model_channels"]).half().to(dt)
     emb = _lin(sd, "time_embed.2", F.silu(_lin(sd, "time_embed.0", t_emb)))
+    if cfg.get("num_classes") is not None:      # model.py:567-569
+        emb = emb + sd["label_emb.weight"][y]
+    ss = cfg.get("use_scale_shift_norm", False)
     h = x.to(dt)
     context = context.to(dt) if context is not None else None
     hs = []
     for i, layers in enumerate(inputs):
-        h = _run_layers(sd, "input_blocks.%d" % i, layers, h, emb, context, depth)
+        h = _run_layers(sd, "input_blocks.%d" % i, layers, h, emb, context, depth, ss)
         hs.append(h)
         if taps is not None:
             taps["input_blocks.%d" % i] = h
-    h = _run_layers(sd, "middle_block", middle, h, emb, context, depth)
+    h = _run_layers(sd, "middle_block", middle, h, emb, context, depth, ss)
     if taps is not None:
         taps["middle_block"] = h
     for i, layers in enumerate(outputs):
         h = torch.cat([h, hs.pop()], dim=1)
-        h = _run_layers(sd, "output_blocks.%d" % i, layers, h, emb, context, depth)
+        h = _run_layers(sd, "output_blocks.%d" % i, layers, h, emb, context, depth, ss)
         if taps is not None:
             taps["output_blocks.%d" % i] = h
     h = F.silu(_gn(sd, "out.0", h, 1e-5))

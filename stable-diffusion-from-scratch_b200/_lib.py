@@ -82,9 +82,11 @@ SIGNATURES = {
     "sdb_nchw_to_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "sdb_nhwc_to_nchw": (_I, [_P, _P, _I, _I, _I, _P]),
     "sdb_groupnorm_ws_bytes": (_L, [_I, _I, _I, _I]),
-    "sdb_groupnorm_nhwc": (_I, [_P, _I, _P, _I, _I, _I, _I, _F, _P, _P, _I, _I, _P, _I, _P, _P, _P, _P]),
+    "sdb_groupnorm_nhwc": (_I, [_P, _I, _P, _I, _I, _I, _I, _F, _P, _P, _L, _I, _I, _P, _I, _P, _P, _P, _P]),
+    "sdb_scale_shift_affine": (_I, [_P, _P, _P, _L, _I, _I, _P, _P, _P]),
+    "sdb_avgpool2x2": (_I, [_P, _I, _I, _I, _I, _P, _I, _P]),
     "sdb_groupnorm_from_colstats": (_I, [_P, _I, _P, C.POINTER(C.c_longlong), _P, _I, _P, C.POINTER(C.c_longlong), _I, _I, _I, _F,
-                                         _P, _P, _I, _I, _P, _I, _P, _P, _P]),
+                                         _P, _P, _L, _I, _I, _P, _I, _P, _P, _P]),
     "sdb_layernorm": (_I, [_P, _I, _I, _F, _P, _P, _P, _I, _P]),
     "sdb_cast_concat": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _P, _I, _P]),
     "sdb_upsample_bilinear2x": (_I, [_P, _I, _I, _I, _I, _P, _I, _P]),

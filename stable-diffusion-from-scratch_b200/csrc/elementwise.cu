@@ -316,6 +316,47 @@ __global__ void q_sample_kernel(const float* __restrict__ x0, const float* __res
     }
 }
 
+// ---- scale-shift GroupNorm affine rows and 2x2 average pooling (UNet variants) ----------------
+__global__ void scale_shift_affine_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                          const float* __restrict__ ss, long long ld_ss, int C, long long n,
+                                          float* __restrict__ go, float* __restrict__ bo) {
+    pdl_trigger();
+    pdl_wait();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / C;
+        const int c = (int)(i - b * C);
+        const float one_plus = 1.0f + ss[b * ld_ss + c];
+        go[i] = gamma[c] * one_plus;
+        bo[i] = fmaf(beta[c], one_plus, ss[b * ld_ss + C + c]);
+    }
+}
+
+template <bool OUT_BF16>
+__global__ void avgpool2x2_kernel(const float* __restrict__ x, int H, int W, int C, long long total_vec, void* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
+    const int OH = H >> 1, OW = W >> 1, V = C >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(i % V);
+        long long pix = i / V;
+        const int ow = (int)(pix % OW);
+        long long t = pix / OW;
+        const int oh = (int)(t % OH);
+        const long long img = t / OH;
+        const float* p = x + ((img * H + 2 * oh) * W + 2 * ow) * (long long)C + 4 * v;
+        const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + C);
+        const float4 c = *reinterpret_cast<const float4*>(p + (long long)W * C), d = *reinterpret_cast<const float4*>(p + (long long)W * C + C);
+        // summation order of ATen's avg_pool2d: row-major over the window, then one division
+        float4 r;
+        r.x = (((a.x + b.x) + c.x) + d.x) * 0.25f;
+        r.y = (((a.y + b.y) + c.y) + d.y) * 0.25f;
+        r.z = (((a.z + b.z) + c.z) + d.z) * 0.25f;
+        r.w = (((a.w + b.w) + c.w) + d.w) * 0.25f;
+        if (OUT_BF16) reinterpret_cast<uint2*>(out)[i] = make_uint2(pack_bf16x2(r.x, r.y), pack_bf16x2(r.z, r.w));
+        else reinterpret_cast<float4*>(out)[i] = r;
+    }
+}
+
 // ---- bilinear x2 upsample, align_corners=True (DDPM/models/layers.py:68-72), NHWC ----------------
 template <bool OUT_BF16>
 __global__ void upsample_bilinear2x_kernel(const float* __restrict__ x, int H, int W, int C, long long total_vec,
@@ -510,6 +551,26 @@ int sdb_q_sample(const float* x0, const float* noise, const float* a, const floa
     const long long n = (long long)B * per;
     launch_pdl(q_sample_kernel, dim3(grid_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, x0, noise, a, c, per, n, out);
     return check_launch("q_sample_kernel");
+}
+
+int sdb_scale_shift_affine(const float* gamma, const float* beta, const float* ss, long long ld_ss, int N, int C,
+                           float* gamma_out, float* beta_out, void* stream) {
+    SDB_REQUIRE(gamma && beta && ss && gamma_out && beta_out, "scale_shift_affine: null pointer");
+    SDB_REQUIRE(N > 0 && C > 0 && ld_ss >= 2LL * C, "scale_shift_affine: bad shape N=%d C=%d ld=%lld", N, C, ld_ss);
+    const long long n = (long long)N * C;
+    launch_pdl(scale_shift_affine_kernel, dim3(grid_for(n, 256)), dim3(256), 0, (cudaStream_t)stream,
+        gamma, beta, ss, ld_ss, C, n, gamma_out, beta_out);
+    return check_launch("scale_shift_affine_kernel");
+}
+
+int sdb_avgpool2x2(const float* x, int N, int H, int W, int C, void* out, int out_dtype, void* stream) {
+    SDB_REQUIRE(x && out, "avgpool2x2: null pointer");
+    SDB_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && H % 2 == 0 && W % 2 == 0 && C % 4 == 0, "avgpool2x2: bad shape %dx%dx%dx%d", N, H, W, C);
+    SDB_REQUIRE(out_dtype == SDB_F32 || out_dtype == SDB_BF16, "avgpool2x2: bad out_dtype");
+    const long long tv = (long long)N * (H / 2) * (W / 2) * (C / 4);
+    if (out_dtype == SDB_BF16) launch_pdl(avgpool2x2_kernel<true>, dim3(grid_for(tv, 256)), dim3(256), 0, (cudaStream_t)stream, x, H, W, C, tv, out);
+    else launch_pdl(avgpool2x2_kernel<false>, dim3(grid_for(tv, 256)), dim3(256), 0, (cudaStream_t)stream, x, H, W, C, tv, out);
+    return check_launch("avgpool2x2_kernel");
 }
 
 }  // extern "C"

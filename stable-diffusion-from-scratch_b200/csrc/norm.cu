@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(1024, 1)      // <= 64 registers: two ~480-thr
 gn_apply_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1,
                 int HW, int groups, int V, int R, int rows_per_chunk,
                 const float2* __restrict__ stats, const float* __restrict__ gamma,
-                const float* __restrict__ beta, int act, void* __restrict__ out,
+                const float* __restrict__ beta, long long gb_stride, int act, void* __restrict__ out,
                 __nv_bfloat16* __restrict__ raw_out) {
     pdl_trigger();
     const int C = C0 + C1;
@@ -240,8 +240,9 @@ gn_apply_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ 
     }
     float sc[4], sh[4];
     {
-        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c));
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + c));
+        // gb_stride != 0: per-sample affine rows (the scale-shift ResBlock folds (1 + scale), shift into gamma / beta)
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + (long long)n * gb_stride + c));
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + (long long)n * gb_stride + c));
         const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -313,7 +314,7 @@ template <bool OUT_BF16, bool EXACT, bool RAW>
 __global__ void __launch_bounds__(1024, 1)
 gn_cluster_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1,
                   int HW, int groups, int V, int R, int rows_per_cta, int cs, float eps,
-                  const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+                  const float* __restrict__ gamma, const float* __restrict__ beta, long long gb_stride, int act,
                   void* __restrict__ out, __nv_bfloat16* __restrict__ raw_out) {
     extern __shared__ double gsm[];
     pdl_trigger();
@@ -409,8 +410,9 @@ gn_cluster_kernel(const float* __restrict__ x0, int C0, const float* __restrict_
     // ---- pass 2: normalise + affine (+ SiLU) ----
     float sc[4], sh[4];
     {
-        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c));
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + c));
+        // gb_stride != 0: per-sample affine rows (the scale-shift ResBlock folds (1 + scale), shift into gamma / beta)
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + (long long)n * gb_stride + c));
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + (long long)n * gb_stride + c));
         const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -493,14 +495,14 @@ static int gnc_max_cluster() {
 
 template <bool BF, bool EX, bool RW>
 static int launch_gn_cluster(const float* x0, int C0, const float* x1, int C1, int N, int HW, int groups, float eps,
-                             const float* gamma, const float* beta, int act, void* out, __nv_bfloat16* raw, cudaStream_t st,
-                             bool* launched) {
+                             const float* gamma, const float* beta, long long gb_stride, int act, void* out, __nv_bfloat16* raw,
+                             cudaStream_t st, bool* launched) {
     *launched = false;
     const int max_cs = gnc_max_cluster<BF, EX, RW>();
     GncGeom g;
     if (max_cs < 2 || !gnc_geom(HW, C0 + C1, groups, max_cs, &g)) return SDB_OK;
     launch_pdl_cluster(gn_cluster_kernel<BF, EX, RW>, dim3(g.cs, N), dim3(g.threads), g.smem, st, g.cs,
-                       x0, C0, x1, C1, HW, groups, g.V, g.R, g.rows_per_cta, g.cs, eps, gamma, beta, act, out, raw);
+                       x0, C0, x1, C1, HW, groups, g.V, g.R, g.rows_per_cta, g.cs, eps, gamma, beta, gb_stride, act, out, raw);
     *launched = true;
     return check_launch("gn_cluster_kernel");
 }
@@ -609,7 +611,7 @@ long long sdb_groupnorm_ws_bytes(int N, int HW, int C, int groups) {
 }
 
 int sdb_groupnorm_nhwc(const float* x0, int C0, const float* x1, int C1, int N, int HW, int groups,
-                       float eps, const float* gamma, const float* beta, int act, int exact,
+                       float eps, const float* gamma, const float* beta, long long gb_stride, int act, int exact,
                        void* out, int out_dtype, void* raw_out, void* ws, int* counters, void* stream) {
     const int C = C0 + C1;
     SDB_REQUIRE(x0 && out && ws && gamma && beta && counters, "groupnorm: null pointer");
@@ -619,13 +621,14 @@ int sdb_groupnorm_nhwc(const float* x0, int C0, const float* x1, int C1, int N, 
     SDB_REQUIRE(groups > 0 && C % groups == 0, "groupnorm: C=%d not divisible by groups=%d", C, groups);
     SDB_REQUIRE(C / 4 <= 1024, "groupnorm: C=%d too wide", C);
     SDB_REQUIRE(out_dtype == SDB_F32 || out_dtype == SDB_BF16, "groupnorm: bad out_dtype");
-    SDB_REQUIRE((((uintptr_t)gamma | (uintptr_t)beta) & 15) == 0, "groupnorm: gamma/beta must be 16-byte aligned");
+    SDB_REQUIRE((((uintptr_t)gamma | (uintptr_t)beta) & 15) == 0 && gb_stride % 4 == 0 && gb_stride >= 0,
+                "groupnorm: gamma/beta (and their per-sample stride) must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     __nv_bfloat16* raw = reinterpret_cast<__nv_bfloat16*>(raw_out);
     if (gn_cluster_enabled() && N <= 65535) {
         bool launched = false;
         int rc = SDB_OK;
-#define TRY_CLUSTER(BF, EX, RW) rc = launch_gn_cluster<BF, EX, RW>(x0, C0, x1, C1, N, HW, groups, eps, gamma, beta, act, out, raw, st, &launched)
+#define TRY_CLUSTER(BF, EX, RW) rc = launch_gn_cluster<BF, EX, RW>(x0, C0, x1, C1, N, HW, groups, eps, gamma, beta, gb_stride, act, out, raw, st, &launched)
         if (raw) {
             if (out_dtype == SDB_BF16) { if (exact) TRY_CLUSTER(true, true, true); else TRY_CLUSTER(true, false, true); }
             else                       { if (exact) TRY_CLUSTER(false, true, true); else TRY_CLUSTER(false, false, true); }
@@ -654,7 +657,7 @@ int sdb_groupnorm_nhwc(const float* x0, int C0, const float* x1, int C1, int N, 
     const dim3 grid_a(ga.chunks, N);
 #define LAUNCH_APPLY(BF, EX, RW)                                                                         \
     launch_pdl(gn_apply_kernel<BF, EX, RW>, dim3(grid_a), dim3(ga.threads), 0, st, x0, C0, x1, C1, HW, groups, ga.V, ga.R, \
-                                                             ga.rows_per_chunk, stats, gamma, beta, act, out, raw)
+                                                             ga.rows_per_chunk, stats, gamma, beta, gb_stride, act, out, raw)
     if (raw) {
         if (out_dtype == SDB_BF16) { if (exact) LAUNCH_APPLY(true, true, true); else LAUNCH_APPLY(true, false, true); }
         else                       { if (exact) LAUNCH_APPLY(false, true, true); else LAUNCH_APPLY(false, false, true); }
@@ -669,7 +672,7 @@ int sdb_groupnorm_nhwc(const float* x0, int C0, const float* x1, int C1, int N, 
 int sdb_groupnorm_from_colstats(const float* x0, int C0, const float* cs0, const long long* layout0,
                                 const float* x1, int C1, const float* cs1, const long long* layout1,
                                 int N, int HW, int groups, float eps,
-                                const float* gamma, const float* beta, int act, int exact,
+                                const float* gamma, const float* beta, long long gb_stride, int act, int exact,
                                 void* out, int out_dtype, void* raw_out, void* ws, void* stream) {
     const int C = C0 + C1;
     SDB_REQUIRE(x0 && cs0 && out && ws && gamma && beta, "groupnorm_from_colstats: null pointer");
@@ -692,7 +695,8 @@ int sdb_groupnorm_from_colstats(const float* x0, int C0, const float* cs0, const
     SDB_REQUIRE(!cs1 || (s1.spi > 0 && s1.regions >= 1 && (s1.regions - 1) * s1.rstride + (long long)N * s1.spi <= s1.slots),
                 "groupnorm_from_colstats: statistics buffer of source 1 too small");
     SDB_REQUIRE(out_dtype == SDB_F32 || out_dtype == SDB_BF16, "groupnorm_from_colstats: bad out_dtype");
-    SDB_REQUIRE((((uintptr_t)gamma | (uintptr_t)beta) & 15) == 0, "groupnorm_from_colstats: gamma/beta must be 16-byte aligned");
+    SDB_REQUIRE((((uintptr_t)gamma | (uintptr_t)beta) & 15) == 0 && gb_stride % 4 == 0 && gb_stride >= 0,
+                "groupnorm_from_colstats: gamma/beta (and their per-sample stride) must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     float2* stats = reinterpret_cast<float2*>(ws);                 // [N][groups]
     const int total = N * groups;
@@ -704,7 +708,7 @@ int sdb_groupnorm_from_colstats(const float* x0, int C0, const float* cs0, const
     __nv_bfloat16* raw = reinterpret_cast<__nv_bfloat16*>(raw_out);
 #define LAUNCH_APPLY(BF, EX, RW)                                                                         \
     launch_pdl(gn_apply_kernel<BF, EX, RW>, dim3(grid), dim3(g.threads), 0, st, x0, C0, x1, C1, HW, groups, g.V, g.R, \
-               g.rows_per_chunk, stats, gamma, beta, act, out, raw)
+               g.rows_per_chunk, stats, gamma, beta, gb_stride, act, out, raw)
     if (raw) {
         if (out_dtype == SDB_BF16) { if (exact) LAUNCH_APPLY(true, true, true); else LAUNCH_APPLY(true, false, true); }
         else                       { if (exact) LAUNCH_APPLY(false, true, true); else LAUNCH_APPLY(false, false, true); }

@@ -6,10 +6,11 @@ as the reference, so `instantiate_from_config` with `target: sdb200.openai_model
 parameter HOLDERS only (they give the reference's key names / shapes); their `forward` is never
 called — all arithmetic goes through hand-written sm_100a kernels (ops.py), channels-last.
 
-Scope: the SpatialTransformer variant used by Stable Diffusion v1
-(`use_spatial_transformer=True`), ResBlocks without scale-shift / resblock_updown, no class
-conditioning.  Unsupported constructor options raise NotImplementedError instead of silently
-computing something else.
+Scope: SURVEY.md §8a — the SpatialTransformer variant used by Stable Diffusion v1 (`use_spatial_transformer=True`) is the
+hot path — plus the 'next' row f4: the AttentionBlock variants (QKVAttentionLegacy / FlashAttention orders),
+`use_scale_shift_norm`, `resblock_updown` and class conditioning (`num_classes`), built from the same kernels.
+Still unsupported constructor options (dims != 2, conv_resample=False, n_embed) raise NotImplementedError instead of
+silently computing something else.
 """
 import math
 import weakref
@@ -77,19 +78,61 @@ class ResBlock(TimestepBlock):
     def __init__(self, channels, emb_channels, dropout, out_channels=None, use_conv=False,
                  use_scale_shift_norm=False, dims=2, use_checkpoint=False, up=False, down=False):
         super().__init__()
-        if use_scale_shift_norm or up or down or dims != 2 or use_conv:
-            raise NotImplementedError("sdb200 ResBlock: scale-shift / updown / 3x3 skip are outside the hot path")
+        if dims != 2:
+            raise NotImplementedError("sdb200 ResBlock supports dims=2")
         self.channels = channels
         self.emb_channels = emb_channels
         self.out_channels = out_channels or channels
+        self.use_scale_shift_norm = use_scale_shift_norm
+        # h_upd / x_upd (model.py:184-191) are parameter-free: nearest x2 or avg_pool2d(2)
+        self.updown = "up" if up else ("down" if down else None)
+        self.h_upd = self.x_upd = nn.Identity()
         self.in_layers = nn.Sequential(normalization(channels), nn.SiLU(), nn.Conv2d(channels, self.out_channels, 3, padding=1))
-        self.emb_layers = nn.Sequential(nn.SiLU(), nn.Linear(emb_channels, self.out_channels))
+        self.emb_layers = nn.Sequential(nn.SiLU(), nn.Linear(emb_channels, 2 * self.out_channels if use_scale_shift_norm else self.out_channels))
         self.out_layers = nn.Sequential(normalization(self.out_channels), nn.SiLU(), nn.Dropout(p=dropout),
                                         zero_module(nn.Conv2d(self.out_channels, self.out_channels, 3, padding=1)))
         if self.out_channels == channels:
             self.skip_connection = nn.Identity()
+        elif use_conv:
+            self.skip_connection = nn.Conv2d(channels, self.out_channels, 3, padding=1)
         else:
             self.skip_connection = nn.Conv2d(channels, self.out_channels, 1)
+
+
+class QKVAttentionLegacy(nn.Module):
+    """openai_model/attention.py:485-523 (parameter-free): softmax_scale = ch ** -0.25 as the reference passes it."""
+
+    def __init__(self, n_heads):
+        super().__init__()
+        self.n_heads = n_heads
+
+
+class FlashAttention(nn.Module):
+    """openai_model/attention.py:366-399 (parameter-free): softmax_scale = ch ** -0.5; the result is permuted to
+    [N,H,T,ch] before being reshaped to [N,T,H*ch] (kept as executed)."""
+
+    def __init__(self, n_heads):
+        super().__init__()
+        self.n_heads = n_heads
+
+
+class AttentionBlock(nn.Module):
+    """openai_model/attention.py:538-599: GroupNorm32 -> qkv conv1d -> attention -> proj_out conv1d -> + x."""
+
+    def __init__(self, channels, num_heads=1, num_head_channels=-1, use_checkpoint=False, use_new_attention_order=False):
+        super().__init__()
+        self.channels = channels
+        if num_head_channels == -1:
+            self.num_heads = num_heads
+        else:
+            assert channels % num_head_channels == 0, \
+                f"q, k, v channels {channels} is not divisible by num_head_channels {num_head_channels}"
+            self.num_heads = channels // num_head_channels
+        self.use_new_attention_order = use_new_attention_order
+        self.norm = normalization(channels)
+        self.qkv = nn.Conv1d(channels, channels * 3, 1)
+        self.attention = FlashAttention(self.num_heads) if use_new_attention_order else QKVAttentionLegacy(self.num_heads)
+        self.proj_out = zero_module(nn.Conv1d(channels, channels, 1))
 
 
 class CrossAttention(nn.Module):
@@ -182,10 +225,8 @@ class UNetModel(nn.Module):
             assert num_head_channels != -1, 'Either num_heads or num_head_channels has to be set'
         if num_head_channels == -1:
             assert num_heads != -1, 'Either num_heads or num_head_channels has to be set'
-        if not use_spatial_transformer:
-            raise NotImplementedError("sdb200 UNetModel: the AttentionBlock (non-transformer) variant is a 'next' row (SURVEY §8f4)")
-        if num_classes is not None or use_scale_shift_norm or resblock_updown or n_embed is not None or dims != 2 or not conv_resample:
-            raise NotImplementedError("sdb200 UNetModel: class-cond / scale-shift / resblock_updown / codebook heads are outside the hot path")
+        if n_embed is not None or dims != 2 or not conv_resample:
+            raise NotImplementedError("sdb200 UNetModel: codebook heads (n_embed), dims != 2 and conv_resample=False are not built")
 
         self.image_size = image_size
         self.in_channels = in_channels
@@ -210,16 +251,26 @@ class UNetModel(nn.Module):
 
         time_embed_dim = model_channels * 4
         self.time_embed = nn.Sequential(nn.Linear(model_channels, time_embed_dim), nn.SiLU(), nn.Linear(time_embed_dim, time_embed_dim))
+        if self.num_classes is not None:
+            self.label_emb = nn.Embedding(num_classes, time_embed_dim)
 
-        def heads_for(ch, nh):
+        cur_heads = [num_heads]     # the reference reassigns `num_heads` inside its loops (model.py:388-395)
+
+        def attn_for(ch, heads_arg=None):
             if num_head_channels == -1:
-                dim_head = ch // nh
+                dim_head = ch // cur_heads[0]
             else:
-                nh = ch // num_head_channels
+                cur_heads[0] = ch // num_head_channels
                 dim_head = num_head_channels
             if legacy:
-                dim_head = ch // nh
-            return nh, dim_head
+                dim_head = ch // cur_heads[0] if use_spatial_transformer else num_head_channels
+            if use_spatial_transformer:
+                return SpatialTransformer(ch, cur_heads[0], dim_head, depth=transformer_depth, context_dim=context_dim)
+            return AttentionBlock(ch, num_heads=cur_heads[0] if heads_arg is None else heads_arg, num_head_channels=dim_head,
+                                  use_new_attention_order=use_new_attention_order)
+
+        def res(cin, cout=None, **kw):
+            return ResBlock(cin, time_embed_dim, dropout, out_channels=cout, use_scale_shift_norm=use_scale_shift_norm, **kw)
 
         self.input_blocks = nn.ModuleList([TimestepEmbedSequential(nn.Conv2d(in_channels, model_channels, 3, padding=1))])
         input_block_chans = [model_channels]
@@ -227,33 +278,28 @@ class UNetModel(nn.Module):
         ds = 1
         for level, mult in enumerate(channel_mult):
             for _ in range(num_res_blocks):
-                layers = [ResBlock(ch, time_embed_dim, dropout, out_channels=mult * model_channels)]
+                layers = [res(ch, mult * model_channels)]
                 ch = mult * model_channels
                 if ds in attention_resolutions:
-                    nh, dh = heads_for(ch, num_heads)
-                    layers.append(SpatialTransformer(ch, nh, dh, depth=transformer_depth, context_dim=context_dim))
+                    layers.append(attn_for(ch))
                 self.input_blocks.append(TimestepEmbedSequential(*layers))
                 input_block_chans.append(ch)
             if level != len(channel_mult) - 1:
-                self.input_blocks.append(TimestepEmbedSequential(Downsample(ch, conv_resample, out_channels=ch)))
+                self.input_blocks.append(TimestepEmbedSequential(
+                    res(ch, ch, down=True) if resblock_updown else Downsample(ch, conv_resample, out_channels=ch)))
                 input_block_chans.append(ch)
                 ds *= 2
-        nh, dh = heads_for(ch, num_heads)
-        self.middle_block = TimestepEmbedSequential(
-            ResBlock(ch, time_embed_dim, dropout),
-            SpatialTransformer(ch, nh, dh, depth=transformer_depth, context_dim=context_dim),
-            ResBlock(ch, time_embed_dim, dropout))
+        self.middle_block = TimestepEmbedSequential(res(ch), attn_for(ch), res(ch))
         self.output_blocks = nn.ModuleList([])
         for level, mult in list(enumerate(channel_mult))[::-1]:
             for i in range(num_res_blocks + 1):
                 ich = input_block_chans.pop()
-                layers = [ResBlock(ch + ich, time_embed_dim, dropout, out_channels=model_channels * mult)]
+                layers = [res(ch + ich, model_channels * mult)]
                 ch = model_channels * mult
                 if ds in attention_resolutions:
-                    nh, dh = heads_for(ch, num_heads_upsample)
-                    layers.append(SpatialTransformer(ch, nh, dh, depth=transformer_depth, context_dim=context_dim))
+                    layers.append(attn_for(ch, num_heads_upsample))
                 if level and i == num_res_blocks:
-                    layers.append(Upsample(ch, conv_resample, out_channels=ch))
+                    layers.append(res(ch, ch, up=True) if resblock_updown else Upsample(ch, conv_resample, out_channels=ch))
                     ds //= 2
                 self.output_blocks.append(TimestepEmbedSequential(*layers))
         self.out = nn.Sequential(normalization(ch), nn.SiLU(), zero_module(nn.Conv2d(model_channels, out_channels, 3, padding=1)))
@@ -309,6 +355,8 @@ class UNetModel(nn.Module):
         P["freqs"] = torch.exp(-math.log(10000) * torch.arange(start=0, end=half, dtype=torch.float32) / half).to(dev)
         P["te0"] = (self.time_embed[0].weight.detach().float().contiguous(), self.time_embed[0].bias.detach().float().contiguous())
         P["te2"] = (self.time_embed[2].weight.detach().float().contiguous(), self.time_embed[2].bias.detach().float().contiguous())
+        if self.num_classes is not None:
+            P["label_emb"] = self.label_emb.weight.detach().float().contiguous()
         # all ResBlock emb_layers as ONE skinny GEMM [sum(Cout), emb] (fp32 weights in both modes)
         ws, bs, off = [], [], 0
         for rb in self._res_blocks():
@@ -329,6 +377,10 @@ class UNetModel(nn.Module):
                 P[("op", id(m))] = PackedConv(m.op.weight, m.op.bias, mode, stride=2, pad=1)
             elif isinstance(m, Upsample):
                 P[("conv", id(m))] = PackedConv(m.conv.weight, m.conv.bias, mode, up2=True)
+            elif isinstance(m, AttentionBlock):
+                Cc = m.channels
+                P[("qkv", id(m))] = PackedLinear(m.qkv.weight.reshape(3 * Cc, Cc), m.qkv.bias, mode)
+                P[("aout", id(m))] = PackedLinear(m.proj_out.weight.reshape(Cc, Cc), m.proj_out.bias, mode)
             elif isinstance(m, SpatialTransformer):
                 P[("pin", id(m))] = PackedConv(m.proj_in.weight, m.proj_in.bias, mode)
                 P[("pout", id(m))] = PackedConv(m.proj_out.weight, m.proj_out.bias, mode)
@@ -364,14 +416,32 @@ class UNetModel(nn.Module):
         off, n = P[("emb_off", id(rb))]
         rowvec = emb_all[:, off:off + n]
         sk = P.get(("skip", id(rb)))
+        ss = rb.use_scale_shift_norm
         raw = None
-        if sk is not None and sk.in_dtype == torch.bfloat16:
+        if rb.updown is not None:
+            # 'next' row f4 (resblock_updown): h_upd / x_upd between GroupNorm+SiLU and the conv (model.py:233-238)
+            assert x1 is None
+            h = self._gn(rb.in_layers[0], x, mode, 1, out_dtype=torch.float32)
+            if rb.updown == "up":
+                h = ops.cast_concat(h, None, up=2, out_dtype=c1.in_dtype)
+                x = ops.cast_concat(x, None, up=2, out_dtype=torch.float32)
+            else:
+                h = ops.avgpool2x2(h, out_dtype=c1.in_dtype)
+                x = ops.avgpool2x2(x)
+        elif sk is not None and sk.in_dtype == torch.bfloat16:
             # the 1x1 skip conv's bf16 operand (the raw concat) comes out of the same pass as the normalised one
             h, raw = self._gn(rb.in_layers[0], x, mode, 1, x1=x1, out_dtype=c1.in_dtype, want_raw=True)
         else:
             h = self._gn(rb.in_layers[0], x, mode, 1, x1=x1, out_dtype=c1.in_dtype)
-        h = engine.conv(h, c1, rowvec=rowvec, want_stats=True)      # conv + bias + emb_out[..., None, None]
-        h = self._gn(rb.out_layers[0], h, mode, 1, out_dtype=c2.in_dtype)
+        if ss:
+            # out_norm(h) * (1 + scale) + shift (model.py:244-248): scale / shift folded into per-sample GroupNorm rows
+            h = engine.conv(h, c1, want_stats=True)
+            norm = rb.out_layers[0]
+            g2, b2 = ops.scale_shift_affine(norm.weight, norm.bias, rowvec)
+            h = ops.groupnorm(h, g2, b2, norm.eps, act=1, out_dtype=c2.in_dtype, groups=norm.num_groups, exact=(mode == "fp32"))
+        else:
+            h = engine.conv(h, c1, rowvec=rowvec, want_stats=True)      # conv + bias + emb_out[..., None, None]
+            h = self._gn(rb.out_layers[0], h, mode, 1, out_dtype=c2.in_dtype)
         if sk is not None:
             xs = raw if raw is not None else ops.cast_concat(x, x1, up=1, out_dtype=sk.in_dtype)
             xs = engine.conv(xs, sk)
@@ -379,6 +449,32 @@ class UNetModel(nn.Module):
             assert x1 is None
             xs = x
         return engine.conv(h, c2, residual=xs, want_stats=True)     # conv + bias + skip_connection(x)
+
+    def _attnblock(self, ab, P, mode, x):
+        """AttentionBlock._forward (openai_model/attention.py:588-599), 'next' row f4.  The qkv conv's output channels are
+        (q | k | v) x heads x ch in both attention orders (attention.py:381,509); the tcgen05 kernel writes its result
+        straight into the layout the reference's reshape produces (head-major for FlashAttention's permute, :393-397)."""
+        B, Hh, Ww, Cc = x.shape
+        T = Hh * Ww
+        H = ab.num_heads
+        d = Cc // H
+        new_order = ab.use_new_attention_order
+        scale = d ** -0.5 if new_order else 1.0 / math.sqrt(math.sqrt(d))
+        odt = engine.op_dtype(mode)
+        xn = self._gn(ab.norm, x, mode, 0, out_dtype=odt).reshape(B * T, Cc)
+        o_strides = (H * T * d, d, T * d) if new_order else (T * Cc, Cc, d)
+        if mode == "bf16":
+            dp = head_pad(d)
+            W3 = 3 * H * dp
+            qkv = engine.linear(xn, P[("qkv", id(ab))], out_dtype=odt, col_group=d, col_group_stride=dp, rows_per_item=T,
+                                out=self._padbuf(B * T, W3, d, dp, x.device))
+            o = ops.attention_tc(qkv, qkv[:, H * dp:], qkv[:, 2 * H * dp:], B, H, T, T, d, dp, scale,
+                                 (T * W3, W3, dp), (T * W3, W3, dp), (T * W3, W3, dp), o_strides=o_strides)
+        else:
+            qkv = engine.linear(xn, P[("qkv", id(ab))], rows_per_item=T)                                       # [B*T, 3C]
+            o = self._attn_fp32(qkv, 3 * Cc, 0, qkv, 3 * Cc, Cc, qkv, 3 * Cc, 2 * Cc, B, H, T, T, d, scale, o_strides=o_strides)
+        out = engine.linear(o.reshape(B * T, Cc), P[("aout", id(ab))], residual=x.reshape(B * T, Cc), rows_per_item=T)
+        return out.reshape(B, Hh, Ww, Cc)
 
     def _kv_context(self, blk, P, mode, context):
         """to_k / to_v of the (step-invariant) context, cached per context tensor."""
@@ -446,8 +542,9 @@ class UNetModel(nn.Module):
         return t
 
     @staticmethod
-    def _attn_fp32(q, ldq, qoff, k, ldk, koff, v, ldv, voff, B, H, Sq, Sk, d, scale):
-        """softmax(q k^T * scale) v per (batch, head) with strided fp32 SIMT GEMMs; returns [B*Sq, H*d]."""
+    def _attn_fp32(q, ldq, qoff, k, ldk, koff, v, ldv, voff, B, H, Sq, Sk, d, scale, o_strides=None):
+        """softmax(q k^T * scale) v per (batch, head) with strided fp32 SIMT GEMMs; returns [B*Sq, H*d]
+        (o_strides = (batch, seq, head) element strides of another output layout)."""
         Cc = H * d
         dev = q.device
         scores = torch.empty((B, H, Sq, Sk), dtype=torch.float32, device=dev)
@@ -458,8 +555,9 @@ class UNetModel(nn.Module):
                       sa=(Sq * ldq, d), sb=(Sk * ldk, d), sc=(H * Sq * Sk, Sq * Sk))
         Pm = ops.softmax_rows(scores, scale)
         out = torch.empty((B * Sq, Cc), dtype=torch.float32, device=dev)
-        ops.gemm_simt(Pm, vv, out=out, b_kn=True, M=Sq, N=d, K=Sk, lda=Sk, ldb=ldv, ldc=Cc, batch=(B, H),
-                      sa=(H * Sq * Sk, Sq * Sk), sb=(Sk * ldv, d), sc=(Sq * Cc, d))
+        o_bs, o_ss, o_hs = o_strides if o_strides is not None else (Sq * Cc, Cc, d)
+        ops.gemm_simt(Pm, vv, out=out, b_kn=True, M=Sq, N=d, K=Sk, lda=Sk, ldb=ldv, ldc=o_ss, batch=(B, H),
+                      sa=(H * Sq * Sk, Sq * Sk), sb=(Sk * ldv, d), sc=(o_bs, o_hs))
         return out
 
     def _st(self, st, P, mode, x, context):
@@ -485,6 +583,8 @@ class UNetModel(nn.Module):
                 x1 = None
             elif isinstance(layer, SpatialTransformer):
                 h = self._st(layer, P, mode, h, context)
+            elif isinstance(layer, AttentionBlock):
+                h = self._attnblock(layer, P, mode, h)
             elif isinstance(layer, Downsample):
                 pc = P[("op", id(layer))]
                 hx = ops.cast_concat(h, None, out_dtype=pc.in_dtype) if pc.in_dtype == torch.bfloat16 else h
@@ -503,12 +603,14 @@ class UNetModel(nn.Module):
         return h
 
     # ---- forward ----------------------------------------------------------------------------------
-    def _forward_nhwc(self, x_nchw, t_f32, context, mode):
+    def _forward_nhwc(self, x_nchw, t_f32, context, mode, y=None):
         P = self._pack(mode)
         t_emb = ops.timestep_embedding(t_f32, P["freqs"], round_fp16=self.t_emb_fp16_round)
         e = ops.skinny_linear(t_emb, P["te0"][0], P["te0"][1], act_out=1)        # Linear -> SiLU
         # time_embed[2] then every ResBlock's SiLU -> Linear (openai_model/model.py:195-201), batched
         emb = ops.skinny_linear(e, P["te2"][0], P["te2"][1])
+        if y is not None:                                                        # emb + label_emb(y), model.py:567-569
+            emb = ops.add(emb, ops.gather_rows(P["label_emb"], y))
         emb_all = ops.skinny_linear(emb, P["emb_w"], P["emb_b"], act_in=1)
         h = ops.nchw_to_nhwc(x_nchw, out_dtype=P["conv_in"].in_dtype, pad_to=P["conv_in"].cin)
         hs = []
@@ -529,15 +631,18 @@ class UNetModel(nn.Module):
         x [N,C,H,W], timesteps [N] (int or float), context [N,S,context_dim] -> [N,out_channels,H,W] in x.dtype."""
         assert (y is not None) == (self.num_classes is not None), "must specify y if and only if the model is class-conditional"
         from ._lib import require_cuda
-        require_cuda(x, timesteps, context)
+        require_cuda(x, timesteps, context, y)
         mode = self.compute_mode
         xin = x.float().contiguous()
         tin = timesteps.float().contiguous()
-        cin = context.float().contiguous()
-        if self.use_cuda_graph:
+        cin = context.float().contiguous() if context is not None else None
+        if y is not None:
+            assert y.shape == (x.shape[0],)
+            y = y.to(torch.int64).contiguous()
+        if self.use_cuda_graph and y is None and cin is not None:
             out = self._graph_forward(xin, tin, cin, mode, ctx_src=context)
         else:
-            out = self._forward_nhwc(xin, tin, cin, mode)
+            out = self._forward_nhwc(xin, tin, cin, mode, y=y)
         return out if x.dtype == torch.float32 else out.to(x.dtype)
 
     # ---- CUDA graph replay of one UNet call ------------------------------------------------------------

@@ -56,10 +56,15 @@ def _gn_ticket_buffer(dev, n):
 
 def groupnorm(x0, gamma, beta, eps, act=0, out_dtype=torch.float32, x1=None, groups=32, exact=False, want_raw=False):
     """GroupNorm(groups) over the channel-concat of x0 (and x1) [N,H,W,C*], optional SiLU.
-    want_raw=True also returns the un-normalised bf16 concat (written by the same pass)."""
+    want_raw=True also returns the un-normalised bf16 concat (written by the same pass).
+    gamma / beta: [C] shared by the batch, or [N, C] per-sample rows (scale_shift_affine)."""
     require_cuda(x0, x1, gamma, beta)
     assert x0.dtype == torch.float32 and x0.is_contiguous()
     N, H, W, C0 = x0.shape
+    gbs = 0
+    if gamma.dim() == 2:
+        assert gamma.shape == beta.shape and gamma.shape[0] == N and gamma.stride(1) == 1 and beta.stride() == gamma.stride()
+        gbs = gamma.stride(0)
     C1 = 0
     if x1 is not None:
         assert x1.dtype == torch.float32 and x1.is_contiguous() and x1.shape[:3] == x0.shape[:3]
@@ -76,7 +81,7 @@ def groupnorm(x0, gamma, beta, eps, act=0, out_dtype=torch.float32, x1=None, gro
         lay0 = (C.c_longlong * 4)(*cs0[1:5])
         lay1 = (C.c_longlong * 4)(*cs1[1:5]) if cs1 else None
         check(lib.sdb_groupnorm_from_colstats(ptr(x0), C0, ptr(cs0[0]), lay0, ptr(x1), C1, ptr(cs1[0]) if cs1 else 0, lay1,
-                                              N, H * W, groups, float(eps), ptr(gamma), ptr(beta),
+                                              N, H * W, groups, float(eps), ptr(gamma), ptr(beta), gbs,
                                               int(act), int(bool(exact)), ptr(out), dtype_code(out_dtype), ptr(raw), ptr(ws),
                                               stream_ptr()), "groupnorm_from_colstats")
         return (out, raw) if want_raw else out
@@ -86,11 +91,35 @@ def groupnorm(x0, gamma, beta, eps, act=0, out_dtype=torch.float32, x1=None, gro
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x0.device)
     out = torch.empty((N, H, W, Ct), dtype=out_dtype, device=x0.device)
     raw = torch.empty((N, H, W, Ct), dtype=torch.bfloat16, device=x0.device) if want_raw else None
-    check(lib.sdb_groupnorm_nhwc(ptr(x0), C0, ptr(x1), C1, N, H * W, groups, float(eps), ptr(gamma), ptr(beta),
+    check(lib.sdb_groupnorm_nhwc(ptr(x0), C0, ptr(x1), C1, N, H * W, groups, float(eps), ptr(gamma), ptr(beta), gbs,
                                  int(act), int(bool(exact)), ptr(out), dtype_code(out_dtype), ptr(raw), ptr(ws),
                                  ptr(_gn_ticket_buffer(x0.device, N)), stream_ptr()),
           "groupnorm")
     return (out, raw) if want_raw else out
+
+
+def scale_shift_affine(gamma, beta, ss):
+    """Per-sample GroupNorm affine rows for `norm(h) * (1 + scale) + shift` (openai_model/model.py:244-248):
+    ss [N, 2C] fp32 (any row stride) = (scale | shift) -> (gamma * (1 + scale), beta * (1 + scale) + shift), each [N, C]."""
+    require_cuda(gamma, beta, ss)
+    N, C2 = ss.shape
+    Cc = C2 // 2
+    assert ss.dtype == torch.float32 and ss.stride(1) == 1 and gamma.numel() == Cc
+    go = torch.empty((N, Cc), dtype=torch.float32, device=ss.device)
+    bo = torch.empty((N, Cc), dtype=torch.float32, device=ss.device)
+    check(_L().sdb_scale_shift_affine(ptr(gamma), ptr(beta), ptr(ss), ss.stride(0), N, Cc, ptr(go), ptr(bo), stream_ptr()),
+          "scale_shift_affine")
+    return go, bo
+
+
+def avgpool2x2(x, out_dtype=torch.float32):
+    """x [N,H,W,C] fp32 -> [N,H/2,W/2,C]: avg_pool2d(kernel 2, stride 2) (openai_model/model.py:88-93)."""
+    require_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    N, H, W, Cc = x.shape
+    out = torch.empty((N, H // 2, W // 2, Cc), dtype=out_dtype, device=x.device)
+    check(_L().sdb_avgpool2x2(ptr(x), N, H, W, Cc, ptr(out), dtype_code(out_dtype), stream_ptr()), "avgpool2x2")
+    return out
 
 
 def layernorm(x, gamma, beta, eps=1e-5, out_dtype=torch.float32):
@@ -549,9 +578,9 @@ def gemm_tc(A, W, bias=None, residual=None, out_dtype=torch.float32, geglu=False
     return out
 
 
-def attention_tc(q, k, v, B, H, Sq, Sk, d, dpad, scale, q_strides, k_strides, v_strides, out=None):
+def attention_tc(q, k, v, B, H, Sq, Sk, d, dpad, scale, q_strides, k_strides, v_strides, out=None, o_strides=None):
     """q/k/v: bf16 tensors (any views) whose (batch, seq, head) element strides are given; heads padded to dpad.
-    Returns out [B, Sq, H*d] bf16."""
+    Returns out [B, Sq, H*d] bf16; o_strides = (batch, seq, head) element strides of another output layout."""
     require_cuda(q, k, v)
     assert q.dtype == k.dtype == v.dtype == torch.bfloat16
     if out is None:
@@ -561,7 +590,7 @@ def attention_tc(q, k, v, B, H, Sq, Sk, d, dpad, scale, q_strides, k_strides, v_
     a.q_bs, a.q_ss, a.q_hs = q_strides
     a.k_bs, a.k_ss, a.k_hs = k_strides
     a.v_bs, a.v_ss, a.v_hs = v_strides
-    a.o_bs, a.o_ss, a.o_hs = Sq * H * d, H * d, d
+    a.o_bs, a.o_ss, a.o_hs = o_strides if o_strides is not None else (Sq * H * d, H * d, d)
     a.B, a.H, a.Sq, a.Sk, a.d, a.dpad = B, H, Sq, Sk, d, dpad
     a.scale = float(scale)
     check(_L().sdb_attention_fwd(C.byref(a), stream_ptr()), "attention_fwd")

@@ -35,6 +35,28 @@ def test_unet_eps_parity(cuda, name, mode):
     assert e_ref <= EPS_TOL[mode] and e_64 <= EPS_TOL[mode]
 
 
+@pytest.mark.parametrize("name", ["unet_var_legacy", "unet_var_neworder"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_unet_variant_eps_parity(cuda, name, mode):
+    """'next' row f4: the non-transformer UNetModel variants (AttentionBlock in both attention orders, use_scale_shift_norm,
+    resblock_updown, num_classes) against the reference's eps on the same weights and inputs."""
+    from sdb200.openai_model import UNetModel
+    g = load_golden(name + ".pt")
+    net = UNetModel(**g["cfg"], compute_mode=mode)
+    net.load_state_dict(W.make_state_dict(g["key_shapes"], g["seed"]))
+    net = net.cuda()
+    x = W.seeded_randn(g["x_shape"], g["seed"] + 1).cuda()
+    y = g["y"].cuda() if g["y"] is not None else None
+    eps = net(x, g["t"].cuda(), None, y)
+    e = rel(eps, g["eps_f64"])
+    print("%s %s: eps rel-L2 %.3e" % (name, mode, e))
+    assert eps.shape == g["eps_ref"].shape
+    assert e <= EPS_TOL[mode]
+    if y is not None:
+        with pytest.raises(AssertionError):
+            net(x, g["t"].cuda(), None)            # class-conditional model needs y (model.py:561-563)
+
+
 def test_unet_batch_invariance_and_graph(cuda):
     """Size-independent properties at the benchmark shape: sample i of a batch equals the same sample run
     alone (nothing reduces over the batch), and CUDA-graph replay equals eager execution bit for bit."""

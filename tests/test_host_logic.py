@@ -47,11 +47,23 @@ def test_unsupported_options_raise():
     base = dict(image_size=8, in_channels=4, model_channels=32, out_channels=4, num_res_blocks=1, attention_resolutions=[1],
                 num_heads=2)
     with pytest.raises(NotImplementedError):
-        UNetModel(**base)                                              # AttentionBlock variant
+        UNetModel(**base, use_spatial_transformer=True, context_dim=8, n_embed=16)      # codebook head
     with pytest.raises(NotImplementedError):
-        UNetModel(**base, use_spatial_transformer=True, context_dim=8, use_scale_shift_norm=True)
+        UNetModel(**base, use_spatial_transformer=True, context_dim=8, dims=3)
     with pytest.raises(AssertionError):
         UNetModel(**base, use_spatial_transformer=True)                # context_dim missing (reference assert, model.py:317-318)
+    with pytest.raises(AssertionError):
+        UNetModel(**base, context_dim=8)                               # context without the spatial transformer (model.py:320-321)
+
+
+def test_unet_variant_state_dict_keys_match_reference():
+    """'next' row f4: AttentionBlock / scale-shift / resblock_updown / class-conditional variants keep the reference's keys."""
+    from sdb200.openai_model import UNetModel
+    for name in ("unet_var_legacy", "unet_var_neworder"):
+        g = load_golden(name + ".pt")
+        with torch.device("meta"):
+            m = UNetModel(**g["cfg"])
+        assert _keys(m) == [(k, tuple(s)) for k, s in g["key_shapes"]]
 
 
 def test_sampler_schedule_bit_exact_vs_reference_tables():

@@ -37,6 +37,19 @@ def test_vae_restatement_matches_reference(name):
     assert R.rel_l2(g["img_ref"], g["img_f64"]) < 1e-5
 
 
+@pytest.mark.parametrize("name", ["unet_var_legacy", "unet_var_neworder"])
+def test_unet_variant_restatement_matches_reference(name):
+    """'next' row f4: AttentionBlock (both attention orders), scale-shift norm, resblock_updown, class conditioning."""
+    g = load_golden(name + ".pt")
+    sd = _sd(g)
+    x = W.seeded_randn(g["x_shape"], g["seed"] + 1)
+    with torch.no_grad():
+        eps = R.unet_forward(sd, g["cfg"], x, g["t"], None, y=g["y"])
+    assert R.rel_l2(eps, g["eps_ref"]) < 1e-5
+    assert R.rel_l2(g["eps_ref"], g["eps_f64"]) < 1e-5
+    assert float(g["eps_ref"].abs().max()) > 0.1
+
+
 def test_vae_encoder_restatement_matches_reference():
     """'next' row f3: Encoder + quant_conv + posterior moments, and stochastic_encode, against the reference's outputs."""
     g = load_golden("vae_enc_tiny.pt")
