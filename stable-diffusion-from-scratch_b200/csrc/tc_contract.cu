@@ -339,7 +339,9 @@ __device__ __forceinline__ void epilogue_fast(const TcP& p, uint32_t taddr, cons
         // time-embedding row: one load per chunk when the whole tile belongs to one image, else one per row; it is added
         // LAST in both cases, so a sample's bits do not depend on whether its tile is shared with another sample
         float4 rv4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (HAS_ADD && rowv && rv_uniform) rv4 = ldg_f4_or_zero(rowv + (long long)img0 * p.ldv + cn, col_ok);
+        // (mask == 0: every row of this warp lies outside the problem — the phantom m-tile of an odd pair, or a tile past
+        // the last image — and img0 may be >= NB: nothing is stored, so nothing may be loaded either)
+        if (HAS_ADD && rowv && rv_uniform) rv4 = ldg_f4_or_zero(rowv + (long long)img0 * p.ldv + cn, col_ok && mask != 0u && img0 < p.NB);
         uint32_t r[32];
         tmem_ld_x32(taddr + c0, r);
         if (GEGLU) {
