@@ -41,6 +41,7 @@ struct TcP {
     int split_k;
     int tiles_n;
     int m_pairs;            // pair kernel: number of 256-row tile pairs
+    int off32;              // every element offset into out / residual / workspace fits 32 bits (the fast epilogue's addressing)
     // conv
     int conv;
     int kw, stride, pad_h, pad_w;
@@ -292,14 +293,16 @@ __device__ __forceinline__ void epilogue_fast(const TcP& p, uint32_t taddr, cons
     const int rsel = lane >> 3;
     const uint32_t stage_a = smem_u32(stage), sbias_a = smem_u32(s_bias);
     const long long ldo = MODE == EPI_PARTIAL ? (long long)p.N : p.ldc;
-    // rows this lane stores after the transpose: 4*i + rsel
-    long long roff[8];
+    // rows this lane stores after the transpose: 4*i + rsel.  32-bit element offsets (the launcher checked that they fit):
+    // with 64-bit ones ptxas kept the pixel indices and re-derived px * ld (two 64-bit IMADs + carries) and px >= 0 in front
+    // of every load and store, ~1/4 of the epilogue's instructions (profiles/r01_ncu_epilogue.txt)
+    uint32_t roff[8];
     uint32_t mask = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const long long px = __shfl_sync(0xffffffffu, row_pix, 4 * i + rsel);
         if (px >= 0) mask |= 1u << i;
-        roff[i] = px * ldo;
+        roff[i] = (uint32_t)px * (uint32_t)ldo;
     }
     const float* const resid = (HAS_ADD && p.residual) ? p.residual : nullptr;
     const float* rowv = (HAS_ADD && p.rowvec && p.conv) ? p.rowvec : nullptr;
@@ -318,7 +321,7 @@ __device__ __forceinline__ void epilogue_fast(const TcP& p, uint32_t taddr, cons
         const int cn_ = nb + ch * CH + cq;
         const bool live = resid != nullptr && ch < NCHUNK && cn_ < n_out;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) dst[i] = ldg_f4_or_zero(resid + roff[i] + cn_, live && ((mask >> i) & 1u));
+        for (int i = 0; i < 8; ++i) dst[i] = ldg_f4_or_zero(resid + (roff[i] + (uint32_t)cn_), live && ((mask >> i) & 1u));
     };
     if (HAS_ADD) fetch_residual(ch0, addn);
     mbar_wait(acc_ready, acc_parity);
@@ -375,7 +378,7 @@ __device__ __forceinline__ void epilogue_fast(const TcP& p, uint32_t taddr, cons
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             float4 v = lds128(stage_a + 4 * ((4 * i + rsel) * EPI_LD + cq));
-            v.x += cadd.x; v.y += cadd.y; v.z += cadd.z; v.w += cadd.w;
+            if (MODE == EPI_F32 || MODE == EPI_BF16) { v.x += cadd.x; v.y += cadd.y; v.z += cadd.z; v.w += cadd.w; }
             if (HAS_ADD) {
                 v.x += addv[i].x; v.y += addv[i].y; v.z += addv[i].z; v.w += addv[i].w;
                 float4 q4 = rv4;
@@ -389,14 +392,12 @@ __device__ __forceinline__ void epilogue_fast(const TcP& p, uint32_t taddr, cons
                     cs_q.x = fmaf(v.x, v.x, cs_q.x); cs_q.y = fmaf(v.y, v.y, cs_q.y);
                     cs_q.z = fmaf(v.z, v.z, cs_q.z); cs_q.w = fmaf(v.w, v.w, cs_q.w);
                 }
-                if (ok) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + roff[i] + cn) = v;
+                if (ok) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (roff[i] + (uint32_t)cn)) = v;
             } else if (MODE == EPI_PARTIAL) {
-                if (ok) *reinterpret_cast<float4*>(ws + roff[i] + cn) = v;
-            } else if (MODE == EPI_BF16 || p.out_bf16) {
-                if (ok) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + roff[i] + dn) =
+                if (ok) *reinterpret_cast<float4*>(ws + (roff[i] + (uint32_t)cn)) = v;
+            } else {      // EPI_BF16, EPI_GEGLU (the fast path takes GEGLU only with a bf16 output, see epilogue_warp)
+                if (ok) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (roff[i] + (uint32_t)dn)) =
                             make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
-            } else {
-                if (ok) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + roff[i] + cn) = v;
             }
         }
         if (want_cs) {
@@ -425,11 +426,11 @@ __device__ __forceinline__ void epilogue_warp(const TcP& p, uint32_t taddr, cons
                                               uint64_t* acc_ready, uint32_t acc_parity, int slot) {
     const int n_out = p.geglu ? p.N / 2 : p.N;
     const bool partial = p.split_k > 1;
-    const bool fast_ok = (n_out % 4 == 0) && (p.ldc % 4 == 0) && (p.ldv % 4 == 0) &&
+    const bool fast_ok = p.off32 && (n_out % 4 == 0) && (p.ldc % 4 == 0) && (p.ldv % 4 == 0) &&
                          ((reinterpret_cast<uintptr_t>(p.out) | reinterpret_cast<uintptr_t>(p.residual) |
                            reinterpret_cast<uintptr_t>(p.rowvec) | reinterpret_cast<uintptr_t>(p.ws)) & 15) == 0 &&
                          (!p.col_group || (p.col_group % 4 == 0 && p.col_group_stride % 4 == 0)) &&
-                         (p.residual == nullptr || partial || p.ldr == p.ldc) && !(p.geglu && partial);
+                         (p.residual == nullptr || partial || p.ldr == p.ldc) && !(p.geglu && (partial || !p.out_bf16));
 #define SDB_EPI(MODE, ADD) epilogue_fast<BN, MODE, ADD>(p, taddr, s_bias, stage, lane, n0, nt, row_pix, row_img, split, ch0, chstep, acc_ready, acc_parity, slot)
     if (!fast_ok) {
         epilogue_generic<BN>(p, taddr, s_bias, stage, lane, n0, nt, row_pix, row_img, split, ch0, chstep, acc_ready, acc_parity, slot);
@@ -593,25 +594,25 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 //   warp 1 : MMA issuer (leader CTA only); tcgen05.commit multicasts "slot free" / "accumulator
 //            ready" to the barriers of both CTAs
 //   warp 2 : TMEM allocator
-//   warps 4..11 : epilogue, two warps per TMEM lane quarter (warp & 3), alternating 32-column chunks
-constexpr int TC2_THREADS = 384;
-constexpr int TC2_EPI_WARPS = 8;
-
-template <int BN>
+//   warps 4..4+EW-1 : epilogue, EW/4 warps per TMEM lane quarter (warp & 3), interleaved 32-column chunks.
+// EW = 8 in the product; 16 exists for the measurement build only (see launch_tc_pair).
+template <int BN, int EW>
 struct Tc2Cfg {
+    static constexpr int THREADS = 128 + 32 * EW;
     static constexpr int B_HALF_BYTES = (BN / 2) * TC_BK * 2;
     static constexpr int STAGE_BYTES = TC_A_BYTES + B_HALF_BYTES;       // per CTA
-    static constexpr int STAGES_RAW = (184 * 1024) / STAGE_BYTES;
+    static constexpr int STAGES_RAW = (184 * 1024 - (EW - 8) * EPI_WARP_BYTES) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int ACC_STRIDE = 256;                                // TMEM columns between the two accumulators
-    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 512 + BN * 4 + TC2_EPI_WARPS * EPI_WARP_BYTES;
+    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 512 + BN * 4 + EW * EPI_WARP_BYTES;
 };
 
-template <int BN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
+template <int BN, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
 tc_contract_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcP p) {
     pdl_trigger();
-    using Cfg = Tc2Cfg<BN>;
+    using Cfg = Tc2Cfg<BN, EW>;
+    constexpr int TC2_EPI_WARPS = EW;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -720,7 +721,7 @@ tc_contract_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             }
         }
     } else if (warp >= 4) {
-        // ================= epilogue (warps 4..11 -> TMEM lane quarter warp & 3, chunk parity (warp - 4) >> 2) ====
+        // ================= epilogue (warps 4.. -> TMEM lane quarter warp & 3, chunk phase (warp - 4) >> 2 of EW/4) ====
         const int et = threadIdx.x - 128;
         const int lg = warp & 3;
         const int half = (warp - 4) >> 2;
@@ -770,7 +771,7 @@ tc_contract_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             const long long pix = row_of(mt, img);
             const uint32_t taddr = tmem_d + ((uint32_t)(lg * 32) << 16) + buf * Cfg::ACC_STRIDE;
             if (warp == 4 && lane == 0) TC_TRACE(3, it);
-            epilogue_warp<BN>(p, taddr, s_bias, stage, lane, n0, nt, pix, img, split, half, 2, &tfull_bar[buf], (it >> 1) & 1,
+            epilogue_warp<BN>(p, taddr, s_bias, stage, lane, n0, nt, pix, img, split, half, EW / 4, &tfull_bar[buf], (it >> 1) & 1,
                               mt * 4 + lg);
             if (warp == 4 && lane == 0) TC_TRACE(4, it);
             tcgen05_fence_before();
@@ -870,12 +871,12 @@ static int sm_count_cached() {
     return n;
 }
 
-template <int BN>
-static int launch_tc_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, TcP& p, int m_tiles, cudaStream_t st) {
-    using Cfg = Tc2Cfg<BN>;
+template <int BN, int EW>
+static int launch_tc_pair_ew(const CUtensorMap& tmA, const CUtensorMap& tmB, TcP& p, int m_tiles, cudaStream_t st) {
+    using Cfg = Tc2Cfg<BN, EW>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc_contract_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(tc_contract_pair_kernel<BN, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) { set_last_error("tc_contract(pair): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SDB_ERR_CUDA; }
         attr_set = true;
     }
@@ -883,8 +884,23 @@ static int launch_tc_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, TcP& p
     long long units = (long long)p.m_pairs * p.tiles_n * p.split_k;
     int pairs = sm_count_cached() / 2;
     if (units < pairs) pairs = (int)units;
-    launch_pdl(tc_contract_pair_kernel<BN>, dim3(dim3(2 * pairs)), dim3(TC2_THREADS), Cfg::SMEM_BYTES, st, tmA, tmB, p);
+    launch_pdl(tc_contract_pair_kernel<BN, EW>, dim3(dim3(2 * pairs)), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, tmA, tmB, p);
     return check_launch("tc_contract_pair_kernel");
+}
+
+// Epilogue warps of the pair kernel: 8.  A 16-warp build (-DSDB_TC_EW16, then SDB200_TC_EW=16 at run time) was measured on
+// B200 and rejected: K = 320 GEGLU 77.7 -> 92.6 us, K = 320 bf16-out 44.8 -> 50.4 us, K = 320 fp32 + residual 40.1 -> 54.6 us,
+// whole UNet call 12.69 -> 13.01 ms (profiles/r01_epilogue_warps.txt).  The epilogue of the short-K layers is bound by its
+// instruction count (~24 warp instructions per output element, ~3.1 k issue slots per scheduler and unit against 2.6 k clocks
+// of MMA at K = 320), not by latency that more warps could hide; 16 warps also spill (548 B) under the 96-register cap.
+template <int BN>
+static int launch_tc_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, TcP& p, int m_tiles, cudaStream_t st) {
+#ifdef SDB_TC_EW16
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("SDB200_TC_EW"); forced = e ? atoi(e) : 0; }
+    if (forced == 16) return launch_tc_pair_ew<BN, 16>(tmA, tmB, p, m_tiles, st);
+#endif
+    return launch_tc_pair_ew<BN, 8>(tmA, tmB, p, m_tiles, st);
 }
 
 // Kernel selection: 1 = CTA-pair persistent kernel for BN >= 128 (default), 0 = one-CTA kernel everywhere.
@@ -979,7 +995,11 @@ static int make_plan(const sdb_tc_args* a, TcPlan* pl) {
         SDB_REQUIRE(a->NB > 0 && a->IH > 0 && a->IW > 0 && a->OH > 0 && a->OW > 0, "tc_contract: bad conv dims");
         SDB_REQUIRE(a->M == a->NB * a->OH * a->OW, "tc_contract: M != NB*OH*OW");
         SDB_REQUIRE(a->cout_pad >= a->N, "tc_contract: cout_pad < N");
-        pick_tile(a->OW, a->OH, a->NB, a->stride, &pl->tw, &pl->th, &pl->tn);
+        // The pixel-block shape is chosen for a NOMINAL batch of 8 images, not the actual one: it decides whether a tile holds
+        // one image (then the epilogue can emit GroupNorm column statistics) or several, and in bf16 mode two statistics
+        // paths that differ by 1e-7 decorrelate to the bf16 noise level within a few layers (measured 4.4e-3 at an 80x80
+        // latent) — sample i of a batch must come out bit-identical to the same sample run alone.
+        pick_tile(a->OW, a->OH, 8, a->stride, &pl->tw, &pl->th, &pl->tn);
         pl->tiles_w = ceil_div(a->OW, pl->tw); pl->tiles_h = ceil_div(a->OH, pl->th);
         pl->m_tiles = pl->tiles_w * pl->tiles_h * ceil_div(a->NB, pl->tn);
         const long long OHF = a->OHF > 0 ? a->OHF : a->OH, OWF = a->OWF > 0 ? a->OWF : a->OW;
@@ -1094,6 +1114,10 @@ extern "C" int sdb_tc_contract(const sdb_tc_args* a, void* stream) {
         SDB_REQUIRE(((uintptr_t)a->ws & 15) == 0, "tc_contract: workspace must be 16-byte aligned");
         p.ws = reinterpret_cast<float*>(a->ws);
         p.ws_split_stride = pl.rows_out * a->N;
+    }
+    {
+        const long long ld_max = a->ldc > a->N ? a->ldc : a->N;
+        p.off32 = (pl.rows_out + 1) * ld_max + a->N < (1LL << 32) ? 1 : 0;
     }
     p.colstats = a->colstats;
     p.colstats_sq = a->colstats ? a->colstats_slots * (long long)a->N : 0;

@@ -62,9 +62,9 @@ def test_unet_sd_ragged_latents_graph(cuda, latent, B):
     """BASELINE.json configs[4] shapes (96x96 latent) and other latents that are not multiples of 64: feature maps of
     12x12 / 10x10 / 5x5 pixels give partial tiles and odd tile counts (the CTA-pair kernel then runs a phantom m-tile).
     Inside a CUDA graph's private pool an out-of-bounds read faults instead of passing silently; graph replay must equal
-    eager execution bit for bit.  Sample i of the batch against the same sample run alone: at these shapes the tile /
-    statistics-slot geometry may depend on the batch size (summation order of the GroupNorm statistics), so the check is
-    a tolerance far below the bf16 error, not bit equality (bit equality holds at the 64x64 benchmark shape, next test)."""
+    eager execution bit for bit, and sample i of the batch must equal the same sample run alone bit for bit (every kernel /
+    tile / statistics-path choice is made from the per-sample geometry, never from the batch size: in bf16 mode two paths
+    that differ by 1e-7 decorrelate to the bf16 noise level within a few layers)."""
     g = load_golden("unet_sd.pt")
     net = _unet(g, "bf16")
     x = W.seeded_randn((B, 4, latent, latent), 7).cuda()
@@ -79,9 +79,7 @@ def test_unet_sd_ragged_latents_graph(cuda, latent, B):
         torch.cuda.synchronize()
         assert torch.equal(out, eager)
     net.use_cuda_graph = False
-    e1 = rel(net(x[1:2], t[1:2], ctx[1:2]), eager[1:2].cpu())
-    print("latent %d: sample alone vs in a batch of %d: rel-L2 %.3e" % (latent, B, e1))
-    assert e1 <= 2e-3
+    assert torch.equal(net(x[1:2], t[1:2], ctx[1:2]), eager[1:2])
 
 
 def test_unet_batch_invariance_and_graph(cuda):
