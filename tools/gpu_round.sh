@@ -2,7 +2,7 @@
 # One GPU-box visit: tests, bench, launch list, full ncu captures of the top kernels.
 mkdir -p gpurun_out
 rm -f gpurun_out/*.ncu-rep
-bash tools/gpu_tests.sh
+[ -n "$SKIP_TESTS" ] || bash tools/gpu_tests.sh
 python bench.py > gpurun_out/bench_full.log 2>&1; echo "bench rc=$?"; tail -c 3000 gpurun_out/bench_full.log
 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref.log 2>&1; echo "ref rc=$?"; tail -c 800 gpurun_out/bench_ref.log
 timeout 600 python tools/bench_layers.py --batch 8 --variants 1 --json gpurun_out/layers_unet_b8.json > gpurun_out/layers_unet_b8.log 2>&1; echo "layers rc=$?"
