@@ -91,6 +91,12 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
     return y;
 #endif
 }
+// Chunks (of 8 exponentials, 16 per key tile) after which a softmax warp hands the MUFU phase to its partner on the same
+// scheduler.  16 = strict alternation.  One warp alone sustains only ~12 clk per exponential (dependency-bound) against the
+// pipe's 8, two concurrent warps 9.4 combined (tools/ubench/xu_rate.cu), so a partial overlap fills the idle MUFU slots.
+#ifndef SDB_ATTN_HANDOVER
+#define SDB_ATTN_HANDOVER 11
+#endif
 #ifndef SDB_ATTN_POLY
 #define SDB_ATTN_POLY 0         // exponentials out of every 8 evaluated on the FMA pipe instead of MUFU.EX2
 #endif
@@ -366,10 +372,13 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 const int chunk = (c0 & 63) >> 3;
                 sts128(prow + (c0 >> 6) * 16384 + ((chunk ^ (row & 7)) << 4),
                        pack_p_bf16x2(e[0], e[1]), pack_p_bf16x2(e[2], e[3]), pack_p_bf16x2(e[4], e[5]), pack_p_bf16x2(e[6], e[7]));
+                // early hand-over: the other warp's exponentials start under the tail of this warp's (see SDB_ATTN_HANDOVER)
+                if (G == 2 && SDB_ATTN_HANDOVER < 16 && c0 == 8 * (SDB_ATTN_HANDOVER - 1))
+                    asm volatile("bar.arrive %0, 64;" ::"r"(bar_other) : "memory");
             }
             l += sum0 + sum1;
             AT_TRACE(6);
-            if (G == 2) asm volatile("bar.arrive %0, 64;" ::"r"(bar_other) : "memory");           // hand the MUFU over
+            if (G == 2 && SDB_ATTN_HANDOVER >= 16) asm volatile("bar.arrive %0, 64;" ::"r"(bar_other) : "memory");   // hand the MUFU over
             tcgen05_fence_before();
             fence_proxy_async_smem();               // P visible to the tensor core (async proxy)
             mbar_arrive(&p_full[g * PB + pb]);
