@@ -97,6 +97,9 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 #ifndef SDB_ATTN_HANDOVER
 #define SDB_ATTN_HANDOVER 11
 #endif
+#ifndef SDB_ATTN_MAXCHAINS
+#define SDB_ATTN_MAXCHAINS 2
+#endif
 #ifndef SDB_ATTN_POLY
 #define SDB_ATTN_POLY 0         // exponentials out of every 8 evaluated on the FMA pipe instead of MUFU.EX2
 #endif
@@ -317,6 +320,18 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 128; ++j) if (j >= kvalid) r[j] = 0xff800000u;   // -inf
             }
+#if SDB_ATTN_MAXCHAINS == 4
+            // four independent 3-input max chains of 16 (a chain link costs the ALU latency, not an issue slot)
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 128; j += 8) {
+                mx0 = fmax3(mx0, __uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+                mx1 = fmax3(mx1, __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                mx2 = fmax3(mx2, __uint_as_float(r[j + 4]), __uint_as_float(r[j + 5]));
+                mx3 = fmax3(mx3, __uint_as_float(r[j + 6]), __uint_as_float(r[j + 7]));
+            }
+            const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c;
+#else
             float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
             for (int j = 0; j < 128; j += 4) {
@@ -324,6 +339,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 mx1 = fmax3(mx1, __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
             }
             const float mx = fmaxf(mx0, mx1) * c;
+#endif
             const bool need = mx > m_used + 8.0f;
             float alpha = 1.0f;
             if (need) { alpha = ex2_approx(m_used - mx); m_used = mx; }
