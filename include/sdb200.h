@@ -248,8 +248,11 @@ int sdb_tc_set_pair_kernel(int enable);
 
 /* ---- fused attention forward (bf16, tcgen05) ---------------------------------------------------
  * Replaces flash_attn_func(q,k,v, softmax_scale, causal=False) (openai_model/attention.py:106-112).
- * q [B,Sq,H,dpad], k/v [B,Sk,H,dpad] bf16 with explicit element strides; heads zero-padded from d
- * to dpad (multiple of 64, <= 192). out [B,Sq,H*d] bf16 (row stride ldo). */
+ * q [B,Sq,H,*], k/v [B,Sk,H,*] bf16 with explicit element strides.  The kernel works on heads of dpad (multiple of 64,
+ * <= 192) channels: dense == 0: the heads are stored zero-padded from d to dpad channels; dense != 0: the heads are stored
+ * with their d channels only (e.g. the plain [rows, H*d] output of a projection GEMM) and the TMA tensor maps are d wide,
+ * so the pad channels of every shared-memory tile are the zeros TMA fills in for out-of-bounds elements.
+ * out [B,Sq,H,d] bf16 with explicit strides. */
 typedef struct sdb_attn_args {
     const void* q; const void* k; const void* v; void* out;
     long long q_bs, q_ss, q_hs;   /* batch / seq / head strides (elements) */
@@ -258,6 +261,7 @@ typedef struct sdb_attn_args {
     long long o_bs, o_ss, o_hs;
     int B, H, Sq, Sk, d, dpad;
     float scale;
+    int dense;
 } sdb_attn_args;
 int sdb_attention_fwd(const sdb_attn_args* args /* host */, void* stream);
 

@@ -69,6 +69,7 @@ class AttnArgs(C.Structure):
         ("o_bs", C.c_longlong), ("o_ss", C.c_longlong), ("o_hs", C.c_longlong),
         ("B", C.c_int), ("H", C.c_int), ("Sq", C.c_int), ("Sk", C.c_int), ("d", C.c_int), ("dpad", C.c_int),
         ("scale", C.c_float),
+        ("dense", C.c_int),
     ]
 
 

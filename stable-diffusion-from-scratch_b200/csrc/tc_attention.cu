@@ -444,13 +444,14 @@ static int launch_attn(const sdb_attn_args* a, cudaStream_t st) {
     int box[4] = {64, 1, 128, 1};
     int es[4] = {1, 1, 1, 1};
     {
-        long long dims[4] = {DPAD, a->H, a->Sq, a->B};
+        // dense heads: the map is only d channels wide, the rest of each 64-channel box is out of bounds = zero-filled
+        long long dims[4] = {a->dense ? a->d : DPAD, a->H, a->Sq, a->B};
         long long str[3] = {a->q_hs, a->q_ss, a->q_bs};
         int rc = make_tmap_bf16(&tmQ, a->q, 4, dims, str, box, es);
         if (rc) return rc;
     }
     {
-        long long dims[4] = {DPAD, a->H, a->Sk, a->B};
+        long long dims[4] = {a->dense ? a->d : DPAD, a->H, a->Sk, a->B};
         long long str[3] = {a->k_hs, a->k_ss, a->k_bs};
         int rc = make_tmap_bf16(&tmK, a->k, 4, dims, str, box, es);
         if (rc) return rc;

@@ -13,6 +13,7 @@ Still unsupported constructor options (dims != 2, conv_resample=False, n_embed) 
 silently computing something else.
 """
 import math
+import os
 import weakref
 
 import torch
@@ -248,6 +249,7 @@ class UNetModel(nn.Module):
         self.t_emb_fp16_round = True     # `t_emb.half()`, openai_model/model.py:566
         self.conv_in_tensor_cores = False
         self.use_cuda_graph = False
+        self.dense_heads = os.environ.get("SDB200_DENSE_HEADS", "1") != "0"     # q/k/v layout, see _tblock (0 = zero-padded heads)
 
         time_embed_dim = model_channels * 4
         self.time_embed = nn.Sequential(nn.Linear(model_channels, time_embed_dim), nn.SiLU(), nn.Linear(time_embed_dim, time_embed_dim))
@@ -465,11 +467,10 @@ class UNetModel(nn.Module):
         o_strides = (H * T * d, d, T * d) if new_order else (T * Cc, Cc, d)
         if mode == "bf16":
             dp = head_pad(d)
-            W3 = 3 * H * dp
-            qkv = engine.linear(xn, P[("qkv", id(ab))], out_dtype=odt, col_group=d, col_group_stride=dp, rows_per_item=T,
-                                out=self._padbuf(B * T, W3, d, dp, x.device))
-            o = ops.attention_tc(qkv, qkv[:, H * dp:], qkv[:, 2 * H * dp:], B, H, T, T, d, dp, scale,
-                                 (T * W3, W3, dp), (T * W3, W3, dp), (T * W3, W3, dp), o_strides=o_strides)
+            qkv = engine.linear(xn, P[("qkv", id(ab))], out_dtype=odt, rows_per_item=T)                       # dense [B*T, 3C]
+            W3 = 3 * Cc
+            o = ops.attention_tc(qkv, qkv[:, Cc:], qkv[:, 2 * Cc:], B, H, T, T, d, dp, scale,
+                                 (T * W3, W3, d), (T * W3, W3, d), (T * W3, W3, d), o_strides=o_strides, dense=True)
         else:
             qkv = engine.linear(xn, P[("qkv", id(ab))], rows_per_item=T)                                       # [B*T, 3C]
             o = self._attn_fp32(qkv, 3 * Cc, 0, qkv, 3 * Cc, Cc, qkv, 3 * Cc, 2 * Cc, B, H, T, T, d, scale, o_strides=o_strides)
@@ -493,8 +494,11 @@ class UNetModel(nn.Module):
             if cb is None:
                 cb = ops.cast_concat(context.reshape(1, 1, B * Sk, Cc).contiguous(), None, out_dtype=torch.bfloat16).reshape(B * Sk, Cc)
                 self._ctx_cache[("ctx_bf16", context.data_ptr(), context._version)] = cb
-            dp = head_pad(d)
-            kv = engine.linear(cb, P[("kv2", id(blk))], out_dtype=torch.bfloat16, col_group=d, col_group_stride=dp, rows_per_item=Sk)   # [B*Sk, 2*H*dp]
+            if self.dense_heads:
+                kv = engine.linear(cb, P[("kv2", id(blk))], out_dtype=torch.bfloat16, rows_per_item=Sk)                                   # [B*Sk, 2*H*d]
+            else:
+                dp = head_pad(d)
+                kv = engine.linear(cb, P[("kv2", id(blk))], out_dtype=torch.bfloat16, col_group=d, col_group_stride=dp, rows_per_item=Sk)   # [B*Sk, 2*H*dp]
         else:
             kv = engine.linear(context.reshape(B * Sk, Cc), P[("kv2", id(blk))], rows_per_item=Sk)                                      # [B*Sk, 2*H*d]
         if len(self._ctx_cache) > 256:
@@ -510,7 +514,24 @@ class UNetModel(nn.Module):
         odt = engine.op_dtype(mode)
         Sk = context.shape[1]
         kv = self._kv_context(blk, P, mode, context)
-        if mode == "bf16":
+        if mode == "bf16" and self.dense_heads:
+            # q / k / v are the plain projection outputs ([rows, H*d], heads side by side); the attention kernel's tensor maps
+            # are d channels wide and TMA zero-fills the pad channels of each 64-channel tile.  Against the zero-padded layout
+            # (below, kept for A/B measurements) the projections write whole lines instead of 80 of every 128 bytes.
+            dp = head_pad(d)
+            W3 = 3 * Cc
+            a = ops.layernorm(t, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps, out_dtype=odt)
+            qkv = engine.linear(a, P[("qkv1", id(blk))], out_dtype=odt, rows_per_item=S)                      # [B*S, 3C]
+            o = ops.attention_tc(qkv, qkv[:, Cc:], qkv[:, 2 * Cc:], B, H, S, S, d, dp, a1.scale,
+                                 (S * W3, W3, d), (S * W3, W3, d), (S * W3, W3, d), dense=True)
+            t = engine.linear(o.reshape(B * S, Cc), P[("o1", id(blk))], residual=t, rows_per_item=S)
+            a = ops.layernorm(t, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps, out_dtype=odt)
+            q = engine.linear(a, P[("q2", id(blk))], out_dtype=odt, rows_per_item=S)                          # [B*S, C]
+            W2 = 2 * Cc
+            o = ops.attention_tc(q, kv, kv[:, Cc:], B, H, S, Sk, d, dp, a2.scale,
+                                 (S * Cc, Cc, d), (Sk * W2, W2, d), (Sk * W2, W2, d), dense=True)
+            t = engine.linear(o.reshape(B * S, Cc), P[("o2", id(blk))], residual=t, rows_per_item=S)
+        elif mode == "bf16":
             dp = head_pad(d)
             W3 = 3 * H * dp
             a = ops.layernorm(t, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps, out_dtype=odt)

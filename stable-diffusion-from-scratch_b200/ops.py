@@ -578,8 +578,9 @@ def gemm_tc(A, W, bias=None, residual=None, out_dtype=torch.float32, geglu=False
     return out
 
 
-def attention_tc(q, k, v, B, H, Sq, Sk, d, dpad, scale, q_strides, k_strides, v_strides, out=None, o_strides=None):
-    """q/k/v: bf16 tensors (any views) whose (batch, seq, head) element strides are given; heads padded to dpad.
+def attention_tc(q, k, v, B, H, Sq, Sk, d, dpad, scale, q_strides, k_strides, v_strides, out=None, o_strides=None, dense=False):
+    """q/k/v: bf16 tensors (any views) whose (batch, seq, head) element strides are given; heads stored padded to dpad
+    channels, or (dense=True) with their d channels only.
     Returns out [B, Sq, H*d] bf16; o_strides = (batch, seq, head) element strides of another output layout."""
     require_cuda(q, k, v)
     assert q.dtype == k.dtype == v.dtype == torch.bfloat16
@@ -593,5 +594,6 @@ def attention_tc(q, k, v, B, H, Sq, Sk, d, dpad, scale, q_strides, k_strides, v_
     a.o_bs, a.o_ss, a.o_hs = o_strides if o_strides is not None else (Sq * H * d, H * d, d)
     a.B, a.H, a.Sq, a.Sk, a.d, a.dpad = B, H, Sq, Sk, d, dpad
     a.scale = float(scale)
+    a.dense = int(bool(dense))
     check(_L().sdb_attention_fwd(C.byref(a), stream_ptr()), "attention_fwd")
     return out

@@ -36,6 +36,17 @@ def test_attention_tc(cuda, B, H, Sq, Sk, d):
                            (Sq * H * dp, H * dp, dp), (Sk * H * dp, H * dp, dp), (Sk * H * dp, H * dp, dp))
     assert out.shape == (B, Sq, H * d)
     assert rel(out, ref) < 1e-2, (B, H, Sq, Sk, d)
+    # dense heads (d channels in memory, q | k | v side by side in one [rows, 3*H*d] projection output): the pad channels of
+    # the tiles come from TMA's out-of-bounds zero fill — same bits as the padded layout
+    if Sq == Sk:
+        qkv = torch.cat([q.reshape(B * Sq, H * d), k.reshape(B * Sk, H * d), v.reshape(B * Sk, H * d)], 1).contiguous()
+        W3 = 3 * H * d
+        st = (Sq * W3, W3, d)
+        out_d = ops.attention_tc(qkv, qkv[:, H * d:], qkv[:, 2 * H * d:], B, H, Sq, Sk, d, dp, scale, st, st, st, dense=True)
+    else:
+        out_d = ops.attention_tc(q.contiguous(), k.contiguous(), v.contiguous(), B, H, Sq, Sk, d, dp, scale,
+                                 (Sq * H * d, H * d, d), (Sk * H * d, H * d, d), (Sk * H * d, H * d, d), dense=True)
+    assert torch.equal(out_d, out)
 
 
 def test_attention_tc_large_logits(cuda):
