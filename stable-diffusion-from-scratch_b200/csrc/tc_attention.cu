@@ -80,7 +80,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 #ifndef SDB_ATTN_VARIANT
-#define SDB_ATTN_VARIANT 0      // measurement builds: bit 0 = 2-input max, bit 1 = integer bf16 pack (tools/attn_variants.sh)
+#define SDB_ATTN_VARIANT 0      // measurement builds: bit 0 = 2-input max, bit 1 = integer bf16 pack (tools/gpu_attn_variants.sh)
 #endif
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
 #if SDB_ATTN_VARIANT & 1

@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from sdb200 import _lib, ops
 from sdb200.engine import PackedLinear, head_pad
-lib = _lib.load(os.environ.get("SDB200_LIB") or None)   # measurement builds (tools/attn_variants.sh) pass their own library
+lib = _lib.load(os.environ.get("SDB200_LIB") or None)   # measurement builds (tools/gpu_attn_variants.sh) pass their own library
 torch.manual_seed(0)
 kind = sys.argv[1]
 v = [int(x) for x in sys.argv[2:]]
