@@ -82,6 +82,9 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------------
 # CPU reference arm: the oracle restatement of the reference's own PyTorch path, on the host cores
 # ------------------------------------------------------------------------------------------------------
+_CPU_REF_STATE = {}
+
+
 def cpu_reference_images_per_s(ddim_steps, repeats=1):
     """Bounded sample: one fp32 UNet call (B=1, 64x64 latent, 77x768 context) and one VAE decode
     (1x4x64x64 -> 512x512) of the oracle restatement; images/s = 1 / (ddim_steps * t_unet + t_decode)."""
@@ -91,9 +94,11 @@ def cpu_reference_images_per_s(ddim_steps, repeats=1):
     from oracle.golden import load_golden
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    gu, gv = load_golden("unet_sd.pt"), load_golden("vae_sd_z16.pt")
-    sdu = W.make_state_dict(gu["key_shapes"], 1)
-    sdv = W.make_state_dict(gv["key_shapes"], 2)
+    if not _CPU_REF_STATE:          # random-init weights of the reference's shapes, generated once per process
+        gu, gv = load_golden("unet_sd.pt"), load_golden("vae_sd_z16.pt")
+        _CPU_REF_STATE["sdu"] = W.make_state_dict(gu["key_shapes"], 1)
+        _CPU_REF_STATE["sdv"] = W.make_state_dict(gv["key_shapes"], 2)
+    sdu, sdv = _CPU_REF_STATE["sdu"], _CPU_REF_STATE["sdv"]
     x, ctx = W.seeded_randn((1, 4, 64, 64), 3), W.seeded_randn((1, 77, 768), 4)
     t = torch.tensor([500])
     tu, td = [], []
@@ -110,17 +115,34 @@ def cpu_reference_images_per_s(ddim_steps, repeats=1):
 
 
 def run_reference(a):
+    """Reference arm: the reference's own CPU PyTorch path (its oracle restatement — the Python reference cannot travel to
+    the GPU box) on all host threads, same metric / unit / workload as the sdb200 arm.  One "step" of the workload is a
+    batch of `--batch` images (DDIM-50 + decode); each of the W + K steps times a BOUNDED SAMPLE of it — one UNet call and
+    one VAE decode at B=1 — and extrapolates t_image = ddim_steps * t_unet + t_decode (nothing on the path reduces over
+    the batch).  The K timed samples are averaged."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ips, cores, t_unet, t_dec = cpu_reference_images_per_s(a.ddim_steps, repeats=max(1, min(a.steps, 3)))
-    sample = "oracle restatement of the reference PyTorch path, fp32, %d host threads: 1 UNet call B=1 (%.2f s) + 1 VAE decode " \
-             "B=1 (%.2f s); images/s = 1/(%d*t_unet + t_decode)" % (cores, t_unet, t_dec, a.ddim_steps)
+    B = a.batch
+    world = max(1, a.gpus)
+    per_image = []
+    for i in range(max(0, a.warmup) + max(1, a.steps)):
+        ips1, cores, t_unet, t_dec = cpu_reference_images_per_s(a.ddim_steps, repeats=1)
+        if i >= a.warmup:
+            per_image.append((1.0 / ips1, t_unet, t_dec))
+    t_img = sum(p[0] for p in per_image) / len(per_image)
+    t_unet = sum(p[1] for p in per_image) / len(per_image)
+    t_dec = sum(p[2] for p in per_image) / len(per_image)
+    ips = 1.0 / t_img
+    sample = "oracle restatement of the reference PyTorch path, fp32, %d host threads; per step 1 UNet call B=1 (%.2f s) + 1 VAE " \
+             "decode B=1 (%.2f s), extrapolated: t_image = %d*t_unet + t_decode, step = %d images" % (cores, t_unet, t_dec, a.ddim_steps, B)
     line = {
         "impl": "reference", "metric": "512px DDIM-50 images/sec", "value": ips, "unit": "images/s", "n_gpus": a.gpus,
-        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 / ips, "higher_is_better": True, "scaling": "weak",
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * t_img * B, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "SD-1.x UNet DDIM-50 + VAE decode, 64x64x4 latent -> 512x512x3, ctx 77x768", "global_batch": 1},
+        "config": {"workload": "SD-1.x UNet DDIM-%d + VAE decode, 64x64x4 latent -> 512x512x3, ctx 77x768, batch %d per GPU"
+                               % (a.ddim_steps, B), "global_batch": B * world, "per_gpu_batch": B,
+                   "note": "host CPU only (one process, rank 0): the value does not grow with n_gpus"},
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
