@@ -151,3 +151,47 @@ def test_launch_plan_table_is_well_formed():
         assert variant in (1, 2) and bn in (32, 64, 128, 160, 256) and 1 <= sk <= 16
         assert not (variant == 2 and bn < 128)
         assert best_us <= auto_us
+
+
+def test_next_row_modules_have_no_cpu_fallback():
+    """'next' rows f3 / f4 run on the same kernels: CPU tensors raise instead of silently computing in PyTorch."""
+    from sdb200 import _lib, ops
+    from sdb200.autoencoder import DiagonalGaussianDistribution
+    with pytest.raises(_lib.SdbError):
+        DiagonalGaussianDistribution(torch.zeros(1, 8, 2, 2))
+    with pytest.raises(_lib.SdbError):
+        ops.q_sample(torch.zeros(2, 4), torch.zeros(2, 4), torch.ones(2), torch.ones(2))
+    with pytest.raises(_lib.SdbError):
+        ops.avgpool2x2(torch.zeros(1, 2, 2, 4))
+    with pytest.raises(_lib.SdbError):
+        ops.scale_shift_affine(torch.ones(4), torch.zeros(4), torch.zeros(2, 8))
+
+
+def test_bench_reference_arm_line(monkeypatch, capsys):
+    """bench.py --impl reference: one JSON line with the sdb200 arm's metric / unit / workload, steps and warm-up honoured,
+    e2e == value with zero copy bytes, cpu_baseline describing the run (the timed sample itself is stubbed here)."""
+    import json
+    import sys
+    import bench
+    calls = []
+
+    def fake(ddim_steps, repeats=1):
+        calls.append(ddim_steps)
+        return 1.0 / (ddim_steps * 2.0 + 4.0), 16, 2.0, 4.0
+    monkeypatch.setattr(bench, "cpu_reference_images_per_s", fake)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--impl", "reference", "--gpus", "2", "--steps", "3", "--warmup", "2"])
+    monkeypatch.setenv("RANK", "0")
+    bench.main()
+    out = [l for l in capsys.readouterr().out.splitlines() if l.startswith("{")]
+    assert len(out) == 1 and len(calls) == 5
+    d = json.loads(out[0])
+    assert d["impl"] == "reference" and d["metric"] == "512px DDIM-50 images/sec" and d["unit"] == "images/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 2 and d["steps"] == 3 and d["warmup"] == 2
+    assert d["config"]["workload"] == "SD-1.x UNet DDIM-50 + VAE decode, 64x64x4 latent -> 512x512x3, ctx 77x768, batch 8 per GPU"
+    assert abs(d["value"] - 1.0 / 104.0) < 1e-12 and abs(d["ms_per_step"] - 8 * 104.0 * 1000.0) < 1e-6
+    assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 16 and d["cpu_baseline"]["value"] == d["value"]
+    # every other rank exits without work
+    monkeypatch.setenv("RANK", "1")
+    bench.main()
+    assert capsys.readouterr().out.strip() == ""
