@@ -6,6 +6,8 @@ Same constructor / method signatures and the same duck-typed `model` interface a
 Schedule tables are built on the host with the reference's own mixed torch/numpy arithmetic so the
 four per-step coefficients are bit-identical fp32 values.
 """
+import weakref
+
 import numpy as np
 import torch
 
@@ -45,6 +47,8 @@ def _f32(v):
 
 
 class DDIMSampler(object):
+    _cfg_ctx = None
+
     def __init__(self, model, schedule="linear", **kwargs):
         super().__init__()
         self.model = model
@@ -191,6 +195,16 @@ class DDIMSampler(object):
         e_uncond = None
         if unconditional_conditioning is None or unconditional_guidance_scale == 1.:
             e_t = self.model.apply_model(x, t, c)
+        elif isinstance(c, torch.Tensor) and isinstance(unconditional_conditioning, torch.Tensor):
+            # one 2B call like the reference (ddim.py:176-179).  The concatenated conditioning is built once per (uc, c)
+            # pair and reused for every step, so a UNet that caches the context K/V projections keeps hitting its cache.
+            hit = self._cfg_ctx
+            key = (c.data_ptr(), c._version, unconditional_conditioning.data_ptr(), unconditional_conditioning._version)
+            if hit is None or hit[0] != key or hit[1]() is not c or hit[2]() is not unconditional_conditioning:
+                hit = (key, weakref.ref(c), weakref.ref(unconditional_conditioning), torch.cat([unconditional_conditioning, c]))
+                self._cfg_ctx = hit
+            e_uncond, e_t = self.model.apply_model(torch.cat([x] * 2), torch.cat([t] * 2), hit[3]).chunk(2)
+            e_uncond, e_t = e_uncond.contiguous(), e_t.contiguous()
         else:
             e_uncond = self.model.apply_model(x, t, unconditional_conditioning)
             e_t = self.model.apply_model(x, t, c)

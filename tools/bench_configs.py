@@ -59,3 +59,26 @@ for B in (8, 16):
     tf = B * VAE_GFLOP / ms
     print(json.dumps({"config": "VAE decode 64x64x4 -> 512x512x3, bf16 (micro-batches of %d)" % vae.micro_batch, "batch": B, "ms": round(ms, 2),
                       "images_per_s": round(B / ms * 1e3, 1), "model_tflops": round(tf, 1), "frac_of_tensor_peak": round(tf / PEAK, 4)}), flush=True)
+
+# classifier-free guidance 7.5 (two UNet calls per DDIM step; SURVEY.md §8d asks for it to be reported separately)
+if "--cfg" in sys.argv:
+    from sdb200.pipeline import LatentDiffusion
+    del vae
+    torch.cuda.empty_cache()
+    ld = LatentDiffusion(compute_mode="bf16")
+    for m in ld.modules():
+        if isinstance(m, (torch.nn.Conv2d, torch.nn.Linear)) and float(m.weight.detach().abs().max()) == 0.0:
+            m.reset_parameters()
+    ld = ld.to(dev)
+    ld.model.diffusion_model.use_cuda_graph = True
+    B = 8
+    c = torch.randn(B, 77, 768, device=dev)
+    uc = torch.randn(B, 77, 768, device=dev)
+    x_T = torch.randn(B, 4, 64, 64, device=dev)
+    for scale in (1.0, 7.5):
+        fn = lambda: ld.txt2img(c, B, ddim_steps=50, shape=(4, 64, 64), x_T=x_T, unconditional_guidance_scale=scale,
+                                unconditional_conditioning=uc if scale != 1.0 else None)
+        ms = timed(fn, warm=1, reps=1)
+        print(json.dumps({"config": "txt2img DDIM-50 + decode through LatentDiffusion.txt2img, batch 8, guidance scale %.1f" % scale,
+                          "batch": B, "ms": round(ms, 1), "images_per_s": round(B / ms * 1e3, 2),
+                          "unet_calls_per_step": 1 if scale == 1.0 else 2}), flush=True)
