@@ -148,6 +148,16 @@ int sdb_ddim_step(const float* x, const float* e_cond, const float* e_uncond, fl
                   const float* noise, float sqrt_at, float sqrt_aprev, float dir_coef, float sigma_t,
                   float sqrt_one_minus_at, float temperature, float* x_prev, float* pred_x0, long long n,
                   void* stream);
+/* Second half of the same update for the quantize_denoised branch (ldm/diffusion/ddim.py:198-205): pred_x0 is GIVEN
+ * (the caller replaced it by first_stage_model.quantize(pred_x0)), x_prev = sqrt_aprev*pred_x0 + dir_coef*e + sigma_t*noise*temperature. */
+int sdb_ddim_xprev(const float* pred_x0, const float* e_cond, const float* e_uncond, float cfg_scale, const float* noise,
+                   float sqrt_aprev, float dir_coef, float sigma_t, float temperature, float* x_prev, long long n, void* stream);
+/* Inpainting blend of ddim_sampling (ldm/diffusion/ddim.py:144-149) fused with LatentDiffusion.q_sample
+ * (ldm/diffusion/ddpm.py:407-412): img_orig = a[b]*x0 + c[b]*noise; out = img_orig*mask + (1 - mask)*img.
+ * x0 / noise / img / out [B,C,HW] fp32, mask [B,Cm,HW] with Cm == 1 (broadcast over channels) or Cm == C; a / c: B per-sample
+ * coefficients (sqrt_alphas_cumprod[t], sqrt_one_minus_alphas_cumprod[t]); individually rounded fp32 operations. */
+int sdb_inpaint_blend(const float* x0, const float* noise, const float* a, const float* c, const float* mask, const float* img,
+                      int B, int C, int Cm, long long HW, float* out, void* stream);
 
 /* ---- VAE posterior and img2img entry ('next' row f3) ------------------------------------------
  * sdb_diag_gaussian replaces DiagonalGaussianDistribution.__init__ / .sample

@@ -174,6 +174,111 @@ def gen_vae_enc(name, ddconfig, B, res, seed):
     save(name + ".pt", out)
 
 
+def gen_sd_traj(name="sd_traj", steps_kept=(0, 12, 25, 37, 49)):
+    """BASELINE config C2 at its own size: the UNMODIFIED reference UNetModel (SD-1.x kwargs) driven by the reference
+    DDIMSampler (DDIM/ddim.py) for a full DDIM-50 run at B=1, 64x64x4 latent, 77x768 context, then the reference ldm
+    Decoder on z / 0.18215 (ldm/diffusion/ddpm.py:1095) -> 3x512x512.  Stored: (x_t, t, e_t) at five steps of the
+    reference trajectory (teacher-forced eps checks), the final latent and the decoded image (PSNR check).
+    UNet weights = seed 31 (same as unet_sd.pt), VAE weights = seed 51 (same as vae_sd_z16.pt)."""
+    import contextlib
+    import io
+    import time
+    cfg = R.SD_UNET_CFG
+    net = RH.build_unet(cfg)
+    ks_u = W.key_shapes_of(net)
+    sdu = W.make_state_dict(ks_u, 31)
+    net.load_state_dict(sdu, strict=True)
+    dec = RH.build_decoder(R.SD_VAE_DDCONFIG)
+    ks_v = [("decoder." + k, s) for k, s in W.key_shapes_of(dec)] + [("post_quant_conv.weight", (4, 4, 1, 1)), ("post_quant_conv.bias", (4,))]
+    sdv = W.make_state_dict(ks_v, 51)
+    dec.load_state_dict({k[len("decoder."):]: v for k, v in sdv.items() if k.startswith("decoder.")}, strict=True)
+    x_T = W.seeded_randn((1, 4, 64, 64), 2)       # SURVEY.md 8d: C2 seeds
+    ctx = W.seeded_randn((1, 77, 768), 3)
+    rec = []
+
+    def fn(x, t, c):
+        e = RH.run_unet(net, x, t, c)
+        rec.append((x.clone(), int(t[0]), e.clone()))
+        return e
+
+    ref = RH.make_cpu_sampler(R.ModelShim(fn, R.sd_alphas_cumprod()))
+    t0 = time.perf_counter()
+    with torch.no_grad(), RH.quiet(), contextlib.redirect_stderr(io.StringIO()):
+        z_ref, _ = ref.sample(S=50, batch_size=1, shape=(4, 64, 64), conditioning=ctx, verbose=False, x_T=x_T, eta=0.)
+    t_traj = time.perf_counter() - t0
+    assert len(rec) == 50
+    with torch.no_grad(), RH.quiet():
+        pq = torch.nn.functional.conv2d(z_ref / 0.18215, sdv["post_quant_conv.weight"], sdv["post_quant_conv.bias"])
+        img_ref = dec(pq)
+    print("%s: reference DDIM-50 %.1f s; z std %.3f max %.2f; img mean %.3f std %.3f, %.1f%% inside [-1,1]"
+          % (name, t_traj, float(z_ref.std()), float(z_ref.abs().max()), float(img_ref.mean()), float(img_ref.std()),
+             100 * float((img_ref.abs() <= 1).float().mean())))
+    kept = []
+    worst = 0.0
+    for i in steps_kept:
+        x_t, t, e_t = rec[i]
+        with torch.no_grad():
+            e_or = R.unet_forward(sdu, cfg, x_t, torch.tensor([t]), ctx)
+        err = R.rel_l2(e_or, e_t)
+        worst = max(worst, err)
+        print("   step %2d (t=%d): restatement vs reference eps rel-L2 = %.3e, x_t std %.3f, eps std %.3f"
+              % (i, t, err, float(x_t.std()), float(e_t.std())))
+        assert err < 2e-5, err
+        kept.append(dict(i=i, t=t, x_t=x_t, e_t=e_t))
+    with torch.no_grad():
+        img_or = R.autoencoder_decode(sdv, R.SD_VAE_DDCONFIG, z_ref / 0.18215)
+    err_img = R.rel_l2(img_or, img_ref)
+    print("   decode restatement vs reference rel-L2 = %.3e" % err_img)
+    assert err_img < 2e-5, err_img
+    save(name + ".pt", dict(cfg=cfg, ddconfig=R.SD_VAE_DDCONFIG, unet_seed=31, vae_seed=51, unet_key_shapes=ks_u, vae_key_shapes=ks_v,
+                            x_T_seed=2, ctx_seed=3, steps=kept, all_t=[r[1] for r in rec], z_ref=z_ref.clone(),
+                            img_ref=img_ref.clone(), restate_err=worst, restate_err_img=err_img, ref_seconds=t_traj))
+
+
+def gen_vae_full(name="vae_sd_z64"):
+    """BASELINE config C3 at its own size (B=1): the reference ldm Decoder on a 64x64x4 latent -> 3x512x512.
+    `img_f64` is the float64 restatement rounded to fp32 for storage (3e-8 relative, against a 1e-5 bound)."""
+    ddconfig = R.SD_VAE_DDCONFIG
+    dec = RH.build_decoder(ddconfig)
+    ks = [("decoder." + k, s) for k, s in W.key_shapes_of(dec)] + [("post_quant_conv.weight", (4, 4, 1, 1)), ("post_quant_conv.bias", (4,))]
+    sd = W.make_state_dict(ks, 51)
+    dec.load_state_dict({k[len("decoder."):]: v for k, v in sd.items() if k.startswith("decoder.")}, strict=True)
+    z = W.seeded_randn((1, 4, 64, 64), 4)         # SURVEY.md 8d: C3 seed
+    with torch.no_grad(), RH.quiet():
+        pq = torch.nn.functional.conv2d(z, sd["post_quant_conv.weight"], sd["post_quant_conv.bias"])
+        img_ref = dec(pq)
+        img_or = R.autoencoder_decode(sd, ddconfig, z)
+        img64 = R.autoencoder_decode({k: v.double() for k, v in sd.items()}, ddconfig, z.double())
+    err = R.rel_l2(img_or, img_ref)
+    print("%s: restatement vs reference rel-L2 = %.3e (img std %.3f); fp32 reference vs f64 %.3e"
+          % (name, err, float(img_ref.std()), R.rel_l2(img_ref, img64)))
+    assert err < 2e-5, err
+    save(name + ".pt", dict(ddconfig=ddconfig, seed=51, z_seed=4, key_shapes=ks, z_shape=(1, 4, 64, 64), img_ref=img_ref.clone(),
+                            img_f64=img64.float().clone(), restate_err=err))
+
+
+def gen_unet_96(name="unet_sd_96"):
+    """BASELINE config C5 at its own size (B=1): one reference UNetModel step on a 96x96x4 latent (S = 9216 tokens)."""
+    cfg = R.SD_UNET_CFG
+    net = RH.build_unet(cfg)
+    ks = W.key_shapes_of(net)
+    sd = W.make_state_dict(ks, 31)
+    net.load_state_dict(sd, strict=True)
+    x = W.seeded_randn((1, 4, 96, 96), 5)         # SURVEY.md 8d: C5 seed
+    ctx = W.seeded_randn((1, 77, 768), 3)
+    t = torch.tensor([500], dtype=torch.long)
+    eps_ref = RH.run_unet(net, x, t, ctx)
+    with torch.no_grad():
+        eps_or = R.unet_forward(sd, cfg, x, t, ctx)
+        eps64 = R.unet_forward({k: v.double() for k, v in sd.items()}, cfg, x.double(), t, ctx.double())
+    err = R.rel_l2(eps_or, eps_ref)
+    print("%s: restatement vs reference rel-L2 = %.3e (eps std %.3f); fp32 reference vs f64 %.3e"
+          % (name, err, float(eps_ref.std()), R.rel_l2(eps_ref, eps64)))
+    assert err < 2e-5, err
+    save(name + ".pt", dict(cfg=cfg, seed=31, key_shapes=ks, x_shape=(1, 4, 96, 96), x_seed=5, ctx_shape=(1, 77, 768), ctx_seed=3,
+                            t=t, eps_ref=eps_ref.clone(), eps_f64=eps64.clone(), restate_err=err))
+
+
 def toy_model_fn(x, t, c):
     """A cheap analytic eps-model so that sampler goldens do not depend on any network."""
     s = torch.sin(t.float() * 0.01).view(-1, 1, 1, 1)
@@ -256,6 +361,36 @@ def gen_ddim():
     save("ddim.pt", out)
 
 
+def gen_ddim_mask():
+    """Inpainting branch of ddim_sampling (ldm/diffusion/ddim.py:144-149): the reference sampler driven with mask / x0 and a
+    model shim whose q_sample restates LatentDiffusion.q_sample (ldm/diffusion/ddpm.py:407-412; the class itself needs
+    pytorch_lightning and cannot be imported) with a FIXED noise tensor, so the trajectory is reproducible on any device."""
+    import contextlib
+    import io
+    out = {}
+    ac = R.sd_alphas_cumprod()
+    for S, cm in ((10, 1), (20, 4)):
+        x_T = W.seeded_randn((2, 4, 8, 8), 101)
+        x0 = W.seeded_randn((2, 4, 8, 8), 102)
+        fixed = torch.from_numpy(np.random.Generator(np.random.PCG64(103)).random(size=(2, 4, 8, 8)).astype(np.float32))
+        mask = (W.seeded_randn((2, cm, 8, 8), 104) > 0).float()
+        c = W.seeded_randn((2, 5, 6), 105)
+
+        def make_shim():
+            sh = R.ModelShim(toy_model_fn, ac)
+            base = sh.q_sample
+            sh.q_sample = lambda xs, t, noise=None: base(xs, t, noise=fixed)
+            return sh
+        ref = RH.make_cpu_sampler(make_shim())
+        with RH.quiet(), contextlib.redirect_stderr(io.StringIO()):
+            z_ref, _ = ref.sample(S=S, batch_size=2, shape=(4, 8, 8), conditioning=c, verbose=False, x_T=x_T, eta=0., mask=mask, x0=x0)
+        orc = R.DDIMOracle(make_shim())
+        z, _ = orc.sample(S, 2, (4, 8, 8), conditioning=c, eta=0., x_T=x_T, mask=mask, x0=x0)
+        assert torch.equal(z, z_ref), "inpainting trajectory restatement is not bit-exact"
+        out["traj_mask.S%d.cm%d" % (S, cm)] = dict(x_T=x_T, x0=x0, q_noise=fixed, mask=mask, c=c, z=z_ref)
+    save("ddim_mask.pt", out)
+
+
 def gen_ddpm():
     net = RH.build_ddpm_unet()
     ks = W.key_shapes_of(net)
@@ -312,6 +447,14 @@ def main():
             gen_unet_variant(name, cfg, seed=81 + 10 * i)
     if a.part in ("all", "vae_enc"):
         gen_vae_enc("vae_enc_tiny", TINY_VAE_DDCONFIG, B=2, res=32, seed=61)
+    if a.part in ("all", "ddim_mask"):
+        gen_ddim_mask()
+    if a.part in ("all", "sd_full", "sd_traj"):
+        gen_sd_traj()
+    if a.part in ("all", "sd_full", "vae_full"):
+        gen_vae_full()
+    if a.part in ("all", "sd_full", "unet_96"):
+        gen_unet_96()
     if a.part == "ddpm":
         gen_ddpm()
     if a.part == "all":   # the DDPM tree's top-level `models` package clashes with ldm's aliases

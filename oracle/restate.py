@@ -437,10 +437,21 @@ class ModelShim:
         self.alphas_cumprod = torch.tensor(ac, dtype=torch.float32)
         self.alphas_cumprod_prev = torch.tensor(np.append(1., ac[:-1]), dtype=torch.float32)
         self.betas = torch.tensor(1. - ac / np.append(1., ac[:-1]), dtype=torch.float32)
+        self._ac64 = ac
         self.fn = fn
 
     def apply_model(self, x, t, c):
         return self.fn(x, t, c)
+
+    def q_sample(self, x_start, t, noise=None):
+        """LatentDiffusion.q_sample, ldm/diffusion/ddpm.py:407-412, as written: the default draw is torch.rand_like
+        (uniform); sqrt_alphas_cumprod = to_torch(np.sqrt(alphas_cumprod)) (:212-213), gathered per sample (util.py:96-99)."""
+        if noise is None:
+            noise = torch.rand_like(x_start)
+        ac = self.alphas_cumprod.double().numpy() if not hasattr(self, "_ac64") else self._ac64
+        sa = torch.tensor(np.sqrt(ac), dtype=torch.float32).gather(-1, t).reshape(-1, *((1,) * (x_start.dim() - 1)))
+        sc = torch.tensor(np.sqrt(1. - ac), dtype=torch.float32).gather(-1, t).reshape(-1, *((1,) * (x_start.dim() - 1)))
+        return sa * x_start + sc * noise
 
 
 def sd_alphas_cumprod():
@@ -500,7 +511,7 @@ class DDIMOracle:
 
     def sample(self, S, batch_size, shape, conditioning=None, eta=0., x_T=None, temperature=1.,
                unconditional_guidance_scale=1., unconditional_conditioning=None, log_every_t=100,
-               record=None):
+               record=None, mask=None, x0=None):
         """sample + ddim_sampling, ddim.py:56-165. `record`, if a list, receives (x_t, t, e_t) per step."""
         self.make_schedule(S, ddim_eta=eta)
         C, H, W = shape
@@ -512,6 +523,9 @@ class DDIMOracle:
         for i, step in enumerate(time_range):
             index = total - i - 1
             ts = torch.full((batch_size,), int(step), dtype=torch.long)
+            if mask is not None:          # inpainting branch, ddim.py:144-149
+                img_orig = self.model.q_sample(x0, ts)
+                img = img_orig * mask + (1. - mask) * img
             x_in = img
             img, pred_x0, e_t = self.p_sample_ddim(
                 img, conditioning, ts, index, temperature=temperature,

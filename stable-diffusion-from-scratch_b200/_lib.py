@@ -100,6 +100,8 @@ SIGNATURES = {
     "sdb_gather_rows": (_I, [_P, _P, _I, _I, _P, _P]),
     "sdb_skinny_linear": (_I, [_P, _I, _I, _P, _P, _I, _I, _I, _P, _P]),
     "sdb_ddim_step": (_I, [_P, _P, _P, _F, _P, _F, _F, _F, _F, _F, _F, _P, _P, _L, _P]),
+    "sdb_ddim_xprev": (_I, [_P, _P, _P, _F, _P, _F, _F, _F, _F, _P, _L, _P]),
+    "sdb_inpaint_blend": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _L, _P, _P]),
     "sdb_diag_gaussian": (_I, [_P, _P, _I, _I, _L, _P, _P, _P, _P, _P, _P]),
     "sdb_q_sample": (_I, [_P, _P, _P, _P, _I, _L, _P, _P]),
     "sdb_simt_contract": (_I, [C.POINTER(SimtArgs), _P]),
@@ -153,6 +155,19 @@ def dtype_code(dt):
 
 
 def require_cuda(*tensors):
+    """Every operand must live on ONE CUDA device and that device must be the current one: kernels are enqueued on the
+    current device's current stream (`stream_ptr`), so a tensor elsewhere would be dereferenced by the wrong GPU.  The
+    module-level entry points (UNetModel.forward, AutoencoderKL.decode, ...) switch to their input's device themselves."""
+    dev = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise SdbError("sdb200 kernels need CUDA tensors (got %s); there is no CPU fallback" % t.device)
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise SdbError("sdb200 op got operands on different devices (%s and %s)" % (dev, t.device))
+    if dev is not None and dev.index != torch.cuda.current_device():
+        raise SdbError("sdb200 op got tensors on %s while the current CUDA device is cuda:%d; wrap the call in "
+                       "`with torch.cuda.device(tensor.device):`" % (dev, torch.cuda.current_device()))

@@ -82,11 +82,34 @@ def make_attn(in_channels, attn_type="vanilla"):
     raise NotImplementedError("sdb200 VAE: linear attention is outside the hot path")
 
 
+def _fingerprint(module):
+    """(first parameter's address, device, sum of parameter versions): changes when parameters are replaced, moved or
+    written in place (load through a parent module, EMA copy_to, ...)."""
+    ps = module.__dict__.get("_param_list")
+    if ps is None:
+        ps = module.__dict__["_param_list"] = list(module.parameters())
+    return (ps[0].data_ptr(), ps[0].device, sum(p._version for p in ps))
+
+
 class _VaeNet(nn.Module):
     """Packing and block execution shared by Encoder and Decoder."""
 
+    def __init__(self):
+        super().__init__()
+        # a parent's load_state_dict recurses through _load_from_state_dict and never reaches the override below
+        self.register_load_state_dict_post_hook(lambda module, incompatible_keys: module._invalidate())
+
     def _invalidate(self):
         self._packed = {}
+        self.__dict__.pop("_param_list", None)
+        self.__dict__.pop("_fp_seen", None)
+
+    def _check_weights(self):
+        fp = _fingerprint(self)
+        if fp != self.__dict__.get("_fp_seen"):
+            if self.__dict__.get("_fp_seen") is not None:
+                self._invalidate()
+            self.__dict__["_fp_seen"] = fp
 
     def load_state_dict(self, *a, **k):
         r = super().load_state_dict(*a, **k)
@@ -99,6 +122,7 @@ class _VaeNet(nn.Module):
         return r
 
     def _pack(self, mode):
+        self._check_weights()
         if mode in self._packed:
             return self._packed[mode]
         P = {}
@@ -252,9 +276,10 @@ class Encoder(_VaeNet):
     def forward(self, x):
         """x [N, in_channels, H, W] -> [N, 2*z_channels, h, w] (fp32 in, fp32 out)."""
         from ._lib import require_cuda
-        require_cuda(x)
-        h = ops.nchw_to_nhwc(x.float().contiguous())
-        out = ops.nhwc_to_nchw(self._forward_nhwc(h, self.compute_mode))
+        with torch.cuda.device(x.device):
+            require_cuda(x)
+            h = ops.nchw_to_nhwc(x.float().contiguous())
+            out = ops.nhwc_to_nchw(self._forward_nhwc(h, self.compute_mode))
         return out if x.dtype == torch.float32 else out.to(x.dtype)
 
 
@@ -370,10 +395,11 @@ class Decoder(_VaeNet):
     def forward(self, z):
         """z [N, z_channels, h, w] -> [N, out_ch, 8h, 8w] (fp32 in, fp32 out)."""
         from ._lib import require_cuda
-        require_cuda(z)
-        self.last_z_shape = z.shape
-        h = ops.nchw_to_nhwc(z.float().contiguous())
-        out = ops.nhwc_to_nchw(self._forward_nhwc(h, self.compute_mode))
+        with torch.cuda.device(z.device):
+            require_cuda(z)
+            self.last_z_shape = z.shape
+            h = ops.nchw_to_nhwc(z.float().contiguous())
+            out = ops.nhwc_to_nchw(self._forward_nhwc(h, self.compute_mode))
         return out if z.dtype == torch.float32 else out.to(z.dtype)
 
 
@@ -414,33 +440,51 @@ class AutoencoderKL(nn.Module):
                     del sd[k]
         self.load_state_dict(sd, strict=False)
 
-    def load_state_dict(self, *a, **k):
-        r = super().load_state_dict(*a, **k)
+    def _invalidate(self):
         self.decoder._invalidate()
         self.encoder._invalidate()
         self._pq = None
         self._q = None
+
+    def load_state_dict(self, *a, **k):
+        r = super().load_state_dict(*a, **k)
+        self._invalidate()
+        return r
+
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        self._invalidate()
         return r
 
     _pq = None
     _q = None
+
+    def _packed_1x1(self, slot, conv):
+        """quant_conv / post_quant_conv packed for the fp32 SIMT kernel (C_in = 4 or 8), re-packed whenever the layer's
+        parameters were replaced or written in place."""
+        fp = (conv.weight.data_ptr(), conv.weight._version, conv.bias.data_ptr(), conv.bias._version)
+        cur = getattr(self, slot)
+        if cur is None or cur[0] != fp:
+            cur = (fp, PackedConv(conv.weight, conv.bias, "fp32"))
+            setattr(self, slot, cur)
+        return cur[1]
 
     @torch.no_grad()
     def encode(self, x):
         """AutoencoderKL.encode (autoencoder.py:331-335): Encoder, quant_conv (1x1, 8->8), posterior.
         x [N,3,H,W] in [-1,1] -> DiagonalGaussianDistribution over [N,embed_dim,H/8,W/8]."""
         from ._lib import require_cuda
-        require_cuda(x)
-        mode = self.encoder.compute_mode
-        if self._q is None:
-            self._q = PackedConv(self.quant_conv.weight, self.quant_conv.bias, "fp32")     # C_in = 8: SIMT fp32 kernel in both modes
-        xf = x.float().contiguous()
-        outs = []
-        for i in range(0, xf.shape[0], self.micro_batch):
-            h = self.encoder._forward_nhwc(ops.nchw_to_nhwc(xf[i:i + self.micro_batch].contiguous()), mode)
-            outs.append(ops.nhwc_to_nchw(engine.conv(h, self._q)))
-        moments = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
-        return DiagonalGaussianDistribution(moments)
+        with torch.cuda.device(x.device):
+            require_cuda(x)
+            mode = self.encoder.compute_mode
+            qc = self._packed_1x1("_q", self.quant_conv)                                   # C_in = 8: SIMT fp32 kernel in both modes
+            xf = x.float().contiguous()
+            outs = []
+            for i in range(0, xf.shape[0], self.micro_batch):
+                h = self.encoder._forward_nhwc(ops.nchw_to_nhwc(xf[i:i + self.micro_batch].contiguous()), mode)
+                outs.append(ops.nhwc_to_nchw(engine.conv(h, qc)))
+            moments = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+            return DiagonalGaussianDistribution(moments)
 
     @torch.no_grad()
     def decode(self, z):
@@ -448,20 +492,18 @@ class AutoencoderKL(nn.Module):
         Large batches are decoded in micro-batches of `micro_batch` images (activations at 512^2 are
         ~0.5 GB/image); results are identical because nothing on the path reduces over the batch."""
         from ._lib import require_cuda
-        require_cuda(z)
-        mode = self.decoder.compute_mode
-        if self._pq is None or self._pq[0] != mode:
-            # C_in = 4: SIMT fp32 kernel in both modes
-            self._pq = (mode, PackedConv(self.post_quant_conv.weight, self.post_quant_conv.bias, "fp32"))
-        pq = self._pq[1]
-        zf = z.float().contiguous()
-        N = zf.shape[0]
-        outs = []
-        for i in range(0, N, self.micro_batch):
-            h = ops.nchw_to_nhwc(zf[i:i + self.micro_batch].contiguous())
-            h = engine.conv(h, pq)
-            outs.append(ops.nhwc_to_nchw(self.decoder._forward_nhwc(h, mode)))
-        out = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+        with torch.cuda.device(z.device):
+            require_cuda(z)
+            mode = self.decoder.compute_mode
+            pq = self._packed_1x1("_pq", self.post_quant_conv)                             # C_in = 4: SIMT fp32 kernel in both modes
+            zf = z.float().contiguous()
+            N = zf.shape[0]
+            outs = []
+            for i in range(0, N, self.micro_batch):
+                h = ops.nchw_to_nhwc(zf[i:i + self.micro_batch].contiguous())
+                h = engine.conv(h, pq)
+                outs.append(ops.nhwc_to_nchw(self.decoder._forward_nhwc(h, mode)))
+            out = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
         return out if z.dtype == torch.float32 else out.to(z.dtype)
 
     def forward(self, input, sample_posterior=True):

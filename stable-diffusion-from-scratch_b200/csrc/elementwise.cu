@@ -257,27 +257,69 @@ __global__ void skinny_linear_kernel(const float* __restrict__ x, int M, int K, 
 // ---- DDIM update (reference ldm/diffusion/ddim.py:175-205) --------------------------------------
 // Every operation is a separately rounded fp32 op (__f*_rn blocks FMA contraction) so that, given
 // the same eps, x_prev / pred_x0 are bit-identical to the eager reference arithmetic.
-__global__ void ddim_step_kernel(const float* __restrict__ x, const float* __restrict__ e_c,
-                                 const float* __restrict__ e_u, float cfg, const float* __restrict__ noise,
-                                 float sqrt_at, float sqrt_aprev, float dir_coef, float sigma_t,
-                                 float sqrt_one_minus_at, float temperature,
-                                 float* __restrict__ x_prev, float* __restrict__ pred_x0, long long n) {
+// One element of the update; `p0_in` != NULL: pred_x0 is given (quantize_denoised branch, ddim.py:198-199) and only x_prev is formed.
+__device__ __forceinline__ void ddim_update_1(float xv, float e, bool has_u, float u, float cfg, bool has_nz, float nzv,
+                                              float sqrt_at, float sqrt_aprev, float dir_coef, float sigma_t,
+                                              float sqrt_one_minus_at, float temperature, bool p0_given, float& p0, float& xp) {
+    if (has_u) e = __fadd_rn(u, __fmul_rn(cfg, __fsub_rn(e, u)));
+    if (!p0_given) p0 = __fdiv_rn(__fsub_rn(xv, __fmul_rn(sqrt_one_minus_at, e)), sqrt_at);
+    const float dir = __fmul_rn(dir_coef, e);
+    float nz = 0.f;
+    if (has_nz) nz = __fmul_rn(__fmul_rn(sigma_t, nzv), temperature);
+    xp = __fadd_rn(__fadd_rn(__fmul_rn(sqrt_aprev, p0), dir), nz);
+}
+
+// VEC = 4: 128-bit loads / stores (every pointer 16-byte aligned, n % 4 == 0), VEC = 1: any alignment.  HBM-bound:
+// 16 B / element at eta = 0 (x, e in; x_prev, pred_x0 out), + 4 with noise, + 4 with classifier-free guidance.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+ddim_step_kernel(const float* __restrict__ x, const float* __restrict__ e_c, const float* __restrict__ e_u, float cfg,
+                 const float* __restrict__ noise, const float* __restrict__ p0_in, float sqrt_at, float sqrt_aprev, float dir_coef,
+                 float sigma_t, float sqrt_one_minus_at, float temperature, float* __restrict__ x_prev,
+                 float* __restrict__ pred_x0, long long n) {
     pdl_trigger();
     pdl_wait();
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        float e = e_c[i];
-        if (e_u) {
-            float u = e_u[i];
-            e = __fadd_rn(u, __fmul_rn(cfg, __fsub_rn(e, u)));
+    const long long nv = n / VEC;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+        if (VEC == 4) {
+            const float4 e4 = __ldg(reinterpret_cast<const float4*>(e_c) + i);
+            float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f), n4 = u4, x4 = u4, p4 = u4, o4;
+            if (e_u) u4 = __ldg(reinterpret_cast<const float4*>(e_u) + i);
+            if (noise) n4 = __ldg(reinterpret_cast<const float4*>(noise) + i);
+            if (p0_in) p4 = __ldg(reinterpret_cast<const float4*>(p0_in) + i);
+            else x4 = __ldg(reinterpret_cast<const float4*>(x) + i);
+            const bool hu = e_u != nullptr, hn = noise != nullptr, pg = p0_in != nullptr;
+            ddim_update_1(x4.x, e4.x, hu, u4.x, cfg, hn, n4.x, sqrt_at, sqrt_aprev, dir_coef, sigma_t, sqrt_one_minus_at, temperature, pg, p4.x, o4.x);
+            ddim_update_1(x4.y, e4.y, hu, u4.y, cfg, hn, n4.y, sqrt_at, sqrt_aprev, dir_coef, sigma_t, sqrt_one_minus_at, temperature, pg, p4.y, o4.y);
+            ddim_update_1(x4.z, e4.z, hu, u4.z, cfg, hn, n4.z, sqrt_at, sqrt_aprev, dir_coef, sigma_t, sqrt_one_minus_at, temperature, pg, p4.z, o4.z);
+            ddim_update_1(x4.w, e4.w, hu, u4.w, cfg, hn, n4.w, sqrt_at, sqrt_aprev, dir_coef, sigma_t, sqrt_one_minus_at, temperature, pg, p4.w, o4.w);
+            reinterpret_cast<float4*>(x_prev)[i] = o4;
+            if (pred_x0) reinterpret_cast<float4*>(pred_x0)[i] = p4;
+        } else {
+            float p0 = p0_in ? p0_in[i] : 0.f, xp;
+            ddim_update_1(p0_in ? 0.f : x[i], e_c[i], e_u != nullptr, e_u ? e_u[i] : 0.f, cfg, noise != nullptr, noise ? noise[i] : 0.f,
+                          sqrt_at, sqrt_aprev, dir_coef, sigma_t, sqrt_one_minus_at, temperature, p0_in != nullptr, p0, xp);
+            x_prev[i] = xp;
+            if (pred_x0) pred_x0[i] = p0;
         }
-        float xv = x[i];
-        float p0 = __fdiv_rn(__fsub_rn(xv, __fmul_rn(sqrt_one_minus_at, e)), sqrt_at);
-        float dir = __fmul_rn(dir_coef, e);
-        float nz = 0.f;
-        if (noise) nz = __fmul_rn(__fmul_rn(sigma_t, noise[i]), temperature);
-        float xp = __fadd_rn(__fadd_rn(__fmul_rn(sqrt_aprev, p0), dir), nz);
-        x_prev[i] = xp;
-        pred_x0[i] = p0;
+    }
+}
+
+// ---- inpainting blend of ddim_sampling (ldm/diffusion/ddim.py:144-149) with q_sample (ldm/diffusion/ddpm.py:407-412) fused:
+//   img_orig = a[b] * x0 + c[b] * noise;   out = img_orig * mask + (1 - mask) * img
+// mask [B, Cm, HW] with Cm in {1, C} (broadcast over channels); separately rounded fp32 operations like the eager reference.
+__global__ void inpaint_blend_kernel(const float* __restrict__ x0, const float* __restrict__ noise, const float* __restrict__ a,
+                                     const float* __restrict__ c, const float* __restrict__ mask, const float* __restrict__ img,
+                                     int C, int Cm, long long HW, long long n, float* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
+    const long long per = (long long)C * HW;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / per, r = i - b * per;
+        const long long mi = Cm == 1 ? b * HW + r % HW : i;
+        const float m = mask[mi];
+        const float orig = __fadd_rn(__fmul_rn(a[b], x0[i]), __fmul_rn(c[b], noise[i]));
+        out[i] = __fadd_rn(__fmul_rn(orig, m), __fmul_rn(__fsub_rn(1.0f, m), img[i]));
     }
 }
 
@@ -521,16 +563,47 @@ int sdb_skinny_linear(const float* x, int M, int K, const float* W, const float*
     return check_launch("skinny_linear_kernel");
 }
 
+static int launch_ddim(const float* x, const float* e_cond, const float* e_uncond, float cfg_scale, const float* noise,
+                       const float* p0_in, float sqrt_at, float sqrt_aprev, float dir_coef, float sigma_t, float sqrt_one_minus_at,
+                       float temperature, float* x_prev, float* pred_x0, long long n, void* stream) {
+    const uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(e_cond) | reinterpret_cast<uintptr_t>(e_uncond) |
+                         reinterpret_cast<uintptr_t>(noise) | reinterpret_cast<uintptr_t>(p0_in) | reinterpret_cast<uintptr_t>(x_prev) |
+                         reinterpret_cast<uintptr_t>(pred_x0);
+    if ((al & 15) == 0 && n % 4 == 0) {
+        launch_pdl(ddim_step_kernel<4>, dim3(grid_for(n / 4, 256)), dim3(256), 0, (cudaStream_t)stream,
+            x, e_cond, e_uncond, cfg_scale, noise, p0_in, sqrt_at, sqrt_aprev, dir_coef, sigma_t, sqrt_one_minus_at, temperature, x_prev, pred_x0, n);
+    } else {
+        launch_pdl(ddim_step_kernel<1>, dim3(grid_for(n, 256)), dim3(256), 0, (cudaStream_t)stream,
+            x, e_cond, e_uncond, cfg_scale, noise, p0_in, sqrt_at, sqrt_aprev, dir_coef, sigma_t, sqrt_one_minus_at, temperature, x_prev, pred_x0, n);
+    }
+    return check_launch("ddim_step_kernel");
+}
+
 int sdb_ddim_step(const float* x, const float* e_cond, const float* e_uncond, float cfg_scale,
                   const float* noise, float sqrt_at, float sqrt_aprev, float dir_coef, float sigma_t,
                   float sqrt_one_minus_at, float temperature, float* x_prev, float* pred_x0, long long n,
                   void* stream) {
     SDB_REQUIRE(x && e_cond && x_prev && pred_x0 && n > 0, "ddim_step: bad args");
     SDB_REQUIRE(noise || sigma_t == 0.0f, "ddim_step: sigma_t != 0 needs a noise tensor");
-    launch_pdl(ddim_step_kernel, dim3(grid_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, 
-        x, e_cond, e_uncond, cfg_scale, noise, sqrt_at, sqrt_aprev, dir_coef, sigma_t, sqrt_one_minus_at,
-        temperature, x_prev, pred_x0, n);
-    return check_launch("ddim_step_kernel");
+    return launch_ddim(x, e_cond, e_uncond, cfg_scale, noise, nullptr, sqrt_at, sqrt_aprev, dir_coef, sigma_t, sqrt_one_minus_at,
+                       temperature, x_prev, pred_x0, n, stream);
+}
+
+int sdb_ddim_xprev(const float* pred_x0, const float* e_cond, const float* e_uncond, float cfg_scale, const float* noise,
+                   float sqrt_aprev, float dir_coef, float sigma_t, float temperature, float* x_prev, long long n, void* stream) {
+    SDB_REQUIRE(pred_x0 && e_cond && x_prev && n > 0, "ddim_xprev: bad args");
+    SDB_REQUIRE(noise || sigma_t == 0.0f, "ddim_xprev: sigma_t != 0 needs a noise tensor");
+    return launch_ddim(nullptr, e_cond, e_uncond, cfg_scale, noise, pred_x0, 1.0f, sqrt_aprev, dir_coef, sigma_t, 0.0f,
+                       temperature, x_prev, nullptr, n, stream);
+}
+
+int sdb_inpaint_blend(const float* x0, const float* noise, const float* a, const float* c, const float* mask, const float* img,
+                      int B, int C, int Cm, long long HW, float* out, void* stream) {
+    SDB_REQUIRE(x0 && noise && a && c && mask && img && out, "inpaint_blend: null pointer");
+    SDB_REQUIRE(B > 0 && C > 0 && HW > 0 && (Cm == 1 || Cm == C), "inpaint_blend: bad shape B=%d C=%d Cm=%d", B, C, Cm);
+    const long long n = (long long)B * C * HW;
+    launch_pdl(inpaint_blend_kernel, dim3(grid_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, x0, noise, a, c, mask, img, C, Cm, HW, n, out);
+    return check_launch("inpaint_blend_kernel");
 }
 
 int sdb_diag_gaussian(const float* moments, const float* noise, int N, int C, long long HW, float* mean, float* logvar,

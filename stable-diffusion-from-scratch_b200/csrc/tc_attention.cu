@@ -459,7 +459,10 @@ static int launch_attn(const sdb_attn_args* a, cudaStream_t st) {
         rc = make_tmap_bf16(&tmV, a->v, 4, dims, strv, box, es);
         if (rc) return rc;
     }
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {false};          // the attribute is per device
+    int cur_dev = 0;
+    if (cudaGetDevice(&cur_dev) != cudaSuccess || cur_dev < 0 || cur_dev >= 64) cur_dev = 0;
+    bool& attr_set = attr_set_dev[cur_dev];
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(tc_attention_kernel<DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) { set_last_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SDB_ERR_CUDA; }

@@ -851,7 +851,10 @@ static void pick_tile(int OW, int OH, int NB, int stride, int* tw, int* th, int*
 template <int BN>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcP& p, int m_tiles, cudaStream_t st) {
     using Cfg = TcCfg<BN>;
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {false};          // the attribute is per device
+    int cur_dev = 0;
+    if (cudaGetDevice(&cur_dev) != cudaSuccess || cur_dev < 0 || cur_dev >= 64) cur_dev = 0;
+    bool& attr_set = attr_set_dev[cur_dev];
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(tc_contract_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) { set_last_error("tc_contract: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SDB_ERR_CUDA; }
@@ -863,18 +866,24 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcP& 
 }
 
 static int sm_count_cached() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    static int n[64] = {0};          // per device: the launch goes to the CURRENT device
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (n[dev] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        n[dev] = v;
     }
-    return n;
+    return n[dev];
 }
 
 template <int BN, int EW>
 static int launch_tc_pair_ew(const CUtensorMap& tmA, const CUtensorMap& tmB, TcP& p, int m_tiles, cudaStream_t st) {
     using Cfg = Tc2Cfg<BN, EW>;
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {false};          // the attribute is per device
+    int cur_dev = 0;
+    if (cudaGetDevice(&cur_dev) != cudaSuccess || cur_dev < 0 || cur_dev >= 64) cur_dev = 0;
+    bool& attr_set = attr_set_dev[cur_dev];
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(tc_contract_pair_kernel<BN, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) { set_last_error("tc_contract(pair): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SDB_ERR_CUDA; }

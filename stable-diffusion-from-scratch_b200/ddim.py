@@ -54,9 +54,10 @@ class DDIMSampler(object):
         self.model = model
         self.ddpm_num_timesteps = model.num_timesteps
         self.schedule = schedule
-        # The reference always draws torch.randn in p_sample_ddim, even when sigma == 0 (util.py:264-267).
-        # The draw cannot change the result when sigma == 0; set True to also advance the RNG identically.
-        self.consume_rng_like_reference = False
+        # The reference always draws torch.randn in p_sample_ddim, even when sigma == 0 (util.py:264-267).  The draw cannot
+        # change the result when sigma == 0, but it advances the global RNG: anything seeded before `sample()` and drawn
+        # after it sees the reference's stream only if the draw is made here too.  Set False to skip the idle draws.
+        self.consume_rng_like_reference = True
 
     def register_buffer(self, name, attr):
         if type(attr) == torch.Tensor:
@@ -67,6 +68,7 @@ class DDIMSampler(object):
 
     def make_schedule(self, ddim_num_steps, ddim_discretize="uniform", ddim_eta=0., verbose=True):
         """ddim.py:25-54. Host-side, once per `sample`."""
+        self.__dict__.pop("_coef_cache", None)      # derived per-step coefficients belong to ONE schedule
         self.ddim_timesteps = make_ddim_timesteps(ddim_discr_method=ddim_discretize, num_ddim_timesteps=ddim_num_steps,
                                                   num_ddpm_timesteps=self.ddpm_num_timesteps, verbose=verbose)
         alphas_cumprod = self.model.alphas_cumprod
@@ -142,8 +144,7 @@ class DDIMSampler(object):
             ts = torch.full((b,), int(step), device=device, dtype=torch.long)
             if mask is not None:
                 assert x0 is not None
-                img_orig = self.model.q_sample(x0, ts)
-                img = img_orig * mask + (1. - mask) * img
+                img = self._inpaint_blend(x0, ts, mask, img)
             img, pred_x0 = self.p_sample_ddim(img, cond, ts, index=index, use_original_steps=ddim_use_original_steps,
                                               quantize_denoised=quantize_denoised, temperature=temperature,
                                               noise_dropout=noise_dropout, score_corrector=score_corrector,
@@ -158,6 +159,27 @@ class DDIMSampler(object):
                 intermediates['x_inter'].append(img)
                 intermediates['pred_x0'].append(pred_x0)
         return img, intermediates
+
+    def _inpaint_blend(self, x0, ts, mask, img):
+        """ddim.py:144-149: img_orig = model.q_sample(x0, ts); img = img_orig * mask + (1 - mask) * img.  When the model is
+        a LatentDiffusion-like object with the schedule buffers q_sample reads (ldm/diffusion/ddpm.py:407-412), q_sample and
+        the blend run as ONE kernel; q_sample's draw is torch.rand_like, exactly as the reference makes it.  Any other
+        `model.q_sample` is honoured as given and only the blend is fused."""
+        fused = getattr(self.model, "q_sample_coefficients", None)
+        if fused is not None:
+            a, c = fused(ts)
+            noise = torch.rand_like(x0)                      # ddpm.py:409 (uniform, as written)
+        else:
+            a = torch.ones((x0.shape[0],), device=x0.device)
+            c = torch.zeros((x0.shape[0],), device=x0.device)
+            noise = x0
+            x0 = self.model.q_sample(x0, ts)
+        f = lambda t: t.float().contiguous()
+        m = mask.to(x0.device)
+        if m.dim() == x0.dim() and m.shape[1] not in (1, x0.shape[1]):
+            raise ValueError("mask %s does not broadcast over x0 %s" % (tuple(m.shape), tuple(x0.shape)))
+        m = f(m.expand(x0.shape[0], m.shape[1], *x0.shape[2:])) if m.dim() == x0.dim() else f(m.expand_as(x0))
+        return ops.inpaint_blend(f(x0), f(noise), f(a), f(c), m, f(img))
 
     def coefficients(self, index, use_original_steps=False):
         """The fp32 scalars a_t, a_prev, sigma_t, sqrt(1-a_t) that ddim.py:191-194 broadcast to [b,1,1,1]."""
@@ -174,11 +196,7 @@ class DDIMSampler(object):
         the 50 SD DDIM-50 alphas land 1 ulp off IEEE — so calling the same routine is what keeps the update
         bit-identical to the CPU-executed reference; cached per (index, schedule).)"""
         key = (index, use_original_steps)
-        cache = self.__dict__.setdefault("_coef_cache", {})
-        tag = (id(self.ddim_alphas), id(self.ddim_sigmas))
-        if cache.get("tag") != tag:
-            cache.clear()
-            cache["tag"] = tag
+        cache = self.__dict__.setdefault("_coef_cache", {})      # dropped by make_schedule
         if key not in cache:
             a_t, a_prev, sigma_t, s1m = self.coefficients(index, use_original_steps)
             ta, tp, ts = torch.full((1, 1, 1, 1), a_t), torch.full((1, 1, 1, 1), a_prev), torch.full((1, 1, 1, 1), sigma_t)
@@ -214,23 +232,32 @@ class DDIMSampler(object):
                 e_t = e_uncond + unconditional_guidance_scale * (e_t - e_uncond)
                 e_uncond = None
             e_t = score_corrector.modify_score(self.model, e_t, x, t, c, **corrector_kwargs)
-        if quantize_denoised or noise_dropout > 0.:
-            raise NotImplementedError("sdb200 DDIMSampler: quantize_denoised / noise_dropout are outside the hot path")
-
         sqrt_at, sqrt_aprev, dir_coef, sigma_t, s1m = self.derived_coefficients(index, use_original_steps)
 
         noise = None
-        if sigma_t != 0.0 or self.consume_rng_like_reference:
+        if sigma_t != 0.0 or self.consume_rng_like_reference or noise_dropout > 0.:
             if repeat_noise:
                 noise = torch.randn((1, *x.shape[1:]), device=x.device).repeat(x.shape[0], *((1,) * (len(x.shape) - 1)))
             else:
                 noise = torch.randn(x.shape, device=x.device)
-            if sigma_t == 0.0:
-                noise = None
-        xf = x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous()
-        ef = e_t if (e_t.dtype == torch.float32 and e_t.is_contiguous()) else e_t.float().contiguous()
-        x_prev, pred_x0 = ops.ddim_step(xf, ef, sqrt_at, sqrt_aprev, dir_coef, sigma_t, s1m, e_uncond=e_uncond,
-                                        cfg_scale=unconditional_guidance_scale, noise=noise, temperature=temperature)
+        k_sigma, k_temp = sigma_t, temperature
+        if noise_dropout > 0.:
+            # ddim.py:202-204: dropout acts on the PRODUCT sigma_t * noise * temperature; the mask draw is torch's own RNG
+            # (host-library plumbing like randn), so the product is formed here and enters the kernel with unit coefficients
+            noise = torch.nn.functional.dropout(torch.full((1, 1, 1, 1), sigma_t, device=x.device) * noise * temperature, p=noise_dropout)
+            k_sigma, k_temp = 1.0, 1.0
+        elif sigma_t == 0.0:
+            noise = None
+        f = lambda t_: t_ if (t_ is None or (t_.dtype == torch.float32 and t_.is_contiguous())) else t_.float().contiguous()
+        xf, ef, uf, nf = f(x), f(e_t), f(e_uncond), f(noise)
+        x_prev, pred_x0 = ops.ddim_step(xf, ef, sqrt_at, sqrt_aprev, dir_coef, k_sigma, s1m, e_uncond=uf,
+                                        cfg_scale=unconditional_guidance_scale, noise=nf, temperature=k_temp)
+        if quantize_denoised:
+            # ddim.py:198-199: pred_x0 is replaced by the first stage's codebook projection before x_prev is formed
+            pred_x0, _, *_ = self.model.first_stage_model.quantize(pred_x0)
+            pred_x0 = f(pred_x0)
+            x_prev = ops.ddim_xprev(pred_x0, ef, sqrt_aprev, dir_coef, k_sigma, e_uncond=uf, cfg_scale=unconditional_guidance_scale,
+                                    noise=nf, temperature=k_temp)
         return x_prev, pred_x0
 
     @torch.no_grad()

@@ -307,7 +307,9 @@ class UNetModel(nn.Module):
         self.out = nn.Sequential(normalization(ch), nn.SiLU(), zero_module(nn.Conv2d(model_channels, out_channels, 3, padding=1)))
 
         self._packed = {}        # mode -> packed weights
-        self._ctx_cache = {}     # (mode, context identity) -> per-layer projected K/V
+        self._ctx_cache = {}     # (mode, block, id(context)) -> (weakref(context), version, projected K/V)
+        # a parent's load_state_dict (e.g. LatentDiffusion's) never calls the override below: drop the packed copies from a hook
+        self.register_load_state_dict_post_hook(lambda module, incompatible_keys: module._invalidate())
         self._kv_pinned = None   # graph mode: {id(block): projected K/V of the static context buffer}
         self._graphs = {}
         self._padbufs = {}       # (rows, width, d, dp) -> zero-initialised padded-head projection buffer
@@ -318,6 +320,8 @@ class UNetModel(nn.Module):
         self._ctx_cache = {}
         self._graphs = {}
         self._padbufs = {}
+        self.__dict__.pop("_param_list", None)
+        self.__dict__.pop("_fp_seen", None)
 
     def _padbuf(self, rows, width, d, dp, dev):
         """Persistent [rows, width] bf16 buffer for q/k/v heads stored padded from d to dp channels.  The GEMM
@@ -339,6 +343,21 @@ class UNetModel(nn.Module):
         r = super()._apply(fn, *a, **k)
         self._invalidate()
         return r
+
+    def _weights_fingerprint(self):
+        """Changes whenever a parameter is replaced or written in place (EMA `copy_to`, optimizer step, a parent module's
+        load_state_dict — which recurses through `_load_from_state_dict` and never reaches the override above)."""
+        ps = self.__dict__.get("_param_list")
+        if ps is None:
+            ps = self.__dict__["_param_list"] = list(self.parameters())
+        return (ps[0].data_ptr(), ps[0].device, sum(p._version for p in ps))
+
+    def _check_weights(self):
+        fp = self._weights_fingerprint()
+        if fp != self.__dict__.get("_fp_seen"):
+            if self.__dict__.get("_fp_seen") is not None:
+                self._invalidate()
+            self.__dict__["_fp_seen"] = fp
 
     def _res_blocks(self):
         for m in self.modules():
@@ -477,23 +496,40 @@ class UNetModel(nn.Module):
         out = engine.linear(o.reshape(B * T, Cc), P[("aout", id(ab))], residual=x.reshape(B * T, Cc), rows_per_item=T)
         return out.reshape(B, Hh, Ww, Cc)
 
-    def _kv_context(self, blk, P, mode, context):
-        """to_k / to_v of the (step-invariant) context, cached per context tensor."""
+    def _ctx_lookup(self, key, src):
+        """Cache entries are valid only for the SAME live tensor object, unmodified since: a data_ptr()/shape key alone
+        collides when the allocator hands a freed conditioning's address to the next prompt's."""
+        hit = self._ctx_cache.get(key)
+        if hit is not None and hit[0]() is src and hit[1] == src._version:
+            return hit[2]
+        return None
+
+    def _ctx_store(self, key, src, val):
+        if len(self._ctx_cache) > 256:
+            self._ctx_cache = {k: v for k, v in self._ctx_cache.items() if v[0]() is not None}
+            if len(self._ctx_cache) > 256:
+                self._ctx_cache.clear()
+        self._ctx_cache[key] = (weakref.ref(src), src._version, val)
+
+    def _kv_context(self, blk, P, mode, context, src=None):
+        """to_k / to_v of the (step-invariant) context, cached per LIVE context tensor (`src` = the caller's own tensor
+        object when `context` is a converted temporary of it)."""
         pinned = self._kv_pinned
         if pinned is not None:                       # CUDA-graph mode: projections live in their own graph (see _graph_forward)
             return pinned[id(blk)]
-        key = (mode, id(blk), context.data_ptr(), context._version, tuple(context.shape))
-        hit = self._ctx_cache.get(key)
+        src = context if src is None else src
+        key = (mode, id(blk), id(src))
+        hit = self._ctx_lookup(key, src)
         if hit is not None:
             return hit
         a2 = blk.attn2
         H, d = a2.heads, a2.dim_head
         B, Sk, Cc = context.shape
         if mode == "bf16":
-            cb = self._ctx_cache.get(("ctx_bf16", context.data_ptr(), context._version))
+            cb = self._ctx_lookup(("ctx_bf16", id(src)), src)
             if cb is None:
                 cb = ops.cast_concat(context.reshape(1, 1, B * Sk, Cc).contiguous(), None, out_dtype=torch.bfloat16).reshape(B * Sk, Cc)
-                self._ctx_cache[("ctx_bf16", context.data_ptr(), context._version)] = cb
+                self._ctx_store(("ctx_bf16", id(src)), src, cb)
             if self.dense_heads:
                 kv = engine.linear(cb, P[("kv2", id(blk))], out_dtype=torch.bfloat16, rows_per_item=Sk)                                   # [B*Sk, 2*H*d]
             else:
@@ -501,9 +537,7 @@ class UNetModel(nn.Module):
                 kv = engine.linear(cb, P[("kv2", id(blk))], out_dtype=torch.bfloat16, col_group=d, col_group_stride=dp, rows_per_item=Sk)   # [B*Sk, 2*H*dp]
         else:
             kv = engine.linear(context.reshape(B * Sk, Cc), P[("kv2", id(blk))], rows_per_item=Sk)                                      # [B*Sk, 2*H*d]
-        if len(self._ctx_cache) > 256:
-            self._ctx_cache.clear()
-        self._ctx_cache[key] = kv
+        self._ctx_store(key, src, kv)
         return kv
 
     def _tblock(self, blk, P, mode, t, B, S, context, final_dtype=torch.float32):
@@ -513,7 +547,7 @@ class UNetModel(nn.Module):
         Cc = H * d
         odt = engine.op_dtype(mode)
         Sk = context.shape[1]
-        kv = self._kv_context(blk, P, mode, context)
+        kv = self._kv_context(blk, P, mode, context, src=self.__dict__.get("_ctx_src"))
         if mode == "bf16" and self.dense_heads:
             # q / k / v are the plain projection outputs ([rows, H*d], heads side by side); the attention kernel's tensor maps
             # are d channels wide and TMA zero-fills the pad channels of each 64-channel tile.  Against the zero-padded layout
@@ -652,18 +686,25 @@ class UNetModel(nn.Module):
         x [N,C,H,W], timesteps [N] (int or float), context [N,S,context_dim] -> [N,out_channels,H,W] in x.dtype."""
         assert (y is not None) == (self.num_classes is not None), "must specify y if and only if the model is class-conditional"
         from ._lib import require_cuda
-        require_cuda(x, timesteps, context, y)
-        mode = self.compute_mode
-        xin = x.float().contiguous()
-        tin = timesteps.float().contiguous()
-        cin = context.float().contiguous() if context is not None else None
-        if y is not None:
-            assert y.shape == (x.shape[0],)
-            y = y.to(torch.int64).contiguous()
-        if self.use_cuda_graph and y is None and cin is not None:
-            out = self._graph_forward(xin, tin, cin, mode, ctx_src=context)
-        else:
-            out = self._forward_nhwc(xin, tin, cin, mode, y=y)
+        with torch.cuda.device(x.device):
+            require_cuda(x, timesteps, context, y)
+            self._check_weights()
+            mode = self.compute_mode
+            xin = x.float().contiguous()
+            tin = timesteps.float().contiguous()
+            cin = context.float().contiguous() if context is not None else None
+            if y is not None:
+                assert y.shape == (x.shape[0],)
+                y = y.to(torch.int64).contiguous()
+            if self.use_cuda_graph and y is None and cin is not None:
+                out = self._graph_forward(xin, tin, cin, mode, ctx_src=context)
+            else:
+                # K/V projections of the conditioning are cached against the CALLER's tensor object (cin may be a temporary)
+                self.__dict__["_ctx_src"] = context if cin is not context else None
+                try:
+                    out = self._forward_nhwc(xin, tin, cin, mode, y=y)
+                finally:
+                    self.__dict__["_ctx_src"] = None
         return out if x.dtype == torch.float32 else out.to(x.dtype)
 
     # ---- CUDA graph replay of one UNet call ------------------------------------------------------------

@@ -236,17 +236,65 @@ def skinny_linear(x, W, bias=None, act_in=0, act_out=0):
     return y
 
 
+def _f32c(name, t, like=None):
+    if t is None:
+        return
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise _lib.SdbError("%s must be a contiguous fp32 tensor (got %s, contiguous=%s)" % (name, t.dtype, t.is_contiguous()))
+    if like is not None and t.numel() != like.numel():
+        raise _lib.SdbError("%s has %d elements, expected %d" % (name, t.numel(), like.numel()))
+
+
 def ddim_step(x, e_cond, sqrt_at, sqrt_aprev, dir_coef, sigma_t, sqrt_one_minus_at, e_uncond=None, cfg_scale=1.0,
               noise=None, temperature=1.0):
-    """One fused DDIM update; the five scalars are the fp32 per-step coefficients (see DDIMSampler.derived_coefficients)."""
+    """One fused DDIM update; the five scalars are the fp32 per-step coefficients (see DDIMSampler.derived_coefficients).
+    Every tensor operand must be contiguous fp32 with x's element count (the kernel reads n fp32 values from each)."""
     require_cuda(x, e_cond, e_uncond, noise)
-    assert x.dtype == torch.float32 and e_cond.dtype == torch.float32 and x.is_contiguous() and e_cond.is_contiguous()
+    _f32c("x", x)
+    _f32c("e_cond", e_cond, x)
+    _f32c("e_uncond", e_uncond, x)
+    _f32c("noise", noise, x)
     x_prev = torch.empty_like(x)
     pred_x0 = torch.empty_like(x)
     check(_L().sdb_ddim_step(ptr(x), ptr(e_cond), ptr(e_uncond), float(cfg_scale), ptr(noise), float(sqrt_at), float(sqrt_aprev),
                              float(dir_coef), float(sigma_t), float(sqrt_one_minus_at), float(temperature), ptr(x_prev),
                              ptr(pred_x0), x.numel(), stream_ptr()), "ddim_step")
     return x_prev, pred_x0
+
+
+def ddim_xprev(pred_x0, e_cond, sqrt_aprev, dir_coef, sigma_t, e_uncond=None, cfg_scale=1.0, noise=None, temperature=1.0):
+    """x_prev from a GIVEN pred_x0 (quantize_denoised branch of p_sample_ddim, ldm/diffusion/ddim.py:198-205)."""
+    require_cuda(pred_x0, e_cond, e_uncond, noise)
+    _f32c("pred_x0", pred_x0)
+    _f32c("e_cond", e_cond, pred_x0)
+    _f32c("e_uncond", e_uncond, pred_x0)
+    _f32c("noise", noise, pred_x0)
+    x_prev = torch.empty_like(pred_x0)
+    check(_L().sdb_ddim_xprev(ptr(pred_x0), ptr(e_cond), ptr(e_uncond), float(cfg_scale), ptr(noise), float(sqrt_aprev),
+                              float(dir_coef), float(sigma_t), float(temperature), ptr(x_prev), pred_x0.numel(), stream_ptr()),
+          "ddim_xprev")
+    return x_prev
+
+
+def inpaint_blend(x0, noise, a, c, mask, img):
+    """(a[b]*x0 + c[b]*noise) * mask + (1 - mask) * img: q_sample + the mask blend of ddim_sampling in one kernel
+    (ldm/diffusion/ddim.py:144-149, ldm/diffusion/ddpm.py:407-412).  x0 / noise / img [B,C,H,W]; mask [B,1,H,W] or [B,C,H,W]."""
+    require_cuda(x0, noise, a, c, mask, img)
+    _f32c("x0", x0)
+    _f32c("noise", noise, x0)
+    _f32c("img", img, x0)
+    _f32c("a", a)
+    _f32c("c", c)
+    _f32c("mask", mask)
+    B, Cc = x0.shape[0], x0.shape[1]
+    HW = x0.numel() // (B * Cc)
+    Cm = mask.numel() // (B * HW)
+    if a.numel() != B or c.numel() != B or Cm * B * HW != mask.numel() or Cm not in (1, Cc):
+        raise _lib.SdbError("inpaint_blend: mask %s does not broadcast over x0 %s" % (tuple(mask.shape), tuple(x0.shape)))
+    out = torch.empty_like(x0)
+    check(_L().sdb_inpaint_blend(ptr(x0), ptr(noise), ptr(a), ptr(c), ptr(mask), ptr(img), B, Cc, Cm, HW, ptr(out), stream_ptr()),
+          "inpaint_blend")
+    return out
 
 
 def diag_gaussian(moments, noise=None):
@@ -400,7 +448,7 @@ def _tc_launch(a, what):
         check(-1, what)
     ws = None
     if need > 0:
-        ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+        ws = torch.empty(need, dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
         a.ws, a.ws_bytes = ws.data_ptr(), need
     check(lib.sdb_tc_contract(C.byref(a), stream_ptr()), what)
 

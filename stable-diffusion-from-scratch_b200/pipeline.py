@@ -71,6 +71,7 @@ class LatentDiffusion(nn.Module):
         self.register_buffer("betas", to_t(betas))
         self.register_buffer("alphas_cumprod", to_t(alphas_cumprod))
         self.register_buffer("alphas_cumprod_prev", to_t(alphas_cumprod_prev))
+        self.register_buffer("sqrt_alphas_cumprod", to_t(np.sqrt(alphas_cumprod)))           # ldm/diffusion/ddpm.py:212-213
         self.register_buffer("sqrt_one_minus_alphas_cumprod", to_t(np.sqrt(1. - alphas_cumprod)))
 
     @property
@@ -86,6 +87,23 @@ class LatentDiffusion(nn.Module):
                 cond = [cond]
             cond = {"c_crossattn": cond}
         return self.model(x_noisy, t, **cond)
+
+    def q_sample_coefficients(self, t):
+        """extract_into_tensor(sqrt_alphas_cumprod, t, .) and (sqrt_one_minus_alphas_cumprod, t, .) as two [B] fp32 vectors
+        (ldm/diffusion/ddpm.py:411-412; ldm/modules/diffusionmodules/util.py:96-99)."""
+        t = t.to(self.sqrt_alphas_cumprod.device)
+        return self.sqrt_alphas_cumprod.gather(-1, t).contiguous(), self.sqrt_one_minus_alphas_cumprod.gather(-1, t).contiguous()
+
+    @torch.no_grad()
+    def q_sample(self, x_start, t, noise=None):
+        """ldm/diffusion/ddpm.py:407-412 as written — the default draw is torch.rand_like (uniform), not randn —
+        on the fused q_sample kernel (sdb_q_sample): sqrt(a_t) * x_start + sqrt(1 - a_t) * noise per sample."""
+        from . import ops
+        if noise is None:
+            noise = torch.rand_like(x_start)
+        a, c = self.q_sample_coefficients(t)
+        out = ops.q_sample(x_start.float().contiguous(), noise.float().contiguous(), a, c)
+        return out if x_start.dtype == torch.float32 else out.to(x_start.dtype)
 
     @torch.no_grad()
     def decode_first_stage(self, z):

@@ -167,3 +167,119 @@ def test_ddim_trajectory_vs_reference(cuda):
         assert len(inter["x_inter"]) == t["n_inter"]
         # ... and against the reference's committed trajectory up to that host-libm difference
         assert rel(z, t["z"]) < 1e-6 and rel(inter["pred_x0"][-1], t["last_pred_x0"]) < 1e-6
+
+
+def test_ddim_inpainting_branch_vs_reference(cuda):
+    """mask / x0 branch of ddim_sampling (ldm/diffusion/ddim.py:144-149) against trajectories of the UNMODIFIED reference sampler
+    (tests/golden/ddim_mask.pt): q_sample + blend run as the fused sdb_inpaint_blend kernel, whole trajectory bit for bit
+    against the oracle sampler run here, and at the host-libm level against the committed reference trajectory."""
+    from oracle.make_golden import toy_model_fn
+    from sdb200.ddim import DDIMSampler
+    g = load_golden("ddim_mask.pt")
+
+    class Shim(R.ModelShim):
+        def apply_model(self, x, t, c):
+            return toy_model_fn(x.cpu(), t.cpu(), c.cpu()).cuda()
+
+    for key, t in g.items():
+        S = int(key.split(".S")[1].split(".")[0])
+        fixed = t["q_noise"]
+        shim = Shim(None, R.sd_alphas_cumprod(), device="cuda")
+        shim.betas = shim.betas.cuda()
+        base = shim.q_sample
+        shim.q_sample = lambda xs, ts, noise=None: base(xs.cpu(), ts.cpu(), noise=fixed).cuda()      # honoured as given: only the blend is fused
+        z, _ = DDIMSampler(shim).sample(S, 2, (4, 8, 8), conditioning=t["c"].cuda(), verbose=False, x_T=t["x_T"].cuda(), eta=0.,
+                                        mask=t["mask"].cuda(), x0=t["x0"].cuda())
+        orc_shim = R.ModelShim(toy_model_fn, R.sd_alphas_cumprod())
+        ob = orc_shim.q_sample
+        orc_shim.q_sample = lambda xs, ts, noise=None: ob(xs, ts, noise=fixed)
+        zo, _ = R.DDIMOracle(orc_shim).sample(S, 2, (4, 8, 8), conditioning=t["c"], eta=0., x_T=t["x_T"], mask=t["mask"], x0=t["x0"])
+        assert torch.equal(z.cpu(), zo), key
+        assert rel(z, t["z"]) < 1e-6, key
+
+
+def test_inpaint_blend_and_q_sample_fused(cuda):
+    """sdb_inpaint_blend with per-sample q_sample coefficients (the LatentDiffusion fast path) against the eager arithmetic of
+    ddim.py:146-149 + ddpm.py:411-412 on the same draws: bit-exact, for a [B,1,H,W] and a [B,C,H,W] mask; and
+    LatentDiffusion.q_sample (uniform default draw as the reference writes it) against the oracle's restatement."""
+    from sdb200 import ops
+    from sdb200.pipeline import LatentDiffusion
+    ld = LatentDiffusion(first_stage_config=False, unet=torch.nn.Linear(1, 1)).cuda()
+    B = 3
+    x0, img, noise = randn(B, 4, 16, 16, seed=1), randn(B, 4, 16, 16, seed=2), torch.rand(B, 4, 16, 16, generator=torch.Generator().manual_seed(3)).cuda()
+    ts = torch.tensor([981, 500, 1], device="cuda")
+    a, c = ld.q_sample_coefficients(ts)
+    shim = R.ModelShim(None, R.sd_alphas_cumprod())
+    want_q = shim.q_sample(x0.cpu(), ts.cpu(), noise=noise.cpu())
+    assert torch.equal(ld.q_sample(x0, ts, noise=noise).cpu(), want_q)
+    for cm in (1, 4):
+        mask = (randn(B, cm, 16, 16, seed=4) > 0).float() * 0.75
+        want = want_q * mask.cpu() + (1. - mask.cpu()) * img.cpu()
+        got = ops.inpaint_blend(x0, noise, a, c, mask.contiguous(), img)
+        assert torch.equal(got.cpu(), want), cm
+    torch.manual_seed(5)
+    u = torch.rand_like(x0)
+    torch.manual_seed(5)
+    assert torch.equal(ld.q_sample(x0, ts), ld.q_sample(x0, ts, noise=u))          # default draw = torch.rand_like (ddpm.py:409)
+
+
+def test_ddim_noise_dropout_quantize_and_rng(cuda):
+    """The optional branches of p_sample_ddim (ldm/diffusion/ddim.py:198-204) and the sampler's RNG consumption:
+    noise_dropout, quantize_denoised (duck-typed first_stage_model.quantize) against the eager arithmetic on the same
+    draws; after sample() at eta = 0 the CUDA generator has advanced exactly as if randn(shape) had been drawn every
+    step, which is what the reference does (noise_like, util.py:264-267)."""
+    from sdb200.ddim import DDIMSampler
+    fn = lambda x, t, c: 0.3 * x + 0.05
+    shim = R.ModelShim(fn, R.sd_alphas_cumprod(), device="cuda")
+    shim.betas = shim.betas.cuda()
+
+    class FS:
+        @staticmethod
+        def quantize(p):
+            return torch.round(p * 4) / 4, None, None
+    shim.first_stage_model = FS()
+    s = DDIMSampler(shim)
+    s.make_schedule(20, ddim_eta=0.7, verbose=False)
+    x = randn(2, 4, 8, 8, seed=7)
+    index = 11
+    ts = torch.full((2,), int(s.ddim_timesteps[index]), device="cuda")
+    a_t = torch.full((2, 1, 1, 1), s.ddim_alphas[index], device="cuda")
+    a_prev = torch.full((2, 1, 1, 1), s.ddim_alphas_prev[index], device="cuda")
+    sigma_t = torch.full((2, 1, 1, 1), s.ddim_sigmas[index], device="cuda")
+    s1m = torch.full((2, 1, 1, 1), s.ddim_sqrt_one_minus_alphas[index], device="cuda")
+    for kw in (dict(noise_dropout=0.25), dict(quantize_denoised=True), dict(quantize_denoised=True, noise_dropout=0.5, temperature=0.8)):
+        torch.manual_seed(11)
+        xp, p0 = s.p_sample_ddim(x, None, ts, index=index, **kw)
+        torch.manual_seed(11)
+        e_t = fn(x, ts, None)
+        pred_x0 = (x - s1m * e_t) / a_t.sqrt()
+        if kw.get("quantize_denoised"):
+            pred_x0 = FS.quantize(pred_x0)[0]
+        dir_xt = (1. - a_prev - sigma_t ** 2).sqrt() * e_t
+        noise = sigma_t * torch.randn(x.shape, device="cuda") * kw.get("temperature", 1.)
+        if kw.get("noise_dropout", 0.) > 0.:
+            noise = torch.nn.functional.dropout(noise, p=kw["noise_dropout"])
+        want = a_prev.sqrt() * pred_x0 + dir_xt + noise
+        assert torch.equal(p0, pred_x0) and torch.equal(xp, want), kw
+    # RNG consumption at eta = 0
+    smp = DDIMSampler(shim)
+    assert smp.consume_rng_like_reference
+    torch.manual_seed(3)
+    smp.sample(10, 2, (4, 8, 8), conditioning=None, verbose=False, x_T=x, eta=0.)
+    after = torch.randn(4, device="cuda")
+    torch.manual_seed(3)
+    for _ in range(10):
+        torch.randn((2, 4, 8, 8), device="cuda")
+    assert torch.equal(after, torch.randn(4, device="cuda"))
+
+
+def test_ddim_step_rejects_wrong_dtype(cuda):
+    """Every operand is read as n contiguous fp32 values: an fp16 e_uncond (what a UNet returns for fp16 latents) must be
+    rejected by the op and normalised by the sampler, never silently mis-read."""
+    from sdb200 import ops
+    from sdb200._lib import SdbError
+    x = randn(2, 4, 8, 8, seed=1)
+    with pytest.raises(SdbError):
+        ops.ddim_step(x, x, 1.0, 1.0, 0.5, 0.0, 0.5, e_uncond=x.half())
+    with pytest.raises(SdbError):
+        ops.ddim_step(x, x, 1.0, 1.0, 0.5, 0.3, 0.5, noise=x[:1])

@@ -71,3 +71,95 @@ def test_sd_vae_decode_full_size(cuda):
     assert psnr >= 40.0
     vae.micro_batch = 2
     assert torch.equal(vae.decode(z), img)
+
+
+# ---- pinned to the UNMODIFIED reference at the configs' own sizes (fixtures: oracle/make_golden.py --part sd_full) -------------
+def _sd_pipeline(mode):
+    from sdb200.pipeline import LatentDiffusion
+    g = load_golden("sd_traj.pt")
+    ld = LatentDiffusion(unet_config=g["cfg"], first_stage_config=g["ddconfig"], compute_mode=mode)
+    ld.model.diffusion_model.load_state_dict(W.make_state_dict(g["unet_key_shapes"], g["unet_seed"]))
+    r = ld.first_stage_model.load_state_dict(W.make_state_dict(g["vae_key_shapes"], g["vae_seed"]), strict=False)
+    assert not r.unexpected_keys
+    return g, ld.cuda()
+
+
+def test_c2_teacher_forced_eps_vs_reference(cuda):
+    """BASELINE configs[1] (C2): per-step eps at five steps of the REFERENCE's own DDIM-50 trajectory (reference x_t in,
+    reference e_t as the truth): <= 1e-5 in the fp32 mode, <= 1e-2 in the bf16 mode — the north-star's stated tolerances."""
+    g, ld = _sd_pipeline("fp32")
+    unet = ld.model.diffusion_model
+    ctx = W.seeded_randn((1, 77, 768), g["ctx_seed"]).cuda()
+    for mode, tol in (("fp32", 1e-5), ("bf16", 1e-2)):
+        unet.compute_mode = mode
+        errs = []
+        for st in g["steps"]:
+            e = ld.apply_model(st["x_t"].cuda(), torch.tensor([st["t"]], device="cuda"), ctx)
+            errs.append(rel(e, st["e_t"]))
+        print("C2 teacher-forced eps vs reference, %s mode, steps %s: %s" % (mode, [s["i"] for s in g["steps"]], ["%.2e" % v for v in errs]))
+        assert max(errs) <= tol, (mode, errs)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_c2_free_running_ddim50_image_psnr_vs_reference(cuda, mode):
+    """C2 end to end: DDIM-50 from the reference's x_T and context, then the 512x512 decode, free-running, against the
+    latent and the IMAGE the unmodified reference produced (PSNR >= 40 dB on the clamp-255 scale)."""
+    g, ld = _sd_pipeline(mode)
+    ld.model.diffusion_model.use_cuda_graph = (mode == "bf16")
+    x_T = W.seeded_randn((1, 4, 64, 64), g["x_T_seed"]).cuda()
+    ctx = W.seeded_randn((1, 77, 768), g["ctx_seed"]).cuda()
+    z, img = ld.txt2img(ctx, 1, ddim_steps=50, shape=(4, 64, 64), x_T=x_T)
+    psnr = R.psnr_255(img.cpu(), g["img_ref"])
+    ez, ei = rel(z, g["z_ref"]), rel(img, g["img_ref"])
+    print("C2 free-running DDIM-50 + decode vs reference, %s mode: latent rel-L2 %.3e, image rel-L2 %.3e, PSNR %.1f dB" % (mode, ez, ei, psnr))
+    assert psnr >= 40.0
+    if mode == "fp32":
+        assert ez <= 1e-4 and ei <= 1e-4          # 50 chained steps of a <= 1e-5 per-step error
+
+
+def test_c3_vae_decode_512_vs_reference(cuda):
+    """BASELINE configs[2] (C3) at its own size: 64x64x4 -> 512x512x3 against the reference Decoder's output.
+    fp32 mode <= 1e-5 (vs the float64 restatement and vs the fp32 reference), bf16 mode PSNR >= 40 dB; a batch of 16
+    (the config's batch) reproduces the single image bit for bit in every slot."""
+    from sdb200.autoencoder import AutoencoderKL
+    g = load_golden("vae_sd_z64.pt")
+    vae = AutoencoderKL(ddconfig=g["ddconfig"], embed_dim=4, compute_mode="fp32")
+    vae.load_state_dict(W.make_state_dict(g["key_shapes"], g["seed"]), strict=False)
+    vae = vae.cuda()
+    z = W.seeded_randn(g["z_shape"], g["z_seed"]).cuda()
+    img32 = vae.decode(z)
+    e64, eref = rel(img32, g["img_f64"]), rel(img32, g["img_ref"])
+    vae.compute_mode = "bf16"
+    img16 = vae.decode(z)
+    psnr = R.psnr_255(img16.cpu(), g["img_ref"])
+    print("C3 decode 512x512 vs reference: fp32 mode rel-L2 %.3e (vs f64 %.3e), bf16 mode rel-L2 %.3e, PSNR %.1f dB"
+          % (eref, e64, rel(img16, g["img_ref"]), psnr))
+    assert e64 <= 1e-5 and eref <= 1e-5
+    assert psnr >= 40.0
+    img_b = vae.decode(z.repeat(16, 1, 1, 1))
+    assert img_b.shape == (16, 3, 512, 512)
+    assert all(torch.equal(img_b[i], img16[0]) for i in range(16))
+
+
+def test_c5_unet_96_vs_reference(cuda):
+    """BASELINE configs[4] (C5) at its own size: one UNet step on a 96x96x4 latent (9216 tokens at the top level) against the
+    unmodified reference's eps; fp32 <= 1e-5, bf16 <= 1e-2; CUDA-graph replay and a batch of 4 reproduce it."""
+    from sdb200.openai_model import UNetModel
+    g = load_golden("unet_sd_96.pt")
+    net = UNetModel(**g["cfg"], compute_mode="fp32")
+    net.load_state_dict(W.make_state_dict(g["key_shapes"], g["seed"]))
+    net = net.cuda()
+    x = W.seeded_randn(g["x_shape"], g["x_seed"]).cuda()
+    ctx = W.seeded_randn(g["ctx_shape"], g["ctx_seed"]).cuda()
+    t = g["t"].cuda()
+    e32 = net(x, t, ctx)
+    net.compute_mode = "bf16"
+    e16 = net(x, t, ctx)
+    print("C5 96x96 UNet step vs reference: fp32 mode %.3e (vs f64 %.3e), bf16 mode %.3e"
+          % (rel(e32, g["eps_ref"]), rel(e32, g["eps_f64"]), rel(e16, g["eps_ref"])))
+    assert rel(e32, g["eps_ref"]) <= 1e-5 and rel(e32, g["eps_f64"]) <= 1e-5
+    assert rel(e16, g["eps_ref"]) <= 1e-2
+    net.use_cuda_graph = True
+    assert torch.equal(net(x, t, ctx), e16)
+    eb = net(x.repeat(4, 1, 1, 1), t.repeat(4), ctx.repeat(4, 1, 1))
+    assert all(torch.equal(eb[i], e16[0]) for i in range(4))

@@ -195,3 +195,107 @@ def test_bench_reference_arm_line(monkeypatch, capsys):
     monkeypatch.setenv("RANK", "1")
     bench.main()
     assert capsys.readouterr().out.strip() == ""
+
+
+def _tiny_unet():
+    from sdb200.openai_model import UNetModel
+    return UNetModel(image_size=8, in_channels=4, model_channels=32, out_channels=4, num_res_blocks=1, attention_resolutions=[1],
+                     num_heads=2, use_spatial_transformer=True, context_dim=8, channel_mult=(1,))
+
+
+def test_context_cache_is_keyed_on_the_live_tensor():
+    """The cross-attention K/V cache must not confuse a new conditioning tensor with a freed one that had the same address,
+    shape and version (data_ptr()-keyed entries collided after the allocator recycled the block)."""
+    net = _tiny_unet()
+    a = torch.zeros(2, 7, 8)
+    key = ("bf16", 1234, id(a))
+    net._ctx_store(key, a, "kv-of-a")
+    assert net._ctx_lookup(key, a) == "kv-of-a"
+    b = torch.zeros(2, 7, 8)
+    assert net._ctx_lookup(key, b) is None                    # same shape / version, different object
+    a.add_(1)
+    assert net._ctx_lookup(key, a) is None                    # modified in place since it was projected
+    net._ctx_store(key, a, "kv-of-a2")
+    del a
+    import gc
+    gc.collect()
+    c = torch.zeros(2, 7, 8)
+    assert net._ctx_lookup(("bf16", 1234, id(c)), c) is None  # even if id() / the address is recycled, the weakref is dead
+    for i in range(400):                                      # bounded: dead entries are dropped
+        t = torch.zeros(1)
+        net._ctx_store(("k", i), t, i)
+    assert len(net._ctx_cache) <= 257
+
+
+def test_packed_weights_are_invalidated_through_a_parent_module():
+    """Packed copies / graphs must be dropped when a checkpoint is loaded through a PARENT (nn.Module.load_state_dict recurses
+    via _load_from_state_dict and never calls the child's override), when .to() is applied to the parent, and when a
+    parameter is written in place (EMA copy_to)."""
+    from sdb200.autoencoder import AutoencoderKL
+    from sdb200.pipeline import LatentDiffusion
+    vae_cfg = dict(double_z=True, z_channels=4, resolution=16, in_channels=3, out_ch=3, ch=32, ch_mult=(1,), num_res_blocks=1,
+                   attn_resolutions=[], dropout=0.0)
+    ld = LatentDiffusion(unet=_tiny_unet(), first_stage_model=AutoencoderKL(ddconfig=vae_cfg, embed_dim=4))
+    unet, vae = ld.model.diffusion_model, ld.first_stage_model
+
+    def poison():
+        unet._packed = {"bf16": "stale"}
+        unet._graphs = {"k": "stale"}
+        vae.decoder._packed = {"bf16": "stale"}
+        vae.encoder._packed = {"bf16": "stale"}
+        vae._pq = ("stale", None)
+        vae._q = ("stale", None)
+
+    def clean():
+        return unet._packed == {} and unet._graphs == {} and vae.decoder._packed == {} and vae.encoder._packed == {}
+
+    poison()
+    ld.load_state_dict(ld.state_dict())
+    assert clean()
+    poison()
+    ld.to(torch.float32)                                       # _apply on the parent
+    assert clean() and vae._pq is None and vae._q is None
+    # in-place parameter update: the fingerprint changes, the next forward re-packs
+    unet._check_weights()
+    unet._packed = {"bf16": "stale"}
+    unet._check_weights()
+    assert unet._packed == {"bf16": "stale"}                    # nothing changed: kept
+    with torch.no_grad():
+        unet.out[2].weight.mul_(0.5)
+    unet._check_weights()
+    assert unet._packed == {}
+    vae.decoder._check_weights()
+    vae.decoder._packed = {"bf16": "stale"}
+    with torch.no_grad():
+        vae.decoder.conv_in.weight.add_(1.0)
+    vae.decoder._check_weights()
+    assert vae.decoder._packed == {}
+    fp0 = (vae.post_quant_conv.weight.data_ptr(), vae.post_quant_conv.weight._version)
+    with torch.no_grad():
+        vae.post_quant_conv.weight.add_(1.0)
+    assert (vae.post_quant_conv.weight.data_ptr(), vae.post_quant_conv.weight._version) != fp0     # what _packed_1x1 keys on
+
+
+def test_sampler_defaults_and_coefficient_cache():
+    """consume_rng_like_reference defaults to the reference's behaviour; the derived-coefficient cache belongs to one
+    schedule (make_schedule drops it) instead of being tagged by recyclable id()s."""
+    from oracle import restate as R
+    from sdb200.ddim import DDIMSampler
+    shim = R.ModelShim(None, R.sd_alphas_cumprod())
+    s = DDIMSampler(shim)
+    assert s.consume_rng_like_reference is True
+    s.make_schedule(50, ddim_eta=0.0, verbose=False)
+    c0 = s.derived_coefficients(10)
+    assert c0[3] == 0.0
+    s.make_schedule(50, ddim_eta=1.0, verbose=False)
+    c1 = s.derived_coefficients(10)
+    assert c1[3] > 0.0 and c1[2] != c0[2]                      # sigma and the direction coefficient follow the new eta
+    s.make_schedule(20, ddim_eta=0.0, verbose=False)
+    assert s.derived_coefficients(10)[0] != c0[0]
+
+
+def test_ops_reject_foreign_devices():
+    """require_cuda: CPU tensors are refused (no fallback) — the device-binding checks need two GPUs and live in the gpu tests."""
+    from sdb200 import _lib
+    with pytest.raises(_lib.SdbError):
+        _lib.require_cuda(torch.zeros(1))

@@ -37,6 +37,29 @@ def test_vae_restatement_matches_reference(name):
     assert R.rel_l2(g["img_ref"], g["img_f64"]) < 1e-5
 
 
+def test_full_size_fixtures_match_reference():
+    """The fixtures of BASELINE configs C2 / C3 / C5 AT THEIR OWN SIZE (oracle/make_golden.py --part sd_full ran the unmodified
+    reference: DDIM-50 trajectory + 512x512 decode, a 64x64-latent decode, a 96x96-latent UNet step): the restatement
+    reproduces one stored trajectory step, and the recorded restatement-vs-reference errors are at the fp32 noise floor."""
+    g = load_golden("sd_traj.pt")
+    assert g["restate_err"] < 1e-5 and g["restate_err_img"] < 1e-5
+    assert [s["i"] for s in g["steps"]] == [0, 12, 25, 37, 49] and len(g["all_t"]) == 50 and g["all_t"][0] == 981 and g["all_t"][-1] == 1
+    assert tuple(g["img_ref"].shape) == (1, 3, 512, 512) and tuple(g["z_ref"].shape) == (1, 4, 64, 64)
+    assert float((g["img_ref"].abs() <= 1).float().mean()) > 0.9          # PSNR on the clamp-255 scale is not saturated
+    st = g["steps"][2]
+    sd = W.make_state_dict(g["unet_key_shapes"], g["unet_seed"])
+    ctx = W.seeded_randn((1, 77, 768), g["ctx_seed"])
+    with torch.no_grad():
+        e = R.unet_forward(sd, g["cfg"], st["x_t"], torch.tensor([st["t"]]), ctx)
+    assert R.rel_l2(e, st["e_t"]) < 1e-5
+    # the trajectory's first input is the seeded x_T, and DDIM's update links consecutive stored quantities
+    assert torch.equal(g["steps"][0]["x_t"], W.seeded_randn((1, 4, 64, 64), g["x_T_seed"]))
+    gv = load_golden("vae_sd_z64.pt")
+    assert gv["restate_err"] < 1e-5 and R.rel_l2(gv["img_ref"], gv["img_f64"]) < 1e-5 and tuple(gv["img_ref"].shape) == (1, 3, 512, 512)
+    g9 = load_golden("unet_sd_96.pt")
+    assert g9["restate_err"] < 1e-5 and R.rel_l2(g9["eps_ref"], g9["eps_f64"]) < 1e-5 and tuple(g9["eps_ref"].shape) == (1, 4, 96, 96)
+
+
 @pytest.mark.parametrize("name", ["unet_var_legacy", "unet_var_neworder"])
 def test_unet_variant_restatement_matches_reference(name):
     """'next' row f4: AttentionBlock (both attention orders), scale-shift norm, resblock_updown, class conditioning."""
