@@ -292,6 +292,35 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t mask) {
                  ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 
+// ---- TMA stores (shared::cta -> global, bulk async-group completion) and rank-5 tile loads ---------------------
+// The epilogue's output / residual tensor maps are rank 5: (column, w, h, image, split) for a conv, (column, row, 0, 0, split)
+// for a GEMM; out-of-bounds elements of a box are clipped on store and zero-filled on load, so edge tiles need no predicates.
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* tm, uint32_t src_smem, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+        ::"l"(tm), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// at most N of this thread's most recent bulk groups may still be READING their shared-memory source
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+// ... may still be in flight at all (global writes performed)
+template <int N>
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_load_5d(uint32_t dst_smem, const CUtensorMap* tm, uint32_t bar_smem, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst_smem), "l"(tm), "r"(bar_smem), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_a(uint32_t bar_smem, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sts128f(uint32_t saddr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // named barrier among a subset of warps
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

@@ -42,6 +42,10 @@ struct TcP {
     int tiles_n;
     int m_pairs;            // pair kernel: number of 256-row tile pairs
     int off32;              // every element offset into out / residual / workspace fits 32 bits (the fast epilogue's addressing)
+    int stages;             // pair kernel: depth of the operand ring (what is left of shared memory after the epilogue staging)
+    int epi_tma;            // pair kernel: 1 = the epilogue stages 32 x 32 boxes in swizzled smem and moves them with TMA
+    int epi_nbuf;           //   staging boxes per epilogue warp (2; 3 when a residual tile is prefetched two chunks ahead)
+    int epi_bw, epi_bh;     //   conv: the 32 rows of a lane quarter are the pixel box bw x bh x 32/(bw*bh) of the tile
     // conv
     int conv;
     int kw, stride, pad_h, pad_w;
@@ -596,15 +600,24 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 //   warp 2 : TMEM allocator
 //   warps 4..4+EW-1 : epilogue, EW/4 warps per TMEM lane quarter (warp & 3), interleaved 32-column chunks.
 // EW = 8 in the product; 16 exists for the measurement build only (see launch_tc_pair).
+constexpr int TC2_MAX_STAGES = 8;
+constexpr int TC2_SMEM_LIMIT = 232448;            // 227 KB: the per-CTA dynamic shared memory limit of sm_100
+constexpr int TEPI_BOX_BYTES = 4096;              // TMA epilogue: one staged box = 32 rows x 128 B (fp32) or 32 rows x 64 B (bf16, half used)
+
 template <int BN, int EW>
 struct Tc2Cfg {
     static constexpr int THREADS = 128 + 32 * EW;
     static constexpr int B_HALF_BYTES = (BN / 2) * TC_BK * 2;
     static constexpr int STAGE_BYTES = TC_A_BYTES + B_HALF_BYTES;       // per CTA
-    static constexpr int STAGES_RAW = (184 * 1024 - (EW - 8) * EPI_WARP_BYTES) / STAGE_BYTES;
-    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int ACC_STRIDE = 256;                                // TMEM columns between the two accumulators
-    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 512 + BN * 4 + EW * EPI_WARP_BYTES;
+    // layout: [<= 1023 alignment slack][ring: stages x (A | B half)][512 B barriers][2 x BN bias floats][pad to 1024][epilogue staging]
+    static constexpr int FIXED_BYTES = 1024 + 512 + 2 * BN * 4 + 1024;
+    __host__ __device__ static constexpr int staging_bytes(int epi_tma, int nbuf) { return epi_tma ? EW * nbuf * TEPI_BOX_BYTES : EW * EPI_WARP_BYTES; }
+    __host__ static int stages_for(int staging) {
+        int st = (TC2_SMEM_LIMIT - FIXED_BYTES - staging) / STAGE_BYTES;
+        return st > TC2_MAX_STAGES ? TC2_MAX_STAGES : st;
+    }
+    __host__ static int smem_bytes(int stages, int staging) { return FIXED_BYTES + stages * STAGE_BYTES + staging; }
 };
 
 template <int BN, int EW>

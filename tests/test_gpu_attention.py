@@ -59,3 +59,23 @@ def test_attention_tc_large_logits(cuda):
     v = randn(B, S, H, d, seed=6).to(torch.bfloat16)
     out = ops.attention_tc(q, k, v, B, H, S, S, d, dp, 0.5, (S * H * d, H * d, d), (S * H * d, H * d, d), (S * H * d, H * d, d))
     assert rel(out, _ref(q, k, v, 0.5)) < 1e-2
+
+
+def test_attention_tc_9216_tokens(cuda):
+    """BASELINE configs[4] (96x96 latent): S = 9216 self-attention at d = 40, 72 key tiles per query tile, against fp64 math
+    (computed per head to bound the checker's memory: one 9216 x 9216 fp64 score matrix is 680 MB)."""
+    from sdb200 import ops
+    B, H, S, d, dp = 1, 8, 9216, 40, 64
+    q = randn(B, S, H, d, seed=11).to(torch.bfloat16)
+    k = randn(B, S, H, d, seed=12).to(torch.bfloat16)
+    v = randn(B, S, H, d, seed=13).to(torch.bfloat16)
+    scale = d ** -0.5
+    C = H * d
+    out = ops.attention_tc(q, k, v, B, H, S, S, d, dp, scale, (S * C, C, d), (S * C, C, d), (S * C, C, d), dense=True)
+    worst = 0.0
+    for h in range(H):
+        ref = _ref(q[:, :, h:h + 1], k[:, :, h:h + 1], v[:, :, h:h + 1], scale)
+        worst = max(worst, rel(out[:, :, h * d:(h + 1) * d], ref))
+        del ref
+    print("attention S=9216 d=40: worst per-head rel-L2 %.3e" % worst)
+    assert worst < 1e-2

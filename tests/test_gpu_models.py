@@ -35,6 +35,29 @@ def test_unet_eps_parity(cuda, name, mode):
     assert e_ref <= EPS_TOL[mode] and e_64 <= EPS_TOL[mode]
 
 
+def test_unet_context_cache_survives_freed_and_reallocated_conditioning(cuda):
+    """prompt 1's conditioning is freed, prompt 2's same-shaped conditioning is handed the same address by
+    the caching allocator (and has _version 0 again).  The eager path's K/V cache must project prompt 2 afresh: the output
+    has to equal a fresh model's, for fp32 contexts and for contexts that need a dtype conversion."""
+    g = load_golden("unet_tiny.pt")
+    x = W.seeded_randn(g["x_shape"], g["seed"] + 1).cuda()
+    t = g["t"].cuda()
+    for dt in (torch.float32, torch.float16):
+        net = _unet(g, "bf16")
+        ctx_a = W.seeded_randn(g["ctx_shape"], 1001).cuda().to(dt)
+        ptr_a = ctx_a.data_ptr()
+        out_a = net(x, t, ctx_a)
+        del ctx_a
+        ctx_b = (W.seeded_randn(g["ctx_shape"], 1002).cuda() * 2).to(dt)
+        recycled = ctx_b.data_ptr() == ptr_a
+        out_b = net(x, t, ctx_b)
+        fresh = _unet(g, "bf16")(x, t, ctx_b)
+        print("context cache: dtype %s, address recycled by the allocator: %s" % (dt, recycled))
+        assert torch.equal(out_b, fresh)
+        assert not torch.equal(out_b, out_a)
+        assert torch.equal(net(x, t, ctx_b), out_b)           # and the second call hits the cache with the same result
+
+
 @pytest.mark.parametrize("name", ["unet_var_legacy", "unet_var_neworder"])
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
 def test_unet_variant_eps_parity(cuda, name, mode):
