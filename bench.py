@@ -37,6 +37,10 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--ddim-steps", type=int, default=DDIM_STEPS)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c5", "c4-strong"],
+                    help="BASELINE.json config: c2 = DDIM-50 + decode, batch 8 per GPU (the headline, default); c3 = VAE decode "
+                         "64x64x4 -> 512x512x3, batch 16; c5 = one UNet step on a 96x96 latent, batch sweep 1..32; c4-strong = the "
+                         "full pipeline at a FIXED global batch of 64 sharded over the GPUs (strong scaling)")
     return ap.parse_args()
 
 
@@ -178,7 +182,7 @@ def run_sdb200(a):
     ld = LatentDiffusion(compute_mode=a.mode)
     # random-init weights; zero_module'd layers re-initialised so eps is not identically 0
     for m in ld.modules():
-        if isinstance(m, (torch.nn.Conv2d, torch.nn.Linear)) and float(m.weight.abs().max()) == 0.0:
+        if isinstance(m, (torch.nn.Conv2d, torch.nn.Linear)) and float(m.weight.detach().abs().max()) == 0.0:
             m.reset_parameters()
     ld = ld.to(dev)
     unet = ld.model.diffusion_model
@@ -243,7 +247,7 @@ def run_sdb200(a):
     ms, ms_e2e = float(t[0]), float(t[1])
 
     # ---- UNet step latency + roofline of the dominant kernel (tcgen05 contraction), device events ----
-    roof, unet_ms, launches_per_unet = None, None, None
+    roof, roof_hbm, unet_ms, launches_per_unet = None, None, None, None
     if rank == 0:
         unet.use_cuda_graph = not a.no_graph
         tt = torch.full((B,), 500, device=dev, dtype=torch.long)
@@ -257,7 +261,8 @@ def run_sdb200(a):
         e1.record()
         torch.cuda.synchronize()
         unet_ms = e0.elapsed_time(e1) / 10
-        roof, launches_per_unet = roofline_pass(unet, x_dev, tt, c_dev, a.mode)
+        unet.use_cuda_graph = False
+        roof, roof_hbm, launches_per_unet = roofline_pass(lambda: unet(x_dev, tt, c_dev), "unet")
         unet.use_cuda_graph = not a.no_graph
 
     if rank == 0:
@@ -286,6 +291,7 @@ def run_sdb200(a):
             "gpu_launches": gl,
             "clocks": sampler.summary(),
             "roofline": roof,
+            "roofline_hbm": roof_hbm,
             "peaks": {"bf16_tflops": tf_peak, "hbm_gbs": hbm_peak, "source": which},
         }
         if not a.skip_cpu_baseline:
@@ -299,55 +305,105 @@ def run_sdb200(a):
         dist.destroy_process_group()
 
 
-def roofline_pass(unet, x, t, ctx, mode):
-    """One eager UNet call with CUDA events around every tcgen05 contraction launch (the dominant kernel):
-    achieved = algorithmic FLOP (2*M*N*K*taps, from the launch arguments) / summed launch durations."""
+def roofline_pass(run, label):
+    """One eager call of `run` with CUDA events around every launch of (a) the tcgen05 contraction — the dominant kernel — and
+    (b) the GroupNorm / LayerNorm kernels, the bandwidth class.  Tensor roofline: achieved = algorithmic FLOP (2*M*N*K*taps,
+    from the launch arguments) / summed launch durations, against the measured sustained bf16 peak.  HBM roofline: achieved =
+    algorithmic bytes (each element read once as fp32 and written once in the output dtype, plus the raw bf16 copy when the
+    same pass emits one) / summed launch durations, against the measured copy bandwidth."""
     import torch
-    from sdb200 import _lib, ops
+    from sdb200 import _lib
     lib = _lib.load()
-    unet.use_cuda_graph = False
-    recs = []
-    orig = lib.sdb_tc_contract
+    tc, bw = [], []
+    names = ("sdb_tc_contract", "sdb_groupnorm_nhwc", "sdb_groupnorm_from_colstats", "sdb_layernorm")
+    orig = {n: getattr(lib, n) for n in names}
 
-    def wrapped(argp, stream):
+    def ev_pair():
+        return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def w_tc(argp, stream):
         a = argp._obj
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0, e1 = ev_pair()
         e0.record()
-        rc = orig(argp, stream)
+        rc = orig["sdb_tc_contract"](argp, stream)
         e1.record()
-        recs.append((2.0 * a.M * a.N * a.K, e0, e1))
+        tc.append((2.0 * a.M * a.N * a.K, e0, e1))
+        return rc
+
+    def w_gn(*args):          # x0, C0, x1, C1, N, HW, groups, eps, gamma, beta, gbs, act, exact, out, out_dtype, raw, ...
+        e0, e1 = ev_pair()
+        e0.record()
+        rc = orig["sdb_groupnorm_nhwc"](*args)
+        e1.record()
+        elems = float(args[4]) * args[5] * (args[1] + args[3])
+        bw.append((elems * (4 + (2 if args[14] == 1 else 4) + (2 if args[15] else 0)), e0, e1, "gn"))
+        return rc
+
+    def w_gc(*args):          # x0, C0, cs0, lay0, x1, C1, cs1, lay1, N, HW, groups, eps, gamma, beta, gbs, act, exact, out, out_dtype, raw, ...
+        e0, e1 = ev_pair()
+        e0.record()
+        rc = orig["sdb_groupnorm_from_colstats"](*args)
+        e1.record()
+        elems = float(args[8]) * args[9] * (args[1] + args[5])
+        bw.append((elems * (4 + (2 if args[18] == 1 else 4) + (2 if args[19] else 0)), e0, e1, "gn_colstats"))
+        return rc
+
+    def w_ln(*args):          # x, rows, C, eps, gamma, beta, out, out_dtype, stream
+        e0, e1 = ev_pair()
+        e0.record()
+        rc = orig["sdb_layernorm"](*args)
+        e1.record()
+        bw.append((float(args[1]) * args[2] * (4 + (2 if args[7] == 1 else 4)), e0, e1, "ln"))
         return rc
 
     for _ in range(2):
-        unet(x, t, ctx)
+        run()
     torch.cuda.synchronize()
     l0 = lib.sdb_launch_count()
-    lib.sdb_tc_contract = wrapped
+    lib.sdb_tc_contract, lib.sdb_groupnorm_nhwc, lib.sdb_groupnorm_from_colstats, lib.sdb_layernorm = w_tc, w_gn, w_gc, w_ln
     try:
         # park the device behind a ~0.1 s spin so the host enqueues the whole call ahead of it: the events then
         # bracket kernel execution only, not host launch gaps
         torch.cuda._sleep(int(2e8))
-        unet(x, t, ctx)
+        run()
         torch.cuda.synchronize()
     finally:
-        lib.sdb_tc_contract = orig
+        for n in names:
+            setattr(lib, n, orig[n])
     launches = lib.sdb_launch_count() - l0
-    if not recs:
-        return None, launches
-    flop = sum(r[0] for r in recs)
-    ms = sum(r[1].elapsed_time(r[2]) for r in recs)
-    tf_peak, _, which = peaks()
-    ach = flop / (ms / 1000.0) / 1e12
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_tc_traffic.json")      # ncu dram bytes per launch of the same kernels (tools/gpu_round.sh)
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp))["dram_bytes_per_launch"]
-        except Exception:
-            traffic = None
-    return ({"bound": "tensor", "kernel": "tc_contract_kernel (tcgen05 implicit-GEMM conv + GEMM)", "achieved": ach,
-             "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": traffic, "launches": len(recs),
-             "sum_ms": ms, "algorithmic_gflop": flop / 1e9, "peak_source": which + " (sustained cuBLAS bf16)"}, launches)
+    tf_peak, hbm_peak, which = peaks()
+    roof = roof_hbm = None
+    if tc:
+        flop = sum(r[0] for r in tc)
+        ms = sum(r[1].elapsed_time(r[2]) for r in tc)
+        ach = flop / (ms / 1000.0) / 1e12
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r02_tc_traffic.json")      # ncu dram bytes per launch of the same kernels
+        if not os.path.exists(tp):
+            tp = os.path.join(ROOT, "profiles", "r01_tc_traffic.json")
+        if os.path.exists(tp) and label == "unet":
+            try:
+                traffic = json.load(open(tp))["dram_bytes_per_launch"]
+            except Exception:
+                traffic = None
+        roof = {"bound": "tensor", "kernel": "tc_contract_pair_kernel / tc_contract_kernel (tcgen05 implicit-GEMM conv + GEMM), %s" % label,
+                "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": traffic, "launches": len(tc),
+                "sum_ms": ms, "algorithmic_gflop": flop / 1e9, "peak_source": which + " (sustained cuBLAS bf16)"}
+    if bw:
+        by, ms = sum(r[0] for r in bw), sum(r[1].elapsed_time(r[2]) for r in bw)
+        ach = by / (ms / 1000.0) / 1e9
+        per = {}
+        for b_, e0, e1, kind in bw:
+            d = per.setdefault(kind, [0.0, 0.0, 0])
+            d[0] += b_
+            d[1] += e0.elapsed_time(e1)
+            d[2] += 1
+        roof_hbm = {"bound": "hbm", "kernel": "GroupNorm(+SiLU) / LayerNorm kernels (gn_apply, gn_cluster, layernorm), %s" % label,
+                    "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "launches": len(bw),
+                    "sum_ms": ms, "algorithmic_mbytes": by / 1e6, "peak_source": which + " (device copy)",
+                    "by_kernel": {k: {"GB/s": v[0] / (v[1] / 1000.0) / 1e9, "ms": v[1], "launches": v[2]} for k, v in per.items()},
+                    "convention": "fp32 read once + output written once (bf16 operand, + the raw bf16 copy when emitted)"}
+    return roof, roof_hbm, launches
 
 
 def main():

@@ -255,6 +255,10 @@ int sdb_tc_contract(const sdb_tc_args* args /* host */, void* stream);
  * (cta_group::2, 256 x BN tiles) for block_n >= 128 [default], 0 = one-CTA 128 x BN kernel everywhere.
  * Returns the previous setting. */
 int sdb_tc_set_pair_kernel(int enable);
+/* Tuning switch (measurement only, bit-identical results either way): 1 = the CTA-pair kernel's epilogue stages 32 x 32 boxes
+ * in swizzled shared memory and moves them with TMA (cp.async.bulk.tensor stores, residual tiles by TMA loads) whenever the
+ * output layout allows [default], 0 = register-store epilogue everywhere.  Returns the previous setting. */
+int sdb_tc_set_tma_epilogue(int enable);
 
 /* ---- fused attention forward (bf16, tcgen05) ---------------------------------------------------
  * Replaces flash_attn_func(q,k,v, softmax_scale, causal=False) (openai_model/attention.py:106-112).

@@ -314,6 +314,11 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst_smem, const CUtensorMap
         ::"r"(dst_smem), "l"(tm), "r"(bar_smem), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
 }
+// pull one box of a rank-5 tensor into L2 ahead of the TMA load that will fetch it into shared memory
+__device__ __forceinline__ void tma_prefetch_l2_5d(const CUtensorMap* tm, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];"
+                 ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx_a(uint32_t bar_smem, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_smem), "r"(bytes) : "memory");
 }

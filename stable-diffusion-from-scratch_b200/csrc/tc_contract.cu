@@ -91,6 +91,7 @@ struct TcCfg {
 };
 
 constexpr int EPI_LD = 36;                        // floats per staged row: 16-B aligned, conflict-free for 128-bit access
+constexpr int TEPI_BOX_BYTES = 4096;              // TMA epilogue: one staged box = 32 rows x 128 B (fp32) or 32 rows x 64 B (bf16, half used)
 constexpr int EPI_WARP_BYTES = 32 * EPI_LD * 4;   // one 32 x 32 fp32 chunk per epilogue warp
 
 __device__ __forceinline__ float4 ldg_f4_or_zero(const float* p, bool pred) {
@@ -587,6 +588,236 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
 }
 
+// ---- TMA epilogue of the pair kernel ---------------------------------------------------------------------------
+// One epilogue warp owns the 32 rows of a TMEM lane quarter and every other 32-column chunk of the accumulator (two warps per
+// quarter).  tcgen05.ld hands each lane one ROW of a chunk; the lane adds bias / time-embedding row / residual (or forms the
+// GEGLU product), and writes its row into a 32-row staging box in shared memory, 16-byte pieces XOR-swizzled by the row index
+// exactly as the tensor map's swizzle mode expects (conflict-free: the 8 lanes of a store phase hit 8 different bank groups).
+// ONE lane then issues cp.async.bulk.tensor (shared -> global): the TMA unit writes whole 128-byte (fp32) / 64-byte (bf16) row
+// segments and clips rows / columns outside the tensor, so the warp spends no instructions on addresses, predicates or
+// per-row stores, and nothing is transposed.  An fp32 residual tile arrives the same way in the other direction — a TMA load
+// into the box that will hold the result, issued `nbuf - 1` chunks ahead (across work units), completion on a per-box mbarrier —
+// and is updated in place.  The next chunk's tcgen05.ld is in flight while this chunk is processed, and the accumulator is
+// handed back to the MMA issuer as soon as its last chunk sits in registers, before the stores have drained.
+// Replaces epilogue_fast for: fp32 out (+bias, +time-embedding row, +fp32 residual, +GroupNorm column statistics, or split-K
+// partials), bf16 out (+bias), GEGLU -> bf16.  Layouts it does not cover (sub-pixel phase remap, padded-head column remap,
+// bf16 out with residual) keep the register-store epilogue.
+struct UnitBox { int split, nt, mt, col0, w, h, n; };
+
+template <int BN, int MODE, bool HAS_RES>
+__device__ __forceinline__ void epilogue_tma_units(const TcP& p, const CUtensorMap* tmC, const CUtensorMap* tmR, uint32_t tmem_d,
+                                                   float* s_bias2, uint32_t stg_a, uint64_t* rbar, uint64_t* tfull_bar,
+                                                   uint32_t tempty_leader0, uint32_t tempty_leader1, int warp, int lane, uint32_t rank,
+                                                   int pair, int npairs, int units) {
+    constexpr bool GEGLU = MODE == EPI_GEGLU;
+    constexpr bool OUT16 = MODE != EPI_F32;
+    constexpr int COLS = GEGLU ? BN / 2 : BN;
+    constexpr int NCHUNK = (COLS + 31) / 32;
+    constexpr int CPW_MAX = (NCHUNK + 1) / 2;
+    constexpr int ACC_STRIDE = 256;
+    const int lg = warp & 3, half = (warp - 4) >> 2;
+    const int et = threadIdx.x - 128;
+    const int cpw = (NCHUNK - half + 1) / 2;             // chunks of this warp per work unit: half, half + 2, ...
+    const int nbuf = p.epi_nbuf, lead = nbuf - 1;
+    const bool partial = p.split_k > 1;
+    const float* const biasp = partial ? nullptr : p.bias;
+    const float* const rowv = (!partial && p.rowvec && p.conv && MODE == EPI_F32) ? p.rowvec : nullptr;
+    const bool want_cs = MODE == EPI_F32 && p.colstats != nullptr && !partial;
+    const int n_out = GEGLU ? p.N / 2 : p.N;
+    const int r0 = lg * 32;
+    int iw0 = 0, ih0 = 0, in0 = 0;                        // origin of this quarter's pixel box inside a conv tile
+    if (p.conv) { iw0 = r0 % p.tw; ih0 = (r0 / p.tw) % p.th; in0 = r0 / (p.tw * p.th); }
+
+    auto unit_box = [&](int u) -> UnitBox {
+        UnitBox b;
+        b.split = u % p.split_k;
+        const int t = u / p.split_k;
+        b.nt = t % p.tiles_n;
+        b.mt = (t / p.tiles_n) * 2 + (int)rank;
+        b.col0 = GEGLU ? b.nt * (BN / 2) : b.nt * BN;
+        if (p.conv) {
+            const int tww = b.mt % p.tiles_w, thh = (b.mt / p.tiles_w) % p.tiles_h, tnb = b.mt / (p.tiles_w * p.tiles_h);
+            b.w = tww * p.tw + iw0; b.h = thh * p.th + ih0; b.n = tnb * p.tn + in0;
+        } else {
+            b.w = b.mt * TC_BM + r0; b.h = 0; b.n = 0;
+        }
+        return b;
+    };
+    // residual tile of this warp's chunk number `qq` (counted over all its work units) -> staging box qq % nbuf
+    auto issue_residual = [&](uint32_t qq) {
+        if (!HAS_RES || lane != 0) return;
+        const int itq = (int)(qq / (uint32_t)cpw), k = (int)(qq % (uint32_t)cpw);
+        const long long u = (long long)pair + (long long)itq * npairs;
+        if (u >= units) return;
+        const UnitBox b = unit_box((int)u);
+        const uint32_t bi = qq % (uint32_t)nbuf;
+        const uint32_t bar = smem_u32(rbar + bi);
+        mbar_arrive_expect_tx_a(bar, 32 * 128);
+        tma_load_5d(stg_a + bi * TEPI_BOX_BYTES, tmR, bar, b.col0 + (half + 2 * k) * 32, b.w, b.h, b.n, 0);
+    };
+
+    // the residual boxes of a whole work unit -> L2, one unit ahead of the TMA loads that bring them into the staging boxes:
+    // those loads are issued only `lead` chunks ahead (the staging is small) and must not each pay a DRAM round trip
+    auto prefetch_residual_unit = [&](long long u) {
+        if (!HAS_RES || lane != 0 || u >= units) return;
+        const UnitBox b = unit_box((int)u);
+        for (int k = 0; k < cpw; ++k) tma_prefetch_l2_5d(tmR, b.col0 + (half + 2 * k) * 32, b.w, b.h, b.n, 0);
+    };
+    prefetch_residual_unit(pair);
+    uint32_t q = 0;                                       // chunks this warp has processed
+    for (int j = 0; j < lead; ++j) issue_residual((uint32_t)j);
+    // bias row of a unit: fetched one unit ahead into a register, published into the unit's half of s_bias2
+    auto bias_of = [&](int u) -> float {
+        if (u >= units || et >= BN || biasp == nullptr) return 0.f;
+        const int n = ((u / p.split_k) % p.tiles_n) * BN + et;
+        return n < p.N ? __ldg(biasp + n) : 0.f;
+    };
+    float bias_next = bias_of(pair);
+    int it = 0;
+    for (int u = pair; u < units; u += npairs, ++it) {
+        const UnitBox ub = unit_box(u);
+        const int buf = it & 1;
+        float* const sb = s_bias2 + buf * BN;
+        if (et < BN) sb[et] = bias_next;
+        bias_next = bias_of(u + npairs);
+        prefetch_residual_unit((long long)u + npairs);
+        named_bar_sync(1, 32 * 8);                        // bias row visible; every warp is done with unit it - 1 (and so with sb of it - 2)
+        const uint32_t sb_a = smem_u32(sb);
+        // rows of this quarter that exist (conv tiles may hang over the image / batch edge; gemm rows past M)
+        uint32_t rowmask = 0xffffffffu;
+        int img_w = 0;
+        if (want_cs || rowv) {
+            bool valid;
+            int img = 0;
+            if (p.conv) {
+                const int row = r0 + lane;
+                const int in_ = row / (p.th * p.tw), rem = row - in_ * (p.th * p.tw);
+                const int ih = rem / p.tw, iw = rem - ih * p.tw;
+                const int tww = ub.mt % p.tiles_w, thh = (ub.mt / p.tiles_w) % p.tiles_h, tnb = ub.mt / (p.tiles_w * p.tiles_h);
+                img = tnb * p.tn + in_;
+                valid = img < p.NB && thh * p.th + ih < p.OH && tww * p.tw + iw < p.OW;
+            } else {
+                valid = ub.mt * TC_BM + r0 + lane < p.M;
+            }
+            rowmask = __ballot_sync(0xffffffffu, valid);
+            img_w = __shfl_sync(0xffffffffu, img, 0);     // the launcher admits a time-embedding row only when a quarter lies in one image
+        }
+        const bool rv_ok = rowv != nullptr && rowmask != 0u && img_w < p.NB;
+        const uint32_t taddr = tmem_d + ((uint32_t)r0 << 16) + buf * ACC_STRIDE;
+        mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
+        tcgen05_fence_after();
+        uint32_t ra[32], rb[32];
+        tmem_ld_x32(taddr + half * 32, ra);
+#pragma unroll
+        for (int k = 0; k < CPW_MAX; ++k) {
+            const int ch = half + 2 * k;
+            if (ch >= NCHUNK) break;                      // warp-uniform
+            uint32_t (&cur)[32] = (k & 1) ? rb : ra;
+            uint32_t (&nxt)[32] = (k & 1) ? ra : rb;
+            const int c0 = ch * 32;
+            const int col = ub.col0 + c0;                 // first output column of the chunk
+            const uint32_t bi = q % (uint32_t)nbuf;
+            const uint32_t sbuf = stg_a + bi * TEPI_BOX_BYTES;
+            uint32_t g[GEGLU ? 32 : 1];
+            if (GEGLU) tmem_ld_x32(taddr + BN / 2 + c0, g);
+            tmem_ld_wait();                               // chunk k (and its gate half) is in registers
+            const bool last = ch + 2 >= NCHUNK;
+            if (!last) {
+                tmem_ld_x32(taddr + c0 + 64, nxt);        // next chunk's read overlaps this chunk's processing
+            } else {
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(buf ? tempty_leader1 : tempty_leader0);   // accumulator drained: back to the MMA issuer
+            }
+            if (HAS_RES) {
+                mbar_wait(rbar + bi, (q / (uint32_t)nbuf) & 1u);  // this chunk's residual tile has landed in its box
+            } else {
+                if (lane == 0) tma_store_wait_read<1>();  // the store of chunk q - 2 has finished reading this box
+                __syncwarp();
+            }
+            if (OUT16) {
+                // bf16 rows of 64 B: four 16-byte pieces, piece j at (j ^ ((row >> 1) & 3)) (SWIZZLE_64B)
+                const uint32_t rowa = sbuf + lane * 64;
+                const uint32_t sw = (uint32_t)(lane >> 1) & 3u;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float v[8];
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        const float4 b4 = lds128(sb_a + 4 * (c0 + 8 * j + 4 * h2));
+                        float x0 = __uint_as_float(cur[8 * j + 4 * h2 + 0]) + b4.x, x1 = __uint_as_float(cur[8 * j + 4 * h2 + 1]) + b4.y;
+                        float x2 = __uint_as_float(cur[8 * j + 4 * h2 + 2]) + b4.z, x3 = __uint_as_float(cur[8 * j + 4 * h2 + 3]) + b4.w;
+                        if (GEGLU) {
+                            const float4 bg = lds128(sb_a + 4 * (BN / 2 + c0 + 8 * j + 4 * h2));
+                            x0 *= gelu_erf_fast(__uint_as_float(g[(8 * j + 4 * h2 + 0) % (GEGLU ? 32 : 1)]) + bg.x);
+                            x1 *= gelu_erf_fast(__uint_as_float(g[(8 * j + 4 * h2 + 1) % (GEGLU ? 32 : 1)]) + bg.y);
+                            x2 *= gelu_erf_fast(__uint_as_float(g[(8 * j + 4 * h2 + 2) % (GEGLU ? 32 : 1)]) + bg.z);
+                            x3 *= gelu_erf_fast(__uint_as_float(g[(8 * j + 4 * h2 + 3) % (GEGLU ? 32 : 1)]) + bg.w);
+                        }
+                        v[4 * h2 + 0] = x0; v[4 * h2 + 1] = x1; v[4 * h2 + 2] = x2; v[4 * h2 + 3] = x3;
+                    }
+                    sts128(rowa + ((((uint32_t)j) ^ sw) << 4), pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                           pack_bf16x2(v[6], v[7]));
+                }
+            } else {
+                // fp32 rows of 128 B: eight 16-byte pieces, piece j at (j ^ (row & 7)) (SWIZZLE_128B); residual updated in place
+                const uint32_t rowa = sbuf + lane * 128;
+                const uint32_t sw = (uint32_t)lane & 7u;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t pa = rowa + ((((uint32_t)j) ^ sw) << 4);
+                    float4 v = make_float4(__uint_as_float(cur[4 * j]), __uint_as_float(cur[4 * j + 1]), __uint_as_float(cur[4 * j + 2]),
+                                           __uint_as_float(cur[4 * j + 3]));
+                    if (!partial) {
+                        const float4 b4 = lds128(sb_a + 4 * (c0 + 4 * j));
+                        v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+                    }
+                    if (HAS_RES) {
+                        const float4 r4 = lds128(pa);
+                        v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
+                    }
+                    if (rowv) {
+                        // time-embedding row of this quarter's image (same address in every lane: one broadcast transaction), added last
+                        const float4 t4 = ldg_f4_or_zero(rowv + (long long)img_w * p.ldv + col + 4 * j, rv_ok && col + 4 * j < p.N);
+                        v.x += t4.x; v.y += t4.y; v.z += t4.z; v.w += t4.w;
+                    }
+                    sts128f(pa, v.x, v.y, v.z, v.w);
+                }
+            }
+            fence_proxy_async_smem();                     // generic-proxy writes -> visible to the TMA unit
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_5d(tmC, sbuf, col, ub.w, ub.h, ub.n, ub.split);
+                tma_store_commit();
+            }
+            if (want_cs) {
+                // GroupNorm column statistics of the stored values: lane j owns column col + j and walks the 32 staged rows
+                float cs = 0.f, cq = 0.f;
+#pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                    if ((rowmask >> r) & 1u) {
+                        const float x = lds32(sbuf + r * 128 + ((((uint32_t)(lane >> 2)) ^ (uint32_t)(r & 7)) << 4) + ((lane & 3) << 2));
+                        cs += x;
+                        cq = fmaf(x, x, cq);
+                    }
+                }
+                if (col + lane < n_out) {
+                    float* dst = p.colstats + (long long)(ub.mt * 4 + lg) * p.N + col + lane;
+                    dst[0] = cs;
+                    dst[p.colstats_sq] = cq;
+                }
+            }
+            if (HAS_RES) {
+                if (lane == 0) tma_store_wait_read<1>();  // store of chunk q - 1 done reading -> its box takes the residual of chunk q + lead
+                issue_residual(q + (uint32_t)lead);
+            }
+            ++q;
+        }
+    }
+    if (lane == 0) tma_store_wait_all<0>();               // every store of this warp has landed before the CTA retires
+    __syncwarp();
+}
+
 // ---- CTA-pair persistent kernel ------------------------------------------------------------------
 // A cluster of two CTAs (one per SM of a TPC) owns a 256 x BN output tile: tcgen05.mma.cta_group::2
 // with M = 256, each CTA staging its own 128 rows of A and HALF of the B tile (BN/2 rows), so the
@@ -602,7 +833,6 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 // EW = 8 in the product; 16 exists for the measurement build only (see launch_tc_pair).
 constexpr int TC2_MAX_STAGES = 8;
 constexpr int TC2_SMEM_LIMIT = 232448;            // 227 KB: the per-CTA dynamic shared memory limit of sm_100
-constexpr int TEPI_BOX_BYTES = 4096;              // TMA epilogue: one staged box = 32 rows x 128 B (fp32) or 32 rows x 64 B (bf16, half used)
 
 template <int BN, int EW>
 struct Tc2Cfg {
@@ -622,21 +852,24 @@ struct Tc2Cfg {
 
 template <int BN, int EW>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
-tc_contract_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcP p) {
+tc_contract_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const TcP p) {
     pdl_trigger();
     using Cfg = Tc2Cfg<BN, EW>;
     constexpr int TC2_EPI_WARPS = EW;
-    constexpr int STAGES = Cfg::STAGES;
+    const int STAGES = p.stages;                     // ring depth: what the epilogue staging leaves of the 227 KB
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * TC_A_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tfull_bar = empty_bar + STAGES;        // [2] accumulator ready   (arrives: MMA commit, multicast)
+    uint64_t* empty_bar = full_bar + TC2_MAX_STAGES;
+    uint64_t* tfull_bar = empty_bar + TC2_MAX_STAGES;   // [2] accumulator ready   (arrives: MMA commit, multicast)
     uint64_t* tempty_bar = tfull_bar + 2;            // [2] accumulator drained (leader's copy is the one waited on)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    float* s_bias = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 512);
+    uint64_t* res_bar = tempty_bar + 4;              // [EW][3] TMA epilogue: residual tile landed in staging box b of warp w
+    float* s_bias = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 512);      // [2][BN] (the register-store epilogue uses half 0)
+    uint8_t* staging = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_bias + 2 * BN) + 1023) & ~(uintptr_t)1023);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -648,6 +881,7 @@ tc_contract_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 2 * TC2_EPI_WARPS); }
+        for (int b = 0; b < 3 * EW && EW == 8; ++b) mbar_init(&res_bar[b], 1);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -733,6 +967,19 @@ tc_contract_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                 TC_TRACE(2, it);
             }
         }
+    } else if (warp >= 4 && EW == 8 && p.epi_tma) {
+        // ================= epilogue through TMA (see epilogue_tma_units) =================
+        const uint32_t tl0 = mapa_u32(&tempty_bar[0], 0), tl1 = mapa_u32(&tempty_bar[1], 0);
+        const uint32_t stg_a = smem_u32(staging) + (uint32_t)(warp - 4) * (uint32_t)(p.epi_nbuf * TEPI_BOX_BYTES);
+        uint64_t* rbar = res_bar + 3 * (warp - 4);
+#define SDB_TEPI(MODE, RES) epilogue_tma_units<BN, MODE, RES>(p, &tmC, &tmR, tmem_d, s_bias, stg_a, rbar, tfull_bar, tl0, tl1, warp, lane, rank, pair, npairs, units)
+        if (p.geglu) {
+            if constexpr (BN % 64 == 0) SDB_TEPI(EPI_GEGLU, false);
+        } else if (p.split_k > 1) SDB_TEPI(EPI_F32, false);
+        else if (p.out_bf16) SDB_TEPI(EPI_BF16, false);
+        else if (p.residual != nullptr) SDB_TEPI(EPI_F32, true);
+        else SDB_TEPI(EPI_F32, false);
+#undef SDB_TEPI
     } else if (warp >= 4) {
         // ================= epilogue (warps 4.. -> TMEM lane quarter warp & 3, chunk phase (warp - 4) >> 2 of EW/4) ====
         const int et = threadIdx.x - 128;
@@ -741,7 +988,7 @@ tc_contract_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         const int row = lg * 32 + lane;
         const uint32_t tempty_leader0 = mapa_u32(&tempty_bar[0], 0);
         const uint32_t tempty_leader1 = mapa_u32(&tempty_bar[1], 0);
-        float* stage = s_bias + BN + (warp - 4) * (EPI_WARP_BYTES / 4);
+        float* stage = reinterpret_cast<float*>(staging) + (warp - 4) * (EPI_WARP_BYTES / 4);
         // output row (pixel / token) of this lane's tile row in m-tile `mt`, -1 = outside the problem
         auto row_of = [&](int mt, int& img) -> long long {
             img = 0;
@@ -822,21 +1069,22 @@ PFN_encodeTiled get_encode_tiled() {
     return fn;
 }
 
-// rank-R bf16 tensor map, 128B swizzle, zero OOB fill. dims/strides innermost first; strides in
-// elements for dims 1..R-1.
-int make_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const long long* dims, const long long* strides_elems,
-                   const int* box, const int* estr) {
+// rank-R tensor map, zero OOB fill. dims/strides innermost first; strides in elements for dims 1..R-1.
+// elem_bytes 2 = bf16, 4 = fp32; swizzle_bytes 128 / 64 (shared-memory swizzle mode of the box).
+int make_tmap(CUtensorMap* tm, const void* base, int elem_bytes, int swizzle_bytes, int rank, const long long* dims,
+              const long long* strides_elems, const int* box, const int* estr) {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) { set_last_error("cuTensorMapEncodeTiled unavailable"); return SDB_ERR_NOTMA; }
     cuuint64_t gdim[5], gstr[4];
     cuuint32_t bdim[5], es[5];
     for (int i = 0; i < rank; ++i) { gdim[i] = (cuuint64_t)dims[i]; bdim[i] = (cuuint32_t)box[i]; es[i] = (cuuint32_t)estr[i]; }
-    for (int i = 0; i + 1 < rank; ++i) gstr[i] = (cuuint64_t)strides_elems[i] * 2;
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = (cuuint64_t)strides_elems[i] * (cuuint64_t)elem_bytes;
     if (((uintptr_t)base & 15) != 0) { set_last_error("tensor map base %p not 16-byte aligned", base); return SDB_ERR_INVALID; }
     for (int i = 0; i + 1 < rank; ++i)
         if (gstr[i] % 16) { set_last_error("tensor map stride %llu not a multiple of 16 bytes", (unsigned long long)gstr[i]); return SDB_ERR_INVALID; }
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    CUresult r = enc(tm, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+                     const_cast<void*>(base), gdim, gstr, bdim, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_last_error("cuTensorMapEncodeTiled failed: CUresult %d (rank %d dims %lld %lld box %d %d)", (int)r, rank,
@@ -844,6 +1092,11 @@ int make_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const long long*
         return SDB_ERR_CUDA;
     }
     return SDB_OK;
+}
+
+int make_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const long long* dims, const long long* strides_elems,
+                   const int* box, const int* estr) {
+    return make_tmap(tm, base, 2, 128, rank, dims, strides_elems, box, estr);
 }
 
 // choose the pixel-block decomposition tw x th x tn = 128 with the fewest tiles
@@ -891,22 +1144,28 @@ static int sm_count_cached() {
 }
 
 template <int BN, int EW>
-static int launch_tc_pair_ew(const CUtensorMap& tmA, const CUtensorMap& tmB, TcP& p, int m_tiles, cudaStream_t st) {
+static int launch_tc_pair_ew(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR, TcP& p,
+                             int m_tiles, cudaStream_t st) {
     using Cfg = Tc2Cfg<BN, EW>;
     static bool attr_set_dev[64] = {false};          // the attribute is per device
     int cur_dev = 0;
     if (cudaGetDevice(&cur_dev) != cudaSuccess || cur_dev < 0 || cur_dev >= 64) cur_dev = 0;
     bool& attr_set = attr_set_dev[cur_dev];
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc_contract_pair_kernel<BN, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(tc_contract_pair_kernel<BN, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_LIMIT);
         if (e != cudaSuccess) { set_last_error("tc_contract(pair): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SDB_ERR_CUDA; }
         attr_set = true;
     }
+    if (EW != 8) p.epi_tma = 0;
+    const int staging = Cfg::staging_bytes(p.epi_tma, p.epi_nbuf);
+    p.stages = Cfg::stages_for(staging);
+    if (p.stages < 2) { set_last_error("tc_contract(pair): no room for an operand ring (BN %d)", BN); return SDB_ERR_INVALID; }
     p.m_pairs = (m_tiles + 1) / 2;
     long long units = (long long)p.m_pairs * p.tiles_n * p.split_k;
     int pairs = sm_count_cached() / 2;
     if (units < pairs) pairs = (int)units;
-    launch_pdl(tc_contract_pair_kernel<BN, EW>, dim3(dim3(2 * pairs)), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, tmA, tmB, p);
+    launch_pdl(tc_contract_pair_kernel<BN, EW>, dim3(dim3(2 * pairs)), dim3(Cfg::THREADS), Cfg::smem_bytes(p.stages, staging), st,
+               tmA, tmB, tmC, tmR, p);
     return check_launch("tc_contract_pair_kernel");
 }
 
@@ -916,13 +1175,14 @@ static int launch_tc_pair_ew(const CUtensorMap& tmA, const CUtensorMap& tmB, TcP
 // instruction count (~24 warp instructions per output element, ~3.1 k issue slots per scheduler and unit against 2.6 k clocks
 // of MMA at K = 320), not by latency that more warps could hide; 16 warps also spill (548 B) under the 96-register cap.
 template <int BN>
-static int launch_tc_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, TcP& p, int m_tiles, cudaStream_t st) {
+static int launch_tc_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR, TcP& p,
+                          int m_tiles, cudaStream_t st) {
 #ifdef SDB_TC_EW16
     static int forced = -1;
     if (forced < 0) { const char* e = getenv("SDB200_TC_EW"); forced = e ? atoi(e) : 0; }
-    if (forced == 16) return launch_tc_pair_ew<BN, 16>(tmA, tmB, p, m_tiles, st);
+    if (forced == 16) return launch_tc_pair_ew<BN, 16>(tmA, tmB, tmC, tmR, p, m_tiles, st);
 #endif
-    return launch_tc_pair_ew<BN, 8>(tmA, tmB, p, m_tiles, st);
+    return launch_tc_pair_ew<BN, 8>(tmA, tmB, tmC, tmR, p, m_tiles, st);
 }
 
 // Kernel selection: 1 = CTA-pair persistent kernel for BN >= 128 (default), 0 = one-CTA kernel everywhere.
@@ -934,6 +1194,20 @@ static bool pair_kernel_enabled() {
         g_pair_kernel = (e && strcmp(e, "single") == 0) ? 0 : 1;
     }
     return g_pair_kernel == 1;
+}
+
+// TMA epilogue switches: SDB200_TC_EPI=regs forces the register-store epilogue everywhere (A/B measurements);
+// SDB200_TC_EPI_MAXKB = largest number of 64-wide k-blocks per work unit for which the TMA epilogue is used (longer
+// contractions hide any epilogue behind their mainloop and keep the deeper operand ring instead).
+static int g_tma_epilogue = -1;
+static bool tma_epilogue_enabled() {
+    if (g_tma_epilogue < 0) { const char* e = getenv("SDB200_TC_EPI"); g_tma_epilogue = (e && strcmp(e, "regs") == 0) ? 0 : 1; }
+    return g_tma_epilogue == 1;
+}
+static int tma_epilogue_max_kblocks() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SDB200_TC_EPI_MAXKB"); v = e ? atoi(e) : 40; }
+    return v;
 }
 
 // ---- split-K: deterministic reduction of the per-split partial tiles --------------------------------
@@ -1070,6 +1344,12 @@ extern "C" int sdb_tc_set_pair_kernel(int enable) {
     return prev;
 }
 
+extern "C" int sdb_tc_set_tma_epilogue(int enable) {
+    int prev = tma_epilogue_enabled() ? 1 : 0;
+    g_tma_epilogue = enable ? 1 : 0;
+    return prev;
+}
+
 extern "C" long long sdb_tc_workspace_bytes(const sdb_tc_args* a) {
     if (!a) return -1;
     // what the automatic split choice would need if a workspace were supplied
@@ -1189,11 +1469,63 @@ extern "C" int sdb_tc_contract(const sdb_tc_args* a, void* stream) {
     }
     SDB_REQUIRE((long long)m_tiles * p.tiles_n < (1LL << 31), "tc_contract: grid too large");
     cudaStream_t st = (cudaStream_t)stream;
+    CUtensorMap tmC, tmR;
+    memset(&tmC, 0, sizeof(tmC));
+    memset(&tmR, 0, sizeof(tmR));
+    if (use_pair && tma_epilogue_enabled()) {
+        // ---- TMA epilogue (epilogue_tma_units): short-K launches whose output layout is a plain [rows, N] / NHWC tensor ----
+        const bool partial = p.split_k > 1;
+        const bool out16 = !partial && p.out_bf16;
+        const int kb_split = pl.kblocks / p.split_k;
+        const int ebytes = out16 ? 2 : 4;
+        bool ok = !a->col_group && kb_split <= tma_epilogue_max_kblocks();
+        void* obase = partial ? (void*)p.ws : a->out;
+        const long long ldo = partial ? (long long)a->N : a->ldc;
+        ok = ok && ((uintptr_t)obase & 15) == 0 && (ldo * ebytes) % 16 == 0;
+        if (conv) ok = ok && p.out_sh == 1 && p.out_sw == 1 && p.out_oh == 0 && p.out_ow == 0 && p.OHF == p.OH && p.OWF == p.OW;
+        const bool has_res = a->residual != nullptr && !partial;
+        if (has_res) ok = ok && !out16 && ((uintptr_t)a->residual & 15) == 0 && a->ldr % 4 == 0;
+        if (a->geglu) ok = ok && out16 && (bn / 2) % 32 == 0;
+        if (a->rowvec && conv && !partial)
+            ok = ok && !out16 && p.tw * p.th >= 32 && a->N % 4 == 0 && a->ldv % 4 == 0 && ((uintptr_t)a->rowvec & 15) == 0;
+        if (ok) {
+            int bw = 32, bh = 1, bnn = 1;
+            if (conv) { bw = p.tw < 32 ? p.tw : 32; bh = p.th < 32 / bw ? p.th : 32 / bw; bnn = 32 / (bw * bh); }
+            const long long S = p.split_k;
+            long long dims[5], str[4];
+            int box[5] = {32, bw, bh, bnn, 1}, es5[5] = {1, 1, 1, 1, 1};
+            if (conv) {
+                dims[0] = a->N; dims[1] = p.OW; dims[2] = p.OH; dims[3] = p.NB; dims[4] = S;
+                str[0] = ldo; str[1] = ldo * p.OW; str[2] = ldo * p.OW * p.OH; str[3] = partial ? p.ws_split_stride : ldo * p.OW * p.OH * p.NB;
+            } else {
+                dims[0] = a->N; dims[1] = a->M; dims[2] = 1; dims[3] = 1; dims[4] = S;
+                str[0] = ldo; str[1] = ldo * a->M; str[2] = ldo * a->M; str[3] = partial ? p.ws_split_stride : ldo * a->M;
+            }
+            if (a->geglu) dims[0] = a->N / 2;
+            rc = make_tmap(&tmC, obase, ebytes, out16 ? 64 : 128, 5, dims, str, box, es5);
+            if (rc == SDB_OK && has_res) {
+                const long long ldr = a->ldr;
+                dims[4] = 1;
+                if (conv) { str[0] = ldr; str[1] = ldr * p.OW; str[2] = ldr * p.OW * p.OH; str[3] = ldr * p.OW * p.OH * p.NB; }
+                else { str[0] = ldr; str[1] = ldr * a->M; str[2] = ldr * a->M; str[3] = ldr * a->M; }
+                rc = make_tmap(&tmR, a->residual, 4, 128, 5, dims, str, box, es5);
+            }
+            if (rc == SDB_OK) {
+                p.epi_tma = 1;
+                p.epi_bw = bw; p.epi_bh = bh;
+                // a residual tile is prefetched nbuf - 1 chunks ahead: two ahead while the ring can spare the smem (short K)
+                p.epi_nbuf = has_res ? (kb_split <= 24 ? 3 : 2) : 2;
+            } else {
+                rc = SDB_OK;              // odd strides etc.: the register-store epilogue takes any layout
+            }
+        }
+    }
+    if (!p.epi_tma) p.epi_nbuf = 0;
     if (use_pair) {
         switch (bn) {
-            case 128: rc = launch_tc_pair<128>(tmA, tmB, p, m_tiles, st); break;
-            case 160: rc = launch_tc_pair<160>(tmA, tmB, p, m_tiles, st); break;
-            default: rc = launch_tc_pair<256>(tmA, tmB, p, m_tiles, st); break;
+            case 128: rc = launch_tc_pair<128>(tmA, tmB, tmC, tmR, p, m_tiles, st); break;
+            case 160: rc = launch_tc_pair<160>(tmA, tmB, tmC, tmR, p, m_tiles, st); break;
+            default: rc = launch_tc_pair<256>(tmA, tmB, tmC, tmR, p, m_tiles, st); break;
         }
     } else {
         switch (bn) {

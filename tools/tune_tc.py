@@ -59,24 +59,25 @@ print("distinct contractions:", len(shapes), flush=True)
 
 
 def timed(fn, nrot, iters, warm=None):
-    """Mean device time of fn(i) bracketed by events, one launch at a time.  `warm(i)` (untimed) re-writes the A operand first,
-    so that it sits in L2 as it does in the real step (it was just produced by the preceding norm kernel) while the
-    rotated weights / residual / output come from DRAM."""
-    for i in range(2):
+    """Device time per launch of `iters` BACK-TO-BACK launches (operands rotated through nrot copies), best of 3 rounds.  The
+    device is parked behind a ~1 ms spin while the host enqueues the round, so the events bracket kernel execution only —
+    launch latency (~20 us for an isolated launch, more than most of these kernels run) and host gaps do not count, and
+    consecutive launches overlap through programmatic dependent launch as they do inside the captured UNet graph."""
+    for i in range(3):
         fn(i % nrot)
     torch.cuda.synchronize()
-    evs = []
-    for i in range(iters):
-        if warm is not None:
-            warm(i % nrot)
+    best = None
+    for rep in range(3):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda._sleep(int(3e6))
         e0.record()
-        fn(i % nrot)
+        for i in range(iters):
+            fn(i % nrot)
         e1.record()
-        evs.append((e0, e1))
-    torch.cuda.synchronize()
-    ts = sorted(a.elapsed_time(b) for a, b in evs)
-    return ts[len(ts) // 2] * 1e3                      # median, us
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / iters * 1e3
+        best = us if best is None else min(best, us)
+    return best
 
 
 out_f = open(a.out, "w")
