@@ -406,10 +406,258 @@ def roofline_pass(run, label):
     return roof, roof_hbm, launches
 
 
+# ------------------------------------------------------------------------------------------------------
+# the other BASELINE.json configs, driver-runnable: --config c3 | c5 | c4-strong
+# ------------------------------------------------------------------------------------------------------
+def _dist_setup():
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    return rank, world, local, dev
+
+
+def _reinit_zero_modules(mod):
+    import torch
+    for m in mod.modules():
+        if isinstance(m, (torch.nn.Conv2d, torch.nn.Linear)) and float(m.weight.detach().abs().max()) == 0.0:
+            m.reset_parameters()
+
+
+def _timed_steps(fn, steps, warmup, world):
+    """W untimed + K timed calls of fn bracketed by barrier + synchronize, CUDA events, MAX over ranks (ms for the K steps)."""
+    import torch
+    import torch.distributed as dist
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(max(3, warmup)):
+        fn()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    sync_all()
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+
+def run_c3(a):
+    """BASELINE configs[2]: VAE decode 64x64x4 -> 512x512x3, batch 16 per GPU (micro-batches of 8): images/s, tensor roofline of
+    the contractions and HBM roofline of the GroupNorm passes of one decode."""
+    import torch
+    rank, world, local, dev = _dist_setup()
+    from sdb200 import _lib
+    from sdb200.autoencoder import AutoencoderKL
+    from sdb200.distributed import per_sample_randn, shard_range
+    from sdb200.pipeline import SD_VAE_DDCONFIG
+    lib = _lib.load()
+    B = 16 if a.batch == 8 else a.batch
+    torch.manual_seed(0)
+    vae = AutoencoderKL(ddconfig=SD_VAE_DDCONFIG, embed_dim=4, compute_mode=a.mode).to(dev)
+    lo, hi = shard_range(B * world, rank, world)
+    z_host = per_sample_randn(range(lo, hi), (4, 64, 64), 4000).pin_memory()
+    img_host = torch.empty((B, 3, 512, 512), dtype=torch.float32).pin_memory()
+    z_dev = z_host.to(dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.sdb_launch_count()
+    ms = _timed_steps(lambda: vae.decode(z_dev), a.steps, a.warmup, world)
+    launches = int((lib.sdb_launch_count() - l0) * a.steps / (a.steps + max(3, a.warmup)))
+
+    def e2e():
+        img = vae.decode(z_host.to(dev, non_blocking=True))
+        img_host.copy_(img, non_blocking=True)
+    ms_e2e = _timed_steps(e2e, a.steps, 1, world)
+    sampler.stop_flag = True
+    if rank != 0:
+        return
+    roof, roof_hbm, _ = roofline_pass(lambda: vae.decode(z_dev[:8]), "vae decode, batch 8")
+    tf_peak, hbm_peak, which = peaks()
+    ips = B * world * a.steps / (ms / 1000.0)
+    line = {
+        "metric": "VAE decode 512px images/sec", "value": ips, "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": a.mode if a.mode != "fp32" else "f32", "data": "synthetic",
+        "config": {"workload": "ldm VAE Decoder, latent 64x64x4 -> 512x512x3, batch %d per GPU (BASELINE.json configs[2])" % B,
+                   "global_batch": B * world, "per_gpu_batch": B, "micro_batch": vae.micro_batch,
+                   "l2": "one decode touches ~5 GB of activations per micro-batch, far beyond the 126 MB L2; no flush"},
+        "model_tflops_per_gpu": ips / world * VAE_GFLOP_PER_IMAGE / 1e3,
+        "model_frac_of_tensor_peak": ips / world * VAE_GFLOP_PER_IMAGE / 1e3 / tf_peak,
+        "e2e": {"value": B * world * a.steps / (ms_e2e / 1000.0), "unit": "images/s", "h2d_bytes_per_step": int(z_host.numel() * 4),
+                "d2h_bytes_per_step": int(img_host.numel() * 4)},
+        "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "roofline_hbm": roof_hbm,
+        "peaks": {"bf16_tflops": tf_peak, "hbm_gbs": hbm_peak, "source": which},
+    }
+    print(json.dumps(line))
+
+
+def run_c5(a):
+    """BASELINE configs[4]: one UNet step on a 96x96x4 latent (9216 tokens at the top level), batch sweep 1..32: step latency,
+    achieved TFLOP/s against the algorithmic 2148.12 GFLOP/sample, and the per-kernel rooflines at batch 8."""
+    import torch
+    rank, world, local, dev = _dist_setup()
+    if rank != 0:
+        return
+    from sdb200 import _lib
+    from sdb200.openai_model import UNetModel
+    from sdb200.pipeline import SD_UNET_CONFIG
+    lib = _lib.load()
+    GF96 = 2148.12
+    torch.manual_seed(0)
+    net = UNetModel(**SD_UNET_CONFIG, compute_mode=a.mode)
+    _reinit_zero_modules(net)
+    net = net.to(dev)
+    net.use_cuda_graph = not a.no_graph
+    tf_peak, hbm_peak, which = peaks()
+    sampler = ClockSampler(local)
+    sampler.start()
+    sweep = []
+    launches = 0
+    for B in (1, 2, 4, 8, 16, 32):
+        x = torch.randn(B, 4, 96, 96, device=dev)
+        t = torch.full((B,), 500, device=dev, dtype=torch.long)
+        c = torch.randn(B, 77, 768, device=dev)
+        ms = _timed_steps(lambda: net(x, t, c), max(a.steps, 5), a.warmup, 1) / max(a.steps, 5)
+        tf = B * GF96 / ms
+        sweep.append({"batch": B, "ms": ms, "tflops": tf, "frac_of_tensor_peak": tf / tf_peak})
+        if B == 8:
+            x_host, c_host = x.cpu().pin_memory(), c.cpu().pin_memory()
+            out_host = torch.empty((B, 4, 96, 96)).pin_memory()
+
+            def e2e():
+                out_host.copy_(net(x_host.to(dev, non_blocking=True), t, c_host.to(dev, non_blocking=True)), non_blocking=True)
+            ms_e2e = _timed_steps(e2e, max(a.steps, 5), 1, 1) / max(a.steps, 5)
+            net.use_cuda_graph = False
+            roof, roof_hbm, launches = roofline_pass(lambda: net(x, t, c), "unet 96x96, batch 8")
+            net.use_cuda_graph = not a.no_graph
+    sampler.stop_flag = True
+    b8 = [r for r in sweep if r["batch"] == 8][0]
+    line = {
+        "metric": "UNet step latency ms (96x96 latent, batch 8)", "value": b8["ms"], "unit": "ms", "n_gpus": 1, "steps": max(a.steps, 5),
+        "warmup": max(3, a.warmup), "ms_per_step": b8["ms"], "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+        "dtype": a.mode if a.mode != "fp32" else "f32", "data": "synthetic",
+        "config": {"workload": "SD-1.x UNetModel forward, latent 96x96x4 (768 px), ctx 77x768, batch sweep 1-32 (BASELINE.json configs[4])",
+                   "global_batch": 8, "cuda_graph": not a.no_graph, "algorithmic_gflop_per_sample": GF96,
+                   "l2": "1.7 GB of bf16 weights streamed per call; no flush"},
+        "sweep": sweep,
+        "e2e": {"value": ms_e2e, "unit": "ms", "h2d_bytes_per_step": int(8 * 4 * 96 * 96 * 4 + 8 * 77 * 768 * 4), "d2h_bytes_per_step": int(8 * 4 * 96 * 96 * 4)},
+        "gpu_launches": int(launches * max(a.steps, 5)), "clocks": sampler.summary(), "roofline": roof, "roofline_hbm": roof_hbm,
+        "peaks": {"bf16_tflops": tf_peak, "hbm_gbs": hbm_peak, "source": which},
+    }
+    print(json.dumps(line))
+
+
+def run_c4_strong(a):
+    """BASELINE configs[3] as STRONG scaling: a fixed global batch of 64 images (DDIM-50 + decode), sample i seeded by its global
+    index, sharded contiguously over the N GPUs, each rank running its 64/N samples in batches of 8; one NCCL all-gather of
+    the decoded images at the end."""
+    import torch
+    rank, world, local, dev = _dist_setup()
+    from sdb200 import _lib
+    from sdb200.distributed import gather_images, per_sample_randn, shard_range
+    from sdb200.pipeline import LatentDiffusion
+    lib = _lib.load()
+    GB = 64
+    torch.manual_seed(0)
+    ld = LatentDiffusion(compute_mode=a.mode)
+    _reinit_zero_modules(ld)
+    ld = ld.to(dev)
+    ld.model.diffusion_model.use_cuda_graph = not a.no_graph
+    lo, hi = shard_range(GB, rank, world)
+    x_host = per_sample_randn(range(lo, hi), (4, 64, 64), 1000).pin_memory()
+    c_host = per_sample_randn(range(lo, hi), (77, 768), 2000).pin_memory()
+    mb = 8
+
+    def step():
+        imgs = []
+        for i in range(0, hi - lo, mb):
+            xd = x_host[i:i + mb].to(dev, non_blocking=True)
+            cd = c_host[i:i + mb].to(dev, non_blocking=True)
+            imgs.append(ld.txt2img(cd, xd.shape[0], ddim_steps=a.ddim_steps, shape=(4, 64, 64), x_T=xd)[1])
+        img = torch.cat(imgs, 0) if len(imgs) > 1 else imgs[0]
+        return gather_images(img, GB) if world > 1 else img
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.sdb_launch_count()
+    # warm-up: W >= 3 passes over ONE micro-batch (graph capture, weight packing), then the timed full-batch steps
+    xw, cw = x_host[:mb].to(dev), c_host[:mb].to(dev)
+    for _ in range(max(3, a.warmup)):
+        ld.txt2img(cw, xw.shape[0], ddim_steps=a.ddim_steps, shape=(4, 64, 64), x_T=xw)
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    sampler.stop_flag = True
+    if rank == 0:
+        tf_peak, hbm_peak, which = peaks()
+        ips = GB * a.steps / (ms / 1000.0)
+        flop_per_image = (a.ddim_steps * UNET_GFLOP_PER_SAMPLE + VAE_GFLOP_PER_IMAGE) * 1e9
+        line = {
+            "metric": "512px DDIM-50 images/sec", "value": ips, "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": a.mode if a.mode != "fp32" else "f32", "data": "synthetic",
+            "config": {"workload": "SD-1.x UNet DDIM-%d + VAE decode, 64x64x4 latent -> 512x512x3, ctx 77x768, FIXED global batch 64 sharded "
+                                   "over the GPUs in batches of 8 (BASELINE.json configs[3])" % a.ddim_steps,
+                       "global_batch": GB, "per_gpu_batch": hi - lo, "micro_batch": mb, "cuda_graph": not a.no_graph,
+                       "warmup_note": "warm-up passes run one micro-batch of 8 (graph capture, packing); every timed step runs the full 64",
+                       "l2": "1.7 GB bf16 weights streamed per UNet call; no flush"},
+            "model_tflops_per_gpu": ips / world * flop_per_image / 1e12,
+            "model_frac_of_tensor_peak": ips / world * flop_per_image / 1e12 / tf_peak,
+            "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": int(x_host.numel() * 4 + c_host.numel() * 4), "d2h_bytes_per_step": 0,
+                    "note": "inputs start in pinned host memory and are copied per micro-batch inside the timed region; the gathered "
+                            "images stay on the device"},
+            "gpu_launches": int(lib.sdb_launch_count() - l0), "clocks": sampler.summary(),
+            "limiting_term": "per-GPU work is 64/N images in batches of 8; at N = 8 each GPU runs ONE batch of 8 (the weak-scaling point), "
+                             "so strong scaling is linear in N up to the all-gather of 201 MB of fp32 images",
+            "peaks": {"bf16_tflops": tf_peak, "hbm_gbs": hbm_peak, "source": which},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.config == "c3":
+        run_c3(a)
+    elif a.config == "c5":
+        run_c5(a)
+    elif a.config == "c4-strong":
+        run_c4_strong(a)
     else:
         run_sdb200(a)
 

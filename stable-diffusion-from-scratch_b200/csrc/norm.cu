@@ -207,14 +207,20 @@ __global__ void gn_stats_kernel(const float* __restrict__ x0, int C0, const floa
 // the current block is processed, so every SM keeps ~100 KB of loads in flight from the first to the last row.
 constexpr int GNA_UB = 4;
 
-template <bool OUT_BF16, bool EXACT, bool RAW>
+// FUSED: the (mean, rstd) of the sample's groups are folded from the producer's column statistics in the prologue of every
+// CTA (warp per group, fp64, fixed order) instead of by a separate gn_colstats_finalize launch — for small maps, where the
+// statistics of one sample are a few tens of KB and the finalize launch costs more than the whole normalisation.
+constexpr int GNA_MAX_GROUPS = 64;
+
+template <bool OUT_BF16, bool EXACT, bool RAW, bool FUSED>
 __global__ void __launch_bounds__(1024, 1)      // <= 64 registers: two ~480-thread CTAs per SM; C up to 4096 in one CTA row
 gn_apply_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1,
                 int HW, int groups, int V, int R, int rows_per_chunk,
                 const float2* __restrict__ stats, const float* __restrict__ gamma,
                 const float* __restrict__ beta, long long gb_stride, int act, void* __restrict__ out,
-                __nv_bfloat16* __restrict__ raw_out) {
+                __nv_bfloat16* __restrict__ raw_out, const CsSrc s0, const CsSrc s1, double count, float eps) {
     pdl_trigger();
+    __shared__ float2 s_stats[FUSED ? GNA_MAX_GROUPS : 1];
     const int C = C0 + C1;
     const int n = blockIdx.y, chunk = blockIdx.x;
     const int v = threadIdx.x % V, rr = threadIdx.x / V;
@@ -238,6 +244,52 @@ gn_apply_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ 
         cur[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (rb + i * R < row1) cur[i] = ld_stream_f4(p + (long long)rb * ld + i * rstep);
     }
+    if (FUSED) {
+        // (1) thread per channel: sum of the sample's slots (independent loads, four slots in flight), fp64, slot order;
+        // (2) warp per group: fold its channels from shared memory in channel order.
+        extern __shared__ double2 s_ch[];                  // [C] (sum, sum of squares) per channel
+        for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+            const bool first = ch < s0.C;
+            const CsSrc& sr = first ? s0 : s1;
+            const int cch = first ? ch : ch - s0.C;
+            double S = 0.0, Q = 0.0;
+            for (int region = 0; region < sr.regions; ++region) {
+                const long long base = (long long)region * sr.rstride + (long long)n * sr.spi;
+                for (long long sl0 = 0; sl0 < sr.spi; sl0 += 4) {
+                    float a[4], q[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        a[u] = 0.f; q[u] = 0.f;
+                        if (sl0 + u < sr.spi) {
+                            a[u] = __ldcg(sr.cs + (base + sl0 + u) * sr.C + cch);
+                            q[u] = __ldcg(sr.cs + (sr.slots + base + sl0 + u) * sr.C + cch);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { S += (double)a[u]; Q += (double)q[u]; }
+                }
+            }
+            s_ch[ch] = make_double2(S, Q);
+        }
+        __syncthreads();
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = (blockDim.x + 31) >> 5;
+        for (int g = warp; g < groups; g += nwarps) {
+            double S = 0.0, Q = 0.0;
+            for (int j = lane; j < cpg; j += 32) { const double2 v = s_ch[g * cpg + j]; S += v.x; Q += v.y; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                S += __shfl_xor_sync(0xffffffffu, S, o);
+                Q += __shfl_xor_sync(0xffffffffu, Q, o);
+            }
+            if (lane == 0) {
+                const double mean = S / count;
+                double var = Q / count - mean * mean;
+                if (var < 0.0) var = 0.0;
+                s_stats[g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+            }
+        }
+        __syncthreads();
+    }
     float sc[4], sh[4];
     {
         // gb_stride != 0: per-sample affine rows (the scale-shift ResBlock folds (1 + scale), shift into gamma / beta)
@@ -246,7 +298,7 @@ gn_apply_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ 
         const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            float2 st = __ldcg(stats + n * groups + (c + j) / cpg);
+            const float2 st = FUSED ? s_stats[(c + j) / cpg] : __ldcg(stats + n * groups + (c + j) / cpg);
             sc[j] = st.y * gg[j];
             sh[j] = bb[j] - st.x * st.y * gg[j];
         }
@@ -598,6 +650,17 @@ layernorm_kernel(const float* __restrict__ x, int rows, int C, float eps,
 
 static inline int ln_rows_per_warp(int nv) { (void)nv; return 1; }
 
+// largest per-sample statistics block (bytes) that the apply CTAs fold themselves (SDB200_GN_FUSED_MAX, measurement switch)
+static long long gn_fused_stats_max_bytes() {
+    static long long v = -1;
+    // Default 0 = off.  Measured on B200 (profiles/r02_gn_fused_stats.txt): folding the statistics in every apply CTA costs more
+    // than the finalize launch it saves — 22.5 vs 12.7 us at N=8, HW=256, C=1280 and 14.5 vs 10.7 us at HW=64 — because each of
+    // the ~300 CTAs serialises load -> barrier -> fold -> barrier before its first row, while the finalize kernel overlaps the
+    // producer's tail through programmatic dependent launch.
+    if (v < 0) { const char* e = getenv("SDB200_GN_FUSED_MAX"); v = e ? atoll(e) : 0; }
+    return v;
+}
+
 }  // namespace sdb
 
 using namespace sdb;
@@ -655,9 +718,11 @@ int sdb_groupnorm_nhwc(const float* x0, int C0, const float* x1, int C1, int N, 
     if (rc) return rc;
     const GnGeom ga = gn_apply_geom(N, HW, C);
     const dim3 grid_a(ga.chunks, N);
+    CsSrc nos;
+    memset(&nos, 0, sizeof(nos));
 #define LAUNCH_APPLY(BF, EX, RW)                                                                         \
-    launch_pdl(gn_apply_kernel<BF, EX, RW>, dim3(grid_a), dim3(ga.threads), 0, st, x0, C0, x1, C1, HW, groups, ga.V, ga.R, \
-                                                             ga.rows_per_chunk, stats, gamma, beta, gb_stride, act, out, raw)
+    launch_pdl(gn_apply_kernel<BF, EX, RW, false>, dim3(grid_a), dim3(ga.threads), 0, st, x0, C0, x1, C1, HW, groups, ga.V, ga.R, \
+                                                             ga.rows_per_chunk, stats, gamma, beta, gb_stride, act, out, raw, nos, nos, 0.0, eps)
     if (raw) {
         if (out_dtype == SDB_BF16) { if (exact) LAUNCH_APPLY(true, true, true); else LAUNCH_APPLY(true, false, true); }
         else                       { if (exact) LAUNCH_APPLY(false, true, true); else LAUNCH_APPLY(false, false, true); }
@@ -700,15 +765,24 @@ int sdb_groupnorm_from_colstats(const float* x0, int C0, const float* cs0, const
     cudaStream_t st = (cudaStream_t)stream;
     float2* stats = reinterpret_cast<float2*>(ws);                 // [N][groups]
     const int total = N * groups;
-    launch_pdl(gn_colstats_finalize_kernel, dim3(total), dim3(GNF_THREADS), 0, st, s0, s1, groups, (double)HW * (C / groups), eps, stats);
-    int rc = check_launch("gn_colstats_finalize_kernel");
-    if (rc) return rc;
+    const double count = (double)HW * (C / groups);
+    // One sample's statistics small enough (a property of the per-sample geometry, never of the batch) -> every apply CTA folds
+    // them itself and the finalize launch disappears; otherwise that would multiply the L2 traffic of the pass.
+    const long long stat_bytes = ((long long)s0.regions * s0.spi * C0 + (long long)s1.regions * s1.spi * C1) * 8;
+    const bool fused = stat_bytes <= gn_fused_stats_max_bytes() && groups <= GNA_MAX_GROUPS && (long long)C * 16 <= 40 * 1024;
+    int rc = SDB_OK;
+    if (!fused) {
+        launch_pdl(gn_colstats_finalize_kernel, dim3(total), dim3(GNF_THREADS), 0, st, s0, s1, groups, count, eps, stats);
+        rc = check_launch("gn_colstats_finalize_kernel");
+        if (rc) return rc;
+    }
     GnGeom g = gn_apply_geom(N, HW, C);
     dim3 grid(g.chunks, N);
     __nv_bfloat16* raw = reinterpret_cast<__nv_bfloat16*>(raw_out);
-#define LAUNCH_APPLY(BF, EX, RW)                                                                         \
-    launch_pdl(gn_apply_kernel<BF, EX, RW>, dim3(grid), dim3(g.threads), 0, st, x0, C0, x1, C1, HW, groups, g.V, g.R, \
-               g.rows_per_chunk, stats, gamma, beta, gb_stride, act, out, raw)
+#define LAUNCH_APPLY2(BF, EX, RW, FU)                                                                    \
+    launch_pdl(gn_apply_kernel<BF, EX, RW, FU>, dim3(grid), dim3(g.threads), FU ? (size_t)C * 16 : 0, st, x0, C0, x1, C1, HW, groups, g.V, g.R, \
+               g.rows_per_chunk, stats, gamma, beta, gb_stride, act, out, raw, s0, s1, count, eps)
+#define LAUNCH_APPLY(BF, EX, RW) do { if (fused) LAUNCH_APPLY2(BF, EX, RW, true); else LAUNCH_APPLY2(BF, EX, RW, false); } while (0)
     if (raw) {
         if (out_dtype == SDB_BF16) { if (exact) LAUNCH_APPLY(true, true, true); else LAUNCH_APPLY(true, false, true); }
         else                       { if (exact) LAUNCH_APPLY(false, true, true); else LAUNCH_APPLY(false, false, true); }
@@ -717,6 +791,7 @@ int sdb_groupnorm_from_colstats(const float* x0, int C0, const float* cs0, const
         else                       { if (exact) LAUNCH_APPLY(false, true, false); else LAUNCH_APPLY(false, false, false); }
     }
 #undef LAUNCH_APPLY
+#undef LAUNCH_APPLY2
     return check_launch("gn_apply_kernel");
 }
 

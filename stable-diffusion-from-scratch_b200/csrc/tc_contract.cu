@@ -1248,6 +1248,65 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, long long spl
     }
 }
 
+// Same reduction for an fp32 output that feeds a GroupNorm: one CTA = one 32-row slot x 128 columns, and the per-(slot, column)
+// sum / sum of squares of the stored values go to `colstats` ([2][slots][N], the layout gn_colstats_finalize_kernel folds), so the
+// consumer needs no statistics pass of its own.  Thread = (row group of 4 rows, column quad); the 8 row groups of a slot are
+// folded in a fixed order.  rows % 32 == 0 (the launcher checks that a slot never straddles two samples).
+__global__ void __launch_bounds__(256)
+splitk_reduce_stats_kernel(const float* __restrict__ ws, long long split_stride, int splits, long long rows, int N,
+                           const float* __restrict__ bias, const float* __restrict__ rowvec, long long ldv, long long rows_per_img,
+                           const float* __restrict__ residual, long long ldr, float* __restrict__ out, long long ldc,
+                           float* __restrict__ colstats, long long colstats_sq) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float part[8][32][8];
+    const int rg = threadIdx.x >> 5, qi = threadIdx.x & 31;
+    const long long slot = blockIdx.x;
+    const int n = (blockIdx.y * 32 + qi) << 2;
+    const bool col_ok = n < N;
+    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f), cq = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col_ok) {
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const long long m = slot * 32 + rg * 4 + r;
+            float4 acc = __ldcg(reinterpret_cast<const float4*>(ws + m * N + n));
+            for (int sp = 1; sp < splits; ++sp) {
+                const float4 q = __ldcg(reinterpret_cast<const float4*>(ws + sp * split_stride + m * N + n));
+                acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+            }
+            acc.x += b4.x; acc.y += b4.y; acc.z += b4.z; acc.w += b4.w;
+            if (rowvec) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(rowvec + (m / rows_per_img) * ldv + n));
+                acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+            }
+            if (residual) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(residual + m * ldr + n));
+                acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+            }
+            *reinterpret_cast<float4*>(out + m * ldc + n) = acc;
+            cs.x += acc.x; cs.y += acc.y; cs.z += acc.z; cs.w += acc.w;
+            cq.x = fmaf(acc.x, acc.x, cq.x); cq.y = fmaf(acc.y, acc.y, cq.y); cq.z = fmaf(acc.z, acc.z, cq.z); cq.w = fmaf(acc.w, acc.w, cq.w);
+        }
+    }
+    float* pp = part[rg][qi];
+    pp[0] = cs.x; pp[1] = cs.y; pp[2] = cs.z; pp[3] = cs.w; pp[4] = cq.x; pp[5] = cq.y; pp[6] = cq.z; pp[7] = cq.w;
+    __syncthreads();
+    if (rg == 0 && col_ok) {
+        float t[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = part[0][qi][j];
+#pragma unroll
+        for (int g = 1; g < 8; ++g)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t[j] += part[g][qi][j];
+        float* dst = colstats + slot * N + n;
+        *reinterpret_cast<float4*>(dst) = make_float4(t[0], t[1], t[2], t[3]);
+        *reinterpret_cast<float4*>(dst + colstats_sq) = make_float4(t[4], t[5], t[6], t[7]);
+    }
+}
+
 // ---- launch plan: tile width, kernel variant, pixel-block decomposition, split-K ---------------------
 struct TcPlan {
     int bn, use_pair, taps, Kt, kpt, kblocks, tiles_n, m_tiles, split_k;
@@ -1360,12 +1419,28 @@ extern "C" long long sdb_tc_workspace_bytes(const sdb_tc_args* a) {
     return pl.ws_bytes;
 }
 
-// column-statistics layout of a plan: 4 slots (32-row lane quarters) per 128-row m-tile; only for plans whose tiles
-// never straddle two samples and that store their final values themselves (no split-K)
+// Column-statistics layout of a plan.  Without split-K the epilogue writes them: 4 slots (32-row lane quarters) per 128-row
+// m-tile; the slots of a sample must be consecutive: one sample per tile (tn == 1), or tn whole images of >= 32 pixels in one
+// tile; a sample then owns 4 * tiles_w * tiles_h / tn consecutive slots.  With split-K the fixed-order reduction kernel writes them: one slot per 32
+// consecutive output rows, OH * OW / 32 per sample.  Either way only an fp32 output that stores its final values qualifies.
 static bool colstats_supported(const sdb_tc_args* a, const TcPlan& pl) {
-    // (an output remap — sub-pixel phase of an upsampling conv — is fine: the caller gives every phase its own slot region)
-    return a->taps > 0 && pl.tn == 1 && pl.split_k == 1 && !a->geglu && !a->col_group && a->out_dtype == SDB_F32 &&
-           a->N % 4 == 0 && a->ldc % 4 == 0;
+    // (an output remap — sub-pixel phase of an upsampling conv — is fine without split-K: the caller gives every phase its own slot region)
+    if (!(a->taps > 0 && !a->geglu && !a->col_group && a->out_dtype == SDB_F32 && a->N % 4 == 0 && a->ldc % 4 == 0)) return false;
+    if (pl.split_k > 1) return a->out_sh <= 1 && ((long long)a->OH * a->OW) % 32 == 0 && (a->OHF <= 0 || a->OHF == a->OH) && (a->OWF <= 0 || a->OWF == a->OW);
+    // tn > 1: the tile holds tn whole images (tiles_w == tiles_h == 1), image i in rows [i*tw*th, (i+1)*tw*th): its slots are
+    // consecutive as long as an image covers whole 32-row quarters
+    return pl.tn == 1 || (pl.tiles_w * pl.tiles_h == 1 && pl.tw * pl.th >= 32);
+}
+
+static void colstats_layout(const sdb_tc_args* a, const TcPlan& pl, long long* slots, long long* slots_per_item) {
+    if (pl.split_k > 1) {
+        *slots = pl.rows_out / 32;
+        *slots_per_item = ((long long)a->OH * a->OW) / 32;
+    } else {
+        const long long mt = pl.use_pair ? 2LL * ((pl.m_tiles + 1) / 2) : pl.m_tiles;
+        *slots = 4 * mt;
+        *slots_per_item = 4LL * pl.tiles_w * pl.tiles_h / pl.tn;
+    }
 }
 
 extern "C" int sdb_tc_colstats_layout(const sdb_tc_args* a, long long* slots, long long* slots_per_item) {
@@ -1377,9 +1452,7 @@ extern "C" int sdb_tc_colstats_layout(const sdb_tc_args* a, long long* slots, lo
     int rc = make_plan(&t, &pl);
     if (rc) return rc;
     if (!colstats_supported(a, pl)) return SDB_OK;
-    const long long mt = pl.use_pair ? 2LL * ((pl.m_tiles + 1) / 2) : pl.m_tiles;
-    *slots = 4 * mt;
-    *slots_per_item = 4LL * pl.tiles_w * pl.tiles_h;
+    colstats_layout(a, pl, slots, slots_per_item);
     return SDB_OK;
 }
 
@@ -1389,9 +1462,10 @@ extern "C" int sdb_tc_contract(const sdb_tc_args* a, void* stream) {
     int rc = make_plan(a, &pl);
     if (rc) return rc;
     if (a->colstats) {
-        SDB_REQUIRE(colstats_supported(a, pl), "tc_contract: column statistics need a conv plan with one sample per tile, no split-K, fp32 output");
-        const long long mt = pl.use_pair ? 2LL * ((pl.m_tiles + 1) / 2) : pl.m_tiles;
-        SDB_REQUIRE(a->colstats_slots >= 4 * mt, "tc_contract: colstats buffer has %lld slots, needs %lld", a->colstats_slots, 4 * mt);
+        SDB_REQUIRE(colstats_supported(a, pl), "tc_contract: column statistics need an fp32 conv output whose 32-row slots lie inside one sample");
+        long long need_slots = 0, spi_ = 0;
+        colstats_layout(a, pl, &need_slots, &spi_);
+        SDB_REQUIRE(a->colstats_slots >= need_slots, "tc_contract: colstats buffer has %lld slots, needs %lld", a->colstats_slots, need_slots);
         SDB_REQUIRE(((uintptr_t)a->colstats & 15) == 0 && ((uintptr_t)a->out & 15) == 0 && (!a->residual || (((uintptr_t)a->residual & 15) == 0 && a->ldr % 4 == 0)) &&
                     (!a->rowvec || (((uintptr_t)a->rowvec & 15) == 0 && a->ldv % 4 == 0)), "tc_contract: column statistics need 16-byte aligned operands");
     }
@@ -1421,7 +1495,7 @@ extern "C" int sdb_tc_contract(const sdb_tc_args* a, void* stream) {
         const long long ld_max = a->ldc > a->N ? a->ldc : a->N;
         p.off32 = (pl.rows_out + 1) * ld_max + a->N < (1LL << 32) ? 1 : 0;
     }
-    p.colstats = a->colstats;
+    p.colstats = pl.split_k > 1 ? nullptr : a->colstats;      // split-K: the reduction kernel writes them
     p.colstats_sq = a->colstats ? a->colstats_slots * (long long)a->N : 0;
 #ifdef SDB_TC_TRACE
     p.trace = g_trace_ptr;
@@ -1541,6 +1615,15 @@ extern "C" int sdb_tc_contract(const sdb_tc_args* a, void* stream) {
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     const long long rows_per_img = conv ? (long long)p.OHF * p.OWF : 1;
+    if (a->colstats) {
+        SDB_REQUIRE(!p.out_bf16 && ((uintptr_t)a->out & 15) == 0 && a->ldc % 4 == 0 && (!a->bias || ((uintptr_t)a->bias & 15) == 0),
+                    "tc_contract: split-K column statistics need 16-byte aligned fp32 operands");
+        dim3 g((unsigned)(pl.rows_out / 32), (unsigned)((a->N / 4 + 31) / 32));
+        launch_pdl(splitk_reduce_stats_kernel, dim3(g), dim3(256), 0, st, p.ws, p.ws_split_stride, p.split_k, pl.rows_out, a->N, a->bias,
+                   conv ? a->rowvec : nullptr, a->ldv, rows_per_img, a->residual, a->ldr, reinterpret_cast<float*>(a->out), a->ldc,
+                   a->colstats, p.colstats_sq);
+        return check_launch("splitk_reduce_stats_kernel");
+    }
     launch_pdl(splitk_reduce_kernel, dim3(blocks), dim3(256), 0, st, p.ws, p.ws_split_stride, p.split_k, pl.rows_out, a->N, a->bias,
                                                  conv ? a->rowvec : nullptr, a->ldv, rows_per_img, a->residual, a->ldr,
                                                  a->out, a->ldc, p.out_bf16);

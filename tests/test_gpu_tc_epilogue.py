@@ -124,3 +124,29 @@ def test_split_k_partials_through_tma(cuda):
     a, b = _both(lambda: ops.conv_tc(x, wp, bias, 3, 3, pad=1, split_k=8, variant=2))
     assert torch.equal(a, b)
     assert rel(a, nhwc(F.conv2d(nchw(x.float()), w.float(), bias, padding=1))) < 3e-5
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,sk", [(8, 8, 8, 1280, 1280, 8), (8, 8, 8, 1280, 1280, 1), (3, 8, 8, 640, 1280, 1), (8, 16, 16, 1280, 1280, 3),
+                                               (2, 16, 16, 640, 640, 1), (5, 8, 16, 320, 640, 2)])
+def test_colstats_small_maps_and_split_k(cuda, N, H, W, Cin, Cout, sk):
+    """8x8 / 16x16 feature maps: a 128-row tile holds two samples (statistics per 32-row quarter still belong to one), and
+    split-K launches get their statistics from the fixed-order reduction kernel.  The GroupNorm that consumes them must equal
+    the GroupNorm that measures the tensor itself, and sample i of the batch must equal the same sample run alone."""
+    from sdb200 import ops
+    x = randn(N, H, W, Cin, seed=1).to(torch.bfloat16)
+    w = (randn(Cout, Cin, 3, 3, seed=2) * (Cin * 9) ** -0.5).to(torch.bfloat16)
+    b = randn(Cout, seed=3)
+    res = randn(N, H, W, Cout, seed=5)
+    wp = ops.pack_conv_weight(w, torch.bfloat16)
+    g, be = randn(Cout, seed=6), randn(Cout, seed=7)
+    for variant in (1, 2):
+        out = ops.conv_tc(x, wp, b, 3, 3, pad=1, residual=res, variant=variant, split_k=sk, want_stats=True)
+        assert getattr(out, "_sdb_cs", None) is not None, (variant, sk)
+        ref_out = nhwc(F.conv2d(nchw(x.float()), w.float(), b, padding=1)) + res
+        assert rel(out, ref_out) < 3e-5
+        y = ops.groupnorm(out, g, be, 1e-5, act=1, out_dtype=torch.float32)
+        ref = F.silu(F.group_norm(nchw(out).double(), 32, g.double(), be.double(), 1e-5))
+        assert rel(nchw(y), ref) < 2e-5, (variant, sk)
+        out1 = ops.conv_tc(x[1:2].contiguous(), wp, b, 3, 3, pad=1, residual=res[1:2].contiguous(), variant=variant, split_k=sk, want_stats=True)
+        y1 = ops.groupnorm(out1, g, be, 1e-5, act=1, out_dtype=torch.float32)
+        assert torch.equal(out1[0], out[1]) and torch.equal(y1[0], y[1]), (variant, sk)
