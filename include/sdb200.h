@@ -102,7 +102,8 @@ int sdb_cast_concat(const float* x0, int C0, const float* x1, int C1, int N, int
 int sdb_avgpool2x2(const float* x, int N, int H, int W, int C, void* out, int out_dtype, void* stream);
 int sdb_upsample_bilinear2x(const float* x, int N, int H, int W, int C, void* out, int out_dtype, void* stream);
 /* out = act(x) (+ optional cast); act 0 none, 1 SiLU (emb_layers' nn.SiLU, model.py:195-196),
- * 2 GELU-erf (DDPM/models/unet.py:29). n elements. */
+ * 2 GELU-erf (DDPM/models/unet.py:29), 3 quick-GELU x * sigmoid(1.702 x) (the CLIP text tower's MLP, clip_encoder/modules.py:246).
+ * n elements. */
 int sdb_activation(const float* x, void* out, int out_dtype, long long n, int act, void* stream);
 /* GEGLU: out[r, j] = h[r, j] * gelu_erf(h[r, inner + j]) (openai_model/attention.py:140-141).
  * h [rows, 2*inner] fp32 -> out [rows, inner] (out_dtype). */
@@ -112,6 +113,10 @@ int sdb_geglu(const float* h, int rows, int inner, void* out, int out_dtype, voi
  * attention (flash_attn_func semantics, openai_model/attention.py:106-112). */
 int sdb_softmax_rows(const float* s, long long rows, int L, long long lds, float scale, void* out,
                      int out_dtype, long long ldo, void* stream);
+/* the same with a causal mask (fp32-mode attention of the CLIP text tower, clip_encoder/modules.py:246-250): row r belongs to
+ * query r % Sq and sees keys 0 .. r % Sq; masked probabilities are written as exact zeros. */
+int sdb_softmax_rows_causal(const float* s, long long rows, int L, int Sq, long long lds, float scale, void* out,
+                            int out_dtype, long long ldo, void* stream);
 /* out = a + b (fp32), n elements: residual adds that follow a norm (DDPM/models/layers.py:338). */
 int sdb_add(const float* a, const float* b, float* out, long long n, void* stream);
 /* out[n,p,c] = x[n,p,c] + rowvec[n*ldv + c]: `time_emb[:, :, None, None] + h` (DDPM/models/layers.py:331-333). */
@@ -276,6 +281,9 @@ typedef struct sdb_attn_args {
     int B, H, Sq, Sk, d, dpad;
     float scale;
     int dense;
+    /* != 0: causal mask — query i attends to keys 0..i only, as HF CLIPTextModel builds it for the text tower behind
+     * FrozenCLIPEmbedder (clip_encoder/modules.py:212-256); needs Sq == Sk. */
+    int causal;
 } sdb_attn_args;
 int sdb_attention_fwd(const sdb_attn_args* args /* host */, void* stream);
 

@@ -391,6 +391,38 @@ def gen_ddim_mask():
     save("ddim_mask.pt", out)
 
 
+CLIP_TINY_CFG = dict(vocab_size=1000, hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2,
+                     max_position_embeddings=77, layer_norm_eps=1e-5, hidden_act="quick_gelu")
+CLIP_L14_CFG = dict(vocab_size=49408, hidden_size=768, intermediate_size=3072, num_hidden_layers=12, num_attention_heads=12,
+                    max_position_embeddings=77, layer_norm_eps=1e-5, hidden_act="quick_gelu")
+
+
+def gen_clip(name, cfg, B, seed):
+    """'next' row f2: the text tower FrozenCLIPEmbedder calls (clip_encoder/modules.py:246-252) = HuggingFace CLIPTextModel, run
+    here from the installed transformers package with procedurally generated weights; the restatement is asserted equal."""
+    import transformers
+    from transformers import CLIPTextConfig, CLIPTextModel
+    hf = CLIPTextModel(CLIPTextConfig(**cfg)).eval()
+    ks = W.key_shapes_of(hf)
+    sd = W.make_state_dict(ks, seed)
+    missing = hf.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys and all("position_ids" in k for k in missing.missing_keys), missing
+    rng = np.random.Generator(np.random.PCG64(seed + 1))
+    ids = torch.from_numpy(rng.integers(0, cfg["vocab_size"], size=(B, 77), dtype=np.int64))
+    ids[:, 0] = cfg["vocab_size"] - 2            # BOS / EOS ids of the CLIP vocabulary layout
+    ids[:, -1] = cfg["vocab_size"] - 1
+    with torch.no_grad():
+        z_ref = hf(input_ids=ids).last_hidden_state
+        z_or = R.clip_text_forward(sd, cfg, ids)
+        z64 = R.clip_text_forward({k: v.double() for k, v in sd.items()}, cfg, ids)
+    err = R.rel_l2(z_or, z_ref)
+    print("%s: restatement vs transformers %s CLIPTextModel rel-L2 = %.3e (z std %.3f); fp32 library vs f64 %.3e"
+          % (name, transformers.__version__, err, float(z_ref.std()), R.rel_l2(z_ref, z64)))
+    assert err < 2e-5, err
+    save(name + ".pt", dict(cfg=cfg, seed=seed, key_shapes=ks, ids=ids, z_ref=z_ref.clone(), z_f64=z64.float().clone(), restate_err=err,
+                            transformers_version=transformers.__version__))
+
+
 def gen_ddpm():
     net = RH.build_ddpm_unet()
     ks = W.key_shapes_of(net)
@@ -447,6 +479,9 @@ def main():
             gen_unet_variant(name, cfg, seed=81 + 10 * i)
     if a.part in ("all", "vae_enc"):
         gen_vae_enc("vae_enc_tiny", TINY_VAE_DDCONFIG, B=2, res=32, seed=61)
+    if a.part in ("all", "clip"):
+        gen_clip("clip_text_tiny", CLIP_TINY_CFG, B=2, seed=111)
+        gen_clip("clip_text_l14", CLIP_L14_CFG, B=2, seed=121)
     if a.part in ("all", "ddim_mask"):
         gen_ddim_mask()
     if a.part in ("all", "sd_full", "sd_traj"):

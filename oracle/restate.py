@@ -642,6 +642,38 @@ def ddpm_unet_forward(sd, x, time, pe=None):
 
 
 # ----------------------------------------------------------------------------------------------------
+# CLIP text tower behind FrozenCLIPEmbedder (SURVEY.md §8 'next' row f2)
+# ----------------------------------------------------------------------------------------------------
+
+
+def clip_text_forward(sd, cfg, input_ids):
+    """`CLIPTextModel(input_ids).last_hidden_state` as FrozenCLIPEmbedder.forward uses it (clip_encoder/modules.py:246-252).
+    The model itself lives in a third-party dependency (HuggingFace transformers, `transformers==4.49.0` in the reference's
+    req.txt; the image has 5.5): its published algorithm is restated here — token + learned position embedding, pre-LayerNorm
+    transformer layers with causal multi-head self-attention (q scaled by d^-1/2) and a quick-GELU MLP, final LayerNorm —
+    and pinned against the installed library by oracle/make_golden.py (tests/golden/clip_text_*.pt)."""
+    D, H, eps = cfg["hidden_size"], cfg["num_attention_heads"], cfg["layer_norm_eps"]
+    d = D // H
+    B, S = input_ids.shape
+    p = "text_model."
+    x = sd[p + "embeddings.token_embedding.weight"][input_ids] + sd[p + "embeddings.position_embedding.weight"][:S][None]
+    mask = torch.full((S, S), float("-inf"), dtype=x.dtype).triu(1)
+    for i in range(cfg["num_hidden_layers"]):
+        q_ = "%sencoder.layers.%d." % (p, i)
+        h = F.layer_norm(x, (D,), sd[q_ + "layer_norm1.weight"], sd[q_ + "layer_norm1.bias"], eps)
+        q = _lin(sd, q_ + "self_attn.q_proj", h).view(B, S, H, d).transpose(1, 2) * d ** -0.5
+        k = _lin(sd, q_ + "self_attn.k_proj", h).view(B, S, H, d).transpose(1, 2)
+        v = _lin(sd, q_ + "self_attn.v_proj", h).view(B, S, H, d).transpose(1, 2)
+        a = torch.softmax(q @ k.transpose(-1, -2) + mask, dim=-1) @ v
+        x = x + _lin(sd, q_ + "self_attn.out_proj", a.transpose(1, 2).reshape(B, S, D))
+        h = F.layer_norm(x, (D,), sd[q_ + "layer_norm2.weight"], sd[q_ + "layer_norm2.bias"], eps)
+        h = _lin(sd, q_ + "mlp.fc1", h)
+        h = h * torch.sigmoid(1.702 * h) if cfg["hidden_act"] == "quick_gelu" else F.gelu(h)
+        x = x + _lin(sd, q_ + "mlp.fc2", h)
+    return F.layer_norm(x, (D,), sd[p + "final_layer_norm.weight"], sd[p + "final_layer_norm.bias"], eps)
+
+
+# ----------------------------------------------------------------------------------------------------
 # metrics
 # ----------------------------------------------------------------------------------------------------
 

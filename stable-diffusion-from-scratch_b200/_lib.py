@@ -70,6 +70,7 @@ class AttnArgs(C.Structure):
         ("B", C.c_int), ("H", C.c_int), ("Sq", C.c_int), ("Sk", C.c_int), ("d", C.c_int), ("dpad", C.c_int),
         ("scale", C.c_float),
         ("dense", C.c_int),
+        ("causal", C.c_int),
     ]
 
 
@@ -94,6 +95,7 @@ SIGNATURES = {
     "sdb_activation": (_I, [_P, _P, _I, _L, _I, _P]),
     "sdb_geglu": (_I, [_P, _I, _I, _P, _I, _P]),
     "sdb_softmax_rows": (_I, [_P, _L, _I, _L, _F, _P, _I, _L, _P]),
+    "sdb_softmax_rows_causal": (_I, [_P, _L, _I, _I, _L, _F, _P, _I, _L, _P]),
     "sdb_add": (_I, [_P, _P, _P, _L, _P]),
     "sdb_add_rowvec": (_I, [_P, _P, _L, _I, _L, _I, _P, _I, _P]),
     "sdb_timestep_embedding": (_I, [_P, _P, _I, _I, _I, _P, _P]),

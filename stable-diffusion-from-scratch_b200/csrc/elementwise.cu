@@ -83,6 +83,7 @@ __global__ void activation_kernel(const float* __restrict__ x, void* __restrict_
         float v = x[i];
         if (act == 1) v = silu_exact(v);
         else if (act == 2) v = gelu_erf(v);
+        else if (act == 3) v = v / (1.0f + expf(-1.702f * v));      // quick_gelu = x * sigmoid(1.702 x) (CLIP text tower MLP)
         if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
         else reinterpret_cast<float*>(out)[i] = v;
     }
@@ -129,14 +130,24 @@ __global__ void add_kernel(const float* __restrict__ a, const float* __restrict_
 }
 
 // ---- row softmax: one CTA per row, fp32 statistics ----------------------------------------------
+// causal_sq > 0: row r is query r % causal_sq and sees keys 0 .. (r % causal_sq) only (masked probabilities are written as 0)
 template <bool OUT_BF16>
-__global__ void softmax_rows_kernel(const float* __restrict__ s, int L, long long lds, float scale,
-                                    void* __restrict__ out, long long ldo) {
+__global__ void softmax_rows_kernel(const float* __restrict__ s, int L_all, long long lds, float scale,
+                                    void* __restrict__ out, long long ldo, int causal_sq) {
     pdl_trigger();
     pdl_wait();
     __shared__ float red[32];
     const long long row = blockIdx.x;
     const float* p = s + row * lds;
+    int L = L_all;
+    if (causal_sq > 0) {
+        const int qi = (int)(row % causal_sq);
+        L = qi + 1 < L_all ? qi + 1 : L_all;
+        for (int i = L + threadIdx.x; i < L_all; i += blockDim.x) {
+            if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(out)[row * ldo + i] = __float2bfloat16_rn(0.f);
+            else reinterpret_cast<float*>(out)[row * ldo + i] = 0.f;
+        }
+    }
     float m = -INFINITY;
     for (int i = threadIdx.x; i < L; i += blockDim.x) m = fmaxf(m, p[i] * scale);
     m = warp_max(m);
@@ -504,14 +515,25 @@ int sdb_geglu(const float* h, int rows, int inner, void* out, int out_dtype, voi
     return check_launch("geglu_kernel");
 }
 
-int sdb_softmax_rows(const float* s, long long rows, int L, long long lds, float scale, void* out,
-                     int out_dtype, long long ldo, void* stream) {
-    SDB_REQUIRE(s && out && rows > 0 && L > 0, "softmax_rows: bad args");
+static int launch_softmax_rows(const float* s, long long rows, int L, long long lds, float scale, void* out,
+                               int out_dtype, long long ldo, int causal_sq, void* stream) {
+    SDB_REQUIRE(s && out && rows > 0 && L > 0 && causal_sq >= 0, "softmax_rows: bad args");
     SDB_REQUIRE(rows < (1LL << 31), "softmax_rows: too many rows");
     int threads = L >= 1024 ? 256 : (L >= 256 ? 128 : 32);
-    if (out_dtype == SDB_BF16) launch_pdl(softmax_rows_kernel<true>, dim3((unsigned)rows), dim3(threads), 0, (cudaStream_t)stream, s, L, lds, scale, out, ldo);
-    else launch_pdl(softmax_rows_kernel<false>, dim3((unsigned)rows), dim3(threads), 0, (cudaStream_t)stream, s, L, lds, scale, out, ldo);
+    if (out_dtype == SDB_BF16) launch_pdl(softmax_rows_kernel<true>, dim3((unsigned)rows), dim3(threads), 0, (cudaStream_t)stream, s, L, lds, scale, out, ldo, causal_sq);
+    else launch_pdl(softmax_rows_kernel<false>, dim3((unsigned)rows), dim3(threads), 0, (cudaStream_t)stream, s, L, lds, scale, out, ldo, causal_sq);
     return check_launch("softmax_rows_kernel");
+}
+
+int sdb_softmax_rows(const float* s, long long rows, int L, long long lds, float scale, void* out,
+                     int out_dtype, long long ldo, void* stream) {
+    return launch_softmax_rows(s, rows, L, lds, scale, out, out_dtype, ldo, 0, stream);
+}
+
+int sdb_softmax_rows_causal(const float* s, long long rows, int L, int Sq, long long lds, float scale, void* out,
+                            int out_dtype, long long ldo, void* stream) {
+    SDB_REQUIRE(Sq > 0, "softmax_rows_causal: Sq must be positive");
+    return launch_softmax_rows(s, rows, L, lds, scale, out, out_dtype, ldo, Sq, stream);
 }
 
 int sdb_add_rowvec(const float* x, const float* rowvec, long long ldv, int N, long long HW, int C, void* out,

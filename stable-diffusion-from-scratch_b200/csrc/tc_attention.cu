@@ -55,6 +55,7 @@ struct AttnP {
     long long o_bs, o_ss, o_hs;
     int Sq, Sk, d, H;
     float scale_log2;
+    int causal;             // query q sees keys 0 .. q (CLIP text tower); 0 = full attention
 };
 
 template <int DPAD>
@@ -320,6 +321,12 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 128; ++j) if (j >= kvalid) r[j] = 0xff800000u;   // -inf
             }
+            if (p.causal) {
+                // keys after this thread's query are masked; key 0 is always visible, so no row is ever empty
+                const int jmax = q0 + g * 128 + row - t * 128;                       // last visible key of this tile
+#pragma unroll
+                for (int j = 0; j < 128; ++j) if (j > jmax) r[j] = 0xff800000u;
+            }
 #if SDB_ATTN_MAXCHAINS == 4
             // four independent 3-input max chains of 16 (a chain link costs the ALU latency, not an issue slot)
             float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
@@ -475,6 +482,7 @@ static int launch_attn(const sdb_attn_args* a, cudaStream_t st) {
     p.out = a->out; p.o_bs = a->o_bs; p.o_ss = a->o_ss; p.o_hs = a->o_hs;
     p.Sq = a->Sq; p.Sk = a->Sk; p.d = a->d; p.H = a->H;
     p.scale_log2 = a->scale * 1.4426950408889634f;
+    p.causal = a->causal ? 1 : 0;
     dim3 grid((unsigned)ceil_div(a->Sq, 128 * Cfg::G), (unsigned)a->H, (unsigned)a->B);
     launch_pdl(tc_attention_kernel<DPAD>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, tmQ, tmK, tmV, p);
     return check_launch("tc_attention_kernel");
@@ -489,6 +497,7 @@ extern "C" int sdb_attention_fwd(const sdb_attn_args* a, void* stream) {
     SDB_REQUIRE(a->B > 0 && a->H > 0 && a->Sq > 0 && a->Sk > 0 && a->d > 0, "attention: empty problem");
     SDB_REQUIRE(a->d % 8 == 0 && a->dpad % 64 == 0 && a->dpad >= a->d && a->dpad <= 192, "attention: d=%d dpad=%d unsupported", a->d, a->dpad);
     SDB_REQUIRE(a->B <= 65535 && a->H <= 65535, "attention: grid too large");
+    SDB_REQUIRE(!a->causal || a->Sq == a->Sk, "attention: the causal mask needs Sq == Sk (got %d, %d)", a->Sq, a->Sk);
     SDB_REQUIRE(a->o_hs % 8 == 0 && a->o_ss % 8 == 0 && a->o_bs % 8 == 0 && ((uintptr_t)a->out & 15) == 0, "attention: output must be 16-byte aligned per head row");
     cudaStream_t st = (cudaStream_t)stream;
     switch (a->dpad) {

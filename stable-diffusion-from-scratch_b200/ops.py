@@ -184,6 +184,18 @@ def softmax_rows(s, scale, out_dtype=torch.float32):
     return out
 
 
+def softmax_rows_causal(s, scale, Sq, out_dtype=torch.float32):
+    """softmax(scale * s) over the last dim with a causal mask: row r is query r % Sq and sees keys 0 .. r % Sq."""
+    require_cuda(s)
+    assert s.dtype == torch.float32 and s.is_contiguous()
+    Lk = s.shape[-1]
+    rows = s.numel() // Lk
+    out = torch.empty(s.shape, dtype=out_dtype, device=s.device)
+    check(_L().sdb_softmax_rows_causal(ptr(s), rows, Lk, int(Sq), Lk, float(scale), ptr(out), dtype_code(out_dtype), Lk, stream_ptr()),
+          "softmax_rows_causal")
+    return out
+
+
 def add(a, b):
     require_cuda(a, b)
     assert a.dtype == b.dtype == torch.float32 and a.shape == b.shape and a.is_contiguous() and b.is_contiguous()
@@ -626,7 +638,8 @@ def gemm_tc(A, W, bias=None, residual=None, out_dtype=torch.float32, geglu=False
     return out
 
 
-def attention_tc(q, k, v, B, H, Sq, Sk, d, dpad, scale, q_strides, k_strides, v_strides, out=None, o_strides=None, dense=False):
+def attention_tc(q, k, v, B, H, Sq, Sk, d, dpad, scale, q_strides, k_strides, v_strides, out=None, o_strides=None, dense=False,
+                 causal=False):
     """q/k/v: bf16 tensors (any views) whose (batch, seq, head) element strides are given; heads stored padded to dpad
     channels, or (dense=True) with their d channels only.
     Returns out [B, Sq, H*d] bf16; o_strides = (batch, seq, head) element strides of another output layout."""
@@ -643,5 +656,6 @@ def attention_tc(q, k, v, B, H, Sq, Sk, d, dpad, scale, q_strides, k_strides, v_
     a.B, a.H, a.Sq, a.Sk, a.d, a.dpad = B, H, Sq, Sk, d, dpad
     a.scale = float(scale)
     a.dense = int(bool(dense))
+    a.causal = int(bool(causal))
     check(_L().sdb_attention_fwd(C.byref(a), stream_ptr()), "attention_fwd")
     return out

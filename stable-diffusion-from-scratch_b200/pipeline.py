@@ -54,8 +54,10 @@ class DiffusionWrapper(nn.Module):
 class LatentDiffusion(nn.Module):
     def __init__(self, unet_config=None, first_stage_config=None, timesteps=1000, linear_start=0.00085, linear_end=0.0120,
                  beta_schedule="linear", scale_factor=0.18215, conditioning_key="crossattn", compute_mode=None,
-                 unet=None, first_stage_model=None):
+                 unet=None, first_stage_model=None, cond_stage_model=None):
         super().__init__()
+        # optional text conditioner (Diffusion/config.yaml:69-70: FrozenCLIPEmbedder); None = the caller supplies `context` tensors
+        self.cond_stage_model = cond_stage_model
         unet = unet if unet is not None else UNetModel(**(unet_config or SD_UNET_CONFIG), compute_mode=compute_mode)
         self.model = DiffusionWrapper(unet, conditioning_key)
         if first_stage_model is None and first_stage_config is not False:
@@ -87,6 +89,14 @@ class LatentDiffusion(nn.Module):
                 cond = [cond]
             cond = {"c_crossattn": cond}
         return self.model(x_noisy, t, **cond)
+
+    @torch.no_grad()
+    def get_learned_conditioning(self, c):
+        """ldm/diffusion/ddpm.py `get_learned_conditioning`: cond_stage_model.encode(c) (text or token ids -> [B, 77, 768])."""
+        assert self.cond_stage_model is not None, "no cond_stage_model was given"
+        if hasattr(self.cond_stage_model, "encode") and callable(self.cond_stage_model.encode):
+            return self.cond_stage_model.encode(c)
+        return self.cond_stage_model(c)
 
     def q_sample_coefficients(self, t):
         """extract_into_tensor(sqrt_alphas_cumprod, t, .) and (sqrt_one_minus_alphas_cumprod, t, .) as two [B] fp32 vectors

@@ -299,3 +299,20 @@ def test_ops_reject_foreign_devices():
     from sdb200 import _lib
     with pytest.raises(_lib.SdbError):
         _lib.require_cuda(torch.zeros(1))
+
+
+def test_clip_text_state_dict_keys_match_fixture():
+    """FrozenCLIPEmbedder.transformer has HuggingFace CLIPTextModel's parameter names and shapes (ViT-L/14 text tower)."""
+    from oracle.golden import load_golden
+    from sdb200.clip_text import CLIPTextModel, FrozenCLIPEmbedder
+    g = load_golden("clip_text_l14.pt")
+    with torch.device("meta"):
+        m = CLIPTextModel(g["cfg"])
+    mine = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    want = {k: tuple(s) for k, s in g["key_shapes"]}
+    assert mine == want
+    with torch.device("meta"):
+        e = FrozenCLIPEmbedder(config=load_golden("clip_text_tiny.pt")["cfg"])
+    assert all(not p.requires_grad for p in e.parameters()) and e.max_length == 77
+    with pytest.raises(Exception):
+        e.transformer(input_ids=torch.zeros(2, 77, dtype=torch.long))       # CPU tensors: no fallback

@@ -126,3 +126,28 @@ def test_ddim_trajectory_bit_exact():
                                              unconditional_guidance_scale=cfg, unconditional_conditioning=t["uc"])
         assert torch.equal(z, t["z"])
         assert len(inter["x_inter"]) == t["n_inter"]
+
+
+@pytest.mark.parametrize("name", ["clip_text_tiny"])
+def test_clip_text_restatement_matches_library(name):
+    """'next' row f2: the CLIP text tower restatement against HuggingFace CLIPTextModel's output (the fixture), and — when the
+    transformers package is importable — against the library run here on the same procedurally generated weights."""
+    g = load_golden(name + ".pt")
+    sd = _sd(g)
+    with torch.no_grad():
+        z = R.clip_text_forward(sd, g["cfg"], g["ids"])
+    assert R.rel_l2(z, g["z_ref"]) < 1e-5 and R.rel_l2(g["z_ref"], g["z_f64"]) < 1e-5
+    # causality: changing a later token never changes an earlier position
+    ids2 = g["ids"].clone()
+    ids2[:, 40:] = (ids2[:, 40:] + 7) % g["cfg"]["vocab_size"]
+    with torch.no_grad():
+        z2 = R.clip_text_forward(sd, g["cfg"], ids2)
+    assert torch.equal(z2[:, :40], z[:, :40]) and not torch.equal(z2[:, 40:], z[:, 40:])
+    try:
+        from transformers import CLIPTextConfig, CLIPTextModel
+    except Exception:
+        return
+    hf = CLIPTextModel(CLIPTextConfig(**g["cfg"])).eval()
+    hf.load_state_dict(sd, strict=False)
+    with torch.no_grad():
+        assert R.rel_l2(hf(input_ids=g["ids"]).last_hidden_state, g["z_ref"]) < 1e-5
