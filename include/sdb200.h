@@ -287,6 +287,17 @@ typedef struct sdb_attn_args {
 } sdb_attn_args;
 int sdb_attention_fwd(const sdb_attn_args* args /* host */, void* stream);
 
+/* ---- fused attention forward for one WIDE head (d = 256 or 512): the VAE AttnBlock -------------------------------
+ * Replaces  w_ = bmm(q, k) * c**-0.5;  w_ = softmax(w_);  h_ = bmm(v, w_)  of AttnBlock.forward
+ * (ldm/modules/diffusionmodules/model.py:180-204; one head over all C channels, 4096 tokens in the SD decoder's mid block)
+ * without materialising the [Sq, Sk] score matrix: a CTA owns a 128-row query tile and ONE 256-channel half of the output
+ * (the 512 TMEM columns cannot hold S and a 512-wide O), recomputes S = Q K^T over the full d on tcgen05 and accumulates
+ * O[:, half] += P V[:, half].  q / k / v bf16 [B, S, d] with explicit batch / sequence strides in elements (d contiguous,
+ * e.g. the three column blocks of one [B*S, 3d] projection output); out [B, Sq, d] bf16. */
+int sdb_attention_wide_fwd(const void* q, const void* k, const void* v, void* out, long long q_bs, long long q_ss,
+                           long long k_bs, long long k_ss, long long v_bs, long long v_ss, long long o_bs, long long o_ss,
+                           int B, int Sq, int Sk, int d, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

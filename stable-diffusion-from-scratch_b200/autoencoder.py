@@ -91,8 +91,12 @@ def _fingerprint(module):
     return (ps[0].data_ptr(), ps[0].device, sum(p._version for p in ps))
 
 
+FUSED_ATTN_CHANNELS = (256, 512)     # head widths of tc_attention_wide_kernel
+
+
 class _VaeNet(nn.Module):
     """Packing and block execution shared by Encoder and Decoder."""
+    fused_attention = True           # False: AttnBlock as three GEMMs + row softmax per image (the round-1 path, kept for A/B)
 
     def __init__(self):
         super().__init__()
@@ -143,6 +147,10 @@ class _VaeNet(nn.Module):
                 # is added after P.V instead: softmax rows sum to 1, so P (V + 1 b^T) = P V + b^T.
                 P[("v", id(m))] = PackedLinear(m.v.weight.reshape(Cc, Cc), None, mode)
                 P[("vb", id(m))] = m.v.bias.detach().float().contiguous()
+                if mode == "bf16" and Cc in FUSED_ATTN_CHANNELS:
+                    # fused path: one [3C, C] projection (q | k | v side by side), then the wide-head flash kernel
+                    P[("qkv", id(m))] = PackedLinear(torch.cat([m.q.weight, m.k.weight, m.v.weight], 0).reshape(3 * Cc, Cc),
+                                                     torch.cat([m.q.bias, m.k.bias, m.v.bias], 0), mode)
             elif isinstance(m, Upsample):
                 P[("up", id(m))] = PackedConv(m.conv.weight, m.conv.bias, mode, up2=True)
             elif isinstance(m, Downsample):
@@ -182,6 +190,14 @@ class _VaeNet(nn.Module):
         S = Hh * Ww
         odt = engine.op_dtype(mode)
         hn = self._gn(ab.norm, x, mode, 0, odt).reshape(B * S, Cc)
+        if ("qkv", id(ab)) in P and self.fused_attention:
+            # bf16 mode, C = 256 / 512: flash-style kernel, no [S, S] score matrix, no per-image loop
+            qkv = engine.linear(hn, P[("qkv", id(ab))], out_dtype=odt)                          # [B*S, 3C]
+            W3 = 3 * Cc
+            o = ops.attention_wide(qkv, qkv[:, Cc:], qkv[:, 2 * Cc:], B, S, S, Cc, float(int(Cc) ** (-0.5)),
+                                   (S * W3, W3), (S * W3, W3), (S * W3, W3))
+            out = engine.linear(o.reshape(B * S, Cc), P[("proj_out", id(ab))], residual=x.reshape(B * S, Cc))
+            return out.reshape(B, Hh, Ww, Cc)
         q = engine.linear(hn, P[("q", id(ab))], out_dtype=odt)
         k = engine.linear(hn, P[("k", id(ab))], out_dtype=odt)
         scale = float(int(Cc) ** (-0.5))

@@ -659,3 +659,15 @@ def attention_tc(q, k, v, B, H, Sq, Sk, d, dpad, scale, q_strides, k_strides, v_
     a.causal = int(bool(causal))
     check(_L().sdb_attention_fwd(C.byref(a), stream_ptr()), "attention_fwd")
     return out
+
+
+def attention_wide(q, k, v, B, Sq, Sk, d, scale, q_strides, k_strides, v_strides, out=None):
+    """One wide head (d = 256 / 512, the VAE AttnBlock): q / k / v bf16 views with (batch, seq) element strides, channels
+    contiguous.  Returns out [B, Sq, d] bf16."""
+    require_cuda(q, k, v, out)
+    assert q.dtype == k.dtype == v.dtype == torch.bfloat16
+    if out is None:
+        out = torch.empty((B, Sq, d), dtype=torch.bfloat16, device=q.device)
+    check(_L().sdb_attention_wide_fwd(ptr(q), ptr(k), ptr(v), ptr(out), q_strides[0], q_strides[1], k_strides[0], k_strides[1],
+                                      v_strides[0], v_strides[1], Sq * d, d, B, Sq, Sk, d, float(scale), stream_ptr()), "attention_wide_fwd")
+    return out

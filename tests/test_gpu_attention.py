@@ -79,3 +79,37 @@ def test_attention_tc_9216_tokens(cuda):
         del ref
     print("attention S=9216 d=40: worst per-head rel-L2 %.3e" % worst)
     assert worst < 1e-2
+
+
+@pytest.mark.parametrize("B,Sq,Sk,d", [(1, 128, 64, 256), (2, 256, 256, 512), (1, 4096, 4096, 512), (2, 200, 300, 512), (1, 1024, 1024, 256), (3, 77, 130, 512)])
+def test_attention_wide(cuda, B, Sq, Sk, d):
+    """tc_attention_wide_kernel (the VAE AttnBlock's single head of d = C channels, ldm/modules/diffusionmodules/model.py:180-204)
+    against fp64 softmax(q k^T d^-1/2) v on the same bf16 inputs, with q | k | v as column blocks of one projection output
+    (the layout the decoder uses) and ragged sequence lengths."""
+    from sdb200 import ops
+    qkv = randn(B * max(Sq, Sk), 3 * d, seed=1).to(torch.bfloat16)
+    q = qkv[:B * Sq, :d]
+    k = qkv[:B * Sk, d:2 * d]
+    v = qkv[:B * Sk, 2 * d:]
+    scale = d ** -0.5
+    W3 = 3 * d
+    out = ops.attention_wide(q, k, v, B, Sq, Sk, d, scale, (Sq * W3, W3), (Sk * W3, W3), (Sk * W3, W3))
+    qd = q.reshape(B, Sq, d).double()
+    kd = k.reshape(B, Sk, d).double()
+    vd = v.reshape(B, Sk, d).double()
+    ref = torch.softmax(qd @ kd.transpose(1, 2) * scale, -1) @ vd
+    err = rel(out, ref)
+    print("attention_wide B=%d Sq=%d Sk=%d d=%d: rel-L2 %.3e" % (B, Sq, Sk, d, err))
+    assert out.shape == (B, Sq, d) and err < 1e-2
+
+
+def test_attention_wide_large_logits(cuda):
+    """growing logits exercise the lazy rescale of the 256-column O accumulator"""
+    from sdb200 import ops
+    B, S, d = 1, 512, 512
+    q = (randn(B * S, d, seed=4) * 1.5).to(torch.bfloat16)
+    k = (randn(B * S, d, seed=5) * 1.5).to(torch.bfloat16) * torch.linspace(0.2, 3.0, S, device="cuda").view(S, 1).to(torch.bfloat16)
+    v = randn(B * S, d, seed=6).to(torch.bfloat16)
+    out = ops.attention_wide(q, k, v, B, S, S, d, 0.2, (S * d, d), (S * d, d), (S * d, d))
+    ref = torch.softmax(q.double().view(B, S, d) @ k.double().view(B, S, d).transpose(1, 2) * 0.2, -1) @ v.double().view(B, S, d)
+    assert rel(out, ref) < 1e-2

@@ -37,7 +37,7 @@ else:
     z = torch.randn(a.batch, 4, a.latent, a.latent, device=dev)
     run = lambda: net.decode(z)
 
-NAMES = ["sdb_tc_contract", "sdb_attention_fwd", "sdb_groupnorm_nhwc", "sdb_groupnorm_from_colstats", "sdb_layernorm", "sdb_cast_concat",
+NAMES = ["sdb_tc_contract", "sdb_attention_fwd", "sdb_attention_wide_fwd", "sdb_groupnorm_nhwc", "sdb_groupnorm_from_colstats", "sdb_layernorm", "sdb_cast_concat",
          "sdb_simt_contract", "sdb_skinny_linear"]
 
 
@@ -49,6 +49,9 @@ def describe(name, args):
     if name == "sdb_attention_fwd":
         o = args[0]._obj
         return "attn B=%d H=%d Sq=%d Sk=%d d=%d" % (o.B, o.H, o.Sq, o.Sk, o.d), 4.0 * o.B * o.H * o.Sq * o.Sk * o.d
+    if name == "sdb_attention_wide_fwd":
+        B, Sq, Sk, d = args[12], args[13], args[14], args[15]
+        return "attn_wide B=%d Sq=%d Sk=%d d=%d" % (B, Sq, Sk, d), 4.0 * B * Sq * Sk * d
     if name == "sdb_groupnorm_nhwc":
         return "groupnorm N=%d HW=%d C=%d" % (args[4], args[5], args[1] + args[3]), 0.0
     if name == "sdb_groupnorm_from_colstats":

@@ -3,6 +3,8 @@
   one_op.py conv NB H W Cin Cout ksize stride res(0/1) variant bn
   one_op.py attn B H Sq Sk d
   one_op.py gn N HW C act
+  one_op.py attnw B Sq Sk d          (wide single head, VAE AttnBlock)
+  one_op.py ddim n                   (fused DDIM update over n fp32 elements)
 """
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -40,6 +42,16 @@ elif kind == "attn":
     k = torch.zeros(B, Sk, H, dp, device=dev, dtype=torch.bfloat16); k[..., :d] = torch.randn(B, Sk, H, d, device=dev)
     vv = torch.zeros(B, Sk, H, dp, device=dev, dtype=torch.bfloat16); vv[..., :d] = torch.randn(B, Sk, H, d, device=dev)
     fn = lambda: ops.attention_tc(q, k, vv, B, H, Sq, Sk, d, dp, d ** -0.5, (Sq * H * dp, H * dp, dp), (Sk * H * dp, H * dp, dp), (Sk * H * dp, H * dp, dp))
+elif kind == "attnw":
+    B, Sq, Sk, d = v[:4]
+    q = torch.randn(B * Sq, d, device=dev).to(torch.bfloat16)
+    k = torch.randn(B * Sk, d, device=dev).to(torch.bfloat16)
+    vv = torch.randn(B * Sk, d, device=dev).to(torch.bfloat16)
+    fn = lambda: ops.attention_wide(q, k, vv, B, Sq, Sk, d, d ** -0.5, (Sq * d, d), (Sk * d, d), (Sk * d, d))
+elif kind == "ddim":
+    n = v[0]
+    x, e = torch.randn(n, device=dev), torch.randn(n, device=dev)
+    fn = lambda: ops.ddim_step(x, e, 0.9, 0.95, 0.3, 0.0, 0.4)[0]
 elif kind == "gn":
     N, HW, Cc, act = v[:4]
     x = torch.randn(N, HW, 1, Cc, device=dev)
