@@ -15,6 +15,7 @@
 namespace sdb {
 
 constexpr int SBM = 128, SBN = 64, SBK = 16;
+constexpr int SIMT_FLUSH = 16;      // k-tiles per first-level partial sum
 
 struct SimtP {
     const float* A; const float* B; float* out;
@@ -61,11 +62,14 @@ __global__ void __launch_bounds__(256) simt_contract_kernel(const SimtP p) {
     const int b_col = p.b_kn ? (tid & 15) * 4 : (tid & 3) * 4;   // n (kn) or k (nk)
 
     const int ty = tid >> 4, tx = tid & 15;
-    float acc[8][4];
+    // Two-level accumulation: `acc` sums at most SIMT_FLUSH k-tiles (256 products) and is then folded into `tot`.  A single
+    // running fp32 sum over K = 9 * 512 = 4608 products drifts by ~sqrt(K) ulp; the VAE decoder (39 such convs in a row) then
+    // sat at 8.2e-6 of the 1e-5 fp32-mode budget at 512x512.  Blocked summation keeps the growth at ~sqrt(256) + sqrt(K / 256).
+    float acc[8][4], tot[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) { acc[i][j] = 0.f; tot[i][j] = 0.f; }
 
     const int IHU = p.IH * p.up, IWU = p.IW * p.up;
 
@@ -184,7 +188,17 @@ __global__ void __launch_bounds__(256) simt_contract_kernel(const SimtP p) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
         }
+        if ((((k0 / SBK) + 1) % SIMT_FLUSH) == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { tot[i][j] += acc[i][j]; acc[i][j] = 0.f; }
+        }
     }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += tot[i][j];
 
     // ---- epilogue ----
 #pragma unroll

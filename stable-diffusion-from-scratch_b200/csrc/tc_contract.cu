@@ -451,143 +451,6 @@ __device__ __forceinline__ void epilogue_warp(const TcP& p, uint32_t taddr, cons
 #undef SDB_EPI
 }
 
-template <int BN>
-__global__ void __launch_bounds__(192, 2)
-tc_contract_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcP p) {
-    pdl_trigger();
-    if (threadIdx.x == 0) { TC1_TRACE(0); TC1_TRACE(7); }
-    using Cfg = TcCfg<BN>;
-    constexpr int STAGES = Cfg::STAGES;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sA = smem;
-    uint8_t* sB = smem + STAGES * TC_A_BYTES;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* accum_bar = empty_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
-    float* s_bias = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    // ---- tile coordinates ----
-    const int tile = blockIdx.x;
-    const int nt = tile % p.tiles_n, mt = tile / p.tiles_n;
-    const int n0 = nt * BN;
-    const int split = blockIdx.y;
-    const int kb0 = (int)((long long)p.kblocks * split / p.split_k);
-    const int kb1 = (int)((long long)p.kblocks * (split + 1) / p.split_k);
-
-    int m0 = mt * TC_BM;            // gemm mode
-    int ow0 = 0, oh0 = 0, img0 = 0; // conv mode
-    if (p.conv) {
-        int tww = mt % p.tiles_w;
-        int thh = (mt / p.tiles_w) % p.tiles_h;
-        int tnb = mt / (p.tiles_w * p.tiles_h);
-        ow0 = tww * p.tw; oh0 = thh * p.th; img0 = tnb * p.tn;
-    }
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmA);
-        tma_prefetch_desc(&tmB);
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(accum_bar, 1);
-        fence_barrier_init();
-    }
-    if (warp == 1) {
-        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-        tmem_relinquish();
-    }
-    tcgen05_fence_before();
-    __syncthreads();
-    tcgen05_fence_after();
-    const uint32_t tmem_d = *tmem_slot;
-    if (threadIdx.x == 0) TC1_TRACE(1);
-    pdl_wait();                                      // predecessor's outputs (A, residual, ...) are complete and visible
-    if (threadIdx.x == 0) TC1_TRACE(2);
-
-    if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
-            int s = 0; uint32_t ph = 0;
-            for (int kb = kb0; kb < kb1; ++kb) {
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-                const int tap = kb / p.kpt, cs = kb - tap * p.kpt;
-                if (p.conv) {
-                    const int r = tap / p.kw, sx = tap - r * p.kw;
-                    tma_load_4d(sA + s * TC_A_BYTES, &tmA, &full_bar[s], cs * TC_BK,
-                                ow0 * p.stride + sx - p.pad_w, oh0 * p.stride + r - p.pad_h, img0);
-                } else {
-                    tma_load_2d(sA + s * TC_A_BYTES, &tmA, &full_bar[s], cs * TC_BK, m0);
-                }
-                tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, &full_bar[s], cs * TC_BK, tap * p.cout_pad + n0);
-                if (++s == STAGES) { s = 0; ph ^= 1; }
-            }
-        }
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(BN, false, false);
-            int s = 0; uint32_t ph = 0;
-            for (int kb = kb0; kb < kb1; ++kb) {
-                mbar_wait(&full_bar[s], ph);
-                tcgen05_fence_after();
-                const uint64_t adesc = umma_desc_kmajor_sw128(smem_u32(sA + s * TC_A_BYTES));
-                const uint64_t bdesc = umma_desc_kmajor_sw128(smem_u32(sB + s * Cfg::B_BYTES));
-#pragma unroll
-                for (int k = 0; k < TC_BK / 16; ++k) {
-                    // advance 16 bf16 = 32 B along K inside the 128-B swizzle atom: +2 (16-B units)
-                    umma_bf16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-                }
-                umma_commit(&empty_bar[s]);          // smem slot reusable once these MMAs retire
-                if (++s == STAGES) { s = 0; ph ^= 1; }
-            }
-            umma_commit(accum_bar);                  // accumulator complete
-            TC1_TRACE(3);
-        }
-    } else {
-        // ================= epilogue (warps 2..5 -> TMEM lane groups 2,3,0,1) =================
-        const int et = threadIdx.x - 64;             // 0..127
-        for (int i = et; i < BN; i += 128) {
-            int n = n0 + i;
-            s_bias[i] = (p.bias && n < p.N) ? p.bias[n] : 0.f;
-        }
-        named_bar_sync(1, 128);
-
-        const int lg = warp & 3;                     // TMEM lane group this warp may access
-        const int row = lg * 32 + lane;              // row of the 128-row tile
-        long long pix;                               // output row index (pixel / token), -1 = outside the problem
-        int img = 0;
-        if (p.conv) {
-            int in_ = row / (p.th * p.tw);
-            int rem = row - in_ * (p.th * p.tw);
-            int ih = rem / p.tw, iw = rem - ih * p.tw;
-            img = img0 + in_;
-            int oh = oh0 + ih, ow = ow0 + iw;
-            bool valid = (img < p.NB) && (oh < p.OH) && (ow < p.OW);
-            pix = valid ? ((long long)img * p.OHF + (oh * p.out_sh + p.out_oh)) * p.OWF + (ow * p.out_sw + p.out_ow) : -1;
-        } else {
-            pix = (m0 + row) < p.M ? m0 + row : -1;
-        }
-        prefetch_residual_row(p, pix, n0, BN);
-        // once the accumulator is ready every TMA load has been consumed: the A ring doubles as the transpose staging area
-        float* stage = reinterpret_cast<float*>(sA) + (warp - 2) * (EPI_WARP_BYTES / 4);
-        const uint32_t taddr = tmem_d + ((uint32_t)(lg * 32) << 16);
-        if (warp == 2 && lane == 0) TC1_TRACE(4);
-        epilogue_warp<BN>(p, taddr, s_bias, stage, lane, n0, nt, pix, img, split, 0, 1, accum_bar, 0, mt * 4 + lg);
-        if (warp == 2 && lane == 0) TC1_TRACE(5);
-    }
-
-    // ---- teardown ----
-    tcgen05_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tcgen05_fence_after();
-        tmem_dealloc(tmem_d, Cfg::TMEM_COLS);
-    }
-}
-
 // ---- TMA epilogue of the pair kernel ---------------------------------------------------------------------------
 // One epilogue warp owns the 32 rows of a TMEM lane quarter and every other 32-column chunk of the accumulator (two warps per
 // quarter).  tcgen05.ld hands each lane one ROW of a chunk; the lane adds bias / time-embedding row / residual (or forms the
@@ -603,6 +466,104 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 // partials), bf16 out (+bias), GEGLU -> bf16.  Layouts it does not cover (sub-pixel phase remap, padded-head column remap,
 // bf16 out with residual) keep the register-store epilogue.
 struct UnitBox { int split, nt, mt, col0, w, h, n; };
+
+// One 32-row x 32-column chunk of an accumulator (this lane's row in `cur`, GEGLU gate in `g`) -> bias / residual (already in
+// the staging box `sbuf`) / time-embedding row / GEGLU -> swizzled staging box -> ONE TMA store (+ GroupNorm column statistics).
+// Shared by the persistent CTA-pair kernel and the one-CTA kernel.
+template <int BN, int MODE, bool HAS_RES>
+__device__ __forceinline__ void tepi_chunk(const TcP& p, const CUtensorMap* tmC, const uint32_t (&cur)[32], const uint32_t* g,
+                                           uint32_t sb_a, uint32_t sbuf, int c0, int col, const UnitBox& ub, int lane, int lg,
+                                           uint32_t rowmask, int img_w, bool rv_ok, const float* rowv, bool want_cs, bool partial,
+                                           int n_out) {
+    constexpr bool GEGLU = MODE == EPI_GEGLU;
+    constexpr bool OUT16 = MODE != EPI_F32;
+    if (OUT16) {
+        // bf16 rows of 64 B: four 16-byte pieces, piece j at (j ^ ((row >> 1) & 3)) (SWIZZLE_64B)
+        const uint32_t rowa = sbuf + lane * 64;
+        const uint32_t sw = (uint32_t)(lane >> 1) & 3u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float v[8];
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+                const float4 b4 = lds128(sb_a + 4 * (c0 + 8 * j + 4 * h2));
+                float x0 = __uint_as_float(cur[8 * j + 4 * h2 + 0]) + b4.x, x1 = __uint_as_float(cur[8 * j + 4 * h2 + 1]) + b4.y;
+                float x2 = __uint_as_float(cur[8 * j + 4 * h2 + 2]) + b4.z, x3 = __uint_as_float(cur[8 * j + 4 * h2 + 3]) + b4.w;
+                if (GEGLU) {
+                    const float4 bg = lds128(sb_a + 4 * (BN / 2 + c0 + 8 * j + 4 * h2));
+                    x0 *= gelu_erf_fast(__uint_as_float(g[(8 * j + 4 * h2 + 0) % (GEGLU ? 32 : 1)]) + bg.x);
+                    x1 *= gelu_erf_fast(__uint_as_float(g[(8 * j + 4 * h2 + 1) % (GEGLU ? 32 : 1)]) + bg.y);
+                    x2 *= gelu_erf_fast(__uint_as_float(g[(8 * j + 4 * h2 + 2) % (GEGLU ? 32 : 1)]) + bg.z);
+                    x3 *= gelu_erf_fast(__uint_as_float(g[(8 * j + 4 * h2 + 3) % (GEGLU ? 32 : 1)]) + bg.w);
+                }
+                v[4 * h2 + 0] = x0; v[4 * h2 + 1] = x1; v[4 * h2 + 2] = x2; v[4 * h2 + 3] = x3;
+            }
+            sts128(rowa + ((((uint32_t)j) ^ sw) << 4), pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                   pack_bf16x2(v[6], v[7]));
+        }
+    } else {
+        // fp32 rows of 128 B: eight 16-byte pieces, piece j at (j ^ (row & 7)) (SWIZZLE_128B); residual updated in place
+        const uint32_t rowa = sbuf + lane * 128;
+        const uint32_t sw = (uint32_t)lane & 7u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t pa = rowa + ((((uint32_t)j) ^ sw) << 4);
+            float4 v = make_float4(__uint_as_float(cur[4 * j]), __uint_as_float(cur[4 * j + 1]), __uint_as_float(cur[4 * j + 2]),
+                                   __uint_as_float(cur[4 * j + 3]));
+            if (!partial) {
+                const float4 b4 = lds128(sb_a + 4 * (c0 + 4 * j));
+                v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+            }
+            if (HAS_RES) {
+                const float4 r4 = lds128(pa);
+                v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
+            }
+            if (rowv) {
+                // time-embedding row of this quarter's image (same address in every lane: one broadcast transaction), added last
+                const float4 t4 = ldg_f4_or_zero(rowv + (long long)img_w * p.ldv + col + 4 * j, rv_ok && col + 4 * j < p.N);
+                v.x += t4.x; v.y += t4.y; v.z += t4.z; v.w += t4.w;
+            }
+            sts128f(pa, v.x, v.y, v.z, v.w);
+        }
+    }
+    fence_proxy_async_smem();                     // generic-proxy writes -> visible to the TMA unit
+    __syncwarp();
+    if (lane == 0) {
+        tma_store_5d(tmC, sbuf, col, ub.w, ub.h, ub.n, ub.split);
+        tma_store_commit();
+    }
+    if (want_cs) {
+        // GroupNorm column statistics of the stored values, read back from the staged box 128 bits at a time: this lane owns the
+        // column quad 4 * (lane & 7) of rows 4 i + (lane >> 3) (one row = the 8 pieces of a quarter-warp: conflict-free), then the
+        // 4 lanes that share a quad are folded in a fixed order — the same summation order as the register-store epilogue
+        const int rsel = lane >> 3;
+        const uint32_t qd = (uint32_t)lane & 7u;
+        float4 cs_s = make_float4(0.f, 0.f, 0.f, 0.f), cs_q = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + rsel;
+            const float4 v = lds128(sbuf + r * 128 + ((qd ^ ((uint32_t)r & 7u)) << 4));
+            if ((rowmask >> r) & 1u) {
+                cs_s.x += v.x; cs_s.y += v.y; cs_s.z += v.z; cs_s.w += v.w;
+                cs_q.x = fmaf(v.x, v.x, cs_q.x); cs_q.y = fmaf(v.y, v.y, cs_q.y);
+                cs_q.z = fmaf(v.z, v.z, cs_q.z); cs_q.w = fmaf(v.w, v.w, cs_q.w);
+            }
+        }
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {
+            cs_s.x += __shfl_xor_sync(0xffffffffu, cs_s.x, o); cs_s.y += __shfl_xor_sync(0xffffffffu, cs_s.y, o);
+            cs_s.z += __shfl_xor_sync(0xffffffffu, cs_s.z, o); cs_s.w += __shfl_xor_sync(0xffffffffu, cs_s.w, o);
+            cs_q.x += __shfl_xor_sync(0xffffffffu, cs_q.x, o); cs_q.y += __shfl_xor_sync(0xffffffffu, cs_q.y, o);
+            cs_q.z += __shfl_xor_sync(0xffffffffu, cs_q.z, o); cs_q.w += __shfl_xor_sync(0xffffffffu, cs_q.w, o);
+        }
+        const int cn = col + 4 * (int)qd;
+        if (lane < 8 && cn < n_out) {
+            float* dst = p.colstats + (long long)(ub.mt * 4 + lg) * p.N + cn;
+            *reinterpret_cast<float4*>(dst) = cs_s;
+            *reinterpret_cast<float4*>(dst + p.colstats_sq) = cs_q;
+        }
+    }
+}
 
 template <int BN, int MODE, bool HAS_RES>
 __device__ __forceinline__ void epilogue_tma_units(const TcP& p, const CUtensorMap* tmC, const CUtensorMap* tmR, uint32_t tmem_d,
@@ -735,78 +696,7 @@ __device__ __forceinline__ void epilogue_tma_units(const TcP& p, const CUtensorM
                 if (lane == 0) tma_store_wait_read<1>();  // the store of chunk q - 2 has finished reading this box
                 __syncwarp();
             }
-            if (OUT16) {
-                // bf16 rows of 64 B: four 16-byte pieces, piece j at (j ^ ((row >> 1) & 3)) (SWIZZLE_64B)
-                const uint32_t rowa = sbuf + lane * 64;
-                const uint32_t sw = (uint32_t)(lane >> 1) & 3u;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float v[8];
-#pragma unroll
-                    for (int h2 = 0; h2 < 2; ++h2) {
-                        const float4 b4 = lds128(sb_a + 4 * (c0 + 8 * j + 4 * h2));
-                        float x0 = __uint_as_float(cur[8 * j + 4 * h2 + 0]) + b4.x, x1 = __uint_as_float(cur[8 * j + 4 * h2 + 1]) + b4.y;
-                        float x2 = __uint_as_float(cur[8 * j + 4 * h2 + 2]) + b4.z, x3 = __uint_as_float(cur[8 * j + 4 * h2 + 3]) + b4.w;
-                        if (GEGLU) {
-                            const float4 bg = lds128(sb_a + 4 * (BN / 2 + c0 + 8 * j + 4 * h2));
-                            x0 *= gelu_erf_fast(__uint_as_float(g[(8 * j + 4 * h2 + 0) % (GEGLU ? 32 : 1)]) + bg.x);
-                            x1 *= gelu_erf_fast(__uint_as_float(g[(8 * j + 4 * h2 + 1) % (GEGLU ? 32 : 1)]) + bg.y);
-                            x2 *= gelu_erf_fast(__uint_as_float(g[(8 * j + 4 * h2 + 2) % (GEGLU ? 32 : 1)]) + bg.z);
-                            x3 *= gelu_erf_fast(__uint_as_float(g[(8 * j + 4 * h2 + 3) % (GEGLU ? 32 : 1)]) + bg.w);
-                        }
-                        v[4 * h2 + 0] = x0; v[4 * h2 + 1] = x1; v[4 * h2 + 2] = x2; v[4 * h2 + 3] = x3;
-                    }
-                    sts128(rowa + ((((uint32_t)j) ^ sw) << 4), pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                           pack_bf16x2(v[6], v[7]));
-                }
-            } else {
-                // fp32 rows of 128 B: eight 16-byte pieces, piece j at (j ^ (row & 7)) (SWIZZLE_128B); residual updated in place
-                const uint32_t rowa = sbuf + lane * 128;
-                const uint32_t sw = (uint32_t)lane & 7u;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint32_t pa = rowa + ((((uint32_t)j) ^ sw) << 4);
-                    float4 v = make_float4(__uint_as_float(cur[4 * j]), __uint_as_float(cur[4 * j + 1]), __uint_as_float(cur[4 * j + 2]),
-                                           __uint_as_float(cur[4 * j + 3]));
-                    if (!partial) {
-                        const float4 b4 = lds128(sb_a + 4 * (c0 + 4 * j));
-                        v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-                    }
-                    if (HAS_RES) {
-                        const float4 r4 = lds128(pa);
-                        v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
-                    }
-                    if (rowv) {
-                        // time-embedding row of this quarter's image (same address in every lane: one broadcast transaction), added last
-                        const float4 t4 = ldg_f4_or_zero(rowv + (long long)img_w * p.ldv + col + 4 * j, rv_ok && col + 4 * j < p.N);
-                        v.x += t4.x; v.y += t4.y; v.z += t4.z; v.w += t4.w;
-                    }
-                    sts128f(pa, v.x, v.y, v.z, v.w);
-                }
-            }
-            fence_proxy_async_smem();                     // generic-proxy writes -> visible to the TMA unit
-            __syncwarp();
-            if (lane == 0) {
-                tma_store_5d(tmC, sbuf, col, ub.w, ub.h, ub.n, ub.split);
-                tma_store_commit();
-            }
-            if (want_cs) {
-                // GroupNorm column statistics of the stored values: lane j owns column col + j and walks the 32 staged rows
-                float cs = 0.f, cq = 0.f;
-#pragma unroll
-                for (int r = 0; r < 32; ++r) {
-                    if ((rowmask >> r) & 1u) {
-                        const float x = lds32(sbuf + r * 128 + ((((uint32_t)(lane >> 2)) ^ (uint32_t)(r & 7)) << 4) + ((lane & 3) << 2));
-                        cs += x;
-                        cq = fmaf(x, x, cq);
-                    }
-                }
-                if (col + lane < n_out) {
-                    float* dst = p.colstats + (long long)(ub.mt * 4 + lg) * p.N + col + lane;
-                    dst[0] = cs;
-                    dst[p.colstats_sq] = cq;
-                }
-            }
+            tepi_chunk<BN, MODE, HAS_RES>(p, tmC, cur, g, sb_a, sbuf, c0, col, ub, lane, lg, rowmask, img_w, rv_ok, rowv, want_cs, partial, n_out);
             if (HAS_RES) {
                 if (lane == 0) tma_store_wait_read<1>();  // store of chunk q - 1 done reading -> its box takes the residual of chunk q + lead
                 issue_residual(q + (uint32_t)lead);
@@ -814,8 +704,223 @@ __device__ __forceinline__ void epilogue_tma_units(const TcP& p, const CUtensorM
             ++q;
         }
     }
-    if (lane == 0) tma_store_wait_all<0>();               // every store of this warp has landed before the CTA retires
+    // the staging boxes must outlive the TMA unit's READS of them; the global writes themselves complete asynchronously and are
+    // visible at grid completion like any other store (waiting for them here kept every CTA resident for a DRAM round trip)
+    if (lane == 0) tma_store_wait_read<0>();
     __syncwarp();
+}
+
+// The same epilogue for the one-CTA kernel (one 128 x BN tile per CTA, two CTAs per SM).  Once the accumulator is complete every
+// operand load has been consumed, so the A/B ring is the staging area: each epilogue warp owns one box per 32-column chunk.
+// ALL residual boxes of the warp are requested at once the moment the ring is free (one mbarrier, one L2 round trip — they were
+// prefetched into L2 when the CTA started) instead of one exposed round trip per chunk, which is what kept the K <= 640
+// "+ residual" layers at 2x their memory bound (profiles/r02_ncu_full_summary.txt: long_scoreboard on the residual adds).
+template <int BN, int MODE, bool HAS_RES>
+__device__ __forceinline__ void epilogue_tma_single(const TcP& p, const CUtensorMap* tmC, const CUtensorMap* tmR, uint32_t taddr,
+                                                    uint32_t sb_a, uint32_t stg_a, uint64_t* rbar, uint64_t* accum_bar, const UnitBox& ub,
+                                                    int lane, int lg, uint32_t rowmask, int img_w) {
+    constexpr bool GEGLU = MODE == EPI_GEGLU;
+    constexpr int COLS = GEGLU ? BN / 2 : BN;
+    constexpr int NCHUNK = (COLS + 31) / 32;
+    const bool partial = p.split_k > 1;
+    const float* const rowv = (!partial && p.rowvec && p.conv && MODE == EPI_F32) ? p.rowvec : nullptr;
+    const bool want_cs = MODE == EPI_F32 && p.colstats != nullptr && !partial;
+    const int n_out = GEGLU ? p.N / 2 : p.N;
+    const bool rv_ok = rowv != nullptr && rowmask != 0u && img_w < p.NB;
+    if (HAS_RES && lane == 0) {
+#pragma unroll
+        for (int ch = 0; ch < NCHUNK; ++ch) tma_prefetch_l2_5d(tmR, ub.col0 + ch * 32, ub.w, ub.h, ub.n, 0);
+    }
+    mbar_wait(accum_bar, 0);
+    tcgen05_fence_after();
+    if (HAS_RES && lane == 0) {
+        mbar_arrive_expect_tx_a(smem_u32(rbar), NCHUNK * 32 * 128);
+#pragma unroll
+        for (int ch = 0; ch < NCHUNK; ++ch)
+            tma_load_5d(stg_a + ch * TEPI_BOX_BYTES, tmR, smem_u32(rbar), ub.col0 + ch * 32, ub.w, ub.h, ub.n, 0);
+    }
+    uint32_t ra[32], rb[32];
+    tmem_ld_x32(taddr, ra);
+#pragma unroll
+    for (int ch = 0; ch < NCHUNK; ++ch) {
+        uint32_t (&cur)[32] = (ch & 1) ? rb : ra;
+        uint32_t (&nxt)[32] = (ch & 1) ? ra : rb;
+        const int c0 = ch * 32;
+        uint32_t g[GEGLU ? 32 : 1];
+        if (GEGLU) tmem_ld_x32(taddr + BN / 2 + c0, g);
+        tmem_ld_wait();
+        if (ch + 1 < NCHUNK) tmem_ld_x32(taddr + c0 + 32, nxt);
+        if (HAS_RES && ch == 0) mbar_wait(rbar, 0);
+        tepi_chunk<BN, MODE, HAS_RES>(p, tmC, cur, g, sb_a, stg_a + ch * TEPI_BOX_BYTES, c0, ub.col0 + c0, ub, lane, lg, rowmask, img_w, rv_ok,
+                                      rowv, want_cs, partial, n_out);
+    }
+    if (lane == 0) tma_store_wait_read<0>();               // smem may be released once the TMA unit has read the boxes
+    __syncwarp();
+}
+
+template <int BN>
+__global__ void __launch_bounds__(192, 2)
+tc_contract_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const TcP p) {
+    pdl_trigger();
+    if (threadIdx.x == 0) { TC1_TRACE(0); TC1_TRACE(7); }
+    using Cfg = TcCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * TC_A_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* accum_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    uint64_t* res_bar = accum_bar + 2;               // [4] TMA epilogue: the residual boxes of epilogue warp w have landed
+    float* s_bias = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // ---- tile coordinates ----
+    const int tile = blockIdx.x;
+    const int nt = tile % p.tiles_n, mt = tile / p.tiles_n;
+    const int n0 = nt * BN;
+    const int split = blockIdx.y;
+    const int kb0 = (int)((long long)p.kblocks * split / p.split_k);
+    const int kb1 = (int)((long long)p.kblocks * (split + 1) / p.split_k);
+
+    int m0 = mt * TC_BM;            // gemm mode
+    int ow0 = 0, oh0 = 0, img0 = 0; // conv mode
+    if (p.conv) {
+        int tww = mt % p.tiles_w;
+        int thh = (mt / p.tiles_w) % p.tiles_h;
+        int tnb = mt / (p.tiles_w * p.tiles_h);
+        ow0 = tww * p.tw; oh0 = thh * p.th; img0 = tnb * p.tn;
+    }
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(accum_bar, 1);
+        for (int w = 0; w < 4; ++w) mbar_init(&res_bar[w], 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+    if (threadIdx.x == 0) TC1_TRACE(1);
+    pdl_wait();                                      // predecessor's outputs (A, residual, ...) are complete and visible
+    if (threadIdx.x == 0) TC1_TRACE(2);
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+                const int tap = kb / p.kpt, cs = kb - tap * p.kpt;
+                if (p.conv) {
+                    const int r = tap / p.kw, sx = tap - r * p.kw;
+                    tma_load_4d(sA + s * TC_A_BYTES, &tmA, &full_bar[s], cs * TC_BK,
+                                ow0 * p.stride + sx - p.pad_w, oh0 * p.stride + r - p.pad_h, img0);
+                } else {
+                    tma_load_2d(sA + s * TC_A_BYTES, &tmA, &full_bar[s], cs * TC_BK, m0);
+                }
+                tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, &full_bar[s], cs * TC_BK, tap * p.cout_pad + n0);
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(BN, false, false);
+            int s = 0; uint32_t ph = 0;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&full_bar[s], ph);
+                tcgen05_fence_after();
+                const uint64_t adesc = umma_desc_kmajor_sw128(smem_u32(sA + s * TC_A_BYTES));
+                const uint64_t bdesc = umma_desc_kmajor_sw128(smem_u32(sB + s * Cfg::B_BYTES));
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; ++k) {
+                    // advance 16 bf16 = 32 B along K inside the 128-B swizzle atom: +2 (16-B units)
+                    umma_bf16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);          // smem slot reusable once these MMAs retire
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+            umma_commit(accum_bar);                  // accumulator complete
+            TC1_TRACE(3);
+        }
+    } else {
+        // ================= epilogue (warps 2..5 -> TMEM lane groups 2,3,0,1) =================
+        const int et = threadIdx.x - 64;             // 0..127
+        for (int i = et; i < BN; i += 128) {
+            int n = n0 + i;
+            s_bias[i] = (p.bias && n < p.N) ? p.bias[n] : 0.f;
+        }
+        named_bar_sync(1, 128);
+
+        const int lg = warp & 3;                     // TMEM lane group this warp may access
+        const int row = lg * 32 + lane;              // row of the 128-row tile
+        long long pix;                               // output row index (pixel / token), -1 = outside the problem
+        int img = 0;
+        if (p.conv) {
+            int in_ = row / (p.th * p.tw);
+            int rem = row - in_ * (p.th * p.tw);
+            int ih = rem / p.tw, iw = rem - ih * p.tw;
+            img = img0 + in_;
+            int oh = oh0 + ih, ow = ow0 + iw;
+            bool valid = (img < p.NB) && (oh < p.OH) && (ow < p.OW);
+            pix = valid ? ((long long)img * p.OHF + (oh * p.out_sh + p.out_oh)) * p.OWF + (ow * p.out_sw + p.out_ow) : -1;
+        } else {
+            pix = (m0 + row) < p.M ? m0 + row : -1;
+        }
+        const uint32_t taddr = tmem_d + ((uint32_t)(lg * 32) << 16);
+        if (p.epi_tma) {
+            // ---- TMA epilogue (epilogue_tma_single): the ring is the staging area, one box per (warp, chunk) ----
+            constexpr int NCH = BN / 32 > 0 ? BN / 32 : 1;
+            UnitBox ub;
+            ub.split = split; ub.nt = nt; ub.mt = mt; ub.col0 = p.geglu ? nt * (BN / 2) : n0;
+            const int r0 = lg * 32;
+            if (p.conv) {
+                ub.w = ow0 + r0 % p.tw; ub.h = oh0 + (r0 / p.tw) % p.th; ub.n = img0 + r0 / (p.tw * p.th);
+            } else {
+                ub.w = m0 + r0; ub.h = 0; ub.n = 0;
+            }
+            const uint32_t rowmask = __ballot_sync(0xffffffffu, pix >= 0);
+            const int img_w = __shfl_sync(0xffffffffu, img, 0);
+            const uint32_t stg_a = smem_u32(sA) + (uint32_t)(warp - 2) * (uint32_t)(NCH * TEPI_BOX_BYTES);
+            uint64_t* rbar = &res_bar[warp - 2];
+#define SDB_TEPI1(MODE, RES) epilogue_tma_single<BN, MODE, RES>(p, &tmC, &tmR, taddr, smem_u32(s_bias), stg_a, rbar, accum_bar, ub, lane, lg, rowmask, img_w)
+            if (p.geglu) {
+                if constexpr (BN % 64 == 0) SDB_TEPI1(EPI_GEGLU, false);
+            } else if (p.split_k > 1) SDB_TEPI1(EPI_F32, false);
+            else if (p.out_bf16) SDB_TEPI1(EPI_BF16, false);
+            else if (p.residual != nullptr) SDB_TEPI1(EPI_F32, true);
+            else SDB_TEPI1(EPI_F32, false);
+#undef SDB_TEPI1
+        } else {
+            prefetch_residual_row(p, pix, n0, BN);
+            // once the accumulator is ready every TMA load has been consumed: the A ring doubles as the transpose staging area
+            float* stage = reinterpret_cast<float*>(sA) + (warp - 2) * (EPI_WARP_BYTES / 4);
+            if (warp == 2 && lane == 0) TC1_TRACE(4);
+            epilogue_warp<BN>(p, taddr, s_bias, stage, lane, n0, nt, pix, img, split, 0, 1, accum_bar, 0, mt * 4 + lg);
+            if (warp == 2 && lane == 0) TC1_TRACE(5);
+        }
+    }
+
+    // ---- teardown ----
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_d, Cfg::TMEM_COLS);
+    }
 }
 
 // ---- CTA-pair persistent kernel ------------------------------------------------------------------
@@ -1115,7 +1220,8 @@ static void pick_tile(int OW, int OH, int NB, int stride, int* tw, int* th, int*
 }
 
 template <int BN>
-static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcP& p, int m_tiles, cudaStream_t st) {
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR, TcP& p, int m_tiles,
+                     cudaStream_t st) {
     using Cfg = TcCfg<BN>;
     static bool attr_set_dev[64] = {false};          // the attribute is per device
     int cur_dev = 0;
@@ -1126,8 +1232,11 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcP& 
         if (e != cudaSuccess) { set_last_error("tc_contract: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SDB_ERR_CUDA; }
         attr_set = true;
     }
+    // TMA epilogue: one 4 KB box per (epilogue warp, 32-column chunk) must fit in the operand ring it re-uses
+    constexpr int NCH = BN / 32 > 0 ? BN / 32 : 1;
+    if (4 * NCH * TEPI_BOX_BYTES > Cfg::STAGES * Cfg::STAGE_BYTES) p.epi_tma = 0;
     dim3 grid((unsigned)(m_tiles * p.tiles_n), (unsigned)p.split_k);
-    launch_pdl(tc_contract_kernel<BN>, dim3(grid), dim3(192), Cfg::SMEM_BYTES, st, tmA, tmB, p);
+    launch_pdl(tc_contract_kernel<BN>, dim3(grid), dim3(192), Cfg::SMEM_BYTES, st, tmA, tmB, tmC, tmR, p);
     return check_launch("tc_contract_kernel");
 }
 
@@ -1546,7 +1655,7 @@ extern "C" int sdb_tc_contract(const sdb_tc_args* a, void* stream) {
     CUtensorMap tmC, tmR;
     memset(&tmC, 0, sizeof(tmC));
     memset(&tmR, 0, sizeof(tmR));
-    if (use_pair && tma_epilogue_enabled()) {
+    if (tma_epilogue_enabled()) {
         // ---- TMA epilogue (epilogue_tma_units): short-K launches whose output layout is a plain [rows, N] / NHWC tensor ----
         const bool partial = p.split_k > 1;
         const bool out16 = !partial && p.out_bf16;
@@ -1603,11 +1712,11 @@ extern "C" int sdb_tc_contract(const sdb_tc_args* a, void* stream) {
         }
     } else {
         switch (bn) {
-            case 32: rc = launch_tc<32>(tmA, tmB, p, m_tiles, st); break;
-            case 64: rc = launch_tc<64>(tmA, tmB, p, m_tiles, st); break;
-            case 128: rc = launch_tc<128>(tmA, tmB, p, m_tiles, st); break;
-            case 160: rc = launch_tc<160>(tmA, tmB, p, m_tiles, st); break;
-            default: rc = launch_tc<256>(tmA, tmB, p, m_tiles, st); break;
+            case 32: rc = launch_tc<32>(tmA, tmB, tmC, tmR, p, m_tiles, st); break;
+            case 64: rc = launch_tc<64>(tmA, tmB, tmC, tmR, p, m_tiles, st); break;
+            case 128: rc = launch_tc<128>(tmA, tmB, tmC, tmR, p, m_tiles, st); break;
+            case 160: rc = launch_tc<160>(tmA, tmB, tmC, tmR, p, m_tiles, st); break;
+            default: rc = launch_tc<256>(tmA, tmB, tmC, tmR, p, m_tiles, st); break;
         }
     }
     if (rc || p.split_k == 1) return rc;

@@ -24,14 +24,30 @@ def per_sample_randn(indices, shape, seed_base, device="cpu"):
     return t.to(device)
 
 
+_gather_bufs = {}
+
+
 def gather_images(local, global_batch, group=None):
     """All-gather per-rank image slices [b_r, ...] into [global_batch, ...] on every rank (NCCL on GPUs, gloo on CPU).
-    Slices may differ in length by one, so each rank pads to the maximum before the collective."""
+
+    Equal slices (the usual case: global_batch divisible by the world size) go through ONE `all_gather_into_tensor` straight
+    into a pre-allocated [global_batch, ...] buffer that is reused from call to call — no per-rank list, no padding copy, no
+    concatenation pass over the 200 MB of images.  Slices that differ in length by one are padded to the maximum first.
+    The returned tensor is the reused buffer: clone it if it must survive the next call."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return local
     world = dist.get_world_size(group)
     sizes = [shard_range(global_batch, r, world) for r in range(world)]
-    mx = max(hi - lo for lo, hi in sizes)
+    lens = [hi - lo for lo, hi in sizes]
+    local = local.contiguous()
+    if min(lens) == max(lens):
+        key = (tuple(local.shape), local.dtype, str(local.device), global_batch, id(group))
+        out = _gather_bufs.get(key)
+        if out is None:
+            out = _gather_bufs[key] = torch.empty((global_batch,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local, group=group)
+        return out
+    mx = max(lens)
     pad = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     pad[: local.shape[0]] = local
     bufs = [torch.empty_like(pad) for _ in range(world)]

@@ -30,21 +30,22 @@ GEMM_SHAPES = [(32768, 320, 320), (8192, 640, 640), (2048, 1280, 1280), (1000, 3
                (4096, 1920, 640), (300, 200, 64), (8192, 136, 320)]
 
 
+@pytest.mark.parametrize("variant", [2, 1], ids=["pair", "single"])
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
-def test_gemm_epilogues_agree(cuda, M, N, K):
+def test_gemm_epilogues_agree(cuda, M, N, K, variant):
     from sdb200 import ops
     A = randn(M, K, seed=1).to(torch.bfloat16)
     W = (randn(N, K, seed=2) * K ** -0.5).to(torch.bfloat16)
     bias, res = randn(N, seed=3), randn(M, N, seed=4)
     ref = A.float() @ W.float().T + bias
     for kw, tol in ((dict(residual=res), 2e-5), (dict(), 2e-5), (dict(out_dtype=torch.bfloat16), 4e-3)):
-        a, b = _both(lambda: ops.gemm_tc(A, W, bias, variant=2, **kw))
+        a, b = _both(lambda: ops.gemm_tc(A, W, bias, variant=variant, **kw))
         want = ref + res if "residual" in kw else ref
         assert rel(a, want) < tol, (kw.keys(), rel(a, want))
         assert torch.equal(a, b), kw.keys()
     # no bias, output written into a wider buffer (row pitch > N): the q | k | v layout
     wide = torch.zeros((M, N + 64), dtype=torch.bfloat16, device="cuda")
-    a, b = _both(lambda: ops.gemm_tc(A, W, None, out=wide[:, 32:32 + N], out_dtype=torch.bfloat16, ldc=N + 64, variant=2).clone())
+    a, b = _both(lambda: ops.gemm_tc(A, W, None, out=wide[:, 32:32 + N], out_dtype=torch.bfloat16, ldc=N + 64, variant=variant).clone())
     assert torch.equal(a, b) and rel(a, A.float() @ W.float().T) < 4e-3
     assert float(wide[:, :32].abs().max()) == 0.0 and float(wide[:, 32 + N:].abs().max()) == 0.0     # nothing written outside the columns
 
@@ -62,11 +63,16 @@ def test_geglu_epilogues_agree(cuda, M, C):
     a, b = _both(lambda: engine.linear(A, pl, out_dtype=torch.bfloat16, rows_per_item=M))
     assert rel(a, ref) < 5e-3
     assert torch.equal(a, b)
+    from sdb200 import ops
+    for variant in (1, 2):
+        a2, b2 = _both(lambda: ops.gemm_tc(A, pl.w, pl.bias, out_dtype=torch.bfloat16, geglu=True, block_n=pl.block_n, variant=variant))
+        assert torch.equal(a2, b2) and rel(a2, ref) < 5e-3
 
 
 @pytest.mark.parametrize("N,H,W,Cin,Cout,k", [(8, 64, 64, 320, 320, 1), (8, 32, 32, 640, 640, 1), (2, 16, 16, 1280, 1280, 1), (3, 40, 24, 128, 256, 3),
                                               (2, 8, 8, 320, 640, 1), (1, 96, 96, 320, 320, 1), (2, 64, 64, 128, 128, 3), (5, 20, 12, 256, 320, 3)])
-def test_conv_epilogues_agree(cuda, N, H, W, Cin, Cout, k):
+@pytest.mark.parametrize("variant", [2, 1], ids=["pair", "single"])
+def test_conv_epilogues_agree(cuda, N, H, W, Cin, Cout, k, variant):
     from sdb200 import ops
     x = randn(N, H, W, Cin, seed=1).to(torch.bfloat16)
     w = (randn(Cout, Cin, k, k, seed=2) * (Cin * k * k) ** -0.5).to(torch.bfloat16)
@@ -78,13 +84,14 @@ def test_conv_epilogues_agree(cuda, N, H, W, Cin, Cout, k):
     for kw, want, tol in ((dict(rowvec=rv[:, Cout:], residual=res), base + rv[:, None, None, Cout:] + res, 3e-5),
                           (dict(residual=res), base + res, 3e-5), (dict(rowvec=rv[:, Cout:]), base + rv[:, None, None, Cout:], 3e-5),
                           (dict(), base, 3e-5), (dict(out_dtype=torch.bfloat16), base, 4e-3)):
-        a, bb = _both(lambda: ops.conv_tc(x, wp, b, k, k, pad=k // 2, variant=2, **kw))
+        a, bb = _both(lambda: ops.conv_tc(x, wp, b, k, k, pad=k // 2, variant=variant, **kw))
         assert rel(a, want) < tol, (kw.keys(), rel(a, want))
         assert torch.equal(a, bb), kw.keys()
 
 
 @pytest.mark.parametrize("N,H,W,C", [(2, 64, 64, 320), (3, 32, 32, 640), (2, 16, 16, 1280), (1, 40, 40, 320)])
-def test_colstats_from_tma_epilogue(cuda, N, H, W, C):
+@pytest.mark.parametrize("variant", [2, 1], ids=["pair", "single"])
+def test_colstats_from_tma_epilogue(cuda, N, H, W, C, variant):
     """GroupNorm fed by the statistics the TMA epilogue emits == GroupNorm that measures the tensor itself."""
     from sdb200 import ops
     x = randn(N, H, W, C, seed=1).to(torch.bfloat16)
@@ -95,7 +102,7 @@ def test_colstats_from_tma_epilogue(cuda, N, H, W, C):
     g, be = randn(C, seed=6), randn(C, seed=7)
 
     def run():
-        out = ops.conv_tc(x, wp, b, 1, 1, pad=0, residual=res, variant=2, want_stats=True)
+        out = ops.conv_tc(x, wp, b, 1, 1, pad=0, residual=res, variant=variant, want_stats=True)
         had = getattr(out, "_sdb_cs", None) is not None
         y = ops.groupnorm(out, g, be, 1e-5, act=1, out_dtype=torch.float32)
         return out, y, had
@@ -115,9 +122,10 @@ def test_split_k_partials_through_tma(cuda):
     bias, res = randn(N, seed=3), randn(M, N, seed=4)
     ref = A.float() @ W.float().T + bias + res
     for sk in (2, 5):
-        a, b = _both(lambda: ops.gemm_tc(A, W, bias, residual=res, split_k=sk, variant=2))
-        assert rel(a, ref) < 2e-5
-        assert torch.equal(a, b)
+        for variant in (2, 1):
+            a, b = _both(lambda: ops.gemm_tc(A, W, bias, residual=res, split_k=sk, variant=variant))
+            assert rel(a, ref) < 2e-5
+            assert torch.equal(a, b)
     x = randn(8, 8, 8, 1280, seed=5).to(torch.bfloat16)
     w = (randn(1280, 1280, 3, 3, seed=6) * (1280 * 9) ** -0.5).to(torch.bfloat16)
     wp = ops.pack_conv_weight(w, torch.bfloat16)
