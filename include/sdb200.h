@@ -286,6 +286,11 @@ typedef struct sdb_attn_args {
     int causal;
 } sdb_attn_args;
 int sdb_attention_fwd(const sdb_attn_args* args /* host */, void* stream);
+/* Tuning switch (measurement only): 1 = problems with ONE key tile (Sk <= 128, head pad <= 128, no causal mask — the
+ * cross-attention over the 77 text tokens, openai_model/attention.py:99-112) run on tc_attention_kv1_kernel, whose CTAs keep
+ * K / V resident and walk query items [default; SDB200_XATTN=0 turns it off at load time]; 0 = the key-tile-walking kernel
+ * everywhere.  Returns the previous setting. */
+int sdb_attention_set_short_key_kernel(int enable);
 
 /* ---- fused attention forward for one WIDE head (d = 256 or 512): the VAE AttnBlock -------------------------------
  * Replaces  w_ = bmm(q, k) * c**-0.5;  w_ = softmax(w_);  h_ = bmm(v, w_)  of AttnBlock.forward

@@ -113,6 +113,7 @@ SIGNATURES = {
     "sdb_tc_workspace_bytes": (_L, [C.POINTER(TcArgs)]),
     "sdb_tc_colstats_layout": (_I, [C.POINTER(TcArgs), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "sdb_attention_fwd": (_I, [C.POINTER(AttnArgs), _P]),
+    "sdb_attention_set_short_key_kernel": (_I, [_I]),
     "sdb_attention_wide_fwd": (_I, [_P, _P, _P, _P, _L, _L, _L, _L, _L, _L, _L, _L, _I, _I, _I, _I, _F, _P]),
 }
 

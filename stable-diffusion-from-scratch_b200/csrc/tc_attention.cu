@@ -31,6 +31,7 @@ using namespace ptx;
 
 int make_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const long long* dims, const long long* strides_elems,
                    const int* box, const int* estr);
+int attention_kv1_dispatch(const sdb_attn_args* a, cudaStream_t st);   // tc_attention_kv1.cu: one key tile, CTA walks query items
 
 #ifdef SDB_ATTN_TRACE
 static long long* g_attn_trace = nullptr;
@@ -500,6 +501,10 @@ extern "C" int sdb_attention_fwd(const sdb_attn_args* a, void* stream) {
     SDB_REQUIRE(!a->causal || a->Sq == a->Sk, "attention: the causal mask needs Sq == Sk (got %d, %d)", a->Sq, a->Sk);
     SDB_REQUIRE(a->o_hs % 8 == 0 && a->o_ss % 8 == 0 && a->o_bs % 8 == 0 && ((uintptr_t)a->out & 15) == 0, "attention: output must be 16-byte aligned per head row");
     cudaStream_t st = (cudaStream_t)stream;
+    {
+        const int rc = attention_kv1_dispatch(a, st);     // Sk <= 128 (the text conditioning): 1 = not covered
+        if (rc != 1) return rc;
+    }
     switch (a->dpad) {
         case 64: return launch_attn<64>(a, st);
         case 128: return launch_attn<128>(a, st);

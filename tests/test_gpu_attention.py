@@ -113,3 +113,57 @@ def test_attention_wide_large_logits(cuda):
     out = ops.attention_wide(q, k, v, B, S, S, d, 0.2, (S * d, d), (S * d, d), (S * d, d))
     ref = torch.softmax(q.double().view(B, S, d) @ k.double().view(B, S, d).transpose(1, 2) * 0.2, -1) @ v.double().view(B, S, d)
     assert rel(out, ref) < 1e-2
+
+
+@pytest.mark.parametrize("B,H,Sq,Sk,d", [
+    (8, 8, 4096, 77, 40), (8, 8, 1024, 77, 80), (16, 8, 4096, 77, 40), (2, 8, 300, 77, 40), (1, 2, 700, 128, 80), (3, 5, 513, 50, 64),
+    (1, 8, 100, 8, 40), (2, 4, 256, 96, 80), (1, 1, 2304, 77, 40), (1, 8, 9216, 77, 40)])
+def test_attention_short_keys(cuda, B, H, Sq, Sk, d):
+    """tc_attention_kv1_kernel (one key tile, CTAs walk query items; the cross-attention over the text tokens,
+    openai_model/attention.py:99-112) against fp64 math AND against the key-tile-walking kernel on the same inputs, with
+    ragged query counts, every key-count class (<= 64, 65..80, 81..128) and both head layouts."""
+    from sdb200 import _lib, ops
+    from sdb200.engine import head_pad
+    lib = _lib.load()
+    dp = head_pad(d)
+    q = randn(B, Sq, H, d, seed=21).to(torch.bfloat16)
+    k = randn(B, Sk, H, d, seed=22).to(torch.bfloat16)
+    v = randn(B, Sk, H, d, seed=23).to(torch.bfloat16)
+    scale = d ** -0.5
+    sq, sk = (Sq * H * d, H * d, d), (Sk * H * d, H * d, d)
+
+    def run():
+        return ops.attention_tc(q, k, v, B, H, Sq, Sk, d, dp, scale, sq, sk, sk, dense=True)
+    prev = lib.sdb_attention_set_short_key_kernel(1)
+    try:
+        out = run()
+        lib.sdb_attention_set_short_key_kernel(0)
+        old = run()
+    finally:
+        lib.sdb_attention_set_short_key_kernel(prev)
+    worst = 0.0
+    for b in range(B):
+        worst = max(worst, rel(out[b:b + 1], _ref(q[b:b + 1], k[b:b + 1], v[b:b + 1], scale)))
+    assert worst < 1e-2, worst
+    assert rel(out, old.float()) < 5e-3
+    # zero-padded heads in memory give the same bits as the dense layout
+    if d != dp:
+        def padded(t):
+            p = torch.zeros(t.shape[0], t.shape[1], H, dp, dtype=torch.bfloat16, device=t.device)
+            p[..., :d] = t
+            return p
+        out_p = ops.attention_tc(padded(q), padded(k), padded(v), B, H, Sq, Sk, d, dp, scale,
+                                 (Sq * H * dp, H * dp, dp), (Sk * H * dp, H * dp, dp), (Sk * H * dp, H * dp, dp))
+        assert torch.equal(out_p, out)
+
+
+def test_attention_short_keys_peaked_rows(cuda):
+    """One dominant key per row (logit gap ~40): the exact row max keeps the other 76 probabilities at their true tiny values."""
+    from sdb200 import ops
+    B, H, Sq, Sk, d, dp = 2, 8, 512, 77, 40, 64
+    q = (randn(B, Sq, H, d, seed=31) * 4).to(torch.bfloat16)
+    k = (randn(B, Sk, H, d, seed=32) * 4).to(torch.bfloat16)
+    v = randn(B, Sk, H, d, seed=33).to(torch.bfloat16)
+    st, sk = (Sq * H * d, H * d, d), (Sk * H * d, H * d, d)
+    out = ops.attention_tc(q, k, v, B, H, Sq, Sk, d, dp, 0.5, st, sk, sk, dense=True)
+    assert rel(out, _ref(q, k, v, 0.5)) < 1e-2

@@ -73,6 +73,26 @@ for _ in range(20):
     out = fn()
 e1.record()
 torch.cuda.synchronize()
+if os.environ.get("ONE_OP_GRAPH", "0") == "1":
+    # 20 calls captured in one CUDA graph: launches short enough to be host-bound above (< ~20 us: three cuTensorMapEncode calls
+    # and a ctypes round trip per launch) show their device time
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=side):
+            for _ in range(20):
+                out = fn()
+    torch.cuda.synchronize()
+    gr.replay()
+    torch.cuda.synchronize()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(5):
+        gr.replay()
+    g1.record()
+    torch.cuda.synchronize()
+    print("graph replay: %.2f us/call" % (g0.elapsed_time(g1) / 100 * 1e3))
 if kind == "attn":      # accuracy of (batch 0, head 0) against fp64 softmax(q k^T) v on the same bf16 inputs
     qd, kd, vd = q[0, :, 0, :d].double(), k[0, :, 0, :d].double(), vv[0, :, 0, :d].double()
     ref = torch.softmax(qd @ kd.T * d ** -0.5, -1) @ vd
