@@ -122,6 +122,27 @@ __device__ __forceinline__ float ex2_sel(float x) {
                           (SDB_ATTN_POLY == 3 && (J == 2 || J == 5 || J == 7)) || (SDB_ATTN_POLY == 4 && (J & 1));
     return poly ? ex2_fma(x) : ex2_approx(x);
 }
+#ifndef SDB_ATTN_PACKED
+#define SDB_ATTN_PACKED 1       // FFMA2 / FADD2 in the exponential phase (0 = scalar fp32, the round-1 form)
+#endif
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+    uint64_t v;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+    return v;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
 // two non-negative fp32 -> packed bf16x2 (lo in the low half), round-to-nearest
 __device__ __forceinline__ uint32_t pack_p_bf16x2(float lo, float hi) {
 #if SDB_ATTN_VARIANT & 2
@@ -383,6 +404,42 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             if (G == 2) asm volatile("bar.sync %0, 64;" ::"r"(bar_mine) : "memory");              // my turn on the MUFU
             AT_TRACE(5);
             // p = exp2(s*c - m), row sum, P_g (bf16, K-major SW128: two [128 x 64] blocks)
+#if SDB_ATTN_PACKED
+            // Packed fp32x2 arithmetic (FFMA2 / FADD2): s*c - m for two keys per instruction and pairwise row-sum accumulation,
+            // 2.6 instead of 3.6 issue slots per exponential.  A softmax warp that is alone in its exponential phase is
+            // issue- / dependency-bound (~12 clk per exponential against the MUFU pipe's 8, tools/ubench/xu_rate.cu).
+            uint64_t acc_a = 0ull, acc_b = 0ull;                 // two (lo, hi) fp32 pair accumulators
+            const uint64_t c2 = pack_f32x2(c, c), nm2 = pack_f32x2(-m_used, -m_used);
+#pragma unroll
+            for (int c0 = 0; c0 < 128; c0 += 8) {
+                float e[8];
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) {
+                    const uint64_t x2 = ffma2(pack_f32x2(__uint_as_float(r[c0 + j]), __uint_as_float(r[c0 + j + 1])), c2, nm2);
+                    float x0, x1;
+                    unpack_f32x2(x2, x0, x1);
+                    e[j] = ex2_approx(x0);
+                    e[j + 1] = ex2_approx(x1);
+                }
+                acc_a = fadd2(acc_a, pack_f32x2(e[0], e[1]));
+                acc_b = fadd2(acc_b, pack_f32x2(e[2], e[3]));
+                acc_a = fadd2(acc_a, pack_f32x2(e[4], e[5]));
+                acc_b = fadd2(acc_b, pack_f32x2(e[6], e[7]));
+                const int chunk = (c0 & 63) >> 3;
+                sts128(prow + (c0 >> 6) * 16384 + ((chunk ^ (row & 7)) << 4),
+                       pack_p_bf16x2(e[0], e[1]), pack_p_bf16x2(e[2], e[3]), pack_p_bf16x2(e[4], e[5]), pack_p_bf16x2(e[6], e[7]));
+                if (G == 2 && SDB_ATTN_HANDOVER < 16 && c0 == 8 * (SDB_ATTN_HANDOVER - 1))
+                    asm volatile("bar.arrive %0, 64;" ::"r"(bar_other) : "memory");
+            }
+            float sum0, sum1;
+            {
+                float a0, a1, b0, b1;
+                unpack_f32x2(acc_a, a0, a1);
+                unpack_f32x2(acc_b, b0, b1);
+                sum0 = a0 + a1;
+                sum1 = b0 + b1;
+            }
+#else
             float sum0 = 0.f, sum1 = 0.f;
             const float nm = -m_used;
 #pragma unroll
@@ -400,6 +457,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 if (G == 2 && SDB_ATTN_HANDOVER < 16 && c0 == 8 * (SDB_ATTN_HANDOVER - 1))
                     asm volatile("bar.arrive %0, 64;" ::"r"(bar_other) : "memory");
             }
+#endif
             l += sum0 + sum1;
             AT_TRACE(6);
             if (G == 2 && SDB_ATTN_HANDOVER >= 16) asm volatile("bar.arrive %0, 64;" ::"r"(bar_other) : "memory");   // hand the MUFU over
