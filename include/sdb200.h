@@ -46,6 +46,11 @@ unsigned long long sdb_launch_count(void);
 /* dst_C (0 = C): channel count of dst; channels C..dst_C-1 are written as zeros (the 4-channel latent is padded to 32
  * bf16 channels so that conv_in, openai_model/model.py:365, runs on the tensor cores). */
 int sdb_nchw_to_nhwc(const float* src, void* dst, int dst_dtype, int N, int C, int dst_C, int HW, void* stream);
+/* Same layout change with a bf16 destination of dst_C >= 2*C channels that keeps fp32 information: channels 0..C-1 = bf16(x),
+ * channels C..2C-1 = bf16(x - float(bf16(x))) (the rounding residual), the rest zero.  A bf16 contraction whose weights are
+ * repeated for both halves then sees x to ~2^-17: the UNet's first conv (openai_model/model.py:531, 4 latent channels) runs on
+ * the tensor cores without rounding x_t itself to bf16. */
+int sdb_nchw_to_nhwc_split(const float* src, void* dst /* bf16 */, int N, int C, int dst_C, int HW, void* stream);
 int sdb_nhwc_to_nchw(const float* src, float* dst, int N, int C, int HW, void* stream);
 
 /* ---- GroupNorm(32) [+ SiLU] over NHWC, optional two-source channel concat -------------------

@@ -247,7 +247,7 @@ class UNetModel(nn.Module):
         self.predict_codebook_ids = False
         self.compute_mode = compute_mode or engine.default_mode()
         self.t_emb_fp16_round = True     # `t_emb.half()`, openai_model/model.py:566
-        self.conv_in_tensor_cores = False
+        self.conv_in_tensor_cores = os.environ.get("SDB200_CONV_IN_TC", "1") != "0"   # bf16 mode: first conv on tcgen05 with a split (hi | lo) latent
         self.use_cuda_graph = False
         self.dense_heads = os.environ.get("SDB200_DENSE_HEADS", "1") != "0"     # q/k/v layout, see _tblock (0 = zero-padded heads)
 
@@ -415,10 +415,16 @@ class UNetModel(nn.Module):
                 P[("ff1", id(m))] = PackedLinear(m.ff.net[0].proj.weight, m.ff.net[0].proj.bias, mode, geglu=True)
                 P[("ff2", id(m))] = PackedLinear(m.ff.net[2].weight, m.ff.net[2].bias, mode)
         cin_w = self.input_blocks[0][0].weight
-        if mode == "bf16" and cin_w.shape[1] < 32 and self.conv_in_tensor_cores:
-            # conv_in on the tensor cores: the latent's channels are zero-padded to 32 (a whole 64-byte TMA row).  Off by
-            # default: rounding x_t itself to bf16 moved eps rel-L2 from 7.05e-3 to 7.64e-3 (bound 1e-2) for 0.08 ms
-            cin_w = torch.nn.functional.pad(cin_w.detach(), (0, 0, 0, 0, 0, 32 - cin_w.shape[1]))
+        P["conv_in_split"] = False
+        if mode == "bf16" and 2 * cin_w.shape[1] <= 32 and self.conv_in_tensor_cores:
+            # conv_in on the tensor cores (the SIMT kernel needs 109 us for this 0.75 GFLOP layer at batch 8; tcgen05 ~15 us and
+            # its epilogue hands the following GroupNorm its statistics).  The latent's C channels become a 32-channel operand
+            # (a whole 64-byte TMA row): bf16(x) | bf16(x - bf16(x)) | zeros, with the weights repeated for the residual half, so
+            # x_t itself is NOT rounded to bf16 — rounding it moved eps rel-L2 from 7.05e-3 to 7.64e-3 when this was first tried.
+            c_in = cin_w.shape[1]
+            w = cin_w.detach()
+            cin_w = torch.cat([w, w, w.new_zeros(w.shape[0], 32 - 2 * c_in, w.shape[2], w.shape[3])], 1)
+            P["conv_in_split"] = True
         P["conv_in"] = PackedConv(cin_w, self.input_blocks[0][0].bias, mode)
         P["conv_out"] = PackedConv(self.out[2].weight, self.out[2].bias, mode)
         self._packed[mode] = P
@@ -667,7 +673,7 @@ class UNetModel(nn.Module):
         if y is not None:                                                        # emb + label_emb(y), model.py:567-569
             emb = ops.add(emb, ops.gather_rows(P["label_emb"], y))
         emb_all = ops.skinny_linear(emb, P["emb_w"], P["emb_b"], act_in=1)
-        h = ops.nchw_to_nhwc(x_nchw, out_dtype=P["conv_in"].in_dtype, pad_to=P["conv_in"].cin)
+        h = ops.nchw_to_nhwc(x_nchw, out_dtype=P["conv_in"].in_dtype, pad_to=P["conv_in"].cin, split=P["conv_in_split"])
         hs = []
         for module in self.input_blocks:
             h = self._run_block(module, P, mode, h, None, emb_all, context)

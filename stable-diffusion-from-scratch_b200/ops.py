@@ -18,14 +18,19 @@ def _L():
 
 
 # ---- layout ---------------------------------------------------------------------------------------
-def nchw_to_nhwc(x, out_dtype=torch.float32, pad_to=0):
-    """[N,C,H,W] fp32 -> [N,H,W,C] (or [N,H,W,pad_to] with zero channels appended)."""
+def nchw_to_nhwc(x, out_dtype=torch.float32, pad_to=0, split=False):
+    """[N,C,H,W] fp32 -> [N,H,W,C] (or [N,H,W,pad_to] with zero channels appended).
+    split=True (bf16 output, pad_to >= 2C): channels C..2C-1 hold the bf16 rounding residual x - bf16(x) of channels 0..C-1."""
     require_cuda(x)
     assert x.dtype == torch.float32 and x.is_contiguous()
     N, Cc, H, W = x.shape
     Cd = max(Cc, pad_to)
     out = torch.empty((N, H, W, Cd), dtype=out_dtype, device=x.device)
-    check(_L().sdb_nchw_to_nhwc(ptr(x), ptr(out), dtype_code(out_dtype), N, Cc, Cd, H * W, stream_ptr()), "nchw_to_nhwc")
+    if split:
+        assert out_dtype == torch.bfloat16 and Cd >= 2 * Cc
+        check(_L().sdb_nchw_to_nhwc_split(ptr(x), ptr(out), N, Cc, Cd, H * W, stream_ptr()), "nchw_to_nhwc_split")
+    else:
+        check(_L().sdb_nchw_to_nhwc(ptr(x), ptr(out), dtype_code(out_dtype), N, Cc, Cd, H * W, stream_ptr()), "nchw_to_nhwc")
     return out
 
 

@@ -80,6 +80,13 @@ def test_small_elementwise(cuda):
     padded = ops.nchw_to_nhwc(xi, out_dtype=torch.bfloat16, pad_to=32)          # latent -> 32-channel tensor-core operand
     assert padded.shape == (3, 6, 7, 32) and torch.equal(padded[..., :5], nhwc(xi).to(torch.bfloat16))
     assert float(padded[..., 5:].abs().max()) == 0.0
+    # split operand: bf16(x) | bf16(x - bf16(x)) | zeros — the two halves together carry x to ~2^-17
+    sp = ops.nchw_to_nhwc(xi, out_dtype=torch.bfloat16, pad_to=32, split=True)
+    hi = nhwc(xi).to(torch.bfloat16)
+    assert sp.shape == (3, 6, 7, 32) and torch.equal(sp[..., :5], hi)
+    assert torch.equal(sp[..., 5:10], (nhwc(xi) - hi.float()).to(torch.bfloat16))
+    assert float(sp[..., 10:].abs().max()) == 0.0
+    assert rel(sp[..., :5].float() + sp[..., 5:10].float(), nhwc(xi)) < 2e-5
 
 
 def test_timestep_embedding_and_skinny(cuda):
