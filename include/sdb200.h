@@ -144,6 +144,10 @@ int sdb_gather_rows(const float* table, const long long* idx, int B, int dim, fl
  * 2 GELU-erf (DDPM/models/unet.py:26-31). */
 int sdb_skinny_linear(const float* x, int M, int K, const float* W, const float* bias, int N,
                       int act_in, int act_out, float* y, void* stream);
+/* Same with the weight matrix stored in bf16 ([N,K] row-major, K % 8 == 0; x, bias, y and the accumulation stay fp32): the
+ * bf16 compute mode's form of the 20160 x 1280 ResBlock time-embedding matrix, whose streaming is this kernel's whole cost. */
+int sdb_skinny_linear_bf16w(const float* x, int M, int K, const void* W /* bf16 */, const float* bias, int N,
+                            int act_in, int act_out, float* y, void* stream);
 
 /* ---- DDIM update ---------------------------------------------------------------------------
  * Replaces p_sample_ddim's arithmetic (ldm/diffusion/ddim.py:175-205 == DDIM/ddim.py):

@@ -211,8 +211,8 @@ __global__ void gather_rows_kernel(const float* __restrict__ table, const long l
 }
 
 // ---- skinny linear: M <= 32 rows; one warp per output column, weights streamed once -------------
-template <int MT>
-__global__ void skinny_linear_kernel(const float* __restrict__ x, int M, int K, const float* __restrict__ W,
+template <int MT, bool WBF16>
+__global__ void skinny_linear_kernel(const float* __restrict__ x, int M, int K, const void* __restrict__ Wv,
                                      const float* __restrict__ bias, int N, int act_in, int act_out,
                                      float* __restrict__ y) {
     pdl_trigger();
@@ -226,30 +226,49 @@ __global__ void skinny_linear_kernel(const float* __restrict__ x, int M, int K, 
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int warps = blockDim.x >> 5;
+    constexpr int EPL = WBF16 ? 8 : 4;        // weights per 16-byte load
     for (int n = blockIdx.x * warps + (threadIdx.x >> 5); n < N; n += gridDim.x * warps) {
         float acc[MT];
 #pragma unroll
         for (int m = 0; m < MT; ++m) acc[m] = 0.f;
-        const float* w = W + (long long)n * K;
         // the weight row is streamed once: issue up to KU 16-byte loads per lane before the first FMA (one load in flight
         // per lane made this kernel latency-bound at ~1 TB/s on the 113 MB ResBlock time-embedding matrix)
-        constexpr int KU = 10;
-        for (int k0 = lane * 4; k0 < K; k0 += 128 * KU) {
+        constexpr int KU = WBF16 ? 5 : 10;
+        for (int k0 = lane * EPL; k0 < K; k0 += 32 * EPL * KU) {
             float4 wv[KU];
 #pragma unroll
             for (int u = 0; u < KU; ++u) {
                 wv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (k0 + 128 * u < K) wv[u] = ld_stream_f4(w + k0 + 128 * u);
+                const int k = k0 + 32 * EPL * u;
+                if (k < K) {
+                    if (WBF16) wv[u] = ld_stream_f4(reinterpret_cast<const float*>(reinterpret_cast<const __nv_bfloat16*>(Wv) + (long long)n * K + k));
+                    else wv[u] = ld_stream_f4(reinterpret_cast<const float*>(Wv) + (long long)n * K + k);
+                }
             }
 #pragma unroll
             for (int u = 0; u < KU; ++u) {
-                const int k = k0 + 128 * u;
+                const int k = k0 + 32 * EPL * u;
                 if (k < K) {
+                    if (WBF16) {
+                        // 8 bf16 weights: a bf16 is the high half of the fp32 with the same value
+                        const uint32_t q0 = __float_as_uint(wv[u].x), q1 = __float_as_uint(wv[u].y), q2 = __float_as_uint(wv[u].z), q3 = __float_as_uint(wv[u].w);
+                        const float w0 = __uint_as_float(q0 << 16), w1 = __uint_as_float(q0 & 0xffff0000u), w2 = __uint_as_float(q1 << 16), w3 = __uint_as_float(q1 & 0xffff0000u);
+                        const float w4 = __uint_as_float(q2 << 16), w5 = __uint_as_float(q2 & 0xffff0000u), w6 = __uint_as_float(q3 << 16), w7 = __uint_as_float(q3 & 0xffff0000u);
 #pragma unroll
-                    for (int m = 0; m < MT; ++m) {
-                        if (m < M) {
-                            const float4 xr = *reinterpret_cast<const float4*>(xs + m * K + k);
-                            acc[m] += wv[u].x * xr.x + wv[u].y * xr.y + wv[u].z * xr.z + wv[u].w * xr.w;
+                        for (int m = 0; m < MT; ++m) {
+                            if (m < M) {
+                                const float4 xa = *reinterpret_cast<const float4*>(xs + m * K + k);
+                                const float4 xb = *reinterpret_cast<const float4*>(xs + m * K + k + 4);
+                                acc[m] += (w0 * xa.x + w1 * xa.y + w2 * xa.z + w3 * xa.w) + (w4 * xb.x + w5 * xb.y + w6 * xb.z + w7 * xb.w);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int m = 0; m < MT; ++m) {
+                            if (m < M) {
+                                const float4 xr = *reinterpret_cast<const float4*>(xs + m * K + k);
+                                acc[m] += wv[u].x * xr.x + wv[u].y * xr.y + wv[u].z * xr.z + wv[u].w * xr.w;
+                            }
                         }
                     }
                 }
@@ -464,6 +483,26 @@ static inline int grid_for(long long n, int threads) {
 
 using namespace sdb;
 
+template <bool WBF16>
+static int launch_skinny(const float* x, int M, int K, const void* W, const float* bias, int N, int act_in, int act_out, float* y, void* stream) {
+    SDB_REQUIRE(x && W && y && M > 0 && M <= 32 && K > 0 && K % (WBF16 ? 8 : 4) == 0 && N > 0, "skinny_linear: bad args M=%d K=%d N=%d", M, K, N);
+    SDB_REQUIRE(((uintptr_t)W & 15) == 0, "skinny_linear: W must be 16-byte aligned");
+    size_t smem = (size_t)M * K * sizeof(float);
+    SDB_REQUIRE(smem <= 200 * 1024, "skinny_linear: M*K too large");
+    int threads = 256;
+    int blocks = ceil_div(N, threads / 32);
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    cudaStream_t st = (cudaStream_t)stream;
+#define SK(MT)                                                                                              \
+    do {                                                                                                    \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(skinny_linear_kernel<MT, WBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        launch_pdl(skinny_linear_kernel<MT, WBF16>, dim3(blocks), dim3(threads), smem, st, x, M, K, W, bias, N, act_in, act_out, y);   \
+    } while (0)
+    if (M <= 4) SK(4); else if (M <= 8) SK(8); else if (M <= 16) SK(16); else SK(32);
+#undef SK
+    return check_launch("skinny_linear_kernel");
+}
+
 extern "C" {
 
 int sdb_nchw_to_nhwc(const float* src, void* dst, int dst_dtype, int N, int C, int dst_C, int HW, void* stream) {
@@ -581,21 +620,12 @@ int sdb_gather_rows(const float* table, const long long* idx, int B, int dim, fl
 
 int sdb_skinny_linear(const float* x, int M, int K, const float* W, const float* bias, int N,
                       int act_in, int act_out, float* y, void* stream) {
-    SDB_REQUIRE(x && W && y && M > 0 && M <= 32 && K > 0 && K % 4 == 0 && N > 0, "skinny_linear: bad args M=%d K=%d N=%d", M, K, N);
-    size_t smem = (size_t)M * K * sizeof(float);
-    SDB_REQUIRE(smem <= 200 * 1024, "skinny_linear: M*K too large");
-    int threads = 256;
-    int blocks = ceil_div(N, threads / 32);
-    if (blocks > 148 * 4) blocks = 148 * 4;
-    cudaStream_t st = (cudaStream_t)stream;
-#define SK(MT)                                                                                              \
-    do {                                                                                                    \
-        if (smem > 48 * 1024) cudaFuncSetAttribute(skinny_linear_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        launch_pdl(skinny_linear_kernel<MT>, dim3(blocks), dim3(threads), smem, st, x, M, K, W, bias, N, act_in, act_out, y);   \
-    } while (0)
-    if (M <= 4) SK(4); else if (M <= 8) SK(8); else if (M <= 16) SK(16); else SK(32);
-#undef SK
-    return check_launch("skinny_linear_kernel");
+    return launch_skinny<false>(x, M, K, W, bias, N, act_in, act_out, y, stream);
+}
+
+int sdb_skinny_linear_bf16w(const float* x, int M, int K, const void* W, const float* bias, int N,
+                            int act_in, int act_out, float* y, void* stream) {
+    return launch_skinny<true>(x, M, K, W, bias, N, act_in, act_out, y, stream);
 }
 
 static int launch_ddim(const float* x, const float* e_cond, const float* e_uncond, float cfg_scale, const float* noise,

@@ -200,6 +200,21 @@ class SpatialTransformer(nn.Module):
         self.proj_out = zero_module(nn.Conv2d(inner_dim, in_channels, kernel_size=1, stride=1, padding=0))
 
 
+class _SideResult:
+    """A tensor produced on a side stream; get() makes the consuming stream wait for it (once) and hands it out."""
+
+    def __init__(self, tensor, side, main):
+        self.tensor, self.side, self.main = tensor, side, main
+
+    def get(self):
+        if self.side is not None:
+            self.main.wait_stream(self.side)
+            if not torch.cuda.is_current_stream_capturing():
+                self.tensor.record_stream(self.main)      # allocated on the side stream's pool, read on the main stream
+            self.side = None
+        return self.tensor
+
+
 class UNetModel(nn.Module):
     """The full UNet with attention and timestep embedding (openai_model/model.py:259-595).
 
@@ -249,6 +264,7 @@ class UNetModel(nn.Module):
         self.t_emb_fp16_round = True     # `t_emb.half()`, openai_model/model.py:566
         self.conv_in_tensor_cores = os.environ.get("SDB200_CONV_IN_TC", "1") != "0"   # bf16 mode: first conv on tcgen05 with a split (hi | lo) latent
         self.use_cuda_graph = False
+        self.emb_side_stream = os.environ.get("SDB200_EMB_SIDE_STREAM", "1") != "0"   # time-embedding chain beside conv_in
         self.dense_heads = os.environ.get("SDB200_DENSE_HEADS", "1") != "0"     # q/k/v layout, see _tblock (0 = zero-padded heads)
 
         time_embed_dim = model_channels * 4
@@ -378,7 +394,8 @@ class UNetModel(nn.Module):
         P["te2"] = (self.time_embed[2].weight.detach().float().contiguous(), self.time_embed[2].bias.detach().float().contiguous())
         if self.num_classes is not None:
             P["label_emb"] = self.label_emb.weight.detach().float().contiguous()
-        # all ResBlock emb_layers as ONE skinny GEMM [sum(Cout), emb] (fp32 weights in both modes)
+        # all ResBlock emb_layers as ONE skinny GEMM [sum(Cout), emb]; its 20160 x 1280 matrix is stored in bf16 in the bf16 mode
+        # (like every other weight there): streaming it is the whole cost of the launch (103 MB in fp32)
         ws, bs, off = [], [], 0
         for rb in self._res_blocks():
             lin = rb.emb_layers[1]
@@ -387,6 +404,8 @@ class UNetModel(nn.Module):
             P[("emb_off", id(rb))] = (off, lin.out_features)
             off += lin.out_features
         P["emb_w"] = torch.cat(ws, 0).contiguous()
+        if mode == "bf16" and P["emb_w"].shape[1] % 8 == 0:
+            P["emb_w"] = P["emb_w"].to(torch.bfloat16)
         P["emb_b"] = torch.cat(bs, 0).contiguous()
         for m in self.modules():
             if isinstance(m, ResBlock):
@@ -441,7 +460,6 @@ class UNetModel(nn.Module):
         """ResBlock._forward (openai_model/model.py:232-252); x1 = skip tensor to be channel-concatenated."""
         c1, c2 = P[("c1", id(rb))], P[("c2", id(rb))]
         off, n = P[("emb_off", id(rb))]
-        rowvec = emb_all[:, off:off + n]
         sk = P.get(("skip", id(rb)))
         ss = rb.use_scale_shift_norm
         raw = None
@@ -460,6 +478,7 @@ class UNetModel(nn.Module):
             h, raw = self._gn(rb.in_layers[0], x, mode, 1, x1=x1, out_dtype=c1.in_dtype, want_raw=True)
         else:
             h = self._gn(rb.in_layers[0], x, mode, 1, x1=x1, out_dtype=c1.in_dtype)
+        rowvec = self._emb_rows(emb_all)[:, off:off + n]      # first use of the time embedding: joins its side stream (once)
         if ss:
             # out_norm(h) * (1 + scale) + shift (model.py:244-248): scale / shift folded into per-sample GroupNorm rows
             h = engine.conv(h, c1, want_stats=True)
@@ -476,6 +495,10 @@ class UNetModel(nn.Module):
             assert x1 is None
             xs = x
         return engine.conv(h, c2, residual=xs, want_stats=True)     # conv + bias + skip_connection(x)
+
+    @staticmethod
+    def _emb_rows(emb_all):
+        return emb_all.get() if isinstance(emb_all, _SideResult) else emb_all
 
     def _attnblock(self, ab, P, mode, x):
         """AttentionBlock._forward (openai_model/attention.py:588-599), 'next' row f4.  The qkv conv's output channels are
@@ -664,15 +687,30 @@ class UNetModel(nn.Module):
         return h
 
     # ---- forward ----------------------------------------------------------------------------------
-    def _forward_nhwc(self, x_nchw, t_f32, context, mode, y=None):
-        P = self._pack(mode)
+    def _time_embedding(self, P, t_f32, y):
         t_emb = ops.timestep_embedding(t_f32, P["freqs"], round_fp16=self.t_emb_fp16_round)
         e = ops.skinny_linear(t_emb, P["te0"][0], P["te0"][1], act_out=1)        # Linear -> SiLU
         # time_embed[2] then every ResBlock's SiLU -> Linear (openai_model/model.py:195-201), batched
         emb = ops.skinny_linear(e, P["te2"][0], P["te2"][1])
         if y is not None:                                                        # emb + label_emb(y), model.py:567-569
             emb = ops.add(emb, ops.gather_rows(P["label_emb"], y))
-        emb_all = ops.skinny_linear(emb, P["emb_w"], P["emb_b"], act_in=1)
+        return ops.skinny_linear(emb, P["emb_w"], P["emb_b"], act_in=1)
+
+    def _forward_nhwc(self, x_nchw, t_f32, context, mode, y=None):
+        P = self._pack(mode)
+        if self.emb_side_stream:
+            # The time-embedding chain (4 launches that stream the 20160 x 1280 emb_layers matrix, ~0.1 ms) depends on t only and
+            # is first needed by the first ResBlock's conv epilogue: it runs on a side stream beside the layout change, conv_in
+            # and the first GroupNorm (a fork / join that CUDA-graph capture records as such).
+            main = torch.cuda.current_stream()
+            side = self.__dict__.get("_side_stream")
+            if side is None or side.device != main.device:
+                side = self.__dict__["_side_stream"] = torch.cuda.Stream(device=main.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                emb_all = _SideResult(self._time_embedding(P, t_f32, y), side, main)
+        else:
+            emb_all = self._time_embedding(P, t_f32, y)
         h = ops.nchw_to_nhwc(x_nchw, out_dtype=P["conv_in"].in_dtype, pad_to=P["conv_in"].cin, split=P["conv_in_split"])
         hs = []
         for module in self.input_blocks:
@@ -681,6 +719,7 @@ class UNetModel(nn.Module):
         h = self._run_block(self.middle_block, P, mode, h, None, emb_all, context)
         for module in self.output_blocks:
             h = self._run_block(module, P, mode, h, hs.pop(), emb_all, context)     # torch.cat folded into GN / cast
+        self._emb_rows(emb_all)      # (a model without ResBlocks: still join the side stream)
         co = P["conv_out"]
         h = self._gn(self.out[0], h, mode, 1, out_dtype=co.in_dtype)
         h = engine.conv(h, co)

@@ -240,16 +240,16 @@ def gather_rows(table, idx):
 
 
 def skinny_linear(x, W, bias=None, act_in=0, act_out=0):
-    """y = act_out(act_in(x) @ W^T + bias); x fp32 [M<=32, K], W fp32 [N, K]."""
+    """y = act_out(act_in(x) @ W^T + bias); x fp32 [M<=32, K], W fp32 or bf16 [N, K] (fp32 accumulation either way)."""
     require_cuda(x, W, bias)
-    assert x.dtype == torch.float32 and W.dtype == torch.float32 and x.is_contiguous() and W.is_contiguous()
+    assert x.dtype == torch.float32 and W.dtype in (torch.float32, torch.bfloat16) and x.is_contiguous() and W.is_contiguous()
     M, K = x.shape
     N = W.shape[0]
     y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    fn = _L().sdb_skinny_linear if W.dtype == torch.float32 else _L().sdb_skinny_linear_bf16w
     for i in range(0, M, 32):   # the kernel holds at most 32 rows in shared memory
         m = min(32, M - i)
-        check(_L().sdb_skinny_linear(ptr(x) + 4 * i * K, m, K, ptr(W), ptr(bias), N, act_in, act_out,
-                                     ptr(y) + 4 * i * N, stream_ptr()), "skinny_linear")
+        check(fn(ptr(x) + 4 * i * K, m, K, ptr(W), ptr(bias), N, act_in, act_out, ptr(y) + 4 * i * N, stream_ptr()), "skinny_linear")
     return y
 
 

@@ -107,6 +107,11 @@ def test_timestep_embedding_and_skinny(cuda):
         assert rel(ops.skinny_linear(x, Wt, b, act_in=1), ref) < 2e-6
         assert rel(ops.skinny_linear(x, Wt, b, act_out=1), F.silu(F.linear(x.double(), Wt.double(), b.double()))) < 2e-6
         assert rel(ops.skinny_linear(x, Wt, None, act_out=2), F.gelu(F.linear(x.double(), Wt.double()))) < 2e-6
+        # bf16 weight storage (the bf16 mode's emb_layers matrix): exact against the same bf16-rounded weights
+        W16 = Wt.to(torch.bfloat16)
+        assert rel(ops.skinny_linear(x, W16, b, act_in=1), F.linear(F.silu(x.double()), W16.double(), b.double())) < 2e-6
+    x, W16 = randn(8, 1288, seed=21), (randn(77, 1288, seed=22) * 0.03).to(torch.bfloat16)       # K not a multiple of 256, ragged N
+    assert rel(ops.skinny_linear(x, W16), F.linear(x.double(), W16.double())) < 2e-6
 
 
 def test_ddim_step_bit_exact_vs_reference(cuda):
