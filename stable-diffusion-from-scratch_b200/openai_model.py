@@ -265,6 +265,7 @@ class UNetModel(nn.Module):
         self.conv_in_tensor_cores = os.environ.get("SDB200_CONV_IN_TC", "1") != "0"   # bf16 mode: first conv on tcgen05 with a split (hi | lo) latent
         self.use_cuda_graph = False
         self.emb_side_stream = os.environ.get("SDB200_EMB_SIDE_STREAM", "1") != "0"   # time-embedding chain beside conv_in
+        self.skip_side_stream = os.environ.get("SDB200_SKIP_SIDE_STREAM", "1") != "0"  # ResBlock 1x1 skip conv beside conv1
         self.dense_heads = os.environ.get("SDB200_DENSE_HEADS", "1") != "0"     # q/k/v layout, see _tblock (0 = zero-padded heads)
 
         time_embed_dim = model_channels * 4
@@ -479,6 +480,17 @@ class UNetModel(nn.Module):
         else:
             h = self._gn(rb.in_layers[0], x, mode, 1, x1=x1, out_dtype=c1.in_dtype)
         rowvec = self._emb_rows(emb_all)[:, off:off + n]      # first use of the time embedding: joins its side stream (once)
+        xs_side = None
+        if sk is not None and self.skip_side_stream and mode == "bf16":
+            # skip_connection(x) (a 1x1 conv, memory- / latency-bound) depends only on the block input: it runs on a side stream
+            # beside conv1 + GroupNorm of the main branch and fills the SMs their last waves leave idle; joined before conv2
+            main = torch.cuda.current_stream()
+            side = self.__dict__.get("_side_stream2")
+            if side is None or side.device != main.device:
+                side = self.__dict__["_side_stream2"] = torch.cuda.Stream(device=main.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                xs_side = _SideResult(self._skip_conv(sk, raw, x, x1), side, main)
         if ss:
             # out_norm(h) * (1 + scale) + shift (model.py:244-248): scale / shift folded into per-sample GroupNorm rows
             h = engine.conv(h, c1, want_stats=True)
@@ -489,12 +501,16 @@ class UNetModel(nn.Module):
             h = engine.conv(h, c1, rowvec=rowvec, want_stats=True)      # conv + bias + emb_out[..., None, None]
             h = self._gn(rb.out_layers[0], h, mode, 1, out_dtype=c2.in_dtype)
         if sk is not None:
-            xs = raw if raw is not None else ops.cast_concat(x, x1, up=1, out_dtype=sk.in_dtype)
-            xs = engine.conv(xs, sk)
+            xs = self._emb_rows(xs_side) if xs_side is not None else self._skip_conv(sk, raw, x, x1)
         else:
             assert x1 is None
             xs = x
         return engine.conv(h, c2, residual=xs, want_stats=True)     # conv + bias + skip_connection(x)
+
+    @staticmethod
+    def _skip_conv(sk, raw, x, x1):
+        xs = raw if raw is not None else ops.cast_concat(x, x1, up=1, out_dtype=sk.in_dtype)
+        return engine.conv(xs, sk)
 
     @staticmethod
     def _emb_rows(emb_all):
