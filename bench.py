@@ -118,6 +118,13 @@ def cpu_reference_images_per_s(ddim_steps, repeats=1):
     return 1.0 / (ddim_steps * t_unet + t_dec), cores, t_unet, t_dec
 
 
+def workload_config(ddim_steps, per_gpu_batch, global_batch):
+    """`config` of the C2 workload: the SAME dict in both arms (the driver compares them key by key)."""
+    return {"workload": "SD-1.x UNet DDIM-%d + VAE decode, 64x64x4 latent -> 512x512x3, ctx 77x768, batch %d per GPU" % (ddim_steps, per_gpu_batch),
+            "global_batch": global_batch, "per_gpu_batch": per_gpu_batch,
+            "l2": "no flush between steps: one step touches 1.7 GB of bf16 weights per UNet call x 50 calls + activations, far more than the 126 MB L2"}
+
+
 def run_reference(a):
     """Reference arm: the reference's own CPU PyTorch path (its oracle restatement — the Python reference cannot travel to
     the GPU box) on all host threads, same metric / unit / workload as the sdb200 arm.  One "step" of the workload is a
@@ -144,9 +151,8 @@ def run_reference(a):
         "impl": "reference", "metric": "512px DDIM-50 images/sec", "value": ips, "unit": "images/s", "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * t_img * B, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "SD-1.x UNet DDIM-%d + VAE decode, 64x64x4 latent -> 512x512x3, ctx 77x768, batch %d per GPU"
-                               % (a.ddim_steps, B), "global_batch": B * world, "per_gpu_batch": B,
-                   "note": "host CPU only (one process, rank 0): the value does not grow with n_gpus"},
+        "config": workload_config(a.ddim_steps, B, B * world),
+        "note": "host CPU only (one process, rank 0): the value does not grow with n_gpus",
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -279,10 +285,9 @@ def run_sdb200(a):
             "metric": "512px DDIM-50 images/sec", "value": ips, "unit": "images/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": a.mode if a.mode != "fp32" else "f32", "data": "synthetic",
-            "config": {"workload": "SD-1.x UNet DDIM-%d + VAE decode, 64x64x4 latent -> 512x512x3, ctx 77x768, batch %d per GPU"
-                                   % (a.ddim_steps, B), "global_batch": GB, "per_gpu_batch": B, "cuda_graph": not a.no_graph,
-                       "l2": "activations + weights per step exceed L2 (1.7 GB bf16 weights streamed per UNet call); no flush",
-                       "context_kv": "to_k/to_v of the context projected once per DDIM-50 run (every batch), not per UNet call"},
+            "config": workload_config(a.ddim_steps, B, GB),
+            "run": {"cuda_graph": not a.no_graph,
+                    "context_kv": "to_k/to_v of the context projected once per DDIM-50 run (every batch), not per UNet call"},
             "unet_step_ms": unet_ms,
             "model_tflops_per_gpu": ips / world * flop_per_image / 1e12,
             "model_frac_of_tensor_peak": ips / world * flop_per_image / 1e12 / tf_peak,
@@ -314,8 +319,8 @@ def roofline_pass(run, label):
     import torch
     from sdb200 import _lib
     lib = _lib.load()
-    tc, bw = [], []
-    names = ("sdb_tc_contract", "sdb_groupnorm_nhwc", "sdb_groupnorm_from_colstats", "sdb_layernorm")
+    tc, bw, at = [], [], []
+    names = ("sdb_tc_contract", "sdb_groupnorm_nhwc", "sdb_groupnorm_from_colstats", "sdb_layernorm", "sdb_attention_fwd")
     orig = {n: getattr(lib, n) for n in names}
 
     def ev_pair():
@@ -356,11 +361,22 @@ def roofline_pass(run, label):
         bw.append((float(args[1]) * args[2] * (4 + (2 if args[7] == 1 else 4)), e0, e1, "ln"))
         return rc
 
+    def w_at(argp, stream):
+        a = argp._obj
+        e0, e1 = ev_pair()
+        e0.record()
+        rc = orig["sdb_attention_fwd"](argp, stream)
+        e1.record()
+        at.append((4.0 * a.B * a.H * a.Sq * a.Sk * a.d, float(a.B) * a.H * a.Sq * (80 if a.Sk <= 80 else ((a.Sk + 127) // 128) * 128), e0, e1,
+                   "self" if a.Sq == a.Sk else "cross"))
+        return rc
+
     for _ in range(2):
         run()
     torch.cuda.synchronize()
     l0 = lib.sdb_launch_count()
     lib.sdb_tc_contract, lib.sdb_groupnorm_nhwc, lib.sdb_groupnorm_from_colstats, lib.sdb_layernorm = w_tc, w_gn, w_gc, w_ln
+    lib.sdb_attention_fwd = w_at
     try:
         # park the device behind a ~0.1 s spin so the host enqueues the whole call ahead of it: the events then
         # bracket kernel execution only, not host launch gaps
@@ -403,6 +419,23 @@ def roofline_pass(run, label):
                     "sum_ms": ms, "algorithmic_mbytes": by / 1e6, "peak_source": which + " (device copy)",
                     "by_kernel": {k: {"GB/s": v[0] / (v[1] / 1000.0) / 1e9, "ms": v[1], "launches": v[2]} for k, v in per.items()},
                     "convention": "fp32 read once + output written once (bf16 operand, + the raw bf16 copy when emitted)"}
+    if at and roof is not None:
+        # attention kernels: tensor roofline on the algorithmic 4*B*H*Sq*Sk*d FLOP, and the exponential rate against the
+        # MUFU.EX2 pipe (16 per clock and SM, measured: profiles/r01_xu_rate.txt) at the clock sampled during the timed region
+        ms_a = sum(r[2].elapsed_time(r[3]) for r in at)
+        fl_a = sum(r[0] for r in at)
+        ex_a = sum(r[1] for r in at)
+        per = {}
+        for fl, ex, e0, e1, kind in at:
+            d = per.setdefault(kind, [0.0, 0.0, 0.0, 0])
+            d[0] += fl; d[1] += ex; d[2] += e0.elapsed_time(e1); d[3] += 1
+        mufu_peak = 16.0 * 148 * 1.92e9
+        roof["attention"] = {"kernel": "tc_attention_kernel / tc_attention_kv1_kernel", "launches": len(at), "sum_ms": ms_a,
+                             "achieved": fl_a / (ms_a / 1000.0) / 1e12, "unit": "TFLOP/s", "frac": fl_a / (ms_a / 1000.0) / 1e12 / tf_peak,
+                             "exp_per_s": ex_a / (ms_a / 1000.0), "mufu_frac": ex_a / (ms_a / 1000.0) / mufu_peak,
+                             "mufu_peak": "16 ex2 / clk / SM x 148 SMs x 1.92 GHz",
+                             "by_kind": {k: {"TFLOP/s": v[0] / (v[2] / 1000.0) / 1e12, "mufu_frac": v[1] / (v[2] / 1000.0) / mufu_peak,
+                                             "ms": v[2], "launches": v[3]} for k, v in per.items()}}
     return roof, roof_hbm, launches
 
 

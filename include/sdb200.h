@@ -257,6 +257,11 @@ typedef struct sdb_tc_args {
      * — the statistics pass of the GroupNorm that consumes the output (openai_model/utils.py:15-22) comes for free.
      * Size it with sdb_tc_colstats_layout(); NULL = off. */
     float* colstats; long long colstats_slots;
+    /* != 0: B is a constant of the stream (a weight matrix no earlier launch writes).  The kernels then fetch their first B
+     * tiles BEFORE the programmatic-dependent-launch wait, i.e. while the preceding kernel is still draining: the weights come
+     * from DRAM (1.7 GB streamed per UNet call), so their latency leaves the critical path.  0 = B may have been produced by the
+     * preceding launch (e.g. torch.bmm operands): everything waits. */
+    int b_const;
 } sdb_tc_args;
 /* slots the column statistics of these args occupy and how many consecutive slots belong to one sample (both 0 when
  * the plan cannot produce them: split-K, several samples per tile, bf16 / remapped output). */

@@ -57,6 +57,7 @@ class TcArgs(C.Structure):
         ("rows_per_item", C.c_int),
         ("variant", C.c_int),
         ("colstats", C.c_void_p), ("colstats_slots", C.c_longlong),
+        ("b_const", C.c_int),
     ]
 
 

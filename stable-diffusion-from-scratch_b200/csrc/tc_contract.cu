@@ -46,6 +46,7 @@ struct TcP {
     int epi_tma;            // pair kernel: 1 = the epilogue stages 32 x 32 boxes in swizzled smem and moves them with TMA
     int epi_nbuf;           //   staging boxes per epilogue warp (2; 3 when a residual tile is prefetched two chunks ahead)
     int epi_bw, epi_bh;     //   conv: the 32 rows of a lane quarter are the pixel box bw x bh x 32/(bw*bh) of the tile
+    int b_const;            // B (weights) is not written by the preceding launch: its first tiles are fetched before pdl_wait()
     // conv
     int conv;
     int kw, stride, pad_h, pad_w;
@@ -813,6 +814,17 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     tcgen05_fence_after();
     const uint32_t tmem_d = *tmem_slot;
     if (threadIdx.x == 0) TC1_TRACE(1);
+    // weights do not depend on the preceding launch: arm the first stages and fetch their B tiles while it is still draining
+    int b_pre = 0;
+    if (p.b_const && warp == 0 && lane == 0) {
+        b_pre = kb1 - kb0 < STAGES ? kb1 - kb0 : STAGES;
+        for (int i = 0; i < b_pre; ++i) {
+            const int kb = kb0 + i;
+            const int tap = kb / p.kpt, cs = kb - tap * p.kpt;
+            mbar_arrive_expect_tx(&full_bar[i], Cfg::STAGE_BYTES);
+            tma_load_2d(sB + i * Cfg::B_BYTES, &tmB, &full_bar[i], cs * TC_BK, tap * p.cout_pad + n0);
+        }
+    }
     pdl_wait();                                      // predecessor's outputs (A, residual, ...) are complete and visible
     if (threadIdx.x == 0) TC1_TRACE(2);
 
@@ -821,8 +833,11 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
             for (int kb = kb0; kb < kb1; ++kb) {
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+                const bool pre = kb - kb0 < b_pre;             // stage armed and its B tile requested before pdl_wait()
+                if (!pre) {
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+                }
                 const int tap = kb / p.kpt, cs = kb - tap * p.kpt;
                 if (p.conv) {
                     const int r = tap / p.kw, sx = tap - r * p.kw;
@@ -831,7 +846,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 } else {
                     tma_load_2d(sA + s * TC_A_BYTES, &tmA, &full_bar[s], cs * TC_BK, m0);
                 }
-                tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, &full_bar[s], cs * TC_BK, tap * p.cout_pad + n0);
+                if (!pre) tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, &full_bar[s], cs * TC_BK, tap * p.cout_pad + n0);
                 if (++s == STAGES) { s = 0; ph ^= 1; }
             }
         }
@@ -997,7 +1012,9 @@ tc_contract_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     cluster_sync_all();
     tcgen05_fence_after();
     const uint32_t tmem_d = *tmem_slot;
-    pdl_wait();                                      // predecessor's outputs (A, residual, ...) are complete and visible
+    // the B producer (warp 3) reads nothing but the weights: with b_const it does not wait for the preceding launch, so the first
+    // `stages` B tiles are in flight (from DRAM) while that launch is still draining; everybody else waits
+    if (!(warp == 3 && p.b_const)) pdl_wait();       // predecessor's outputs (A, residual, ...) are complete and visible
 
     if (warp == 0 || warp == 3) {
         // ================= TMA producers (both CTAs): warp 0 loads A, warp 3 loads B =================
@@ -1588,6 +1605,7 @@ extern "C" int sdb_tc_contract(const sdb_tc_args* a, void* stream) {
     p.ldc = a->ldc; p.ldr = a->ldr; p.ldv = a->ldv;
     p.M = a->M; p.N = a->N;
     p.kpt = pl.kpt;
+    p.b_const = a->b_const ? 1 : 0;
     p.kblocks = pl.kblocks;
     p.out_bf16 = a->out_dtype == SDB_BF16;
     p.geglu = a->geglu;

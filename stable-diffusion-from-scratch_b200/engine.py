@@ -65,13 +65,18 @@ class PackedLinear:
         self.bias = None if b is None else b.contiguous()
 
 
+# Packed weights (PackedConv / PackedLinear) are written once, long before any launch that reads them: the tcgen05 kernels may
+# fetch their first weight tiles before the programmatic-dependent-launch wait (sdb_tc_args.b_const).  SDB200_B_CONST=0 = off.
+B_CONST = os.environ.get("SDB200_B_CONST", "1") != "0"
+
+
 def conv(x, pc, rowvec=None, residual=None, out_dtype=torch.float32, up=1, want_stats=False):
     """x [N,H,W,Cin] in pc.in_dtype (fp32 for the SIMT path, bf16 for tcgen05) -> [N,OH,OW,Cout].
     want_stats: the output feeds a GroupNorm — let the tcgen05 epilogue also emit its column statistics."""
     if pc.use_tc:
         assert up == 1
         return ops.conv_tc(x, pc.w, pc.bias, pc.kh, pc.kw, stride=pc.stride, pad=pc.pad, rowvec=rowvec,
-                           residual=residual, out_dtype=out_dtype, want_stats=want_stats, pad_hi=pc.pad_hi)
+                           residual=residual, out_dtype=out_dtype, want_stats=want_stats, pad_hi=pc.pad_hi, b_const=B_CONST)
     return ops.conv_simt(x, pc.w, pc.bias, pc.kh, pc.kw, stride=pc.stride, pad=pc.pad, up=up, rowvec=rowvec,
                          residual=residual, out_dtype=out_dtype, pad_hi=pc.pad_hi)
 
@@ -79,7 +84,7 @@ def conv(x, pc, rowvec=None, residual=None, out_dtype=torch.float32, up=1, want_
 def conv_up2(x, pc, want_stats=False):
     """conv `pc` applied to the nearest-2x upsampling of x [N,H,W,Cin] (bf16 on the tensor-core path)."""
     if pc.w_up2 is not None:
-        return ops.conv_up2_tc(x, pc.w_up2, pc.bias, want_stats=want_stats)
+        return ops.conv_up2_tc(x, pc.w_up2, pc.bias, want_stats=want_stats, b_const=B_CONST)
     return conv(x, pc, up=2)
 
 
@@ -90,7 +95,7 @@ def linear(x, pl, residual=None, out_dtype=torch.float32, col_group=0, col_group
     if pl.use_tc:
         return ops.gemm_tc(x2, pl.w, pl.bias, residual=residual, out_dtype=out_dtype, geglu=pl.geglu,
                            col_group=col_group, col_group_stride=col_group_stride, block_n=pl.block_n,
-                           rows_per_item=rows_per_item, out=out)
+                           rows_per_item=rows_per_item, out=out, b_const=B_CONST)
     assert col_group == 0
     if pl.geglu:
         h = ops.gemm_simt(x2, pl.w, pl.bias)

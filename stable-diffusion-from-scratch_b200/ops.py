@@ -471,7 +471,7 @@ def _tc_launch(a, what):
 
 
 def conv_tc(x, w_rskc, bias, kh, kw, stride=1, pad=0, rowvec=None, residual=None, out_dtype=torch.float32,
-            split_k=0, block_n=0, out=None, phase=None, variant=0, want_stats=False, stats_into=None, pad_hi=None):
+            split_k=0, block_n=0, out=None, phase=None, variant=0, want_stats=False, stats_into=None, pad_hi=None, b_const=False):
     """x [N,IH,IW,Cin] bf16, w [kh*kw,Cout,Cin] bf16 -> [N,OH,OW,Cout].
 
     phase=(sh, sw, oh, ow, OHF, OWF, pad_h, pad_w) writes this conv's OHxOW result into the strided
@@ -513,6 +513,7 @@ def conv_tc(x, w_rskc, bias, kh, kw, stride=1, pad=0, rowvec=None, residual=None
     a.taps, a.kw, a.stride, a.pad_h, a.pad_w = taps, kw, stride, pad_h, pad_w
     a.NB, a.IH, a.IW, a.Cin, a.OH, a.OW = N, IH, IW, Cin, OH, OW
     a.cout_pad = Cout
+    a.b_const = int(bool(b_const))        # weights written by no earlier launch of the stream: fetched before the PDL wait
     if residual is not None:
         assert residual.dtype == torch.float32 and residual.is_contiguous()
     _apply_plan(a, "conv", OH * OW)
@@ -541,6 +542,15 @@ def tc_colstats_layout(a):
 
 
 UP2_PHASES = ((0, 0), (0, 1), (1, 0), (1, 1))
+UP2_TWO_STREAMS = os.environ.get("SDB200_UP2_STREAMS", "1") != "0"
+_up2_streams = {}
+
+
+def _up2_side_stream(device):
+    s = _up2_streams.get(device)
+    if s is None:
+        s = _up2_streams[device] = torch.cuda.Stream(device=device)
+    return s
 
 
 def fold_upsample_weights(w, dtype):
@@ -563,13 +573,14 @@ def fold_upsample_weights(w, dtype):
     return out
 
 
-def conv_up2_tc(x, w_phases, bias, want_stats=False):
+def conv_up2_tc(x, w_phases, bias, want_stats=False, b_const=False):
     """conv3x3(pad 1) of the nearest-2x upsampling of x [N,H,W,Cin] bf16 as four sub-pixel 2x2 convs -> [N,2H,2W,Cout] fp32."""
     require_cuda(x, bias)
     N, H, W, Cin = x.shape
     Cout = w_phases[0].shape[1]
     out = torch.empty((N, 2 * H, 2 * W, Cout), dtype=torch.float32, device=x.device)
     cs = None
+    joins = []
     for p, (py, px) in enumerate(UP2_PHASES):
         ph = (2, 2, py, px, 2 * H, 2 * W, 1 - py, 1 - px)
         if want_stats and p == 0:
@@ -580,8 +591,21 @@ def conv_up2_tc(x, w_phases, bias, want_stats=False):
             slots, spi = tc_colstats_layout(probe)
             if slots > 0:
                 cs = torch.empty((2, 4 * slots, Cout), dtype=torch.float32, device=x.device)
-        conv_tc(x, w_phases[p], bias, 2, 2, stride=1, pad=0, out=out, phase=ph,
-                stats_into=(cs, 4 * slots, p * slots) if cs is not None else None)
+        # the four phases write disjoint sub-lattices of `out`: odd phases go to a side stream (forked from / joined to the
+        # current one, also under graph capture), so two of these small launches share the SMs at any time
+        side = _up2_side_stream(x.device) if (UP2_TWO_STREAMS and (p & 1)) else None
+        if side is not None:
+            main = torch.cuda.current_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                conv_tc(x, w_phases[p], bias, 2, 2, stride=1, pad=0, out=out, phase=ph, b_const=b_const,
+                        stats_into=(cs, 4 * slots, p * slots) if cs is not None else None)
+            joins.append(side)
+        else:
+            conv_tc(x, w_phases[p], bias, 2, 2, stride=1, pad=0, out=out, phase=ph, b_const=b_const,
+                    stats_into=(cs, 4 * slots, p * slots) if cs is not None else None)
+    for side in joins[-1:]:
+        torch.cuda.current_stream().wait_stream(side)
     if cs is not None:
         out._sdb_cs = (cs, 4 * slots, spi, 4, slots)
     return out
@@ -604,7 +628,7 @@ def _fill_conv_args(a, x, w_rskc, bias, out, kh, kw, stride, phase):
 
 
 def gemm_tc(A, W, bias=None, residual=None, out_dtype=torch.float32, geglu=False, col_group=0, col_group_stride=0,
-            split_k=0, block_n=0, out=None, ldc=None, M=None, lda=None, rows_per_item=0, variant=0):
+            split_k=0, block_n=0, out=None, ldc=None, M=None, lda=None, rows_per_item=0, variant=0, b_const=False):
     """out[M,N] = A[M,K] @ W[N,K]^T + bias + residual; A, W bf16 (K contiguous)."""
     require_cuda(A, W, bias, residual, out)
     assert A.dtype == torch.bfloat16 and W.dtype == torch.bfloat16 and W.is_contiguous()
@@ -637,6 +661,7 @@ def gemm_tc(A, W, bias=None, residual=None, out_dtype=torch.float32, geglu=False
     a.variant = variant
     a.taps = 0
     a.rows_per_item = int(rows_per_item)
+    a.b_const = int(bool(b_const))        # W written by no earlier launch of the stream: fetched before the PDL wait
     if rows_per_item:
         _apply_plan(a, "gemm", rows_per_item)
     _tc_launch(a, "tc gemm")
