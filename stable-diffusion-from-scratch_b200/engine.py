@@ -67,7 +67,7 @@ class PackedLinear:
 
 # Packed weights (PackedConv / PackedLinear) are written once, long before any launch that reads them: the tcgen05 kernels may
 # fetch their first weight tiles before the programmatic-dependent-launch wait (sdb_tc_args.b_const).  SDB200_B_CONST=0 = off.
-B_CONST = os.environ.get("SDB200_B_CONST", "1") != "0"
+B_CONST = os.environ.get("SDB200_B_CONST", "0") == "1"
 
 
 def conv(x, pc, rowvec=None, residual=None, out_dtype=torch.float32, up=1, want_stats=False):

@@ -542,7 +542,7 @@ def tc_colstats_layout(a):
 
 
 UP2_PHASES = ((0, 0), (0, 1), (1, 0), (1, 1))
-UP2_TWO_STREAMS = os.environ.get("SDB200_UP2_STREAMS", "1") != "0"
+UP2_TWO_STREAMS = os.environ.get("SDB200_UP2_STREAMS", "0") == "1"
 _up2_streams = {}
 
 
