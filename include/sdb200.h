@@ -39,6 +39,12 @@ const char* sdb_last_error_string(void);       /* thread-local, valid until the 
 int         sdb_device_sm_count(void);         /* SMs of the current device (148 on B200) */
 /* number of kernel launches enqueued by this library in this process (bench `gpu_launches`) */
 unsigned long long sdb_launch_count(void);
+/* Every kernel of the library is launched with programmatic stream serialization (it may start while its predecessor in the
+ * stream drains and blocks in griddepcontrol.wait until that predecessor is complete).  The next `n` launches of the calling
+ * host thread are made WITHOUT the attribute: they start only after ALL prior work of their stream — cross-stream event waits
+ * included — has completed.  Callers use it for the first launch after a fork to / join from a side stream.  Returns the
+ * previous pending count. */
+int sdb_pdl_skip_next(int n);
 
 /* ---- layout ------------------------------------------------------------------------------- */
 /* NCHW fp32 <-> NHWC fp32/bf16.  Replaces nothing arithmetic: the reference computes in NCHW

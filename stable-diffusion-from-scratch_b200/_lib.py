@@ -82,6 +82,7 @@ SIGNATURES = {
     "sdb_last_error_string": (C.c_char_p, []),
     "sdb_device_sm_count": (_I, []),
     "sdb_launch_count": (C.c_ulonglong, []),
+    "sdb_pdl_skip_next": (_I, [_I]),
     "sdb_nchw_to_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "sdb_nchw_to_nhwc_split": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "sdb_nhwc_to_nchw": (_I, [_P, _P, _I, _I, _I, _P]),
@@ -148,6 +149,12 @@ def check(rc, what=""):
 
 def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
+
+
+def stream_fence():
+    """Call right after a cross-stream wait (fork to / join from a side stream): the next kernel launch is made without the
+    programmatic-dependent-launch attribute, so it starts only once everything its stream waits for has completed."""
+    load().sdb_pdl_skip_next(1)
 
 
 def ptr(t):

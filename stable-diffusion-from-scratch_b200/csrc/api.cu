@@ -16,7 +16,11 @@ void set_last_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+// launches of this host thread that must NOT carry the programmatic attribute (see sdb_pdl_skip_next)
+static thread_local int g_pdl_skip = 0;
+
 bool pdl_enabled() {
+    if (g_pdl_skip > 0) { --g_pdl_skip; return false; }
     static int on = -1;
     if (on < 0) {
         const char* e = getenv("SDB200_PDL");
@@ -51,5 +55,11 @@ int sdb_device_sm_count(void) {
 }
 
 unsigned long long sdb_launch_count(void) { return sdb::g_launches.load(std::memory_order_relaxed); }
+
+int sdb_pdl_skip_next(int n) {
+    const int prev = sdb::g_pdl_skip;
+    sdb::g_pdl_skip = n > 0 ? n : 0;
+    return prev;
+}
 
 }  // extern "C"

@@ -19,7 +19,7 @@ import weakref
 import torch
 from torch import nn
 
-from . import engine, ops
+from . import _lib, engine, ops
 from .engine import PackedConv, PackedLinear, head_pad
 
 
@@ -209,6 +209,7 @@ class _SideResult:
     def get(self):
         if self.side is not None:
             self.main.wait_stream(self.side)
+            _lib.stream_fence()                           # the consumer's launch must honour the join
             if not torch.cuda.is_current_stream_capturing():
                 self.tensor.record_stream(self.main)      # allocated on the side stream's pool, read on the main stream
             self.side = None
@@ -490,6 +491,7 @@ class UNetModel(nn.Module):
                 side = self.__dict__["_side_stream2"] = torch.cuda.Stream(device=main.device)
             side.wait_stream(main)
             with torch.cuda.stream(side):
+                _lib.stream_fence()
                 xs_side = _SideResult(self._skip_conv(sk, raw, x, x1), side, main)
         if ss:
             # out_norm(h) * (1 + scale) + shift (model.py:244-248): scale / shift folded into per-sample GroupNorm rows
@@ -724,6 +726,7 @@ class UNetModel(nn.Module):
                 side = self.__dict__["_side_stream"] = torch.cuda.Stream(device=main.device)
             side.wait_stream(main)
             with torch.cuda.stream(side):
+                _lib.stream_fence()
                 emb_all = _SideResult(self._time_embedding(P, t_f32, y), side, main)
         else:
             emb_all = self._time_embedding(P, t_f32, y)

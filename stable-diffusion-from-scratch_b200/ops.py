@@ -542,15 +542,6 @@ def tc_colstats_layout(a):
 
 
 UP2_PHASES = ((0, 0), (0, 1), (1, 0), (1, 1))
-UP2_TWO_STREAMS = os.environ.get("SDB200_UP2_STREAMS", "0") == "1"
-_up2_streams = {}
-
-
-def _up2_side_stream(device):
-    s = _up2_streams.get(device)
-    if s is None:
-        s = _up2_streams[device] = torch.cuda.Stream(device=device)
-    return s
 
 
 def fold_upsample_weights(w, dtype):
@@ -580,7 +571,6 @@ def conv_up2_tc(x, w_phases, bias, want_stats=False, b_const=False):
     Cout = w_phases[0].shape[1]
     out = torch.empty((N, 2 * H, 2 * W, Cout), dtype=torch.float32, device=x.device)
     cs = None
-    joins = []
     for p, (py, px) in enumerate(UP2_PHASES):
         ph = (2, 2, py, px, 2 * H, 2 * W, 1 - py, 1 - px)
         if want_stats and p == 0:
@@ -591,21 +581,8 @@ def conv_up2_tc(x, w_phases, bias, want_stats=False, b_const=False):
             slots, spi = tc_colstats_layout(probe)
             if slots > 0:
                 cs = torch.empty((2, 4 * slots, Cout), dtype=torch.float32, device=x.device)
-        # the four phases write disjoint sub-lattices of `out`: odd phases go to a side stream (forked from / joined to the
-        # current one, also under graph capture), so two of these small launches share the SMs at any time
-        side = _up2_side_stream(x.device) if (UP2_TWO_STREAMS and (p & 1)) else None
-        if side is not None:
-            main = torch.cuda.current_stream()
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                conv_tc(x, w_phases[p], bias, 2, 2, stride=1, pad=0, out=out, phase=ph, b_const=b_const,
-                        stats_into=(cs, 4 * slots, p * slots) if cs is not None else None)
-            joins.append(side)
-        else:
-            conv_tc(x, w_phases[p], bias, 2, 2, stride=1, pad=0, out=out, phase=ph, b_const=b_const,
-                    stats_into=(cs, 4 * slots, p * slots) if cs is not None else None)
-    for side in joins[-1:]:
-        torch.cuda.current_stream().wait_stream(side)
+        conv_tc(x, w_phases[p], bias, 2, 2, stride=1, pad=0, out=out, phase=ph, b_const=b_const,
+                stats_into=(cs, 4 * slots, p * slots) if cs is not None else None)
     if cs is not None:
         out._sdb_cs = (cs, 4 * slots, spi, 4, slots)
     return out

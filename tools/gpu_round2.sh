@@ -42,7 +42,8 @@ cap splitk_conv3x3_1280_8x8                splitk_reduce conv 8 8 8 1280 1280 3 
 cap attn_d40_S4096                         tc_attention_kernel attn 8 8 4096 4096 40
 cap attn_d80_S1024                         tc_attention_kernel attn 8 8 1024 1024 80
 cap attn_d160_S256                         tc_attention_kernel attn 8 8 256 256 160
-cap attn_d40_S4096_Sk77                    tc_attention_kernel attn 8 8 4096 77 40
+cap attn_d40_S4096_Sk77                    tc_attention_kv1 attn 8 8 4096 77 40
+cap attn_d80_S1024_Sk77                    tc_attention_kv1 attn 8 8 1024 77 80
 cap attn_wide_d512_S4096                   tc_attention_wide attnw 8 4096 4096 512
 cap gn_cluster_N8_HW4096_C320              gn_ gn 8 4096 320 1
 cap layernorm_rows32768_C320               layernorm_kernel ln 32768 320
