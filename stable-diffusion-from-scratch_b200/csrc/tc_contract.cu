@@ -1338,17 +1338,29 @@ static int tma_epilogue_max_kblocks() {
 
 // ---- split-K: deterministic reduction of the per-split partial tiles --------------------------------
 // out[m, n] = sum_s ws[s][m][n] + bias[n] + rowvec[m / rows_per_img][n] + residual[m][n]   (4 columns per thread)
+// A conv whose output is remapped into a sub-lattice of a larger tensor (one sub-pixel phase of an upsampling conv) reduces ONLY
+// its own pixels: `rows` then counts the conv's dense output rows (image, oh, ow) and `rm` maps them to rows of the workspace /
+// output lattice.  (Reducing the whole lattice — as this kernel once did — rewrites the other phases' pixels from whatever their
+// workspace entries hold, which is only right while every phase happens to get the same recycled workspace block.)
+struct ReduceRemap { int on, OH, OW, sh, sw, oh0, ow0, OHF, OWF; };
+
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, long long split_stride, int splits, long long rows, int N,
                                      const float* __restrict__ bias, const float* __restrict__ rowvec, long long ldv,
                                      long long rows_per_img, const float* __restrict__ residual, long long ldr,
-                                     void* __restrict__ out, long long ldc, int out_bf16) {
+                                     void* __restrict__ out, long long ldc, int out_bf16, const ReduceRemap rm) {
     pdl_trigger();
     pdl_wait();
     const int nq = N >> 2;
     const long long total = rows * nq;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long m = i / nq;
+        long long m = i / nq;
         const int n = (int)(i - m * nq) << 2;
+        if (rm.on) {
+            const long long img = m / ((long long)rm.OH * rm.OW);
+            const int rem = (int)(m - img * rm.OH * rm.OW);
+            const int oh = rem / rm.OW, ow = rem - oh * rm.OW;
+            m = (img * rm.OHF + (oh * rm.sh + rm.oh0)) * rm.OWF + (ow * rm.sw + rm.ow0);
+        }
         float4 acc = *reinterpret_cast<const float4*>(ws + m * N + n);
         for (int s = 1; s < splits; ++s) {
             float4 q = *reinterpret_cast<const float4*>(ws + s * split_stride + m * N + n);
@@ -1738,7 +1750,16 @@ extern "C" int sdb_tc_contract(const sdb_tc_args* a, void* stream) {
         }
     }
     if (rc || p.split_k == 1) return rc;
-    const long long total = pl.rows_out * (a->N / 4);
+    // remapped output (sub-pixel phase): the reduction visits this conv's own pixels only
+    ReduceRemap rm;
+    memset(&rm, 0, sizeof(rm));
+    long long red_rows = pl.rows_out;
+    if (conv && (p.out_sh != 1 || p.out_sw != 1 || p.out_oh != 0 || p.out_ow != 0 || p.OHF != p.OH || p.OWF != p.OW)) {
+        rm.on = 1; rm.OH = p.OH; rm.OW = p.OW; rm.sh = p.out_sh; rm.sw = p.out_sw; rm.oh0 = p.out_oh; rm.ow0 = p.out_ow;
+        rm.OHF = p.OHF; rm.OWF = p.OWF;
+        red_rows = (long long)p.NB * p.OH * p.OW;
+    }
+    const long long total = red_rows * (a->N / 4);
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     const long long rows_per_img = conv ? (long long)p.OHF * p.OWF : 1;
@@ -1751,8 +1772,8 @@ extern "C" int sdb_tc_contract(const sdb_tc_args* a, void* stream) {
                    a->colstats, p.colstats_sq);
         return check_launch("splitk_reduce_stats_kernel");
     }
-    launch_pdl(splitk_reduce_kernel, dim3(blocks), dim3(256), 0, st, p.ws, p.ws_split_stride, p.split_k, pl.rows_out, a->N, a->bias,
+    launch_pdl(splitk_reduce_kernel, dim3(blocks), dim3(256), 0, st, p.ws, p.ws_split_stride, p.split_k, red_rows, a->N, a->bias,
                                                  conv ? a->rowvec : nullptr, a->ldv, rows_per_img, a->residual, a->ldr,
-                                                 a->out, a->ldc, p.out_bf16);
+                                                 a->out, a->ldc, p.out_bf16, rm);
     return check_launch("splitk_reduce_kernel");
 }

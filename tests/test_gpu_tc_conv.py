@@ -117,3 +117,33 @@ def test_conv_up2_subpixel(cuda, N, H, W, Cin, Cout):
         g2, be2 = randn(C, seed=10) * 0.1 + 1, randn(C, seed=11) * 0.1
         ref2 = nhwc(F.group_norm(nchw(torch.cat([o2, out], -1)).double(), 32, g2.double(), be2.double(), 1e-6))
         assert rel(ops.groupnorm(o2, g2, be2, 1e-6, out_dtype=torch.float32, x1=out, exact=True), ref2) < 2e-6
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,sk", [(8, 8, 8, 1280, 1280, 3), (2, 16, 16, 512, 512, 2), (1, 8, 8, 640, 320, 5)])
+def test_split_k_phase_conv_touches_only_its_own_pixels(cuda, N, H, W, Cin, Cout, sk):
+    """One sub-pixel phase of an upsampling conv run with split-K: the fixed-order reduction must visit this phase's pixels only.
+    The workspace is poisoned with NaN (a same-sized block is filled and handed back to the allocator just before the call) and
+    the other three phases' pixels of `out` hold a sentinel that has to survive."""
+    from sdb200 import _lib, ops
+    x = randn(N, H, W, Cin, seed=1).to(torch.bfloat16)
+    w = (randn(4, Cout, Cin, seed=2) * (Cin * 4) ** -0.5).to(torch.bfloat16)
+    b = randn(Cout, seed=3)
+    for p_, (py, px) in enumerate(ops.UP2_PHASES):
+        ph = (2, 2, py, px, 2 * H, 2 * W, 1 - py, 1 - px)
+        out = torch.full((N, 2 * H, 2 * W, Cout), 7.0, device="cuda")
+        probe = _lib.TcArgs()
+        ops._fill_conv_args(probe, x, w, b, out, 2, 2, 1, ph)
+        probe.split_k = sk
+        need = _lib.load().sdb_tc_workspace_bytes(probe)
+        assert need > 0
+        poison = torch.full((need // 4,), float("nan"), device="cuda")
+        del poison                                     # the next same-sized torch.empty (the workspace) gets this block back
+        ops.conv_tc(x, w, b, 2, 2, stride=1, pad=0, out=out, phase=ph, split_k=sk)
+        ref = ops.conv_tc(x, w, b, 2, 2, stride=1, pad=0, out=torch.full_like(out, 7.0), phase=ph, split_k=1)
+        torch.cuda.synchronize()
+        mine = out[:, py::2, px::2]
+        assert torch.isfinite(out).all()
+        assert rel(mine, ref[:, py::2, px::2]) < 1e-5
+        other = out.clone()
+        other[:, py::2, px::2] = 7.0
+        assert float((other - 7.0).abs().max()) == 0.0, "the reduction wrote pixels of another phase"
