@@ -268,7 +268,14 @@ def run_sdb200(a):
         torch.cuda.synchronize()
         unet_ms = e0.elapsed_time(e1) / 10
         unet.use_cuda_graph = False
-        roof, roof_hbm, launches_per_unet = roofline_pass(lambda: unet(x_dev, tt, c_dev), "unet")
+        # per-launch durations: every kernel alone on the device (the side streams of the graph — time embedding, ResBlock skip
+        # convs — overlap launches, which speeds the step up but makes the overlapped kernels' own brackets longer)
+        side = (unet.emb_side_stream, unet.skip_side_stream)
+        unet.emb_side_stream = unet.skip_side_stream = False
+        try:
+            roof, roof_hbm, launches_per_unet = roofline_pass(lambda: unet(x_dev, tt, c_dev), "unet")
+        finally:
+            unet.emb_side_stream, unet.skip_side_stream = side
         unet.use_cuda_graph = not a.no_graph
 
     if rank == 0:
@@ -579,7 +586,12 @@ def run_c5(a):
                 out_host.copy_(net(x_host.to(dev, non_blocking=True), t, c_host.to(dev, non_blocking=True)), non_blocking=True)
             ms_e2e = _timed_steps(e2e, max(a.steps, 5), 1, 1) / max(a.steps, 5)
             net.use_cuda_graph = False
-            roof, roof_hbm, launches = roofline_pass(lambda: net(x, t, c), "unet 96x96, batch 8")
+            side = (net.emb_side_stream, net.skip_side_stream)      # per-launch durations: every kernel alone on the device
+            net.emb_side_stream = net.skip_side_stream = False
+            try:
+                roof, roof_hbm, launches = roofline_pass(lambda: net(x, t, c), "unet 96x96, batch 8")
+            finally:
+                net.emb_side_stream, net.skip_side_stream = side
             net.use_cuda_graph = not a.no_graph
     sampler.stop_flag = True
     b8 = [r for r in sweep if r["batch"] == 8][0]

@@ -211,7 +211,9 @@ __global__ void gather_rows_kernel(const float* __restrict__ table, const long l
 }
 
 // ---- skinny linear: M <= 32 rows; one warp per output column, weights streamed once -------------
-template <int MT, bool WBF16>
+// NC output columns per warp: the activated input rows are read from shared memory once per NC weight rows (with one column per
+// warp the kernel is bound by those reads — 16 LDS.128 per 16-byte weight load at M = 8 — at ~0.7 TB/s of weight streaming).
+template <int MT, bool WBF16, int NC>
 __global__ void skinny_linear_kernel(const float* __restrict__ x, int M, int K, const void* __restrict__ Wv,
                                      const float* __restrict__ bias, int N, int act_in, int act_out,
                                      float* __restrict__ y) {
@@ -227,47 +229,52 @@ __global__ void skinny_linear_kernel(const float* __restrict__ x, int M, int K, 
     const int lane = threadIdx.x & 31;
     const int warps = blockDim.x >> 5;
     constexpr int EPL = WBF16 ? 8 : 4;        // weights per 16-byte load
-    for (int n = blockIdx.x * warps + (threadIdx.x >> 5); n < N; n += gridDim.x * warps) {
-        float acc[MT];
+    // the weight rows are streamed once: KU 16-byte loads per lane and column are in flight before the first FMA (one load in
+    // flight per lane made this kernel latency-bound at ~1 TB/s on the ResBlock time-embedding matrix)
+    constexpr int KU = (WBF16 ? 5 : 10) / (NC > 1 ? (WBF16 ? 1 : 2) : 1);
+    for (int n0 = (blockIdx.x * warps + (threadIdx.x >> 5)) * NC; n0 < N; n0 += gridDim.x * warps * NC) {
+        float acc[NC][MT];
 #pragma unroll
-        for (int m = 0; m < MT; ++m) acc[m] = 0.f;
-        // the weight row is streamed once: issue up to KU 16-byte loads per lane before the first FMA (one load in flight
-        // per lane made this kernel latency-bound at ~1 TB/s on the 113 MB ResBlock time-embedding matrix)
-        constexpr int KU = WBF16 ? 5 : 10;
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+            for (int m = 0; m < MT; ++m) acc[c][m] = 0.f;
         for (int k0 = lane * EPL; k0 < K; k0 += 32 * EPL * KU) {
-            float4 wv[KU];
+            float4 wv[NC][KU];
 #pragma unroll
-            for (int u = 0; u < KU; ++u) {
-                wv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                const int k = k0 + 32 * EPL * u;
-                if (k < K) {
-                    if (WBF16) wv[u] = ld_stream_f4(reinterpret_cast<const float*>(reinterpret_cast<const __nv_bfloat16*>(Wv) + (long long)n * K + k));
-                    else wv[u] = ld_stream_f4(reinterpret_cast<const float*>(Wv) + (long long)n * K + k);
+            for (int c = 0; c < NC; ++c)
+#pragma unroll
+                for (int u = 0; u < KU; ++u) {
+                    wv[c][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int k = k0 + 32 * EPL * u;
+                    if (k < K && n0 + c < N) {
+                        if (WBF16) wv[c][u] = ld_stream_f4(reinterpret_cast<const float*>(reinterpret_cast<const __nv_bfloat16*>(Wv) + (long long)(n0 + c) * K + k));
+                        else wv[c][u] = ld_stream_f4(reinterpret_cast<const float*>(Wv) + (long long)(n0 + c) * K + k);
+                    }
                 }
-            }
 #pragma unroll
             for (int u = 0; u < KU; ++u) {
                 const int k = k0 + 32 * EPL * u;
                 if (k < K) {
-                    if (WBF16) {
-                        // 8 bf16 weights: a bf16 is the high half of the fp32 with the same value
-                        const uint32_t q0 = __float_as_uint(wv[u].x), q1 = __float_as_uint(wv[u].y), q2 = __float_as_uint(wv[u].z), q3 = __float_as_uint(wv[u].w);
-                        const float w0 = __uint_as_float(q0 << 16), w1 = __uint_as_float(q0 & 0xffff0000u), w2 = __uint_as_float(q1 << 16), w3 = __uint_as_float(q1 & 0xffff0000u);
-                        const float w4 = __uint_as_float(q2 << 16), w5 = __uint_as_float(q2 & 0xffff0000u), w6 = __uint_as_float(q3 << 16), w7 = __uint_as_float(q3 & 0xffff0000u);
 #pragma unroll
-                        for (int m = 0; m < MT; ++m) {
-                            if (m < M) {
-                                const float4 xa = *reinterpret_cast<const float4*>(xs + m * K + k);
+                    for (int m = 0; m < MT; ++m) {
+                        if (m < M) {
+                            const float4 xa = *reinterpret_cast<const float4*>(xs + m * K + k);
+                            if (WBF16) {
                                 const float4 xb = *reinterpret_cast<const float4*>(xs + m * K + k + 4);
-                                acc[m] += (w0 * xa.x + w1 * xa.y + w2 * xa.z + w3 * xa.w) + (w4 * xb.x + w5 * xb.y + w6 * xb.z + w7 * xb.w);
-                            }
-                        }
-                    } else {
 #pragma unroll
-                        for (int m = 0; m < MT; ++m) {
-                            if (m < M) {
-                                const float4 xr = *reinterpret_cast<const float4*>(xs + m * K + k);
-                                acc[m] += wv[u].x * xr.x + wv[u].y * xr.y + wv[u].z * xr.z + wv[u].w * xr.w;
+                                for (int c = 0; c < NC; ++c) {
+                                    // 8 bf16 weights: a bf16 is the high half of the fp32 with the same value
+                                    const uint32_t q0 = __float_as_uint(wv[c][u].x), q1 = __float_as_uint(wv[c][u].y);
+                                    const uint32_t q2 = __float_as_uint(wv[c][u].z), q3 = __float_as_uint(wv[c][u].w);
+                                    acc[c][m] += (__uint_as_float(q0 << 16) * xa.x + __uint_as_float(q0 & 0xffff0000u) * xa.y +
+                                                  __uint_as_float(q1 << 16) * xa.z + __uint_as_float(q1 & 0xffff0000u) * xa.w) +
+                                                 (__uint_as_float(q2 << 16) * xb.x + __uint_as_float(q2 & 0xffff0000u) * xb.y +
+                                                  __uint_as_float(q3 << 16) * xb.z + __uint_as_float(q3 & 0xffff0000u) * xb.w);
+                                }
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < NC; ++c)
+                                    acc[c][m] += wv[c][u].x * xa.x + wv[c][u].y * xa.y + wv[c][u].z * xa.z + wv[c][u].w * xa.w;
                             }
                         }
                     }
@@ -275,14 +282,17 @@ __global__ void skinny_linear_kernel(const float* __restrict__ x, int M, int K, 
             }
         }
 #pragma unroll
-        for (int m = 0; m < MT; ++m) {
-            if (m < M) {
-                float v = warp_sum(acc[m]);
-                if (lane == 0) {
-                    if (bias) v += bias[n];
-                    if (act_out == 1) v = silu_exact(v);
-                    else if (act_out == 2) v = gelu_erf(v);
-                    y[(long long)m * N + n] = v;
+        for (int c = 0; c < NC; ++c) {
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                if (m < M) {
+                    float v = warp_sum(acc[c][m]);
+                    if (lane == 0 && n0 + c < N) {
+                        if (bias) v += bias[n0 + c];
+                        if (act_out == 1) v = silu_exact(v);
+                        else if (act_out == 2) v = gelu_erf(v);
+                        y[(long long)m * N + n0 + c] = v;
+                    }
                 }
             }
         }
@@ -490,15 +500,18 @@ static int launch_skinny(const float* x, int M, int K, const void* W, const floa
     size_t smem = (size_t)M * K * sizeof(float);
     SDB_REQUIRE(smem <= 200 * 1024, "skinny_linear: M*K too large");
     int threads = 256;
-    int blocks = ceil_div(N, threads / 32);
+    // four columns per warp when there are enough columns to keep every SM busy that way (the ResBlock embedding matrix)
+    const int nc = (M <= 8 && N >= 4 * 8 * 148 * 2) ? 4 : 1;
+    int blocks = ceil_div(N, (threads / 32) * nc);
     if (blocks > 148 * 4) blocks = 148 * 4;
     cudaStream_t st = (cudaStream_t)stream;
-#define SK(MT)                                                                                              \
+#define SK(MT, NC)                                                                                          \
     do {                                                                                                    \
-        if (smem > 48 * 1024) cudaFuncSetAttribute(skinny_linear_kernel<MT, WBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        launch_pdl(skinny_linear_kernel<MT, WBF16>, dim3(blocks), dim3(threads), smem, st, x, M, K, W, bias, N, act_in, act_out, y);   \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(skinny_linear_kernel<MT, WBF16, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        launch_pdl(skinny_linear_kernel<MT, WBF16, NC>, dim3(blocks), dim3(threads), smem, st, x, M, K, W, bias, N, act_in, act_out, y);   \
     } while (0)
-    if (M <= 4) SK(4); else if (M <= 8) SK(8); else if (M <= 16) SK(16); else SK(32);
+    if (nc == 4) { if (M <= 4) SK(4, 4); else SK(8, 4); }
+    else if (M <= 4) SK(4, 1); else if (M <= 8) SK(8, 1); else if (M <= 16) SK(16, 1); else SK(32, 1);
 #undef SK
     return check_launch("skinny_linear_kernel");
 }

@@ -112,6 +112,12 @@ def test_timestep_embedding_and_skinny(cuda):
         assert rel(ops.skinny_linear(x, W16, b, act_in=1), F.linear(F.silu(x.double()), W16.double(), b.double())) < 2e-6
     x, W16 = randn(8, 1288, seed=21), (randn(77, 1288, seed=22) * 0.03).to(torch.bfloat16)       # K not a multiple of 256, ragged N
     assert rel(ops.skinny_linear(x, W16), F.linear(x.double(), W16.double())) < 2e-6
+    # many columns (the 20160 x 1280 emb_layers matrix): four columns per warp, ragged last group
+    for M in (3, 8):
+        x, Wb, bb = randn(M, 1280, seed=23), randn(9603, 1280, seed=24) * 0.03, randn(9603, seed=25)
+        assert rel(ops.skinny_linear(x, Wb, bb, act_in=1), F.linear(F.silu(x.double()), Wb.double(), bb.double())) < 2e-6
+        W16 = Wb.to(torch.bfloat16)
+        assert rel(ops.skinny_linear(x, W16, bb, act_in=1), F.linear(F.silu(x.double()), W16.double(), bb.double())) < 2e-6
 
 
 def test_ddim_step_bit_exact_vs_reference(cuda):

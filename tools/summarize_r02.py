@@ -84,3 +84,28 @@ if os.path.exists(src):
                    "launches": len(per_id), "dram_bytes_total": tot, "dram_bytes_per_launch": tot / len(per_id)},
                   open(os.path.join(P, "r02_tc_traffic.json"), "w"))
 print("ok")
+# bench lines, per-layer tables, library bar, same-box A/B, timelines: copied under their round-2 names
+import shutil
+for src, dst in (("bench_full.log", "r02_bench_full.json"), ("bench_ref.log", "r02_bench_ref.json"), ("bench_c3.log", "r02_bench_c3.json"),
+                 ("bench_c5.log", "r02_bench_c5.json")):
+    pth = os.path.join(G, src)
+    if os.path.exists(pth):
+        lines = [l for l in open(pth).read().splitlines() if l.startswith("{")]
+        if lines:
+            open(os.path.join(P, dst), "w").write(lines[-1] + "\n")
+for src, dst in (("layers_unet_b8.log", "r02_layers_unet_b8.txt"), ("layers_vae_b8.log", "r02_layers_vae_b8.txt"),
+                 ("r02_library_bar.txt", "r02_library_bar.txt"), ("ab_unet_step_final.txt", "r02_ab_unet_step.txt"),
+                 ("trace_xattn_all.txt", "r02_xattn_timeline.txt"), ("xattn_variants.txt", "r02_xattn_knockouts.txt"),
+                 ("attn_ab.txt", "r02_attn_packed_ab.txt")):
+    pth = os.path.join(G, src)
+    if os.path.exists(pth):
+        shutil.copyfile(pth, os.path.join(P, dst))
+tl = [os.path.join(G, n) for n in ("trace2_smallk.txt", "trace2_m2048.txt", "trace2_ffout.txt", "trace2_m8192.txt")]
+if all(os.path.exists(t) for t in tl):
+    with open(os.path.join(P, "r02_pair_timeline.txt"), "w") as f:
+        f.write("# round 2: SM-clock timelines of the CTA-pair kernel with the TMA epilogue (tools/trace_pair.py M N K res obf bn; leader CTA of pairs 0 / 36 / 73)\n"
+                "# P0 / P1 producer first / last TMA issue, M0w MMA warp reached the unit, M0 accumulator free, M1 first operands landed, M2 last MMA committed\n")
+        for t in tl:
+            txt = open(t).read()
+            f.write(txt[txt.index("args"):] if "args" in txt else txt)
+print("copied")
