@@ -247,7 +247,9 @@ def whole(emit, dev, flash_attn_func):
                     with torch.cuda.stream(s):
                         unet_lib()
                     torch.cuda.current_stream().wait_stream(s)
-                    with torch.cuda.graph(gph):
+                    # (the restatement builds the timestep frequencies with torch.arange on the host: inside a capture the
+                    # factory functions must default to the GPU, or the host-to-device copy of that table aborts the capture)
+                    with torch.cuda.graph(gph), torch.device(dev):
                         unet_lib()
                     t_graph = timeit(gph.replay, iters=10, warm=3)
                 except Exception as e:                               # noqa: BLE001
