@@ -284,6 +284,10 @@ int sdb_tc_set_pair_kernel(int enable);
  * in swizzled shared memory and moves them with TMA (cp.async.bulk.tensor stores, residual tiles by TMA loads) whenever the
  * output layout allows [default], 0 = register-store epilogue everywhere.  Returns the previous setting. */
 int sdb_tc_set_tma_epilogue(int enable);
+/* Tuning switch (measurement only, bit-identical results either way): 1 = the one-CTA kernel with 160-column tiles issues the
+ * tiles of its last, partial wave (tiles mod SM count) as two sub-tiles of 96 and 64 columns, so the tail of the launch is handed
+ * out in half-size pieces [default; SDB200_TC_TAILSPLIT=0 at load time], 0 = whole tiles only.  Returns the previous setting. */
+int sdb_tc_set_tail_split(int enable);
 
 /* ---- fused attention forward (bf16, tcgen05) ---------------------------------------------------
  * Replaces flash_attn_func(q,k,v, softmax_scale, causal=False) (openai_model/attention.py:106-112).

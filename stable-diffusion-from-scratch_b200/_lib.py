@@ -114,6 +114,7 @@ SIGNATURES = {
     "sdb_tc_contract": (_I, [C.POINTER(TcArgs), _P]),
     "sdb_tc_set_pair_kernel": (_I, [_I]),
     "sdb_tc_set_tma_epilogue": (_I, [_I]),
+    "sdb_tc_set_tail_split": (_I, [_I]),
     "sdb_tc_workspace_bytes": (_L, [C.POINTER(TcArgs)]),
     "sdb_tc_colstats_layout": (_I, [C.POINTER(TcArgs), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "sdb_attention_fwd": (_I, [C.POINTER(AttnArgs), _P]),

@@ -47,6 +47,8 @@ struct TcP {
     int epi_nbuf;           //   staging boxes per epilogue warp (2; 3 when a residual tile is prefetched two chunks ahead)
     int epi_bw, epi_bh;     //   conv: the 32 rows of a lane quarter are the pixel box bw x bh x 32/(bw*bh) of the tile
     int b_const;            // B (weights) is not written by the preceding launch: its first tiles are fetched before pdl_wait()
+    int full_tiles;         // one-CTA kernel: tiles [0, full_tiles) are whole 128 x BN tiles; every later tile is computed by TWO CTAs as a
+                            // 96-column and a (BN - 96)-column sub-tile (tail split against wave quantisation, see launch_tc)
     // conv
     int conv;
     int kw, stride, pad_h, pad_w;
@@ -128,7 +130,7 @@ __device__ __forceinline__ void prefetch_residual_row(const TcP& p, long long pi
 template <int BN>
 __device__ __noinline__ void epilogue_generic(const TcP p /* by value: a reference would force the kernel's parameter block into local memory */, uint32_t taddr, const float* s_bias, float* stage, int lane,
                                               int n0, int nt, long long row_pix, int row_img, int split, int ch0, int chstep,
-                                              uint64_t* acc_ready, uint32_t acc_parity, int slot) {
+                                              uint64_t* acc_ready, uint32_t acc_parity, int slot, int ncols) {
     // rows this lane stores after the transpose: r_i = 4*i + (lane >> 3), i = 0..7
     long long rpix[8];
     int rimg[8];
@@ -176,7 +178,7 @@ __device__ __noinline__ void epilogue_generic(const TcP p /* by value: a referen
 #pragma unroll 1
     for (int ch = ch0; ch < NCHUNK; ch += chstep) {
         const int c0 = ch * CH;
-        if (c0 >= cols || nb + c0 >= n_out) break;                     // warp-uniform
+        if (c0 >= cols || c0 >= ncols || nb + c0 >= n_out) break;      // warp-uniform
         const int cn = nb + c0 + cq;                                    // first of this lane's 4 output columns
         const bool col_ok = cn < n_out;
         float4 addv[8];
@@ -288,7 +290,7 @@ enum { EPI_F32 = 0, EPI_BF16 = 1, EPI_PARTIAL = 2, EPI_GEGLU = 3 };
 template <int BN, int MODE, bool HAS_ADD>
 __device__ __forceinline__ void epilogue_fast(const TcP& p, uint32_t taddr, const float* s_bias, float* stage, int lane,
                                               int n0, int nt, long long row_pix, int row_img, int split, int ch0, int chstep,
-                                              uint64_t* acc_ready, uint32_t acc_parity, int slot) {
+                                              uint64_t* acc_ready, uint32_t acc_parity, int slot, int ncols) {
     constexpr int CH = 32;
     constexpr bool GEGLU = MODE == EPI_GEGLU;
     constexpr int COLS = GEGLU ? BN / 2 : BN;
@@ -335,7 +337,7 @@ __device__ __forceinline__ void epilogue_fast(const TcP& p, uint32_t taddr, cons
 #pragma unroll 1
     for (int ch = ch0; ch < NCHUNK; ch += chstep) {
         const int c0 = ch * CH;
-        if (nb + c0 >= n_out) break;                                    // warp-uniform
+        if (c0 >= ncols || nb + c0 >= n_out) break;                     // warp-uniform
         const int cn = nb + c0 + cq;
         const bool col_ok = cn < n_out;
         float4 addv[8];
@@ -429,7 +431,7 @@ __device__ __forceinline__ void epilogue_fast(const TcP& p, uint32_t taddr, cons
 template <int BN>
 __device__ __forceinline__ void epilogue_warp(const TcP& p, uint32_t taddr, const float* s_bias, float* stage, int lane,
                                               int n0, int nt, long long row_pix, int row_img, int split, int ch0, int chstep,
-                                              uint64_t* acc_ready, uint32_t acc_parity, int slot) {
+                                              uint64_t* acc_ready, uint32_t acc_parity, int slot, int ncols = 1 << 30) {
     const int n_out = p.geglu ? p.N / 2 : p.N;
     const bool partial = p.split_k > 1;
     const bool fast_ok = p.off32 && (n_out % 4 == 0) && (p.ldc % 4 == 0) && (p.ldv % 4 == 0) &&
@@ -437,9 +439,9 @@ __device__ __forceinline__ void epilogue_warp(const TcP& p, uint32_t taddr, cons
                            reinterpret_cast<uintptr_t>(p.rowvec) | reinterpret_cast<uintptr_t>(p.ws)) & 15) == 0 &&
                          (!p.col_group || (p.col_group % 4 == 0 && p.col_group_stride % 4 == 0)) &&
                          (p.residual == nullptr || partial || p.ldr == p.ldc) && !(p.geglu && (partial || !p.out_bf16));
-#define SDB_EPI(MODE, ADD) epilogue_fast<BN, MODE, ADD>(p, taddr, s_bias, stage, lane, n0, nt, row_pix, row_img, split, ch0, chstep, acc_ready, acc_parity, slot)
+#define SDB_EPI(MODE, ADD) epilogue_fast<BN, MODE, ADD>(p, taddr, s_bias, stage, lane, n0, nt, row_pix, row_img, split, ch0, chstep, acc_ready, acc_parity, slot, ncols)
     if (!fast_ok) {
-        epilogue_generic<BN>(p, taddr, s_bias, stage, lane, n0, nt, row_pix, row_img, split, ch0, chstep, acc_ready, acc_parity, slot);
+        epilogue_generic<BN>(p, taddr, s_bias, stage, lane, n0, nt, row_pix, row_img, split, ch0, chstep, acc_ready, acc_parity, slot, ncols);
     } else if (p.geglu) {
         SDB_EPI(EPI_GEGLU, false);
     } else if (partial) {
@@ -719,10 +721,11 @@ __device__ __forceinline__ void epilogue_tma_units(const TcP& p, const CUtensorM
 template <int BN, int MODE, bool HAS_RES>
 __device__ __forceinline__ void epilogue_tma_single(const TcP& p, const CUtensorMap* tmC, const CUtensorMap* tmR, uint32_t taddr,
                                                     uint32_t sb_a, uint32_t stg_a, uint64_t* rbar, uint64_t* accum_bar, const UnitBox& ub,
-                                                    int lane, int lg, uint32_t rowmask, int img_w) {
+                                                    int lane, int lg, uint32_t rowmask, int img_w, int ncols) {
     constexpr bool GEGLU = MODE == EPI_GEGLU;
     constexpr int COLS = GEGLU ? BN / 2 : BN;
     constexpr int NCHUNK = (COLS + 31) / 32;
+    const int nch = ncols >= COLS ? NCHUNK : (ncols + 31) / 32;         // chunks of this CTA's (sub-)tile
     const bool partial = p.split_k > 1;
     const float* const rowv = (!partial && p.rowvec && p.conv && MODE == EPI_F32) ? p.rowvec : nullptr;
     const bool want_cs = MODE == EPI_F32 && p.colstats != nullptr && !partial;
@@ -730,27 +733,29 @@ __device__ __forceinline__ void epilogue_tma_single(const TcP& p, const CUtensor
     const bool rv_ok = rowv != nullptr && rowmask != 0u && img_w < p.NB;
     if (HAS_RES && lane == 0) {
 #pragma unroll
-        for (int ch = 0; ch < NCHUNK; ++ch) tma_prefetch_l2_5d(tmR, ub.col0 + ch * 32, ub.w, ub.h, ub.n, 0);
+        for (int ch = 0; ch < NCHUNK; ++ch)
+            if (ch < nch) tma_prefetch_l2_5d(tmR, ub.col0 + ch * 32, ub.w, ub.h, ub.n, 0);
     }
     mbar_wait(accum_bar, 0);
     tcgen05_fence_after();
     if (HAS_RES && lane == 0) {
-        mbar_arrive_expect_tx_a(smem_u32(rbar), NCHUNK * 32 * 128);
+        mbar_arrive_expect_tx_a(smem_u32(rbar), nch * 32 * 128);
 #pragma unroll
         for (int ch = 0; ch < NCHUNK; ++ch)
-            tma_load_5d(stg_a + ch * TEPI_BOX_BYTES, tmR, smem_u32(rbar), ub.col0 + ch * 32, ub.w, ub.h, ub.n, 0);
+            if (ch < nch) tma_load_5d(stg_a + ch * TEPI_BOX_BYTES, tmR, smem_u32(rbar), ub.col0 + ch * 32, ub.w, ub.h, ub.n, 0);
     }
     uint32_t ra[32], rb[32];
     tmem_ld_x32(taddr, ra);
 #pragma unroll
     for (int ch = 0; ch < NCHUNK; ++ch) {
+        if (ch >= nch) break;                                           // warp-uniform
         uint32_t (&cur)[32] = (ch & 1) ? rb : ra;
         uint32_t (&nxt)[32] = (ch & 1) ? ra : rb;
         const int c0 = ch * 32;
         uint32_t g[GEGLU ? 32 : 1];
         if (GEGLU) tmem_ld_x32(taddr + BN / 2 + c0, g);
         tmem_ld_wait();
-        if (ch + 1 < NCHUNK) tmem_ld_x32(taddr + c0 + 32, nxt);
+        if (ch + 1 < nch) tmem_ld_x32(taddr + c0 + 32, nxt);
         if (HAS_RES && ch == 0) mbar_wait(rbar, 0);
         tepi_chunk<BN, MODE, HAS_RES>(p, tmC, cur, g, sb_a, stg_a + ch * TEPI_BOX_BYTES, c0, ub.col0 + c0, ub, lane, lg, rowmask, img_w, rv_ok,
                                       rowv, want_cs, partial, n_out);
@@ -781,9 +786,17 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // ---- tile coordinates ----
-    const int tile = blockIdx.x;
+    int tile = blockIdx.x;
+    int ncols = BN, n_off = 0;                       // columns of the 128 x BN tile this CTA computes
+    if (tile >= p.full_tiles) {
+        // tail split: the tiles past full_tiles are computed as a 96-column and a (BN - 96)-column sub-tile by two CTAs each, so the
+        // last, partial wave is spread over all SMs in half-size pieces (same K order per output element: identical bits)
+        const int t2 = tile - p.full_tiles;
+        tile = p.full_tiles + (t2 >> 1);
+        if (t2 & 1) { n_off = 96; ncols = BN - 96; } else { ncols = 96; }
+    }
     const int nt = tile % p.tiles_n, mt = tile / p.tiles_n;
-    const int n0 = nt * BN;
+    const int n0 = nt * BN + n_off;
     const int split = blockIdx.y;
     const int kb0 = (int)((long long)p.kblocks * split / p.split_k);
     const int kb1 = (int)((long long)p.kblocks * (split + 1) / p.split_k);
@@ -853,7 +866,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(BN, false, false);
+            const uint32_t idesc = umma_idesc_bf16((uint32_t)ncols, false, false);
             int s = 0; uint32_t ph = 0;
             for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(&full_bar[s], ph);
@@ -911,7 +924,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const int img_w = __shfl_sync(0xffffffffu, img, 0);
             const uint32_t stg_a = smem_u32(sA) + (uint32_t)(warp - 2) * (uint32_t)(NCH * TEPI_BOX_BYTES);
             uint64_t* rbar = &res_bar[warp - 2];
-#define SDB_TEPI1(MODE, RES) epilogue_tma_single<BN, MODE, RES>(p, &tmC, &tmR, taddr, smem_u32(s_bias), stg_a, rbar, accum_bar, ub, lane, lg, rowmask, img_w)
+#define SDB_TEPI1(MODE, RES) epilogue_tma_single<BN, MODE, RES>(p, &tmC, &tmR, taddr, smem_u32(s_bias), stg_a, rbar, accum_bar, ub, lane, lg, rowmask, img_w, ncols)
             if (p.geglu) {
                 if constexpr (BN % 64 == 0) SDB_TEPI1(EPI_GEGLU, false);
             } else if (p.split_k > 1) SDB_TEPI1(EPI_F32, false);
@@ -924,7 +937,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             // once the accumulator is ready every TMA load has been consumed: the A ring doubles as the transpose staging area
             float* stage = reinterpret_cast<float*>(sA) + (warp - 2) * (EPI_WARP_BYTES / 4);
             if (warp == 2 && lane == 0) TC1_TRACE(4);
-            epilogue_warp<BN>(p, taddr, s_bias, stage, lane, n0, nt, pix, img, split, 0, 1, accum_bar, 0, mt * 4 + lg);
+            epilogue_warp<BN>(p, taddr, s_bias, stage, lane, n0, nt, pix, img, split, 0, 1, accum_bar, 0, mt * 4 + lg, ncols);
             if (warp == 2 && lane == 0) TC1_TRACE(5);
         }
     }
@@ -1236,6 +1249,9 @@ static void pick_tile(int OW, int OH, int NB, int stride, int* tw, int* th, int*
     }
 }
 
+static int sm_count_cached();
+static bool tail_split_enabled();
+
 template <int BN>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR, TcP& p, int m_tiles,
                      cudaStream_t st) {
@@ -1252,7 +1268,19 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
     // TMA epilogue: one 4 KB box per (epilogue warp, 32-column chunk) must fit in the operand ring it re-uses
     constexpr int NCH = BN / 32 > 0 ? BN / 32 : 1;
     if (4 * NCH * TEPI_BOX_BYTES > Cfg::STAGES * Cfg::STAGE_BYTES) p.epi_tma = 0;
-    dim3 grid((unsigned)(m_tiles * p.tiles_n), (unsigned)p.split_k);
+    // Tail split (BN = 160): with T tiles on S SMs the slowest SM computes ceil(T / S) of them — 512 tiles of a 64x64, N = 320 layer
+    // at batch 8 are 3.46 per SM, i.e. 4 on some (86 %).  The T mod S tiles of the last, partial wave are issued as two sub-tiles
+    // (96 | 64 columns) each, at the end of the grid, so that the tail is handed out in half-size pieces.  Results are bit-identical
+    // (every output element sums over K in the same order whatever the tile width).
+    const int total = m_tiles * p.tiles_n;
+    p.full_tiles = total;
+    unsigned gx = (unsigned)total;
+    if (BN == 160 && tail_split_enabled() && p.split_k == 1 && !p.geglu) {
+        const int S = sm_count_cached();
+        const int r = total % S;
+        if (total >= S && 100 * r >= 12 * S && 100 * r <= 65 * S) { p.full_tiles = total - r; gx = (unsigned)(total + r); }
+    }
+    dim3 grid(gx, (unsigned)p.split_k);
     launch_pdl(tc_contract_kernel<BN>, dim3(grid), dim3(192), Cfg::SMEM_BYTES, st, tmA, tmB, tmC, tmR, p);
     return check_launch("tc_contract_kernel");
 }
@@ -1320,6 +1348,13 @@ static bool pair_kernel_enabled() {
         g_pair_kernel = (e && strcmp(e, "single") == 0) ? 0 : 1;
     }
     return g_pair_kernel == 1;
+}
+
+// Tail split of the one-CTA kernel (see launch_tc): SDB200_TC_TAILSPLIT=0 turns it off, sdb_tc_set_tail_split at run time
+static int g_tail_split = -1;
+static bool tail_split_enabled() {
+    if (g_tail_split < 0) { const char* e = getenv("SDB200_TC_TAILSPLIT"); g_tail_split = (e && e[0] == '0') ? 0 : 1; }
+    return g_tail_split == 1;
 }
 
 // TMA epilogue switches: SDB200_TC_EPI=regs forces the register-store epilogue everywhere (A/B measurements);
@@ -1538,6 +1573,12 @@ using namespace sdb;
 extern "C" int sdb_tc_set_pair_kernel(int enable) {
     int prev = pair_kernel_enabled() ? 1 : 0;
     g_pair_kernel = enable ? 1 : 0;
+    return prev;
+}
+
+extern "C" int sdb_tc_set_tail_split(int enable) {
+    int prev = tail_split_enabled() ? 1 : 0;
+    g_tail_split = enable ? 1 : 0;
     return prev;
 }
 

@@ -158,3 +158,44 @@ def test_colstats_small_maps_and_split_k(cuda, N, H, W, Cin, Cout, sk):
         out1 = ops.conv_tc(x[1:2].contiguous(), wp, b, 3, 3, pad=1, residual=res[1:2].contiguous(), variant=variant, split_k=sk, want_stats=True)
         y1 = ops.groupnorm(out1, g, be, 1e-5, act=1, out_dtype=torch.float32)
         assert torch.equal(out1[0], out[1]) and torch.equal(y1[0], y[1]), (variant, sk)
+
+
+@pytest.mark.parametrize("tma", [1, 0], ids=["tma_epilogue", "register_epilogue"])
+def test_tail_split_is_bit_identical(cuda, tma):
+    """One-CTA kernel, 160-column tiles: the tiles of the last partial wave issued as 96 | 64-column sub-tiles (sdb_tc_set_tail_split)
+    give the same bits as whole tiles — GEMM with residual, ragged M and N, bf16 output, 3x3 conv with time-embedding row, residual
+    and GroupNorm column statistics — through both epilogues."""
+    from sdb200 import _lib, ops
+    lib = _lib.load()
+    prev_t, prev_e = lib.sdb_tc_set_tail_split(1), lib.sdb_tc_set_tma_epilogue(tma)
+
+    def both(fn):
+        lib.sdb_tc_set_tail_split(1)
+        a = fn()
+        lib.sdb_tc_set_tail_split(0)
+        b = fn()
+        torch.cuda.synchronize()
+        return a, b
+    try:
+        for M, N, K in ((32768, 320, 320), (32768, 320, 1280), (25000, 300, 640), (40000, 640, 320)):
+            A = randn(M, K, seed=1).to(torch.bfloat16)
+            W = (randn(N, K, seed=2) * K ** -0.5).to(torch.bfloat16)
+            bias, res = randn(N, seed=3), randn(M, N, seed=4)
+            for kw in (dict(residual=res), dict(out_dtype=torch.bfloat16), dict()):
+                a, b = both(lambda: ops.gemm_tc(A, W, bias, variant=1, block_n=160, **kw))
+                assert torch.equal(a, b), (M, N, K, kw.keys())
+            want = A.float() @ W.float().T + bias + res
+            assert rel(ops.gemm_tc(A, W, bias, residual=res, variant=1, block_n=160), want) < 2e-5
+        x = randn(8, 64, 64, 320, seed=5).to(torch.bfloat16)
+        wp = ops.pack_conv_weight((randn(320, 320, 3, 3, seed=6) * (320 * 9) ** -0.5).to(torch.bfloat16), torch.bfloat16)
+        b, rv, res = randn(320, seed=7), randn(8, 320, seed=8), randn(8, 64, 64, 320, seed=9)
+        g, be = randn(320, seed=10) * 0.1 + 1, randn(320, seed=11) * 0.1
+
+        def conv():
+            o = ops.conv_tc(x, wp, b, 3, 3, pad=1, rowvec=rv, residual=res, variant=1, block_n=160, want_stats=True)
+            return o, ops.groupnorm(o, g, be, 1e-5, act=1, out_dtype=torch.bfloat16)
+        (o1, y1), (o0, y0) = both(conv)
+        assert torch.equal(o1, o0) and torch.equal(y1, y0)
+    finally:
+        lib.sdb_tc_set_tail_split(prev_t)
+        lib.sdb_tc_set_tma_epilogue(prev_e)
