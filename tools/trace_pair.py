@@ -8,7 +8,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 pk = os.path.join(ROOT, "stable-diffusion-from-scratch_b200")
-so = os.path.join(ROOT, "gpurun_out", "libsdb200_trace.so")
+so = os.path.join(ROOT, "variants", "libsdb200_trace.so")      # prebuilt on the dev box when present (variants/ travels)
+if not os.path.exists(so):
+    so = os.path.join(ROOT, "gpurun_out", "libsdb200_trace.so")
 os.makedirs(os.path.dirname(so), exist_ok=True)
 if not os.path.exists(so):
     srcs = [os.path.join(pk, "csrc", f) for f in sorted(os.listdir(os.path.join(pk, "csrc"))) if f.endswith(".cu")]
