@@ -333,6 +333,8 @@ def roofline_pass(run, label):
     def ev_pair():
         return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
+    replay_tc, replay_bw = [], []          # the launches of each class with their original arguments, in issue order
+
     def w_tc(argp, stream):
         a = argp._obj
         e0, e1 = ev_pair()
@@ -340,6 +342,7 @@ def roofline_pass(run, label):
         rc = orig["sdb_tc_contract"](argp, stream)
         e1.record()
         tc.append((2.0 * a.M * a.N * a.K, e0, e1))
+        replay_tc.append(type(a).from_buffer_copy(a))
         return rc
 
     def w_gn(*args):          # x0, C0, x1, C1, N, HW, groups, eps, gamma, beta, gbs, act, exact, out, out_dtype, raw, ...
@@ -347,6 +350,7 @@ def roofline_pass(run, label):
         e0.record()
         rc = orig["sdb_groupnorm_nhwc"](*args)
         e1.record()
+        replay_bw.append(("sdb_groupnorm_nhwc", args))
         elems = float(args[4]) * args[5] * (args[1] + args[3])
         bw.append((elems * (4 + (2 if args[14] == 1 else 4) + (2 if args[15] else 0)), e0, e1, "gn"))
         return rc
@@ -356,6 +360,7 @@ def roofline_pass(run, label):
         e0.record()
         rc = orig["sdb_groupnorm_from_colstats"](*args)
         e1.record()
+        replay_bw.append(("sdb_groupnorm_from_colstats", args))
         elems = float(args[8]) * args[9] * (args[1] + args[5])
         bw.append((elems * (4 + (2 if args[18] == 1 else 4) + (2 if args[19] else 0)), e0, e1, "gn_colstats"))
         return rc
@@ -365,6 +370,7 @@ def roofline_pass(run, label):
         e0.record()
         rc = orig["sdb_layernorm"](*args)
         e1.record()
+        replay_bw.append(("sdb_layernorm", args))
         bw.append((float(args[1]) * args[2] * (4 + (2 if args[7] == 1 else 4)), e0, e1, "ln"))
         return rc
 
@@ -394,6 +400,34 @@ def roofline_pass(run, label):
         for n in names:
             setattr(lib, n, orig[n])
     launches = lib.sdb_launch_count() - l0
+
+    # Second measurement of each class, without the per-launch event brackets: the class's launches are re-issued BACK TO BACK with
+    # their original arguments and in their original order (nothing else in between, so consecutive launches overlap through
+    # programmatic dependent launch as they do inside the captured graph), 5 passes between ONE pair of events, the device parked
+    # while the host runs ahead.  A pass streams the same 1.7 GB of weights through L2 as the real step; activations are not
+    # L2-warm (their producers do not run), which is pessimistic.  No allocation happens between the call above and the re-issue, so
+    # every pointer in the saved arguments still refers to memory of the same size in the caching allocator.
+    import ctypes as C
+
+    def reissue(items, call, passes=5):
+        if not items:
+            return None
+        st = _lib.stream_ptr()
+        for it in items:
+            call(it, st)
+        torch.cuda.synchronize()
+        e0, e1 = ev_pair()
+        torch.cuda._sleep(int(2e8))
+        e0.record()
+        for _ in range(passes):
+            for it in items:
+                call(it, st)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / passes
+
+    ms_tc_b2b = reissue(replay_tc, lambda a, st: orig["sdb_tc_contract"](C.byref(a), st))
+    ms_bw_b2b = reissue(replay_bw, lambda it, st: orig[it[0]](*it[1]))
     tf_peak, hbm_peak, which = peaks()
     roof = roof_hbm = None
     if tc:
@@ -411,7 +445,17 @@ def roofline_pass(run, label):
                 traffic = None
         roof = {"bound": "tensor", "kernel": "tc_contract_pair_kernel / tc_contract_kernel (tcgen05 implicit-GEMM conv + GEMM), %s" % label,
                 "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": traffic, "launches": len(tc),
-                "sum_ms": ms, "algorithmic_gflop": flop / 1e9, "peak_source": which + " (sustained cuBLAS bf16)"}
+                "sum_ms": ms, "algorithmic_gflop": flop / 1e9, "peak_source": which + " (sustained cuBLAS bf16)",
+                "method": "sum of per-launch CUDA-event brackets (each bracket carries the event pair's own ~1-2 us: conservative)"}
+        if ms_tc_b2b:
+            # headline figures = the back-to-back measurement; the per-launch brackets are kept beside it
+            roof["bracketed"] = {"sum_ms": roof["sum_ms"], "achieved": roof["achieved"], "frac": roof["frac"], "method": roof["method"]}
+            roof["sum_ms"] = ms_tc_b2b
+            roof["achieved"] = flop / (ms_tc_b2b / 1000.0) / 1e12
+            roof["frac"] = roof["achieved"] / tf_peak
+            roof["method"] = ("the %d contraction launches of one call re-issued back to back with their original arguments, in issue order, "
+                              "5 passes between ONE pair of CUDA events (device parked while the host runs ahead); average launch "
+                              "duration = sum_ms / launches" % len(tc))
     if bw:
         by, ms = sum(r[0] for r in bw), sum(r[1].elapsed_time(r[2]) for r in bw)
         ach = by / (ms / 1000.0) / 1e9
@@ -425,7 +469,15 @@ def roofline_pass(run, label):
                     "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "launches": len(bw),
                     "sum_ms": ms, "algorithmic_mbytes": by / 1e6, "peak_source": which + " (device copy)",
                     "by_kernel": {k: {"GB/s": v[0] / (v[1] / 1000.0) / 1e9, "ms": v[1], "launches": v[2]} for k, v in per.items()},
-                    "convention": "fp32 read once + output written once (bf16 operand, + the raw bf16 copy when emitted)"}
+                    "convention": "fp32 read once + output written once (bf16 operand, + the raw bf16 copy when emitted)",
+                    "method": "sum of per-launch CUDA-event brackets (15-20 us kernels: the ~1-2 us of the event pair deflates this figure)"}
+        if ms_bw_b2b:
+            roof_hbm["bracketed"] = {"sum_ms": roof_hbm["sum_ms"], "achieved": roof_hbm["achieved"], "frac": roof_hbm["frac"], "method": roof_hbm["method"]}
+            roof_hbm["sum_ms"] = ms_bw_b2b
+            roof_hbm["achieved"] = by / (ms_bw_b2b / 1000.0) / 1e9
+            roof_hbm["frac"] = roof_hbm["achieved"] / hbm_peak
+            roof_hbm["method"] = ("the %d GroupNorm / LayerNorm launches of one call re-issued back to back with their original arguments, in issue "
+                                  "order, 5 passes between ONE pair of CUDA events" % len(bw))
     if at and roof is not None:
         # attention kernels: tensor roofline on the algorithmic 4*B*H*Sq*Sk*d FLOP, and the exponential rate against the
         # MUFU.EX2 pipe (16 per clock and SM, measured: profiles/r01_xu_rate.txt) at the clock sampled during the timed region
