@@ -122,6 +122,9 @@ __device__ __forceinline__ float ex2_sel(float x) {
                           (SDB_ATTN_POLY == 3 && (J == 2 || J == 5 || J == 7)) || (SDB_ATTN_POLY == 4 && (J & 1));
     return poly ? ex2_fma(x) : ex2_approx(x);
 }
+#ifndef SDB_ATTN_ONES
+#define SDB_ATTN_ONES 1         // row sums from the tensor core: pad channel d of every V tile is set to 1, so O[:, d] = sum_j P_ij
+#endif
 #ifndef SDB_ATTN_PACKED
 #define SDB_ATTN_PACKED 1       // FFMA2 / FADD2 in the exponential phase (0 = scalar fp32, the round-1 form)
 #endif
@@ -154,7 +157,8 @@ __device__ __forceinline__ uint32_t pack_p_bf16x2(float lo, float hi) {
 #endif
 }
 
-template <int DPAD>
+// ONES: head_dim < DPAD, so channel d of every V tile can be set to 1 and the row sums come out of the PV MMA as O[:, d]
+template <int DPAD, bool ONES>
 __global__ void __launch_bounds__(AttnCfg<DPAD>::THREADS, 1)
 tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnP p) {
@@ -247,6 +251,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const uint64_t kdesc0 = umma_desc_kmajor_sw128(smem_u32(sK));
             const uint64_t vdesc0 = umma_desc_mnmajor_sw128(smem_u32(sV), 16384);
             const uint64_t pdesc0 = umma_desc_kmajor_sw128(smem_u32(sP));
+            constexpr bool ones = ONES && SDB_ATTN_ONES;
             mbar_wait(q_full, 0);
             int s = 0; uint32_t ph = 0;        // K ring
             int sv = 0; uint32_t phv = 0;      // V ring (lags by one tile)
@@ -278,6 +283,19 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     const int tp = t - 1;
                     if (g_lo == 0) AT_TRACE_MMA(4);
                     mbar_wait(&v_full[sv], phv);
+                    if (ones) {                      // (with two issuers both patch: same values, each fences before its own MMAs)
+                        // channel d (a pad channel: TMA zero fill or zeros in memory) of all 128 key rows := 1.0 (bf16), in the
+                        // swizzled layout the MMA reads: row r, 16-byte chunk (d / 8) ^ (r & 7) of 64-channel block d / 64
+                        const uint32_t vb = smem_u32(sV) + (uint32_t)sv * Cfg::TILE_BYTES + (uint32_t)(p.d >> 6) * 16384u;
+                        const uint32_t ch = (uint32_t)((p.d & 63) >> 3), within = (uint32_t)(p.d & 7) * 2u;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint32_t r = (uint32_t)(lane + 32 * i);
+                            asm volatile("st.shared.b16 [%0], %1;" ::"r"(vb + r * 128u + ((ch ^ (r & 7u)) << 4) + within), "h"((unsigned short)0x3F80) : "memory");
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                    }
                     if (g_lo == 0) AT_TRACE_MMA(5);
                     const int pb = PB == 2 ? (tp & 1) : 0;         // P buffer of key tile tp
                     const uint64_t vdesc = vdesc0 + (uint64_t)(sv * TILE16);
@@ -316,6 +334,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const uint32_t o_addr = lane_addr + Cfg::o_col(g);
         const uint32_t prow0 = smem_u32(sP + g * PB * Cfg::P_BYTES) + row * 128;
         float m_used = -INFINITY, l = 0.f;
+        constexpr bool ones = ONES && SDB_ATTN_ONES;         // the row sum comes out of the PV MMA (channel d of V is 1)
         const float c = p.scale_log2;
         // Exponential phase ping-pong (G == 2): the two softmax warps of one SM sub-partition share its MUFU unit and its
         // TMEM read port.  Left alone they run in lockstep — both reading S, then both in ex2 at half rate — and the MUFU
@@ -421,10 +440,12 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     e[j] = ex2_approx(x0);
                     e[j + 1] = ex2_approx(x1);
                 }
-                acc_a = fadd2(acc_a, pack_f32x2(e[0], e[1]));
-                acc_b = fadd2(acc_b, pack_f32x2(e[2], e[3]));
-                acc_a = fadd2(acc_a, pack_f32x2(e[4], e[5]));
-                acc_b = fadd2(acc_b, pack_f32x2(e[6], e[7]));
+                if (!ones) {
+                    acc_a = fadd2(acc_a, pack_f32x2(e[0], e[1]));
+                    acc_b = fadd2(acc_b, pack_f32x2(e[2], e[3]));
+                    acc_a = fadd2(acc_a, pack_f32x2(e[4], e[5]));
+                    acc_b = fadd2(acc_b, pack_f32x2(e[6], e[7]));
+                }
                 const int chunk = (c0 & 63) >> 3;
                 sts128(prow + (c0 >> 6) * 16384 + ((chunk ^ (row & 7)) << 4),
                        pack_p_bf16x2(e[0], e[1]), pack_p_bf16x2(e[2], e[3]), pack_p_bf16x2(e[4], e[5]), pack_p_bf16x2(e[6], e[7]));
@@ -470,6 +491,10 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (PB == 2) mbar_wait(&pv_done[g * PB + ((ntiles - 1) & 1)], ((ntiles - 1) >> 1) & 1);   // in-order pipe: the last PV retires last
         else mbar_wait(&pv_done[g], (ntiles - 1) & 1);
         tcgen05_fence_after();
+        if (ones) {
+            l = __uint_as_float(tmem_ld_x1(o_addr + (uint32_t)p.d));      // sum_j P_ij, accumulated (and rescaled) with O
+            tmem_ld_wait();
+        }
         const float inv = 1.0f / l;
         const int q = q0 + g * 128 + row;
         __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)b * p.o_bs + (long long)q * p.o_ss + (long long)h * p.o_hs;
@@ -503,7 +528,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
 }
 
-template <int DPAD>
+template <int DPAD, bool ONES>
 static int launch_attn(const sdb_attn_args* a, cudaStream_t st) {
     using Cfg = AttnCfg<DPAD>;
     CUtensorMap tmQ, tmK, tmV;
@@ -530,7 +555,7 @@ static int launch_attn(const sdb_attn_args* a, cudaStream_t st) {
     if (cudaGetDevice(&cur_dev) != cudaSuccess || cur_dev < 0 || cur_dev >= 64) cur_dev = 0;
     bool& attr_set = attr_set_dev[cur_dev];
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc_attention_kernel<DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(tc_attention_kernel<DPAD, ONES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) { set_last_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SDB_ERR_CUDA; }
         attr_set = true;
     }
@@ -543,7 +568,7 @@ static int launch_attn(const sdb_attn_args* a, cudaStream_t st) {
     p.scale_log2 = a->scale * 1.4426950408889634f;
     p.causal = a->causal ? 1 : 0;
     dim3 grid((unsigned)ceil_div(a->Sq, 128 * Cfg::G), (unsigned)a->H, (unsigned)a->B);
-    launch_pdl(tc_attention_kernel<DPAD>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, tmQ, tmK, tmV, p);
+    launch_pdl(tc_attention_kernel<DPAD, ONES>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, tmQ, tmK, tmV, p);
     return check_launch("tc_attention_kernel");
 }
 
@@ -563,9 +588,12 @@ extern "C" int sdb_attention_fwd(const sdb_attn_args* a, void* stream) {
         const int rc = attention_kv1_dispatch(a, st);     // Sk <= 128 (the text conditioning): 1 = not covered
         if (rc != 1) return rc;
     }
+    // a pad channel exists and the kernel is exponential-bound (64-channel heads): row sums from the PV MMA.  Wider heads are
+    // MMA-paced and lose 0.5-2 % to the V-tile patch in front of every PV issue (profiles/r02_attn_notes.txt)
+    const bool spare = a->d < a->dpad && a->dpad == 64;
     switch (a->dpad) {
-        case 64: return launch_attn<64>(a, st);
-        case 128: return launch_attn<128>(a, st);
-        default: return launch_attn<192>(a, st);
+        case 64: return spare ? launch_attn<64, true>(a, st) : launch_attn<64, false>(a, st);
+        case 128: return spare ? launch_attn<128, true>(a, st) : launch_attn<128, false>(a, st);
+        default: return spare ? launch_attn<192, true>(a, st) : launch_attn<192, false>(a, st);
     }
 }
