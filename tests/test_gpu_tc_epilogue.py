@@ -199,3 +199,30 @@ def test_tail_split_is_bit_identical(cuda, tma):
     finally:
         lib.sdb_tc_set_tail_split(prev_t)
         lib.sdb_tc_set_tma_epilogue(prev_e)
+
+
+@pytest.mark.parametrize("variant", [2, 1], ids=["pair", "single"])
+def test_b_const_is_bit_identical(cuda, variant):
+    """sdb_tc_args.b_const (weight tiles requested before the programmatic-dependent-launch wait) changes when the loads are
+    issued, never what is computed: GEMM and 3x3 conv, back-to-back launches so that a predecessor is actually draining."""
+    from sdb200 import ops
+    A = randn(8192, 640, seed=1).to(torch.bfloat16)
+    W = (randn(640, 640, seed=2) * 640 ** -0.5).to(torch.bfloat16)
+    bias, res = randn(640, seed=3), randn(8192, 640, seed=4)
+    x = randn(4, 32, 32, 320, seed=5).to(torch.bfloat16)
+    wp = ops.pack_conv_weight((randn(320, 320, 3, 3, seed=6) * (320 * 9) ** -0.5).to(torch.bfloat16), torch.bfloat16)
+    cb = randn(320, seed=7)
+    torch.cuda.synchronize()                       # the weights above are complete before any launch may prefetch them
+    outs = {}
+    for flag in (False, True, False, True):
+        g = [ops.gemm_tc(A, W, bias, residual=res, variant=variant, b_const=flag) for _ in range(4)]
+        c = [ops.conv_tc(x, wp, cb, 3, 3, pad=1, variant=variant, b_const=flag) for _ in range(4)]
+        outs.setdefault(flag, []).append((g, c))
+    torch.cuda.synchronize()
+    g0, c0 = outs[False][0][0][0], outs[False][0][1][0]
+    for flag in (False, True):
+        for g, c in outs[flag]:
+            for t in g:
+                assert torch.equal(t, g0)
+            for t in c:
+                assert torch.equal(t, c0)
